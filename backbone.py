@@ -1,0 +1,7 @@
+"""Drop-in shim: `import backbone` from the repository root resolves to the B200-native implementation
+(cfun_b200.backbone), so the reference driver heart_main.py (`from config import Config; import model; import utils`,
+reference heart_main.py:15-17) runs against these layers unmodified."""
+from cfun_b200.backbone import *  # noqa: F401,F403
+from cfun_b200 import backbone as _impl
+
+globals().update({k: v for k, v in vars(_impl).items() if not k.startswith("__")})

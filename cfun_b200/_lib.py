@@ -1,0 +1,87 @@
+"""ctypes binding of libcfun_b200.so (the C ABI in include/cfun_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing or fails to load, importing this module
+raises, and every op raises RuntimeError with cfun_last_error() on a non-zero return code.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libcfun_b200.so")
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("N", "Cin", "Din", "Hin", "Win", "Cout", "Dout", "Hout", "Wout",
+                                       "kD", "kH", "kW", "sD", "sH", "sW", "pD", "pH", "pW")]
+
+
+def _load():
+    # (re)build in-tree when the sources changed (needs nvcc; a no-op digest check otherwise).  Never falls back to a
+    # CPU implementation: if neither a current .so nor nvcc is available this raises.
+    from . import build as _build
+    try:
+        _build.build()
+    except Exception:
+        if not os.path.exists(LIB_PATH):
+            raise
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+_p, _i, _ll, _f, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
+_D = C.POINTER(ConvDesc)
+
+SIGNATURES = {
+    "cfun_last_error": (C.c_char_p, []),
+    "cfun_version": (_i, []),
+    "cfun_device_is_sm100": (_i, []),
+    "cfun_conv3d_workspace_size": (_sz, [_D, _i, _i]),
+    "cfun_conv3d_pick_algo": (_i, [_D, _i]),
+    "cfun_conv3d_fwd": (_i, [_D, _p, _p, _p, _p, _i, _i, _p, _sz, _p]),
+    "cfun_conv3d_bwd_data": (_i, [_D, _p, _p, _p, _i, _p, _sz, _p]),
+    "cfun_conv3d_bwd_weight": (_i, [_D, _p, _p, _p, _p, _i, _p, _sz, _p]),
+    "cfun_fc_fwd": (_i, [_i, _i, _ll, _p, _p, _p, _p, _p]),
+    "cfun_fc_bwd_data": (_i, [_i, _i, _ll, _p, _p, _p, _p]),
+    "cfun_fc_bwd_weight": (_i, [_i, _i, _ll, _p, _p, _p, _p, _p]),
+    "cfun_instnorm_stats": (_i, [_p, _i, _ll, _i, _f, _p, _p, _p, _p]),
+    "cfun_affine_act_fwd": (_i, [_p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p]),
+    "cfun_affine_act_bwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p]),
+    "cfun_instnorm_bwd_apply": (_i, [_p, _p, _p, _p, _p, _i, _ll, _i, _p]),
+    "cfun_maxpool2_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "cfun_maxpool2_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "cfun_pack_split_bf16": (_i, [_p, _p, _p, _ll, _i, _i, _p]),
+    "cfun_roi_crop_resize_fwd": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p]),
+    "cfun_roi_crop_resize_bwd": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p]),
+    "cfun_roi_level": (_i, [_p, _i, _p, _p]),
+    "cfun_sort_workspace_size": (_sz, [_i]),
+    "cfun_sort_desc": (_i, [_p, _i, _p, _p, _sz, _p]),
+    "cfun_decode_clip": (_i, [_p, _p, _p, _i, _i, _p, _i, C.POINTER(C.c_float), C.POINTER(C.c_float), _p, _p, _p]),
+    "cfun_nms_workspace_size": (_sz, [_i]),
+    "cfun_nms3d": (_i, [_p, _i, _f, _i, _p, _p, _p, _sz, _p]),
+    "cfun_gather_boxes": (_i, [_p, _p, _p, _i, C.POINTER(C.c_float), _p, _p]),
+    "cfun_iou3d_eps": (_i, [_p, _p, _i, _p, _p]),
+    "cfun_bbox_overlaps3d": (_i, [_p, _i, _p, _i, _p, _p]),
+    "cfun_box_refinement": (_i, [_p, _p, _i, C.POINTER(C.c_float), _p, _p]),
+    "cfun_mask_target_crop": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
+    "cfun_sobel_edge_workspace_size": (_sz, [_i, _i, _i]),
+    "cfun_sobel_edge_loss_fwd": (_i, [_p, _p, _i, _i, _i, _p, _p, _sz, _p]),
+    "cfun_sobel_edge_loss_bwd": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _sz, _p]),
+    "cfun_sumsq": (_i, [_p, _ll, _p, _p]),
+    "cfun_sgd_clip_step": (_i, [_p, _p, _p, _p, _ll, _p, _f, _f, _f, _f, _i, _p]),
+    "cfun_mold_volume_i16": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)      # AttributeError here == the library does not export a declared symbol
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (rc=%d): %s" % (what, rc, lib.cfun_last_error().decode()))
+
+
+def f6(vals):
+    return (C.c_float * 6)(*[float(v) for v in vals])

@@ -1,0 +1,499 @@
+// Bandwidth-bound passes around the convolutions, all on fp32 NDHWC tensors:
+//   instance-norm statistics, fused (affine -> +residual -> leaky-relu -> nearest x2 -> concat-slice) forward and
+//   backward, instance-norm backward, 2x2x2 max-pool, CT-volume molding.
+// Replaces InstanceNorm3d / LeakyReLU / Dropout3d / Upsample / cat (mask_branch.py:18-20,91-122,124-220), frozen
+// BatchNorm3d + ReLU + residual add (backbone.py:26-114), MaxPool3d (backbone.py:127), mold_image (model.py:1902).
+#include "common.cuh"
+
+namespace cfun {
+
+// Thread layout shared by the per-(n,c) reduction kernels: a block owns `rows_per_block` consecutive voxels of one
+// sample; thread t handles vector-channel q = t % CV (V channels each) of rows r = t / CV, r + R, ...
+struct RowMap {
+  int CV;  // number of channel vectors per row
+  int R;   // rows per iteration
+};
+static RowMap make_rowmap(int C, int V) {
+  RowMap m;
+  m.CV = C / V;
+  m.R = 256 / m.CV;
+  if (m.R < 1) m.R = 1;
+  return m;
+}
+
+template <int V>
+struct Vec;
+template <>
+struct Vec<4> {
+  static __device__ __forceinline__ void load(const float* p, float* v) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct Vec<1> {
+  static __device__ __forceinline__ void load(const float* p, float* v) { v[0] = __ldg(p); }
+  static __device__ __forceinline__ void store(float* p, const float* v) { p[0] = v[0]; }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// instance-norm statistics
+// ---------------------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(256) in_stats_kernel(const float* __restrict__ x, long long S, int C, int CV, int R,
+                                                       long long rows_per_block, double* __restrict__ acc) {
+  extern __shared__ double sm[];  // [2*C]
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * C; i += blockDim.x) sm[i] = 0.0;
+  __syncthreads();
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > S) r1 = S;
+  for (int q = tid % CV, rr = tid / CV; q < CV && rr < R; q += CV * R) {  // executes once for active threads
+    float s[V], ss[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) s[j] = ss[j] = 0.f;
+    const float* base = x + ((long long)n * S) * C + q * V;
+    for (long long r = r0 + rr; r < r1; r += R) {
+      float v[V];
+      Vec<V>::load(base + r * C, v);
+#pragma unroll
+      for (int j = 0; j < V; ++j) { s[j] += v[j]; ss[j] = fmaf(v[j], v[j], ss[j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      atomicAdd(&sm[q * V + j], (double)s[j]);
+      atomicAdd(&sm[C + q * V + j], (double)ss[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < C; i += blockDim.x) {
+    atomicAdd(&acc[((long long)n * C + i) * 2 + 0], sm[i]);
+    atomicAdd(&acc[((long long)n * C + i) * 2 + 1], sm[C + i]);
+  }
+}
+
+__global__ void in_finalize_kernel(const double* __restrict__ acc, long long NC, double invS, float eps,
+                                   float* __restrict__ mean, float* __restrict__ rstd) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= NC) return;
+  double m = acc[2 * i] * invS;
+  double var = acc[2 * i + 1] * invS - m * m;
+  if (var < 0) var = 0;
+  mean[i] = (float)m;
+  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fused affine + residual + leaky relu (+ nearest x2 upsample, + concat slice) : forward
+// ---------------------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(256) affine_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ a,
+                                                             const float* __restrict__ b, int a_nstride,
+                                                             const float* __restrict__ r, float* __restrict__ y, int N,
+                                                             int D, int H, int W, int C, int Ctot, int c_off, int up,
+                                                             float slope) {
+  const int CV = C / V;
+  const long long total = (long long)N * D * H * W * CV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int q = (int)(i % CV);
+    long long vox = i / CV;
+    int c = q * V;
+    float v[V];
+    Vec<V>::load(x + vox * C + c, v);
+    long long t = vox;
+    int w = (int)(t % W); t /= W;
+    int h = (int)(t % H); t /= H;
+    int d = (int)(t % D); t /= D;
+    int n = (int)t;
+    if (a) {
+      float av[V], bv[V];
+      Vec<V>::load(a + (long long)n * a_nstride + c, av);
+      Vec<V>::load(b + (long long)n * a_nstride + c, bv);
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] = fmaf(v[j], av[j], bv[j]);
+    }
+    if (r) {
+      float rv[V];
+      Vec<V>::load(r + vox * C + c, rv);
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] += rv[j];
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * slope;
+    if (up == 1) {
+      Vec<V>::store(y + vox * Ctot + c_off + c, v);
+    } else {
+      const int H2 = H * 2, W2 = W * 2;
+#pragma unroll
+      for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+        for (int dy_ = 0; dy_ < 2; ++dy_)
+#pragma unroll
+          for (int dx_ = 0; dx_ < 2; ++dx_) {
+            long long o = (((long long)n * (D * 2) + (2 * d + dz)) * H2 + (2 * h + dy_)) * W2 + (2 * w + dx_);
+            Vec<V>::store(y + o * Ctot + c_off + c, v);
+          }
+    }
+  }
+}
+
+// backward: per-sample blocks so that instance-norm reductions can be fused
+template <int V>
+__global__ void __launch_bounds__(256) affine_act_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a,
+                                                             const float* __restrict__ b, int a_nstride,
+                                                             const float* __restrict__ r, const float* __restrict__ dy,
+                                                             float* __restrict__ dx, float* __restrict__ dr,
+                                                             double* __restrict__ stat_acc, int D, int H, int W, int C,
+                                                             int Ctot, int c_off, int up, float slope, int CV, int R,
+                                                             long long rows_per_block) {
+  extern __shared__ double sm[];  // [2*C] when stat_acc
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x;
+  const long long S = (long long)D * H * W;
+  if (stat_acc) {
+    for (int i = tid; i < 2 * C; i += blockDim.x) sm[i] = 0.0;
+    __syncthreads();
+  }
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > S) r1 = S;
+  const int q = tid % CV, rr = tid / CV;
+  if (rr < R) {
+    const int c = q * V;
+    float av[V], bv[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) { av[j] = 1.f; bv[j] = 0.f; }
+    if (a) {
+      Vec<V>::load(a + (long long)n * a_nstride + c, av);
+      Vec<V>::load(b + (long long)n * a_nstride + c, bv);
+    }
+    float s1[V], s2[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) s1[j] = s2[j] = 0.f;
+    for (long long row = r0 + rr; row < r1; row += R) {
+      const long long vox = (long long)n * S + row;
+      float xv[V], pre[V], g[V];
+      Vec<V>::load(x + vox * C + c, xv);
+#pragma unroll
+      for (int j = 0; j < V; ++j) pre[j] = fmaf(xv[j], av[j], bv[j]);
+      float xh[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) xh[j] = pre[j];
+      if (r) {
+        float rv[V];
+        Vec<V>::load(r + vox * C + c, rv);
+#pragma unroll
+        for (int j = 0; j < V; ++j) pre[j] += rv[j];
+      }
+      if (up == 1) {
+        Vec<V>::load(dy + vox * Ctot + c_off + c, g);
+      } else {
+        long long t = row;
+        int w = (int)(t % W); t /= W;
+        int h = (int)(t % H); t /= H;
+        int d = (int)t;
+        const int H2 = H * 2, W2 = W * 2;
+#pragma unroll
+        for (int j = 0; j < V; ++j) g[j] = 0.f;
+#pragma unroll
+        for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+          for (int dy_ = 0; dy_ < 2; ++dy_)
+#pragma unroll
+            for (int dx_ = 0; dx_ < 2; ++dx_) {
+              long long o = (((long long)n * (D * 2) + (2 * d + dz)) * H2 + (2 * h + dy_)) * W2 + (2 * w + dx_);
+              float t4[V];
+              Vec<V>::load(dy + o * Ctot + c_off + c, t4);
+#pragma unroll
+              for (int j = 0; j < V; ++j) g[j] += t4[j];
+            }
+      }
+#pragma unroll
+      for (int j = 0; j < V; ++j) g[j] = pre[j] > 0.f ? g[j] : g[j] * slope;
+      if (dr) Vec<V>::store(dr + vox * C + c, g);
+      if (stat_acc) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) { s1[j] += g[j]; s2[j] = fmaf(g[j], xh[j], s2[j]); }
+        Vec<V>::store(dx + vox * C + c, g);
+      } else {
+        float o[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) o[j] = g[j] * av[j];
+        Vec<V>::store(dx + vox * C + c, o);
+      }
+    }
+    if (stat_acc) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        atomicAdd(&sm[c + j], (double)s1[j]);
+        atomicAdd(&sm[C + c + j], (double)s2[j]);
+      }
+    }
+  }
+  if (stat_acc) {
+    __syncthreads();
+    for (int i = tid; i < C; i += blockDim.x) {
+      atomicAdd(&stat_acc[((long long)n * C + i) * 2 + 0], sm[i]);
+      atomicAdd(&stat_acc[((long long)n * C + i) * 2 + 1], sm[C + i]);
+    }
+  }
+}
+
+// dx = a * (g - s1/S - xhat * s2/S),  xhat = x*a + b, g stored in dx
+template <int V>
+__global__ void __launch_bounds__(256) in_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ a,
+                                                           const float* __restrict__ b,
+                                                           const double* __restrict__ stat_acc, float* __restrict__ dx,
+                                                           int N, long long S, int C) {
+  const int CV = C / V;
+  const long long total = (long long)N * S * CV;
+  const double invS = 1.0 / (double)S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int q = (int)(i % CV);
+    long long vox = i / CV;
+    int n = (int)(vox / S);
+    int c = q * V;
+    float xv[V], g[V], av[V], bv[V], o[V];
+    Vec<V>::load(x + vox * C + c, xv);
+    Vec<V>::load(dx + vox * C + c, g);
+    Vec<V>::load(a + (long long)n * C + c, av);
+    Vec<V>::load(b + (long long)n * C + c, bv);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float m1 = (float)(stat_acc[((long long)n * C + c + j) * 2 + 0] * invS);
+      float m2 = (float)(stat_acc[((long long)n * C + c + j) * 2 + 1] * invS);
+      float xh = fmaf(xv[j], av[j], bv[j]);
+      o[j] = av[j] * (g[j] - m1 - xh * m2);
+    }
+    Vec<V>::store(dx + vox * C + c, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 2x2x2 max pool, stride 2 (even extents)
+// ---------------------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(256) maxpool2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int D,
+                                                           int H, int W, int C) {
+  const int CV = C / V, Do = D / 2, Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)N * Do * Ho * Wo * CV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int q = (int)(i % CV);
+    long long t = i / CV;
+    int w = (int)(t % Wo); t /= Wo;
+    int h = (int)(t % Ho); t /= Ho;
+    int d = (int)(t % Do); t /= Do;
+    int n = (int)t;
+    float m[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) m[j] = -INFINITY;
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+      for (int dy_ = 0; dy_ < 2; ++dy_)
+#pragma unroll
+        for (int dx_ = 0; dx_ < 2; ++dx_) {
+          float v[V];
+          Vec<V>::load(x + ((((long long)n * D + 2 * d + dz) * H + 2 * h + dy_) * W + 2 * w + dx_) * C + q * V, v);
+#pragma unroll
+          for (int j = 0; j < V; ++j) m[j] = (v[j] > m[j] || v[j] != v[j]) ? v[j] : m[j];
+        }
+    Vec<V>::store(y + (i / CV) * C + q * V, m);
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                           float* __restrict__ dx, int N, int D, int H, int W, int C) {
+  const int CV = C / V, Do = D / 2, Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)N * Do * Ho * Wo * CV;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int q = (int)(i % CV);
+    long long t = i / CV;
+    int w = (int)(t % Wo); t /= Wo;
+    int h = (int)(t % Ho); t /= Ho;
+    int d = (int)(t % Do); t /= Do;
+    int n = (int)t;
+    float m[V], g[V];
+    int arg[V];
+    Vec<V>::load(dy + (i / CV) * C + q * V, g);
+#pragma unroll
+    for (int j = 0; j < V; ++j) { m[j] = -INFINITY; arg[j] = 0; }
+    float v[8][V];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int dz = k >> 2, dy_ = (k >> 1) & 1, dx_ = k & 1;
+      Vec<V>::load(x + ((((long long)n * D + 2 * d + dz) * H + 2 * h + dy_) * W + 2 * w + dx_) * C + q * V, v[k]);
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+        if (v[k][j] > m[j] || v[k][j] != v[k][j]) { m[j] = v[k][j]; arg[j] = k; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int dz = k >> 2, dy_ = (k >> 1) & 1, dx_ = k & 1;
+      float o[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] = arg[j] == k ? g[j] : 0.f;
+      Vec<V>::store(dx + ((((long long)n * D + 2 * d + dz) * H + 2 * h + dy_) * W + 2 * w + dx_) * C + q * V, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CT volume molding: int16 [H,W,D] -> fp32 [D,H,W], (x - mean) / std
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) i16_stats_kernel(const short* __restrict__ v, long long n, double* __restrict__ acc) {
+  long long s = 0, ss = 0;  // exact integer accumulation
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long t = v[i];
+    s += t;
+    ss += t * t;
+  }
+  double ds = warp_sum((double)s), dss = warp_sum((double)ss);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(acc, ds);
+    atomicAdd(acc + 1, dss);
+  }
+}
+__global__ void mold_transpose_kernel(const short* __restrict__ v, int H, int W, int D, const double* __restrict__ acc,
+                                      float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const double cnt = (double)H * W * D;
+  const double mean = acc[0] / cnt;
+  double var = acc[1] / cnt - mean * mean;
+  if (var < 0) var = 0;
+  const float fm = (float)mean, fr = (float)(1.0 / sqrt(var));
+  const int h = blockIdx.z;
+  const int w0 = blockIdx.y * 32, d0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int w = w0 + j, d = d0 + threadIdx.x;
+    if (w < W && d < D) tile[j][threadIdx.x] = ((float)v[((long long)h * W + w) * D + d] - fm) * fr;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    int d = d0 + j, w = w0 + threadIdx.x;
+    if (w < W && d < D) out[((long long)d * H + h) * W + w] = tile[threadIdx.x][j];
+  }
+}
+
+static int pick_blocks(long long total) {
+  long long b = cdiv(total, 256);
+  long long cap = 32LL * num_sms();
+  return (int)std::max<long long>(1, std::min(b, cap));
+}
+
+}  // namespace cfun
+
+using namespace cfun;
+
+extern "C" int cfun_instnorm_stats(const float* x, int N, long long S, int C, float eps, double* acc, float* mean,
+                                   float* rstd, void* stream) {
+  CFUN_CHECK_ARG(x && acc && mean && rstd && N > 0 && S > 0 && C > 0 && C <= 1024);
+  cudaStream_t st = as_stream(stream);
+  CFUN_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * (size_t)N * C, st));
+  const int V = (C % 4 == 0) ? 4 : 1;
+  CFUN_CHECK_ARG(C / V <= 256);
+  RowMap rm = make_rowmap(C, V);
+  long long rpb = std::max<long long>((long long)rm.R * 8, cdiv(S, std::max<long long>(1, 8LL * num_sms() / N)));
+  dim3 grid((unsigned)cdiv(S, rpb), N);
+  size_t smem = sizeof(double) * 2 * C;
+  if (V == 4) in_stats_kernel<4><<<grid, 256, smem, st>>>(x, S, C, rm.CV, rm.R, rpb, acc);
+  else in_stats_kernel<1><<<grid, 256, smem, st>>>(x, S, C, rm.CV, rm.R, rpb, acc);
+  CFUN_LAUNCH_CHECK();
+  long long NC = (long long)N * C;
+  in_finalize_kernel<<<(unsigned)cdiv(NC, 256), 256, 0, st>>>(acc, NC, 1.0 / (double)S, eps, mean, rstd);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
+extern "C" int cfun_affine_act_fwd(const float* x, const float* a, const float* b, int a_nstride, const float* r,
+                                   float* y, int N, int D, int H, int W, int C, int Ctot, int c_off, int up, float slope,
+                                   void* stream) {
+  CFUN_CHECK_ARG(x && y && N > 0 && D > 0 && H > 0 && W > 0 && C > 0 && Ctot >= c_off + C && c_off >= 0);
+  CFUN_CHECK_ARG(up == 1 || up == 2);
+  CFUN_CHECK_ARG((a == nullptr) == (b == nullptr));
+  cudaStream_t st = as_stream(stream);
+  const bool v4 = (C % 4 == 0) && (Ctot % 4 == 0) && (c_off % 4 == 0) && (a_nstride % 4 == 0);
+  long long total = (long long)N * D * H * W * (v4 ? C / 4 : C);
+  if (v4) affine_act_fwd_kernel<4><<<pick_blocks(total), 256, 0, st>>>(x, a, b, a_nstride, r, y, N, D, H, W, C, Ctot, c_off, up, slope);
+  else affine_act_fwd_kernel<1><<<pick_blocks(total), 256, 0, st>>>(x, a, b, a_nstride, r, y, N, D, H, W, C, Ctot, c_off, up, slope);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
+extern "C" int cfun_affine_act_bwd(const float* x, const float* a, const float* b, int a_nstride, const float* r,
+                                   const float* dy, float* dx, float* dr, double* stat_acc, int N, int D, int H, int W,
+                                   int C, int Ctot, int c_off, int up, float slope, void* stream) {
+  CFUN_CHECK_ARG(x && dy && dx && N > 0 && D > 0 && H > 0 && W > 0 && C > 0 && Ctot >= c_off + C && c_off >= 0);
+  CFUN_CHECK_ARG(up == 1 || up == 2);
+  CFUN_CHECK_ARG((a == nullptr) == (b == nullptr));
+  CFUN_CHECK_ARG(!stat_acc || (a && a_nstride == C && !r));
+  cudaStream_t st = as_stream(stream);
+  if (stat_acc) CFUN_CUDA(cudaMemsetAsync(stat_acc, 0, sizeof(double) * 2 * (size_t)N * C, st));
+  const bool v4 = (C % 4 == 0) && (Ctot % 4 == 0) && (c_off % 4 == 0) && (a_nstride % 4 == 0);
+  const int V = v4 ? 4 : 1;
+  CFUN_CHECK_ARG(C / V <= 256);
+  RowMap rm = make_rowmap(C, V);
+  const long long S = (long long)D * H * W;
+  long long rpb = std::max<long long>((long long)rm.R * 4, cdiv(S, std::max<long long>(1, 8LL * num_sms() / N)));
+  dim3 grid((unsigned)cdiv(S, rpb), N);
+  size_t smem = stat_acc ? sizeof(double) * 2 * C : 0;
+  if (v4) affine_act_bwd_kernel<4><<<grid, 256, smem, st>>>(x, a, b, a_nstride, r, dy, dx, dr, stat_acc, D, H, W, C, Ctot, c_off, up, slope, rm.CV, rm.R, rpb);
+  else affine_act_bwd_kernel<1><<<grid, 256, smem, st>>>(x, a, b, a_nstride, r, dy, dx, dr, stat_acc, D, H, W, C, Ctot, c_off, up, slope, rm.CV, rm.R, rpb);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
+extern "C" int cfun_instnorm_bwd_apply(const float* x, const float* a, const float* b, const double* stat_acc,
+                                       float* dx, int N, long long S, int C, void* stream) {
+  CFUN_CHECK_ARG(x && a && b && stat_acc && dx && N > 0 && S > 0 && C > 0);
+  cudaStream_t st = as_stream(stream);
+  const bool v4 = (C % 4 == 0);
+  long long total = (long long)N * S * (v4 ? C / 4 : C);
+  if (v4) in_bwd_apply_kernel<4><<<pick_blocks(total), 256, 0, st>>>(x, a, b, stat_acc, dx, N, S, C);
+  else in_bwd_apply_kernel<1><<<pick_blocks(total), 256, 0, st>>>(x, a, b, stat_acc, dx, N, S, C);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
+extern "C" int cfun_maxpool2_fwd(const float* x, float* y, int N, int D, int H, int W, int C, void* stream) {
+  CFUN_CHECK_ARG(x && y && N > 0 && C > 0 && D > 0 && H > 0 && W > 0 && D % 2 == 0 && H % 2 == 0 && W % 2 == 0);
+  cudaStream_t st = as_stream(stream);
+  const bool v4 = C % 4 == 0;
+  long long total = (long long)N * (D / 2) * (H / 2) * (W / 2) * (v4 ? C / 4 : C);
+  if (v4) maxpool2_fwd_kernel<4><<<pick_blocks(total), 256, 0, st>>>(x, y, N, D, H, W, C);
+  else maxpool2_fwd_kernel<1><<<pick_blocks(total), 256, 0, st>>>(x, y, N, D, H, W, C);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
+extern "C" int cfun_maxpool2_bwd(const float* x, const float* y, const float* dy, float* dx, int N, int D, int H, int W,
+                                 int C, void* stream) {
+  (void)y;
+  CFUN_CHECK_ARG(x && dy && dx && N > 0 && C > 0 && D > 0 && H > 0 && W > 0 && D % 2 == 0 && H % 2 == 0 && W % 2 == 0);
+  cudaStream_t st = as_stream(stream);
+  const bool v4 = C % 4 == 0;
+  long long total = (long long)N * (D / 2) * (H / 2) * (W / 2) * (v4 ? C / 4 : C);
+  if (v4) maxpool2_bwd_kernel<4><<<pick_blocks(total), 256, 0, st>>>(x, dy, dx, N, D, H, W, C);
+  else maxpool2_bwd_kernel<1><<<pick_blocks(total), 256, 0, st>>>(x, dy, dx, N, D, H, W, C);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
+extern "C" int cfun_mold_volume_i16(const short* vol_hwd, int H, int W, int D, double* acc, float* out_dhw, void* stream) {
+  CFUN_CHECK_ARG(vol_hwd && acc && out_dhw && H > 0 && W > 0 && D > 0);
+  cudaStream_t st = as_stream(stream);
+  CFUN_CUDA(cudaMemsetAsync(acc, 0, 2 * sizeof(double), st));
+  long long n = (long long)H * W * D;
+  i16_stats_kernel<<<pick_blocks(n / 4 + 1), 256, 0, st>>>(vol_hwd, n, acc);
+  CFUN_LAUNCH_CHECK();
+  dim3 grid((unsigned)cdiv(D, 32), (unsigned)cdiv(W, 32), (unsigned)H);
+  mold_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(vol_hwd, H, W, D, acc, out_dhw);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}

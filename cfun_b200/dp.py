@@ -1,0 +1,83 @@
+"""Optimizer tail and volume-level data parallelism.
+
+FlatSGD re-homes every trainable parameter, its gradient and its momentum in three flat fp32 buffers (parameters and
+.grad become views), so that
+  * the global-norm clip (clip_grad_norm_(params, 5.0), reference model.py:1641) + SGD(momentum, selective weight decay,
+    reference model.py:1538-1545,1643) is one sum-of-squares kernel + one fused step kernel, and
+  * data parallelism is exactly ONE NCCL all-reduce (SUM) of the flat gradient per optimizer step over NVLink/NVSwitch --
+    the path shards on independent CT volumes; there is no other collective.
+SUM (not mean) mirrors the reference's un-normalised gradient accumulation over BATCH_SIZE volumes (model.py:1640-1645).
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+class FlatSGD(object):
+    def __init__(self, model, lr, momentum=0.9, weight_decay=1e-4, clip_norm=5.0, process_group=None):
+        self.lr, self.momentum, self.weight_decay, self.clip_norm = lr, momentum, weight_decay, clip_norm
+        self.group = process_group
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        if not named:
+            raise RuntimeError("no trainable parameters")
+        dev = named[0][1].device
+        total = sum(p.numel() for _, p in named)
+        self.flat_param = torch.empty(total, device=dev)
+        self.flat_grad = torch.zeros(total, device=dev)
+        self.flat_mom = torch.zeros(total, device=dev)
+        self.wd_mask = torch.zeros(total, dtype=torch.uint8, device=dev)
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.names, self.slices = [], {}
+        off = 0
+        with torch.no_grad():
+            for n, p in named:
+                k = p.numel()
+                self.flat_param[off:off + k].copy_(p.data.reshape(-1))
+                p.data = self.flat_param[off:off + k].view(p.shape)
+                p.grad = self.flat_grad[off:off + k].view(p.shape)
+                if 'bn' not in n:                       # reference: weight decay skips names containing 'bn'
+                    self.wd_mask[off:off + k] = 1
+                self.names.append(n)
+                self.slices[n] = (off, off + k)
+                off += k
+        self.numel = total
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def allreduce_grads(self):
+        """the one collective of the data-parallel path"""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+
+    def grad_norm(self):
+        self.sumsq.zero_()
+        ops.sumsq_into(self.flat_grad, self.sumsq)
+        return self.sumsq
+
+    def step(self):
+        self.allreduce_grads()
+        self.grad_norm()
+        ops.sgd_clip_step(self.flat_param, self.flat_grad, self.flat_mom, self.wd_mask, self.sumsq, self.clip_norm, self.lr,
+                          self.momentum, self.weight_decay)
+
+
+def flatten_grads_cpu(params):
+    """Device-agnostic piece of the DP path used by the gloo CPU tests: gradient views into one flat buffer."""
+    params = [p for p in params if p.requires_grad]
+    total = sum(p.numel() for p in params)
+    flat = torch.zeros(total, dtype=torch.float32, device=params[0].device)
+    off = 0
+    for p in params:
+        k = p.numel()
+        if p.grad is not None:
+            flat[off:off + k].copy_(p.grad.reshape(-1))
+        p.grad = flat[off:off + k].view(p.shape)
+        off += k
+    return flat
+
+
+def shard_volumes(num_volumes, rank, world):
+    """Volume-level partition: rank r owns volumes r, r+world, ... (independent units, no data-path collective)."""
+    return list(range(rank, num_volumes, world))

@@ -1,0 +1,127 @@
+"""Modified 3-D U-Net mask branch on the cfun_b200 CUDA ops.
+
+Same class name, constructor signature, attribute names and state_dict keys as reference mask_branch.py:11-122; the
+forward (mask_branch.py:124-220) is re-expressed over fused passes: every InstanceNorm3d -> LeakyReLU (-> nearest x2)
+chain, including a preceding Dropout3d channel mask, is one statistics kernel + one apply kernel (ops.instnorm_lrelu),
+and every Conv3d is ops.conv3d."""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .layers import Conv3d, Slot
+
+
+class Modified3DUNet(nn.Module):
+    def __init__(self, in_channels, n_classes, stage, base_n_filter=32):
+        super().__init__()
+        self.in_channels = in_channels
+        self.n_classes = n_classes
+        self.base_n_filter = base_n_filter
+        self.stage = stage
+        b = base_n_filter
+        self.lrelu = Slot("LeakyReLU(0.01)")
+        self.dropout3d = Slot("Dropout3d(p=0.6)")
+        self.upsacle = Slot("Upsample(x2, nearest)")
+        self.dropout_p = 0.6
+        self.use_dropout = True          # LiTS variant has none (LiTS_2017/mask_branch.py:19,130)
+        self.injected_drop = None        # tests: list of 5 per-call channel masks [N,C,1,1,1] (already scaled)
+
+        c3 = lambda ci, co, s=1: Conv3d(ci, co, kernel_size=3, stride=s, padding=1, bias=False)
+        c1 = lambda ci, co: Conv3d(ci, co, kernel_size=1, stride=1, padding=0, bias=False)
+        self.conv3d_c1_1 = c3(in_channels, b)
+        self.conv3d_c1_2 = c3(b, b)
+        self.lrelu_conv_c1 = nn.Sequential(Slot("LeakyReLU"), c3(b, b))
+        self.inorm3d_c1 = Slot("InstanceNorm3d")
+        for lvl, m in ((2, 2), (3, 4), (4, 8), (5, 16)):
+            setattr(self, "conv3d_c%d" % lvl, c3(b * m // 2, b * m, 2))
+            setattr(self, "norm_lrelu_conv_c%d" % lvl, nn.Sequential(Slot("InstanceNorm3d"), Slot("LeakyReLU"), c3(b * m, b * m)))
+            if lvl < 5:
+                setattr(self, "inorm3d_c%d" % lvl, Slot("InstanceNorm3d"))
+        up_block = lambda ci, co: nn.Sequential(Slot("InstanceNorm3d"), Slot("LeakyReLU"), Slot("Upsample x2"), c3(ci, co),
+                                                Slot("InstanceNorm3d"), Slot("LeakyReLU"))
+        cnl = lambda ci, co: nn.Sequential(c3(ci, co), Slot("InstanceNorm3d"), Slot("LeakyReLU"))
+        self.norm_lrelu_upscale_conv_norm_lrelu_l0 = up_block(b * 16, b * 8)
+        self.conv3d_l0 = c1(b * 8, b * 8)
+        self.inorm3d_l0 = Slot("InstanceNorm3d")
+        self.conv_norm_lrelu_l1 = cnl(b * 16, b * 16)
+        self.conv3d_l1 = c1(b * 16, b * 8)
+        self.norm_lrelu_upscale_conv_norm_lrelu_l1 = up_block(b * 8, b * 4)
+        self.conv_norm_lrelu_l2 = cnl(b * 8, b * 8)
+        self.conv3d_l2 = c1(b * 8, b * 4)
+        self.norm_lrelu_upscale_conv_norm_lrelu_l2 = up_block(b * 4, b * 2)
+        self.conv_norm_lrelu_l3 = cnl(b * 4, b * 4)
+        self.conv3d_l3 = c1(b * 4, b * 2)
+        self.norm_lrelu_upscale_conv_norm_lrelu_l3 = up_block(b * 2, b)
+        self.conv_norm_lrelu_l4 = cnl(b * 2, b * 2)
+        self.conv3d_l4 = c1(b * 2, n_classes)
+        self.ds2_1x1_conv3d = c1(b * 8, n_classes)
+        self.ds3_1x1_conv3d = c1(b * 4, n_classes)
+        self.out_upscale_conv = nn.Sequential(Slot("Upsample x2"),
+                                              Conv3d(n_classes, n_classes, kernel_size=5, stride=1, padding=2, bias=False))
+
+    # -- Dropout3d draws: per (sample, channel) keep mask scaled by 1/(1-p) (mask_branch.py:19) ---------------
+    def _drop_masks(self, n, device):
+        if not (self.training and self.use_dropout):
+            return [None] * 5
+        if self.injected_drop is not None:
+            return [m[:n].reshape(n, -1).to(device=device, dtype=torch.float32) for m in self.injected_drop]
+        b, keep = self.base_n_filter, 1.0 - self.dropout_p
+        return [torch.bernoulli(torch.full((n, b * m), keep, device=device)) / keep for m in (1, 2, 4, 8, 16)]
+
+    def forward(self, x):
+        IN = ops.instnorm_lrelu
+        drops = self._drop_masks(x.shape[0], x.device)
+        # level 1 context (mask_branch.py:125-136)
+        out = self.conv3d_c1_1(x)
+        residual_1 = out
+        out = self.conv3d_c1_2(ops.leaky_relu(out))
+        if drops[0] is None:
+            out = ops.leaky_relu(out)
+        else:   # lrelu(dropout(out)): the channel scale folds into the activation pass
+            out = ops.affine_act(out, drops[0], torch.zeros_like(drops[0]), None, 0.01, 1)
+        out = self.lrelu_conv_c1[1](out)
+        out = out + residual_1
+        context_1 = ops.leaky_relu(out)
+        out = IN(out)
+        # levels 2..5 context (mask_branch.py:138-183)
+        ctx = {}
+        for lvl in (2, 3, 4, 5):
+            out = getattr(self, "conv3d_c%d" % lvl)(out)
+            residual = out
+            conv = getattr(self, "norm_lrelu_conv_c%d" % lvl)[2]
+            out = conv(IN(out))
+            out = conv(IN(out, drop=drops[lvl - 1]))     # dropout -> norm -> lrelu -> conv
+            out = out + residual
+            if lvl < 5:
+                out = IN(out)
+                ctx[lvl] = out
+
+        def up_block(seq, t):   # norm -> lrelu -> upsample x2 -> conv -> norm -> lrelu
+            return IN(seq[3](IN(t, up=2)))
+
+        out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l0, out)
+        out = IN(self.conv3d_l0(out))
+        out = torch.cat([out, ctx[4]], dim=1)
+        out = IN(self.conv_norm_lrelu_l1[0](out))
+        out = self.conv3d_l1(out)
+        out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l1, out)
+        out = torch.cat([out, ctx[3]], dim=1)
+        out = IN(self.conv_norm_lrelu_l2[0](out))
+        ds2 = out
+        out = self.conv3d_l2(out)
+        out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l2, out)
+        out = torch.cat([out, ctx[2]], dim=1)
+        out = IN(self.conv_norm_lrelu_l3[0](out))
+        ds3 = out
+        out = self.conv3d_l3(out)
+        out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l3, out)
+        out = torch.cat([out, context_1], dim=1)
+        out = IN(self.conv_norm_lrelu_l4[0](out))
+        out_pred = self.conv3d_l4(out)
+        # deep supervision (mask_branch.py:209-215)
+        s = ops.upsample2x(self.ds2_1x1_conv3d(ds2)) + self.ds3_1x1_conv3d(ds3)
+        out = out_pred + ops.upsample2x(s)
+        if self.stage == 'finetune':   # mask_branch.py:216-218
+            up = ops.upsample2x(out)
+            out = up + self.out_upscale_conv[1](up)
+        return out

@@ -1,0 +1,760 @@
+"""CFUN model (3-D Faster-R-CNN + U-Net mask head) on the cfun_b200 sm_100a CUDA ops.
+
+Drop-in surface of reference model.py: the same module / function names, positional signatures, return structures and
+state_dict keys (FPN:124, proposal_layer:199, RoI_Align:265, pyramid_roi_align:292, bbox_overlaps:377,
+detection_target_layer:414, refine_detections:584, detection_layer:679, RPN:700, Classifier:750, Mask:787, the six
+losses :808-981, compute_losses:984, build_rpn_targets:1090, MaskRCNN:1245, compose/parse_image_meta:1871/1891,
+mold_image:1902).  What changed is where the work runs: every op on the hot path is a hand-written CUDA kernel behind
+the C ABI (include/cfun_b200.h); box sorting / NMS / target assembly stay on the device instead of round-tripping
+through numpy; masks targets are produced as class-index volumes instead of float64 one-hot stacks (see
+detection_target_layer).  CUDA only -- there is no CPU path.
+"""
+import math
+import os
+import re
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from . import utils
+from . import backbone
+from . import mask_branch
+from .layers import Conv3d, FrozenBatchNorm3d, Slot
+
+
+def log(text, array=None):
+    if array is not None:
+        text = text.ljust(25)
+        text += ("shape: {:20}  min: {:10.5f}  max: {:10.5f}".format(str(array.shape), array.min() if array.size else "",
+                                                                     array.max() if array.size else ""))
+    print(text)
+
+
+def _f32(vals, device):
+    return torch.tensor([float(v) for v in vals], dtype=torch.float32, device=device)
+
+
+def compute_backbone_shapes(config, image_shape):
+    """[N, (depth, height, width)] per pyramid level; image_shape is (H, W, D, C) (reference model.py:91-101)."""
+    H, W, D = image_shape[:3]
+    return np.array([[int(math.ceil(D / s)), int(math.ceil(H / s)), int(math.ceil(W / s))] for s in config.BACKBONE_STRIDES])
+
+
+# ---------------------------------------------------------------------------------------------------------
+#  FPN
+# ---------------------------------------------------------------------------------------------------------
+class FPN(nn.Module):
+    def __init__(self, C1, C2, C3, out_channels, config):
+        super().__init__()
+        self.out_channels = out_channels
+        self.C1, self.C2, self.C3 = C1, C2, C3
+        self.P3_conv1 = Conv3d(config.BACKBONE_CHANNELS[1] * 4, out_channels, kernel_size=1, stride=1)
+        self.P3_conv2 = Conv3d(out_channels, out_channels, kernel_size=3, stride=1, padding=1)
+        self.P2_conv1 = Conv3d(config.BACKBONE_CHANNELS[0] * 4, out_channels, kernel_size=1, stride=1)
+        self.P2_conv2 = Conv3d(out_channels, out_channels, kernel_size=3, stride=1, padding=1)
+
+    def forward(self, x):
+        c2 = self.C2(self.C1(x))
+        c3 = self.C3(c2)
+        p3 = self.P3_conv1(c3)
+        p2 = self.P2_conv1(c2) + ops.upsample2x(p3)
+        return [self.P2_conv2(p2), self.P3_conv2(p3)]
+
+
+# ---------------------------------------------------------------------------------------------------------
+#  Proposal layer
+# ---------------------------------------------------------------------------------------------------------
+def apply_box_deltas(boxes, deltas):
+    """[N,6] boxes (z1,y1,x1,z2,y2,x2) refined by [N,6] deltas (reference model.py:155-182), on device."""
+    n = boxes.shape[0]
+    big = 3.0e38
+    out, _ = ops.decode_clip(boxes.detach().float(), deltas.detach().float(), None, None, n, (1,) * 6,
+                             (-big, -big, -big, big, big, big))
+    return out
+
+
+def clip_boxes(boxes, window):
+    lo = _f32([window[0], window[1], window[2]] * 2, boxes.device)
+    hi = _f32([window[3], window[4], window[5]] * 2, boxes.device)
+    return torch.max(torch.min(boxes, hi), lo)
+
+
+def proposal_layer(inputs, proposal_count, nms_threshold, anchors, config=None):
+    """RPN outputs -> normalised proposals [1, n, 6] (reference model.py:199-258), entirely on device:
+    bitonic sort of the fg scores, fused decode+clip of the top PRE_NMS_LIMIT anchors, bit-mask NMS, gather+normalise.
+    One host sync (the kept count sizes the output, as the reference's dynamic shape does)."""
+    probs = inputs[0].squeeze(0)
+    deltas = inputs[1].squeeze(0)
+    A = anchors.shape[0]
+    scores = probs[:, 1].detach().contiguous()
+    order = ops.sort_desc(scores)
+    k = min(config.PRE_NMS_LIMIT, A)
+    height, width, depth = [int(v) for v in config.IMAGE_SHAPE[:3]]
+    boxes, _ = ops.decode_clip(anchors, deltas, None, order, k, config.RPN_BBOX_STD_DEV,
+                               (0, 0, 0, depth, height, width))
+    keep, count = ops.nms3d(boxes, nms_threshold, proposal_count)
+    n = int(count.item())
+    rois = ops.gather_boxes(boxes, keep, count, max(n, 1), (depth, height, width, depth, height, width))[:n]
+    return rois.unsqueeze(0)
+
+
+# ---------------------------------------------------------------------------------------------------------
+#  RoI crop-resize ("RoIAlign")
+# ---------------------------------------------------------------------------------------------------------
+def RoI_Align(feature_map, pool_size, boxes, out_ncdhw=False):
+    """feature_map [C,D,H,W]; boxes [n,6] normalised -> [n,C,*pool_size] (reference model.py:265-289)."""
+    fm = feature_map.unsqueeze(0)
+    return ops.roi_crop_resize(fm, None, boxes, None, pool_size, out_ncdhw)
+
+
+def log2(x):
+    return torch.log(x) / math.log(2.0)
+
+
+def pyramid_roi_align(inputs, pool_size, test_flag=False, out_ncdhw=False):
+    """inputs = [boxes, P2, P3]; one kernel launch covers every box of both levels, output rows stay in box order
+    (the reference gathers per level and sorts back, model.py:334-368).  Gradients flow to the feature maps only."""
+    boxes = inputs[0]
+    if boxes.dim() == 3:
+        boxes = boxes.squeeze(0)
+    maps = [m if m.dim() == 5 else m.unsqueeze(0) for m in inputs[1:]]
+    boxes = boxes.detach()
+    level = ops.roi_level(boxes)
+    return ops.roi_crop_resize(maps[0], maps[1], boxes, level, pool_size, out_ncdhw)
+
+
+# ---------------------------------------------------------------------------------------------------------
+#  Detection targets
+# ---------------------------------------------------------------------------------------------------------
+def bbox_overlaps(boxes1, boxes2):
+    return ops.bbox_overlaps3d(boxes1, boxes2)
+
+
+def _label_volume(gt_masks):
+    """Accepts the reference's one-hot stack [C,D,H,W] (float) or a class-id volume [D,H,W] (int) -> int32 [D,H,W]."""
+    if gt_masks.dim() == 3:
+        return gt_masks.to(torch.int32).contiguous()
+    return torch.argmax(gt_masks, dim=0).to(torch.int32).contiguous()
+
+
+def detection_target_layer(proposals, gt_class_ids, gt_boxes, gt_masks, config):
+    """Sub-samples proposals and builds class / box / mask targets (reference model.py:414-563).
+
+    Same RNG contract as the reference: the two sub-sampling permutations are torch.randperm draws on the host
+    generator, in the same order.  Returns (positive_rois, rois, class_ids, deltas, masks).  `masks` is an int64
+    class-index volume [P, *MASK_SHAPE] (argmax of the reference's float64 one-hot [P,8,*MASK_SHAPE]); set
+    config.DENSE_MASK_TARGETS = True to get the one-hot float64 stack itself.  The losses accept both."""
+    proposals = proposals.squeeze(0) if proposals.dim() == 3 else proposals
+    gt_class_ids = gt_class_ids.squeeze(0) if gt_class_ids.dim() == 2 else gt_class_ids
+    gt_boxes = gt_boxes.squeeze(0) if gt_boxes.dim() == 3 else gt_boxes
+    if gt_masks.dim() in (5, 4) and gt_masks.shape[0] == 1:
+        gt_masks = gt_masks.squeeze(0)
+    dev = proposals.device
+    empty = torch.zeros((0, 6), device=dev)
+    if proposals.shape[0] == 0:
+        return empty, empty, torch.zeros(0, dtype=torch.long, device=dev), empty, torch.zeros(0, device=dev)
+
+    overlaps = bbox_overlaps(proposals, gt_boxes)
+    roi_iou_max = overlaps.max(dim=1)[0]
+    thr = config.DETECTION_TARGET_IOU_THRESHOLD
+    pos_all = torch.nonzero(roi_iou_max >= thr)[:, 0]
+    neg_all = torch.nonzero(roi_iou_max < thr)[:, 0]
+
+    positive_count = 0
+    if pos_all.numel() > 0:
+        want = int(config.TRAIN_ROIS_PER_IMAGE * config.ROI_POSITIVE_RATIO)
+        perm = torch.randperm(pos_all.numel())[:want].to(dev)
+        positive_indices = pos_all[perm]
+        positive_count = positive_indices.numel()
+        positive_rois = proposals[positive_indices]
+        assign = overlaps[positive_indices].max(dim=1)[1]
+        roi_gt_boxes = gt_boxes[assign]
+        roi_gt_class_ids = gt_class_ids[assign]
+        deltas = ops.box_refinement(positive_rois, roi_gt_boxes, config.BBOX_STD_DEV)
+        label = _label_volume(gt_masks)
+        dense = bool(getattr(config, "DENSE_MASK_TARGETS", False))
+        onehot, index = ops.mask_target_crop(label, positive_rois, 8 if gt_masks.dim() == 3 else gt_masks.shape[0],
+                                             config.MASK_SHAPE, onehot=dense, index=not dense)
+        masks = onehot if dense else index
+
+    negative_count = 0
+    if neg_all.numel() > 0 and positive_count > 0:
+        want = int((1.0 / config.ROI_POSITIVE_RATIO) * positive_count - positive_count)
+        perm = torch.randperm(neg_all.numel())[:want].to(dev)
+        negative_indices = neg_all[perm]
+        negative_count = negative_indices.numel()
+        negative_rois = proposals[negative_indices]
+
+    if positive_count > 0 and negative_count > 0:
+        rois = torch.cat((positive_rois, negative_rois), dim=0)
+        class_ids = torch.cat([roi_gt_class_ids.long(), torch.zeros(negative_count, dtype=torch.long, device=dev)], dim=0)
+        deltas = torch.cat([deltas, torch.zeros((negative_count, 6), device=dev)], dim=0)
+        return positive_rois, rois, class_ids, deltas, masks
+    if positive_count > 0:
+        return positive_rois, positive_rois, roi_gt_class_ids.long(), deltas, masks
+    return empty, empty, torch.zeros(0, dtype=torch.long, device=dev), empty, torch.zeros(0, device=dev)
+
+
+# ---------------------------------------------------------------------------------------------------------
+#  Detection layer (inference)
+# ---------------------------------------------------------------------------------------------------------
+def clip_to_window(window, boxes):
+    return clip_boxes(boxes, window)
+
+
+def refine_detections(rois, probs, deltas, window, config):
+    """[N,6] rois + class probs + class deltas -> [n,(z1,y1,x1,z2,y2,x2,class_id,score)] (reference model.py:584-676),
+    including its use of RPN_BBOX_STD_DEV for the head deltas (:610)."""
+    dev = rois.device
+    class_ids = probs.argmax(dim=1)
+    idx = torch.arange(class_ids.shape[0], device=dev)
+    class_scores = probs[idx, class_ids]
+    deltas_specific = deltas[idx, class_ids]
+    refined = apply_box_deltas(rois, deltas_specific * _f32(config.RPN_BBOX_STD_DEV, dev).view(1, 6))
+    height, width, depth = [int(v) for v in config.IMAGE_SHAPE[:3]]
+    refined = refined * _f32([depth, height, width, depth, height, width], dev)
+    refined = torch.round(clip_to_window([float(w) for w in window], refined))
+    keep_bool = class_ids > 0
+    if config.DETECTION_MIN_CONFIDENCE:
+        keep_bool = keep_bool & (class_scores >= config.DETECTION_MIN_CONFIDENCE)
+    keep = torch.nonzero(keep_bool)[:, 0]
+    if keep.numel() == 0:
+        # the reference dies here with UnboundLocalError (model.py:641-662); report it as what it is
+        raise RuntimeError("refine_detections: no RoI passes class>0 and score>=DETECTION_MIN_CONFIDENCE")
+    pre_cls, pre_scores, pre_rois = class_ids[keep], class_scores[keep], refined[keep]
+    nms_keep = []
+    for cid in torch.unique(pre_cls):
+        ixs = torch.nonzero(pre_cls == cid)[:, 0]
+        order = ops.sort_desc(pre_scores[ixs]).long()
+        kk, cnt = ops.nms3d(pre_rois[ixs][order], config.DETECTION_NMS_THRESHOLD, config.DETECTION_MAX_INSTANCES)
+        ck = kk[:int(cnt.item())].long()
+        nms_keep.append(keep[ixs[order[ck]]])
+    nms_keep = torch.unique(torch.cat(nms_keep))
+    mask = torch.zeros(class_ids.shape[0], dtype=torch.bool, device=dev)
+    mask[nms_keep] = True
+    keep = keep[mask[keep]]
+    roi_count = min(config.DETECTION_MAX_INSTANCES, keep.numel())
+    top = ops.sort_desc(class_scores[keep])[:roi_count].long()
+    keep = keep[top]
+    return torch.cat((refined[keep], class_ids[keep].unsqueeze(1).float(), class_scores[keep].unsqueeze(1)), dim=1)
+
+
+def detection_layer(config, rois, mrcnn_class, mrcnn_bbox, image_meta):
+    rois = rois.squeeze(0)
+    _, _, window, _ = parse_image_meta(image_meta)
+    return refine_detections(rois, mrcnn_class, mrcnn_bbox, window[0], config)
+
+
+# ---------------------------------------------------------------------------------------------------------
+#  RPN and heads
+# ---------------------------------------------------------------------------------------------------------
+class RPN(nn.Module):
+    """reference model.py:700-743: 3x3x3 shared conv + ReLU (fused epilogue), two 1x1x1 heads, softmax over (bg, fg).
+    The NDHWC conv output *is* the reference's permute(0,2,3,4,1).contiguous().view(B,-1,K) layout, so the reshape is free."""
+
+    def __init__(self, anchors_per_location, anchor_stride, channel, conv_channel):
+        super().__init__()
+        self.conv_shared = Conv3d(channel, conv_channel, kernel_size=3, stride=anchor_stride, padding=1)
+        self.relu = Slot("ReLU (conv epilogue)")
+        self.conv_class = Conv3d(conv_channel, 2 * anchors_per_location, kernel_size=1, stride=1)
+        self.softmax = nn.Softmax(dim=2)
+        self.conv_bbox = Conv3d(conv_channel, 6 * anchors_per_location, kernel_size=1, stride=1)
+
+    def forward(self, x):
+        x = self.conv_shared(x, relu=True)
+        B = x.shape[0]
+        rpn_class_logits = self.conv_class(x).permute(0, 2, 3, 4, 1).reshape(B, -1, 2)
+        rpn_probs = self.softmax(rpn_class_logits)
+        rpn_bbox = self.conv_bbox(x).permute(0, 2, 3, 4, 1).reshape(B, -1, 6)
+        return [rpn_class_logits, rpn_probs, rpn_bbox]
+
+
+class Classifier(nn.Module):
+    """reference model.py:750-784.  conv1 has kernel == pool size: a 221184 -> fc_size product, weight-bandwidth bound."""
+
+    def __init__(self, channel, pool_size, image_shape, num_classes, fc_size, test_flag=False):
+        super().__init__()
+        self.pool_size = pool_size
+        self.image_shape = image_shape
+        self.fc_size = fc_size
+        self.test_flag = test_flag
+        self.conv1 = Conv3d(channel, fc_size, kernel_size=tuple(pool_size), stride=1)
+        self.bn1 = FrozenBatchNorm3d(fc_size, eps=0.001, momentum=0.01)
+        self.conv2 = Conv3d(fc_size, fc_size, kernel_size=1, stride=1)
+        self.bn2 = FrozenBatchNorm3d(fc_size, eps=0.001, momentum=0.01)
+        self.relu = Slot("ReLU (fused into the BN pass)")
+        self.linear_class = nn.Linear(fc_size, num_classes)
+        self.softmax = nn.Softmax(dim=1)
+        self.linear_bbox = nn.Linear(fc_size, num_classes * 6)
+
+    def forward(self, x, rois):
+        x = pyramid_roi_align([rois] + x, self.pool_size, self.test_flag, out_ncdhw=True)
+        x = ops.fc_conv(x, self.conv1.weight, self.conv1.bias)
+        x = self.bn1(x, relu=True)
+        x = self.bn2(self.conv2(x), relu=True)
+        x = x.reshape(-1, self.fc_size)
+        mrcnn_class_logits = self.linear_class(x)
+        mrcnn_probs = self.softmax(mrcnn_class_logits)
+        mrcnn_bbox = self.linear_bbox(x)
+        return [mrcnn_class_logits, mrcnn_probs, mrcnn_bbox.view(mrcnn_bbox.shape[0], -1, 6)]
+
+
+class Mask(nn.Module):
+    """reference model.py:787-801: crops of the *input volume* (C=1) -> Modified3DUNet -> softmax over classes."""
+
+    def __init__(self, channel, pool_size, num_classes, conv_channel, stage, test_flag=False):
+        super().__init__()
+        self.pool_size = pool_size
+        self.test_flag = test_flag
+        self.modified_u_net = mask_branch.Modified3DUNet(channel, num_classes, stage, conv_channel)
+        self.softmax = nn.Softmax(dim=1)
+
+    def forward(self, x, rois):
+        x = pyramid_roi_align([rois] + x, self.pool_size, self.test_flag)
+        x = self.modified_u_net(x)
+        return x, self.softmax(x)
+
+
+# ---------------------------------------------------------------------------------------------------------
+#  Losses
+# ---------------------------------------------------------------------------------------------------------
+def compute_rpn_class_loss(rpn_match, rpn_class_logits):
+    rpn_match = rpn_match.squeeze(2)
+    anchor_class = (rpn_match == 1).long()
+    ind = torch.nonzero(rpn_match != 0)
+    return F.cross_entropy(rpn_class_logits[ind[:, 0], ind[:, 1], :], anchor_class[ind[:, 0], ind[:, 1]])
+
+
+def compute_rpn_bbox_loss(target_bbox, rpn_match, rpn_bbox):
+    rpn_match = rpn_match.squeeze(2)
+    ind = torch.nonzero(rpn_match == 1)
+    rpn_bbox = rpn_bbox[ind[:, 0], ind[:, 1]]
+    return F.smooth_l1_loss(rpn_bbox, target_bbox[0, :rpn_bbox.shape[0], :])
+
+
+def _zero_loss(like):
+    return torch.zeros(1, device=like.device)
+
+
+def compute_mrcnn_class_loss(target_class_ids, pred_class_logits):
+    if target_class_ids.shape[0] == 0:
+        return _zero_loss(target_class_ids)
+    return F.cross_entropy(pred_class_logits, target_class_ids.long())
+
+
+def compute_mrcnn_bbox_loss(target_bbox, target_class_ids, pred_bbox):
+    if target_class_ids.shape[0] == 0:
+        return _zero_loss(target_class_ids)
+    pos = torch.nonzero(target_class_ids > 0)[:, 0]
+    cls = target_class_ids[pos].long()
+    return F.smooth_l1_loss(pred_bbox[pos, cls, :], target_bbox[pos, :])
+
+
+def _mask_index(target_masks, rows):
+    """class-index volume [P,d,h,w] from either target representation"""
+    if target_masks.dim() == 5:
+        return torch.argmax(target_masks[rows].long(), dim=1)
+    return target_masks[rows]
+
+
+def compute_mrcnn_mask_loss(target_masks, target_class_ids, pred_masks, class_weight=None):
+    """CrossEntropy between the mask logits [P,ncls,d,h,w] and the argmax of the one-hot target (reference :909-935)."""
+    if target_class_ids.shape[0] == 0:
+        return _zero_loss(target_class_ids)
+    pos = torch.nonzero(target_class_ids > 0)[:, 0]
+    y_true = _mask_index(target_masks, pos)
+    return F.cross_entropy(pred_masks[pos], y_true, weight=class_weight)
+
+
+def compute_mrcnn_mask_edge_loss(target_masks, target_class_ids, pred_masks):
+    """3-D Sobel edge-agreement loss (reference :938-981) as one fused stencil kernel (forward) + two (backward)."""
+    if target_class_ids.shape[0] == 0:
+        return _zero_loss(target_class_ids)
+    pos = torch.nonzero(target_class_ids > 0)[:, 0]
+    P = pos.shape[0]
+    tgt = _mask_index(target_masks, torch.arange(P, device=pos.device))     # reference takes target_masks[:P]
+    return ops.sobel_edge_loss(pred_masks[pos], tgt)
+
+
+def compute_losses(rpn_match, rpn_bbox, rpn_class_logits, rpn_pred_bbox, target_class_ids, mrcnn_class_logits,
+                   target_deltas, mrcnn_bbox, target_mask, mrcnn_mask, mrcnn_mask_logits, stage):
+    rpn_class_loss = compute_rpn_class_loss(rpn_match, rpn_class_logits)
+    rpn_bbox_loss = compute_rpn_bbox_loss(rpn_bbox, rpn_match, rpn_pred_bbox)
+    binary_ids = (target_class_ids > 0).long()
+    mrcnn_class_loss = compute_mrcnn_class_loss(binary_ids, mrcnn_class_logits)
+    mrcnn_bbox_loss = compute_mrcnn_bbox_loss(target_deltas, binary_ids, mrcnn_bbox)
+    mrcnn_mask_loss = compute_mrcnn_mask_loss(target_mask, target_class_ids, mrcnn_mask_logits)
+    if stage == 'finetune':
+        mrcnn_mask_edge_loss = compute_mrcnn_mask_edge_loss(target_mask, target_class_ids, mrcnn_mask)
+    else:
+        mrcnn_mask_edge_loss = _zero_loss(rpn_class_logits)
+    return [rpn_class_loss, rpn_bbox_loss, mrcnn_class_loss, mrcnn_bbox_loss, mrcnn_mask_loss, mrcnn_mask_edge_loss]
+
+
+# ---------------------------------------------------------------------------------------------------------
+#  Host-side data preparation (off the hot path; kept so train_model / detect can run)
+# ---------------------------------------------------------------------------------------------------------
+def build_rpn_targets(anchors, gt_boxes, config):
+    """anchor/GT matching and delta targets (reference model.py:1090-1181), vectorised numpy."""
+    n_t = config.RPN_TRAIN_ANCHORS_PER_IMAGE
+    rpn_match = np.zeros([anchors.shape[0]], dtype=np.int32)
+    rpn_bbox = np.zeros((n_t, 6))
+    va = np.prod(anchors[:, 3:] - anchors[:, :3], axis=1)
+    overlaps = np.zeros((anchors.shape[0], gt_boxes.shape[0]))
+    for j, g in enumerate(gt_boxes):
+        lo = np.maximum(anchors[:, :3], g[:3])
+        hi = np.minimum(anchors[:, 3:], g[3:])
+        inter = np.prod(np.maximum(hi - lo, 0)[:, ::-1], axis=1)
+        overlaps[:, j] = inter / (np.prod(g[3:] - g[:3]) + va - inter + 1e-6)
+    amax = np.argmax(overlaps, axis=1)
+    vmax = overlaps[np.arange(overlaps.shape[0]), amax]
+    rpn_match[vmax < 0.3] = -1
+    rpn_match[np.argmax(overlaps, axis=0)] = 1
+    rpn_match[vmax >= 0.7] = 1
+    ids = np.where(rpn_match == 1)[0]
+    extra = len(ids) - n_t // 2
+    if extra > 0:
+        rpn_match[np.random.choice(ids, extra, replace=False)] = 0
+    ids = np.where(rpn_match == -1)[0]
+    extra = len(ids) - (n_t - np.sum(rpn_match == 1))
+    if extra > 0:
+        rpn_match[np.random.choice(ids, extra, replace=False)] = 0
+    ids = np.where(rpn_match == 1)[0]
+    a = anchors[ids]
+    g = gt_boxes[amax[ids]]
+    asz, gsz = a[:, 3:] - a[:, :3], g[:, 3:] - g[:, :3]
+    actr, gctr = a[:, :3] + 0.5 * asz, g[:, :3] + 0.5 * gsz
+    tgt = np.concatenate([(gctr - actr) / asz, np.log(gsz / asz)], axis=1) / np.asarray(config.RPN_BBOX_STD_DEV)
+    rpn_bbox[:len(ids)] = tgt[:n_t]
+    return rpn_match, rpn_bbox
+
+
+def mold_image(images):
+    """(x - mean) / std (reference model.py:1902-1904); the device kernel for int16 volumes is ops.mold_volume_i16."""
+    return (images - images.mean()) / images.std()
+
+
+def compose_image_meta(image_id, image_shape, window, active_class_ids):
+    return np.array([image_id] + list(image_shape) + list(window) + list(active_class_ids))
+
+
+def parse_image_meta(meta):
+    return meta[:, 0], meta[:, 1:5], meta[:, 5:11], meta[:, 11:]
+
+
+def load_image_gt(image, mask, angle, dataset, config, anchors):
+    """Ground truth for one volume (reference model.py:1007-1087).  image [H,W,D,1], mask [H,W,D] class ids.
+    The in-plane rotation augmentation uses scipy.ndimage (nearest neighbour) in place of imgaug."""
+    if angle:
+        import scipy.ndimage as ndi
+        image = ndi.rotate(image, angle, axes=(0, 1), reshape=False, order=0, mode="constant", cval=0)
+        mask = ndi.rotate(mask.astype(np.uint8), angle, axes=(0, 1), reshape=False, order=0, mode="constant", cval=0)
+    mask = mask.astype(np.int32)
+    image = image.transpose((3, 2, 0, 1))
+    mask = mask.transpose((2, 0, 1))
+    bbox = utils.extract_bboxes(np.expand_dims(mask, -1)).astype(np.float64)
+    z1, y1, x1, z2, y2, x2 = bbox[0]
+    d, h, w = z2 - z1, y2 - y1, x2 - x1
+    lo = np.floor(np.maximum(0, [z1 - d * 0.05, y1 - h * 0.05, x1 - w * 0.05]))
+    hi = np.ceil(np.minimum(mask.shape, [z2 + d * 0.05, y2 + h * 0.05, x2 + w * 0.05]))
+    bbox = np.tile(np.concatenate([lo, hi]).astype(np.int32)[None], (config.NUM_CLASSES - 1, 1))
+    masks, class_ids = dataset.process_mask(mask)
+    rpn_match, rpn_bbox = build_rpn_targets(anchors, np.array([bbox[0]]), config)
+    return mold_image(image.astype(np.float32)), rpn_match[:, np.newaxis], rpn_bbox, class_ids, bbox, masks
+
+
+class Dataset(torch.utils.data.Dataset):
+    """reference model.py:1184-1238"""
+
+    def __init__(self, dataset, config):
+        self.image_ids = np.copy(dataset.image_ids)
+        self.dataset = dataset
+        self.config = config
+
+    def __getitem__(self, image_index):
+        image_id = self.image_ids[image_index]
+        image = self.dataset.load_image(image_id)
+        mask = self.dataset.load_mask(image_id)
+        c = self.config
+        image, window, scale, padding, crop = utils.resize_image(image, min_dim=c.IMAGE_MIN_DIM, max_dim=c.IMAGE_MAX_DIM,
+                                                                 min_scale=c.IMAGE_MIN_SCALE, mode=c.IMAGE_RESIZE_MODE)
+        mask = utils.resize_mask(mask, scale, padding, max_dim=c.IMAGE_MAX_DIM, min_dim=c.IMAGE_MIN_DIM, crop=crop,
+                                 mode=c.IMAGE_RESIZE_MODE)
+        active = np.zeros([self.dataset.num_classes], dtype=np.int32)
+        active[self.dataset.source_class_ids[self.dataset.image_info[image_id]["source"]]] = 1
+        return image, compose_image_meta(image_id, image.shape, window, active), mask
+
+    def __len__(self):
+        return self.image_ids.shape[0]
+
+
+# ---------------------------------------------------------------------------------------------------------
+#  MaskRCNN
+# ---------------------------------------------------------------------------------------------------------
+LOSS_NAMES = ["rpn_class_loss", "rpn_bbox_loss", "mrcnn_class_loss", "mrcnn_bbox_loss", "mrcnn_mask_loss",
+              "mrcnn_mask_edge_loss"]
+
+
+class MaskRCNN(nn.Module):
+    """Same constructor, attributes, state_dict (220 entries at HeartConfig widths) and methods as reference
+    model.py:1245-1864."""
+
+    def __init__(self, config, model_dir, test_flag=False):
+        super().__init__()
+        self.epoch = 0
+        self.config = config
+        self.model_dir = model_dir
+        self.build(config=config, test_flag=test_flag)
+        self.initialize_weights()
+
+    def build(self, config, test_flag=False):
+        h, w, d = config.IMAGE_SHAPE[:3]
+        if h / 16 != int(h / 16) or w / 16 != int(w / 16) or d / 16 != int(d / 16):
+            raise Exception("Image size must be dividable by 16. Use 256, 320, 512, ... etc.")
+        factory = getattr(backbone, getattr(config, "BACKBONE", "P3D19"), backbone.P3D19)
+        C1, C2, C3 = factory(config=config).stages()
+        self.fpn = FPN(C1, C2, C3, out_channels=config.TOP_DOWN_PYRAMID_SIZE, config=config)
+        anchors = utils.generate_pyramid_anchors(config.RPN_ANCHOR_SCALES, config.RPN_ANCHOR_RATIOS,
+                                                 compute_backbone_shapes(config, config.IMAGE_SHAPE),
+                                                 config.BACKBONE_STRIDES, config.RPN_ANCHOR_STRIDE)
+        self.anchors = torch.from_numpy(anchors).float()
+        self.rpn = RPN(len(config.RPN_ANCHOR_RATIOS), config.RPN_ANCHOR_STRIDE, config.TOP_DOWN_PYRAMID_SIZE,
+                       config.RPN_CONV_CHANNELS)
+        self.classifier = Classifier(config.TOP_DOWN_PYRAMID_SIZE, config.POOL_SIZE, config.IMAGE_SHAPE, 2,
+                                     config.FPN_CLASSIFY_FC_LAYERS_SIZE, test_flag)
+        self.mask = Mask(1, config.MASK_POOL_SIZE, config.NUM_CLASSES, config.UNET_MASK_BRANCH_CHANNEL, config.STAGE,
+                         test_flag)
+        if not config.TRAIN_BN:
+            for m in self.modules():
+                if isinstance(m, nn.BatchNorm3d):
+                    for p in m.parameters():
+                        p.requires_grad = False
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self.anchors = fn(self.anchors)      # plain attribute in the reference (model.py:1276-1284): follow .cuda()
+        return out
+
+    def initialize_weights(self):
+        for m in self.modules():
+            if isinstance(m, nn.Conv3d):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    m.bias.data.zero_()
+            elif isinstance(m, nn.BatchNorm3d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+            elif isinstance(m, nn.Linear):
+                m.weight.data.normal_(0, 0.01)
+                m.bias.data.zero_()
+
+    def set_trainable(self, layer_regex):
+        for name, p in self.named_parameters():
+            if not bool(re.fullmatch(layer_regex, name)):
+                p.requires_grad = False
+
+    def load_weights(self, file_path):
+        if os.path.exists(file_path):
+            self.load_state_dict(torch.load(file_path), strict=True)
+            print("Weight file loading success!")
+        else:
+            print("Weight file not found ...")
+
+    # -- forward ------------------------------------------------------------------------------------------
+    def predict(self, inputs, mode):
+        molded_images = inputs[0]
+        image_metas = inputs[1]
+        if not molded_images.is_cuda:
+            raise RuntimeError("cfun_b200.MaskRCNN runs on CUDA (sm_100a) only; call .cuda() on the model and inputs")
+        if mode == 'inference':
+            self.eval()
+        elif mode == 'training':
+            self.train()     # BatchNorm stays frozen/eval regardless (FrozenBatchNorm3d)
+        cfg = self.config
+
+        p2_out, p3_out = self.fpn(molded_images)
+        rpn_feature_maps = [p2_out, p3_out]
+        mrcnn_classifier_feature_maps = [p2_out, p3_out]
+        mrcnn_mask_feature_maps = [molded_images, molded_images]
+
+        layer_outputs = [self.rpn(p) for p in rpn_feature_maps]
+        rpn_class_logits, rpn_class, rpn_bbox = [torch.cat(list(o), dim=1) for o in zip(*layer_outputs)]
+
+        proposal_count = cfg.POST_NMS_ROIS_TRAINING if mode == "training" else cfg.POST_NMS_ROIS_INFERENCE
+        rpn_rois = proposal_layer([rpn_class, rpn_bbox], proposal_count=proposal_count,
+                                  nms_threshold=cfg.RPN_NMS_THRESHOLD, anchors=self.anchors, config=cfg)
+        dev = molded_images.device
+        h, w, d = cfg.IMAGE_SHAPE[:3]
+        scale = _f32([d, h, w, d, h, w], dev)
+
+        if mode == 'inference':
+            mrcnn_class_logits, mrcnn_class, mrcnn_bbox = self.classifier(mrcnn_classifier_feature_maps, rpn_rois)
+            detections = detection_layer(cfg, rpn_rois, mrcnn_class, mrcnn_bbox, image_metas)
+            detection_boxes = (detections[:, :6] / scale).unsqueeze(0)
+            _, mrcnn_mask = self.mask(mrcnn_mask_feature_maps, detection_boxes)
+            return [detections.unsqueeze(0), mrcnn_mask.unsqueeze(0)]
+
+        gt_class_ids, gt_boxes, gt_masks = inputs[2], inputs[3], inputs[4]
+        gt_boxes = gt_boxes / scale
+        p_rois, rois, target_class_ids, target_deltas, target_mask = \
+            detection_target_layer(rpn_rois, gt_class_ids, gt_boxes, gt_masks, cfg)
+        empty = torch.zeros(0, device=dev)
+        mrcnn_class_logits = mrcnn_bbox = mrcnn_mask = mrcnn_mask_logits = empty
+        if rois.shape[0] > 0:
+            mrcnn_class_logits, _, mrcnn_bbox = self.classifier(mrcnn_classifier_feature_maps, rois)
+        if p_rois.shape[0] > 0:
+            mrcnn_mask_logits, mrcnn_mask = self.mask(mrcnn_mask_feature_maps, p_rois)
+        return [rpn_class_logits, rpn_bbox, target_class_ids, mrcnn_class_logits, target_deltas, mrcnn_bbox, target_mask,
+                mrcnn_mask, mrcnn_mask_logits]
+
+    def weighted_loss(self, losses):
+        w = self.config.LOSS_WEIGHTS
+        total = 0
+        for name, l in zip(LOSS_NAMES, losses):
+            total = total + w[name] * l
+        return total
+
+    def forward_backward(self, images, image_metas, rpn_match, rpn_bbox, gt_class_ids, gt_boxes, gt_masks):
+        """One volume: predict('training') -> compute_losses -> weighted sum -> backward (reference model.py:1622-1640).
+        Returns (total loss tensor, list of the six loss tensors); gradients accumulate into .grad."""
+        outs = self.predict([images, image_metas, gt_class_ids, gt_boxes, gt_masks], mode='training')
+        rpn_class_logits, rpn_pred_bbox, target_class_ids, mrcnn_class_logits, target_deltas, mrcnn_bbox, target_mask, \
+            mrcnn_mask, mrcnn_mask_logits = outs
+        losses = compute_losses(rpn_match, rpn_bbox, rpn_class_logits, rpn_pred_bbox, target_class_ids, mrcnn_class_logits,
+                                target_deltas, mrcnn_bbox, target_mask, mrcnn_mask, mrcnn_mask_logits, self.config.STAGE)
+        loss = self.weighted_loss(losses)
+        loss.sum().backward()
+        return loss, losses
+
+    # -- inference ------------------------------------------------------------------------------------------
+    def detect(self, images):
+        """reference model.py:1341-1389"""
+        start_time = time.time()
+        molded_images, image_metas, windows = self.mold_inputs(images)
+        molded = torch.from_numpy(molded_images).float().cuda()
+        with torch.no_grad():
+            detections, mrcnn_mask = self.predict([molded, image_metas], mode='inference')
+        detections = detections.detach().cpu().numpy()
+        mrcnn_mask = mrcnn_mask.permute(0, 1, 3, 4, 5, 2).detach().cpu().numpy()
+        print("detect done, using time", time.time() - start_time)
+        results = []
+        for i, image in enumerate(images):
+            rois, class_ids, scores, mask = self.unmold_detections(
+                detections[i], mrcnn_mask[i], [image.shape[3], image.shape[2], image.shape[0], image.shape[1]], windows[i])
+            results.append({"rois": rois, "class_ids": class_ids, "scores": scores, "mask": mask})
+        return results
+
+    def mold_inputs(self, images):
+        molded_images, image_metas, windows = [], [], []
+        c = self.config
+        for image in images:
+            molded, window, scale, padding, crop = utils.resize_image(image, min_dim=c.IMAGE_MIN_DIM, max_dim=c.IMAGE_MAX_DIM,
+                                                                      min_scale=c.IMAGE_MIN_SCALE, mode=c.IMAGE_RESIZE_MODE)
+            molded = mold_image(molded).transpose((3, 2, 0, 1))
+            molded_images.append(molded)
+            windows.append(window)
+            image_metas.append(compose_image_meta(0, image.shape, window, np.zeros([c.NUM_CLASSES], dtype=np.int32)))
+        return np.stack(molded_images), np.stack(image_metas), np.stack(windows)
+
+    def unmold_detections(self, detections, mrcnn_mask, image_shape, window):
+        """reference model.py:1812-1864"""
+        zero_ix = np.where(detections[:, 6] == 0)[0]
+        N = zero_ix[0] if zero_ix.shape[0] > 0 else detections.shape[0]
+        boxes = detections[:N, :6].astype(np.int32)
+        scores = detections[:N, 7]
+        masks = mrcnn_mask[np.arange(N)]
+        sc = np.array([image_shape[1] / (window[3] - window[0]), image_shape[2] / (window[4] - window[1]),
+                       image_shape[3] / (window[5] - window[2])] * 2)
+        sh = np.array(list(window[:3]) * 2)
+        boxes = np.multiply(boxes - sh, sc).astype(np.int32)
+        bad = np.where((boxes[:, 3] - boxes[:, 0]) * (boxes[:, 4] - boxes[:, 1]) * (boxes[:, 5] - boxes[:, 2]) <= 0)[0]
+        if bad.shape[0] > 0:
+            boxes, scores, masks = np.delete(boxes, bad, 0), np.delete(scores, bad, 0), np.delete(masks, bad, 0)
+        full_mask = np.argmax(utils.unmold_mask(masks[0], boxes[0], image_shape), axis=3)
+        boxes[:, [0, 1, 2, 3, 4, 5]] = boxes[:, [1, 2, 0, 4, 5, 3]]
+        return boxes, np.arange(1, 8), scores, full_mask.transpose((1, 2, 0))
+
+    # -- training loop ------------------------------------------------------------------------------------------
+    def make_optimizer(self, learning_rate):
+        """SGD(momentum) with weight decay on every trainable parameter whose name lacks 'bn' (reference :1538-1545),
+        as a fused clip + step kernel over flat buffers (cfun_b200.dp.FlatSGD)."""
+        from .dp import FlatSGD
+        return FlatSGD(self, lr=learning_rate, momentum=self.config.LEARNING_MOMENTUM,
+                       weight_decay=self.config.WEIGHT_DECAY, clip_norm=5.0)
+
+    def train_model(self, train_dataset, val_dataset, learning_rate, epochs):
+        """reference model.py:1516-1572"""
+        train_gen = torch.utils.data.DataLoader(Dataset(train_dataset, self.config), batch_size=1, shuffle=True,
+                                                num_workers=getattr(self.config, "LOADER_WORKERS", 4))
+        val_gen = torch.utils.data.DataLoader(Dataset(val_dataset, self.config), batch_size=1, shuffle=True,
+                                              num_workers=getattr(self.config, "LOADER_WORKERS", 4))
+        self.set_trainable(".*")
+        optimizer = self.make_optimizer(learning_rate)
+        start_datetime = time.strftime("%Y-%m-%d %H:%M:%S", time.localtime())
+        out_dir = os.path.join("./logs/heart", start_datetime)
+        os.makedirs(out_dir, exist_ok=True)
+        total_start = time.time()
+        for epoch in range(self.epoch + 1, epochs + 1):
+            log("Epoch {}/{}.".format(epoch, epochs))
+            t0 = time.time()
+            angle = np.random.randint(-20, 21)
+            stats = self.train_epoch(train_gen, optimizer, self.config.STEPS_PER_EPOCH, angle, train_dataset)
+            print("One Training Epoch time:", int(time.time() - t0), "Total time:", int(time.time() - total_start))
+            if epoch % 5 == 0:
+                vstats = self.valid_epoch(val_gen, self.config.VALIDATION_STEPS, angle, val_dataset)
+                torch.save(self.state_dict(), os.path.join(out_dir, "model%d_loss: %s_val: %s" % (
+                    epoch, round(stats[0], 4), round(vstats[0], 4))))
+        self.epoch = epochs
+
+    def _batch_to_device(self, inputs, angle, dataset):
+        image = inputs[0].squeeze(0).cpu().numpy()
+        mask = inputs[2].squeeze(0).cpu().numpy()
+        images, rpn_match, rpn_bbox, gt_class_ids, gt_boxes, gt_masks = load_image_gt(
+            image, mask, angle, dataset, self.config, self.anchors.cpu().numpy())
+        dev = self.anchors.device
+        return (torch.from_numpy(images).float().unsqueeze(0).to(dev), inputs[1].numpy(),
+                torch.from_numpy(rpn_match).unsqueeze(0).to(dev), torch.from_numpy(rpn_bbox).float().unsqueeze(0).to(dev),
+                torch.from_numpy(gt_class_ids).unsqueeze(0).to(dev), torch.from_numpy(gt_boxes).float().unsqueeze(0).to(dev),
+                torch.from_numpy(gt_masks).float().unsqueeze(0).to(dev))
+
+    def train_epoch(self, datagenerator, optimizer, steps, angle, dataset):
+        sums = np.zeros(7)
+        batch_count, step = 0, 0
+        optimizer.zero_grad()
+        for inputs in datagenerator:
+            batch_count += 1
+            images, metas, rpn_match, rpn_bbox, gt_class_ids, gt_boxes, gt_masks = self._batch_to_device(inputs, angle, dataset)
+            loss, losses = self.forward_backward(images, metas, rpn_match, rpn_bbox, gt_class_ids, gt_boxes, gt_masks)
+            # reference clips after every backward and steps every BATCH_SIZE volumes (model.py:1641-1645)
+            if (batch_count % self.config.BATCH_SIZE) == 0:
+                optimizer.step()
+                optimizer.zero_grad()
+                batch_count = 0
+            vals = torch.stack([loss.detach().reshape(())] + [l.detach().reshape(()) for l in losses]).cpu().numpy()
+            sums += vals / steps
+            if step == steps - 1:
+                break
+            step += 1
+        return tuple(sums)
+
+    def valid_epoch(self, datagenerator, steps, angle, dataset):
+        sums = np.zeros(7)
+        step = 0
+        for inputs in datagenerator:
+            images, metas, rpn_match, rpn_bbox, gt_class_ids, gt_boxes, gt_masks = self._batch_to_device(inputs, angle, dataset)
+            with torch.no_grad():
+                outs = self.predict([images, metas, gt_class_ids, gt_boxes, gt_masks], mode='training')
+                if outs[2].shape[0] == 0:
+                    continue
+                losses = compute_losses(rpn_match, rpn_bbox, outs[0], outs[1], outs[2], outs[3], outs[4], outs[5], outs[6],
+                                        outs[7], outs[8], self.config.STAGE)
+                loss = self.weighted_loss(losses)
+            sums += torch.stack([loss.reshape(())] + [l.reshape(()) for l in losses]).cpu().numpy() / steps
+            if step == steps - 1:
+                break
+            step += 1
+        return tuple(sums)

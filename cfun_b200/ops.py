@@ -1,0 +1,518 @@
+"""torch.autograd Functions over the C ABI of libcfun_b200.so.
+
+Host code stays PyTorch (device memory, streams, autograd bookkeeping); every op body is a hand-written sm_100a CUDA
+kernel reached through ctypes with raw device pointers and the current CUDA stream.  There is no CPU path: tensors must
+live on a CUDA device, and a missing / failing library raises.
+
+Activation layout: logical [N,C,D,H,W] tensors whose memory is N,D,H,W,C (torch.channels_last_3d).
+"""
+import ctypes as C
+import torch
+from torch.autograd import Function
+
+from ._lib import lib, check, ConvDesc, f6
+
+ALGO_AUTO, ALGO_SIMT, ALGO_TC, ALGO_TC1 = 0, 1, 2, 3
+PASS_FWD, PASS_BWD_DATA, PASS_BWD_WEIGHT = 0, 1, 2
+EPI_BIAS, EPI_RELU = 1, 2
+
+# launch accounting for bench.py ("gpu_launches": kernels of OUR library launched in the timed region)
+_calls = {"n": 0}
+
+
+def call_count():
+    return _calls["n"]
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("cfun_b200 ops are CUDA-only (sm_100a); got a %s tensor. There is no CPU fallback."
+                               % t.device)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def is_cl(x):
+    """memory order is exactly N,D,H,W,C and dense"""
+    return x.permute(0, 2, 3, 4, 1).is_contiguous()
+
+
+def to_cl(x):
+    if x.dtype != torch.float32:
+        x = x.float()
+    if is_cl(x):
+        return x
+    return x.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
+
+
+def empty_cl(N, Cc, D, H, W, device, dtype=torch.float32):
+    return torch.empty((N, D, H, W, Cc), device=device, dtype=dtype).permute(0, 4, 1, 2, 3)
+
+
+def zeros_cl(N, Cc, D, H, W, device, dtype=torch.float32):
+    return torch.zeros((N, D, H, W, Cc), device=device, dtype=dtype).permute(0, 4, 1, 2, 3)
+
+
+_ws = {}
+
+
+def workspace(nbytes, device):
+    """Stream-ordered scratch reused by consecutive calls on the same device (grown geometrically)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes * 1.25) + 4096, 1 << 20), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf
+
+
+def _run(name, *args):
+    _calls["n"] += 1
+    check(getattr(lib, name)(*args), name)
+
+
+def _triple(v):
+    return (v, v, v) if isinstance(v, int) else tuple(int(t) for t in v)
+
+
+# --------------------------------------------------------------------------------------------------------
+# conv3d
+# --------------------------------------------------------------------------------------------------------
+def _conv_desc(x_shape, w_shape, stride, padding):
+    N, Cin, D, H, W = x_shape
+    Cout, Cin_w, kD, kH, kW = w_shape
+    if Cin_w != Cin:
+        raise RuntimeError("conv3d: weight expects %d input channels, got %d" % (Cin_w, Cin))
+    s, p = _triple(stride), _triple(padding)
+    Do = (D + 2 * p[0] - kD) // s[0] + 1
+    Ho = (H + 2 * p[1] - kH) // s[1] + 1
+    Wo = (W + 2 * p[2] - kW) // s[2] + 1
+    if min(Do, Ho, Wo) <= 0:
+        raise RuntimeError("conv3d: kernel %s larger than padded input %s" % ((kD, kH, kW), (D, H, W)))
+    return ConvDesc(N, Cin, D, H, W, Cout, Do, Ho, Wo, kD, kH, kW, s[0], s[1], s[2], p[0], p[1], p[2])
+
+
+_default_algo = {"algo": ALGO_AUTO}
+
+
+def set_conv_algo(algo):
+    """ALGO_AUTO (default): tcgen05 where supported else CUDA cores; ALGO_SIMT / ALGO_TC / ALGO_TC1 force one."""
+    _default_algo["algo"] = algo
+
+
+class Conv3dFn(Function):
+    @staticmethod
+    def forward(ctx, x, w, b, stride, padding, relu):
+        _require_cuda(x, w, b)
+        x = to_cl(x)
+        w = w.contiguous()
+        d = _conv_desc(x.shape, w.shape, stride, padding)
+        y = empty_cl(d.N, d.Cout, d.Dout, d.Hout, d.Wout, x.device)
+        algo = _default_algo["algo"]
+        ws_bytes = lib.cfun_conv3d_workspace_size(C.byref(d), PASS_FWD, algo)
+        ws = workspace(ws_bytes, x.device)
+        epi = (EPI_BIAS if b is not None else 0) | (EPI_RELU if relu else 0)
+        _run("cfun_conv3d_fwd", C.byref(d), _ptr(x), _ptr(w), _ptr(b), _ptr(y), epi, algo, _ptr(ws), ws.numel(), _stream())
+        ctx.d = d
+        ctx.relu = relu
+        ctx.has_bias = b is not None
+        ctx.algo = algo
+        ctx.save_for_backward(x, w, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        d = ctx.d
+        dy = to_cl(dy)
+        if ctx.relu:
+            dy = to_cl(torch.where(y > 0, dy, torch.zeros((), device=dy.device)))
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = empty_cl(d.N, d.Cin, d.Din, d.Hin, d.Win, dy.device)
+            ws_bytes = lib.cfun_conv3d_workspace_size(C.byref(d), PASS_BWD_DATA, ctx.algo)
+            ws = workspace(ws_bytes, dy.device)
+            _run("cfun_conv3d_bwd_data", C.byref(d), _ptr(dy), _ptr(w), _ptr(dx), ctx.algo, _ptr(ws), ws.numel(), _stream())
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw = torch.empty_like(w)
+            db = torch.empty(d.Cout, device=dy.device) if ctx.has_bias else None
+            ws_bytes = lib.cfun_conv3d_workspace_size(C.byref(d), PASS_BWD_WEIGHT, ctx.algo)
+            ws = workspace(ws_bytes, dy.device)
+            _run("cfun_conv3d_bwd_weight", C.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), ctx.algo, _ptr(ws),
+                 ws.numel(), _stream())
+        return dx, dw, db, None, None, None
+
+
+def conv3d(x, w, b=None, stride=1, padding=0, relu=False):
+    return Conv3dFn.apply(x, w, b, stride, padding, relu)
+
+
+class FcConvFn(Function):
+    """Conv3d whose kernel covers the whole (un-padded) input: Classifier.conv1 (model.py:758).  x is consumed in
+    NCDHW-contiguous order so K = (ci, kd, kh, kw) matches the checkpoint weight layout with no repack."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        _require_cuda(x, w, b)
+        x = x.contiguous()
+        w = w.contiguous()
+        M, K, Nout = x.shape[0], x[0].numel() if x.shape[0] else w[0].numel(), w.shape[0]
+        y = torch.empty((M, Nout), device=x.device)
+        _run("cfun_fc_fwd", M, Nout, K, _ptr(x), _ptr(w), _ptr(b), _ptr(y), _stream())
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return y.view(M, Nout, 1, 1, 1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        M, Nout = x.shape[0], w.shape[0]
+        K = w[0].numel()
+        dy = dy.reshape(M, Nout).contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            _run("cfun_fc_bwd_data", M, Nout, K, _ptr(dy), _ptr(w), _ptr(dx), _stream())
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(w)
+            db = torch.empty(Nout, device=dy.device) if ctx.has_bias else None
+            _run("cfun_fc_bwd_weight", M, Nout, K, _ptr(dy), _ptr(x), _ptr(dw), _ptr(db), _stream())
+        return dx, dw, db
+
+
+def fc_conv(x, w, b=None):
+    return FcConvFn.apply(x, w, b)
+
+
+# --------------------------------------------------------------------------------------------------------
+# affine / activation / norm
+# --------------------------------------------------------------------------------------------------------
+class AffineActFn(Function):
+    """y = leaky_relu(x * a + b (+ r), slope), optionally nearest-upsampled x2.  a, b: [C] or [N,C] constants."""
+
+    @staticmethod
+    def forward(ctx, x, a, b, r, slope, up):
+        _require_cuda(x, a, b, r)
+        x = to_cl(x)
+        N, Cc, D, H, W = x.shape
+        if r is not None:
+            r = to_cl(r)
+        nstride = 0
+        if a is not None:
+            a = a.contiguous().float()
+            b = b.contiguous().float()
+            nstride = Cc if a.dim() == 2 else 0
+        y = empty_cl(N, Cc, D * up, H * up, W * up, x.device)
+        _run("cfun_affine_act_fwd", _ptr(x), _ptr(a), _ptr(b), nstride, _ptr(r), _ptr(y), N, D, H, W, Cc, Cc, 0, up,
+             float(slope), _stream())
+        ctx.save_for_backward(x, a, b, r)
+        ctx.cfg = (nstride, float(slope), up)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, a, b, r = ctx.saved_tensors
+        nstride, slope, up = ctx.cfg
+        N, Cc, D, H, W = x.shape
+        dy = to_cl(dy)
+        dx = empty_cl(N, Cc, D, H, W, x.device)
+        dr = empty_cl(N, Cc, D, H, W, x.device) if (r is not None and ctx.needs_input_grad[3]) else None
+        _run("cfun_affine_act_bwd", _ptr(x), _ptr(a), _ptr(b), nstride, _ptr(r), _ptr(dy), _ptr(dx), _ptr(dr), None, N, D,
+             H, W, Cc, Cc, 0, up, slope, _stream())
+        return dx, None, None, dr, None, None
+
+
+def affine_act(x, a=None, b=None, r=None, slope=0.0, up=1):
+    return AffineActFn.apply(x, a, b, r, slope, up)
+
+
+def leaky_relu(x, slope=0.01):
+    return AffineActFn.apply(x, None, None, None, slope, 1)
+
+
+def upsample2x(x):
+    return AffineActFn.apply(x, None, None, None, 1.0, 2)
+
+
+class InstNormActFn(Function):
+    """InstanceNorm3d(affine=False, eps) of (x * drop) followed by LeakyReLU(slope) and optional nearest x2 upsampling,
+    as one statistics pass + one apply pass.  drop: None or per-(n,c) Dropout3d scale [N,C] (0 or 1/(1-p))."""
+
+    @staticmethod
+    def forward(ctx, x, drop, eps, slope, up):
+        _require_cuda(x, drop)
+        x = to_cl(x)
+        N, Cc, D, H, W = x.shape
+        S = D * H * W
+        acc = torch.empty(2 * N * Cc, dtype=torch.float64, device=x.device)
+        mean = torch.empty((N, Cc), device=x.device)
+        rstd = torch.empty((N, Cc), device=x.device)
+        _run("cfun_instnorm_stats", _ptr(x), N, S, Cc, float(eps), _ptr(acc), _ptr(mean), _ptr(rstd), _stream())
+        if drop is None:
+            a = rstd
+            b = -mean * rstd
+        else:
+            m = drop.reshape(N, Cc).float()
+            var = 1.0 / (rstd * rstd) - eps
+            rstd2 = torch.rsqrt(m * m * var + eps)
+            a = m * rstd2
+            b = -(m * mean) * rstd2
+        a = a.contiguous()
+        b = b.contiguous()
+        y = empty_cl(N, Cc, D * up, H * up, W * up, x.device)
+        _run("cfun_affine_act_fwd", _ptr(x), _ptr(a), _ptr(b), Cc, None, _ptr(y), N, D, H, W, Cc, Cc, 0, up, float(slope),
+             _stream())
+        ctx.save_for_backward(x, a, b)
+        ctx.cfg = (float(slope), up)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, a, b = ctx.saved_tensors
+        slope, up = ctx.cfg
+        N, Cc, D, H, W = x.shape
+        dy = to_cl(dy)
+        dx = empty_cl(N, Cc, D, H, W, x.device)
+        acc = torch.empty(2 * N * Cc, dtype=torch.float64, device=x.device)
+        _run("cfun_affine_act_bwd", _ptr(x), _ptr(a), _ptr(b), Cc, None, _ptr(dy), _ptr(dx), None, _ptr(acc), N, D, H, W,
+             Cc, Cc, 0, up, slope, _stream())
+        _run("cfun_instnorm_bwd_apply", _ptr(x), _ptr(a), _ptr(b), _ptr(acc), _ptr(dx), N, D * H * W, Cc, _stream())
+        return dx, None, None, None, None
+
+
+def instnorm_lrelu(x, drop=None, eps=1e-5, slope=0.01, up=1):
+    return InstNormActFn.apply(x, drop, eps, slope, up)
+
+
+class MaxPool2Fn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        _require_cuda(x)
+        x = to_cl(x)
+        N, Cc, D, H, W = x.shape
+        y = empty_cl(N, Cc, D // 2, H // 2, W // 2, x.device)
+        _run("cfun_maxpool2_fwd", _ptr(x), _ptr(y), N, D, H, W, Cc, _stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        N, Cc, D, H, W = x.shape
+        dy = to_cl(dy)
+        dx = empty_cl(N, Cc, D, H, W, x.device)
+        _run("cfun_maxpool2_bwd", _ptr(x), None, _ptr(dy), _ptr(dx), N, D, H, W, Cc, _stream())
+        return dx
+
+
+def maxpool2(x):
+    return MaxPool2Fn.apply(x)
+
+
+# --------------------------------------------------------------------------------------------------------
+# RoI crop + resize
+# --------------------------------------------------------------------------------------------------------
+class RoiCropResizeFn(Function):
+    @staticmethod
+    def forward(ctx, f0, f1, boxes, level, pool, out_ncdhw):
+        _require_cuda(f0, f1, boxes, level)
+        f0 = to_cl(f0)
+        f1 = to_cl(f1) if f1 is not None else None
+        boxes = boxes.detach().contiguous().float()
+        n = boxes.shape[0]
+        Cc = f0.shape[1]
+        pd, ph, pw = [int(p) for p in pool]
+        if out_ncdhw:
+            out = torch.empty((n, Cc, pd, ph, pw), device=f0.device)
+        else:
+            out = empty_cl(n, Cc, pd, ph, pw, f0.device)
+        D1, H1, W1 = (f1.shape[2], f1.shape[3], f1.shape[4]) if f1 is not None else (0, 0, 0)
+        _run("cfun_roi_crop_resize_fwd", _ptr(f0), f0.shape[2], f0.shape[3], f0.shape[4], _ptr(f1), D1, H1, W1, Cc,
+             _ptr(boxes), _ptr(level), n, pd, ph, pw, _ptr(out), 1 if out_ncdhw else 0, _stream())
+        ctx.save_for_backward(boxes, level)
+        ctx.cfg = (tuple(f0.shape), tuple(f1.shape) if f1 is not None else None, (pd, ph, pw), out_ncdhw)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        boxes, level = ctx.saved_tensors
+        s0, s1, (pd, ph, pw), out_ncdhw = ctx.cfg
+        n = boxes.shape[0]
+        dout = dout.contiguous() if out_ncdhw else to_cl(dout)
+        need0, need1 = ctx.needs_input_grad[0], (s1 is not None and ctx.needs_input_grad[1])
+        if not (need0 or need1):
+            return None, None, None, None, None, None
+        df0 = zeros_cl(*s0, device=dout.device)
+        df1 = zeros_cl(*s1, device=dout.device) if s1 is not None else None
+        D1, H1, W1 = (s1[2], s1[3], s1[4]) if s1 is not None else (0, 0, 0)
+        _run("cfun_roi_crop_resize_bwd", _ptr(df0), s0[2], s0[3], s0[4], _ptr(df1), D1, H1, W1, s0[1], _ptr(boxes),
+             _ptr(level), n, pd, ph, pw, _ptr(dout), 1 if out_ncdhw else 0, _stream())
+        return (df0 if need0 else None), (df1 if need1 else None), None, None, None, None
+
+
+def roi_crop_resize(f0, f1, boxes, level, pool, out_ncdhw=False):
+    return RoiCropResizeFn.apply(f0, f1, boxes, level, tuple(pool), out_ncdhw)
+
+
+def roi_level(boxes):
+    _require_cuda(boxes)
+    boxes = boxes.detach().contiguous().float()
+    lv = torch.empty(boxes.shape[0], dtype=torch.int32, device=boxes.device)
+    _run("cfun_roi_level", _ptr(boxes), boxes.shape[0], _ptr(lv), _stream())
+    return lv
+
+
+# --------------------------------------------------------------------------------------------------------
+# boxes
+# --------------------------------------------------------------------------------------------------------
+def sort_desc(scores):
+    """indices of `scores` (1-D fp32) in (score descending, index ascending) order, int32"""
+    _require_cuda(scores)
+    scores = scores.detach().contiguous().float()
+    n = scores.numel()
+    order = torch.empty(n, dtype=torch.int32, device=scores.device)
+    if n == 0:
+        return order
+    nb = lib.cfun_sort_workspace_size(n)
+    ws = workspace(nb, scores.device)
+    _run("cfun_sort_desc", _ptr(scores), n, _ptr(order), _ptr(ws), ws.numel(), _stream())
+    return order
+
+
+def decode_clip(anchors, deltas, scores, order, k, std6, window6, score_stride=1, score_offset=0):
+    _require_cuda(anchors, deltas, scores, order)
+    boxes = torch.empty((k, 6), device=anchors.device)
+    sc = torch.empty(k, device=anchors.device) if scores is not None else None
+    _run("cfun_decode_clip", _ptr(anchors.contiguous()), _ptr(deltas.detach().contiguous()),
+         _ptr(scores.detach().contiguous()) if scores is not None else None, score_stride, score_offset, _ptr(order), k,
+         f6(std6), f6(window6), _ptr(boxes), _ptr(sc), _stream())
+    return boxes, sc
+
+
+def nms3d(boxes_sorted, threshold, max_num):
+    """boxes_sorted [n,6] already in descending score order.  Returns (keep int32[max_num], count int32[1]) on device."""
+    _require_cuda(boxes_sorted)
+    b = boxes_sorted.detach().contiguous().float()
+    n = b.shape[0]
+    keep = torch.zeros(max(max_num, 1), dtype=torch.int32, device=b.device)
+    count = torch.zeros(1, dtype=torch.int32, device=b.device)
+    nb = lib.cfun_nms_workspace_size(n)
+    ws = workspace(nb, b.device)
+    _run("cfun_nms3d", _ptr(b), n, float(threshold), int(max_num), _ptr(keep), _ptr(count), _ptr(ws), ws.numel(), _stream())
+    return keep, count
+
+
+def gather_boxes(rows, idx, count, max_rows, div6):
+    out = torch.empty((max_rows, 6), device=rows.device)
+    _run("cfun_gather_boxes", _ptr(rows.contiguous()), _ptr(idx), _ptr(count), max_rows, f6(div6), _ptr(out), _stream())
+    return out
+
+
+def iou_with_eps(box, boxes):
+    """utils.compute_iou: [1,6] against [n,6] -> [1,n]"""
+    _require_cuda(box, boxes)
+    box = box.detach().contiguous().float()
+    boxes = boxes.detach().contiguous().float()
+    out = torch.empty((1, boxes.shape[0]), device=boxes.device)
+    _run("cfun_iou3d_eps", _ptr(box), _ptr(boxes), boxes.shape[0], _ptr(out), _stream())
+    return out
+
+
+def bbox_overlaps3d(b1, b2):
+    _require_cuda(b1, b2)
+    b1 = b1.detach().contiguous().float()
+    b2 = b2.detach().contiguous().float()
+    out = torch.empty((b1.shape[0], b2.shape[0]), device=b1.device)
+    _run("cfun_bbox_overlaps3d", _ptr(b1), b1.shape[0], _ptr(b2), b2.shape[0], _ptr(out), _stream())
+    return out
+
+
+def box_refinement(box, gt_box, std6=(1, 1, 1, 1, 1, 1)):
+    _require_cuda(box, gt_box)
+    box = box.detach().contiguous().float()
+    gt_box = gt_box.detach().contiguous().float()
+    out = torch.empty_like(box)
+    _run("cfun_box_refinement", _ptr(box), _ptr(gt_box), box.shape[0], f6(std6), _ptr(out), _stream())
+    return out
+
+
+def mask_target_crop(label_dhw, rois, ncls, mask_shape, onehot=True, index=True):
+    """label_dhw int32 [D,H,W]; rois [P,6] normalised.  Returns (onehot float64 [P,ncls,*mask_shape] | None,
+    class index int64 [P,*mask_shape] | None)."""
+    _require_cuda(label_dhw, rois)
+    label_dhw = label_dhw.contiguous()
+    assert label_dhw.dtype == torch.int32
+    rois = rois.detach().contiguous().float()
+    P = rois.shape[0]
+    md, mh, mw = [int(m) for m in mask_shape]
+    oh = torch.empty((P, ncls, md, mh, mw), dtype=torch.float64, device=rois.device) if onehot else None
+    ix = torch.empty((P, md, mh, mw), dtype=torch.int64, device=rois.device) if index else None
+    D, H, W = label_dhw.shape
+    _run("cfun_mask_target_crop", _ptr(label_dhw), D, H, W, _ptr(rois), P, ncls, md, mh, mw, _ptr(oh), _ptr(ix), _stream())
+    return oh, ix
+
+
+# --------------------------------------------------------------------------------------------------------
+# Sobel edge loss
+# --------------------------------------------------------------------------------------------------------
+class SobelEdgeLossFn(Function):
+    @staticmethod
+    def forward(ctx, pred, tgt_index):
+        _require_cuda(pred, tgt_index)
+        pred = to_cl(pred)
+        P, ncls, M = pred.shape[0], pred.shape[1], pred.shape[2]
+        assert pred.shape[3] == M and pred.shape[4] == M, "cubic mask crops only (config MASK_SHAPE)"
+        tgt_index = tgt_index.contiguous()
+        assert tgt_index.dtype == torch.int64 and tuple(tgt_index.shape) == (P, M, M, M)
+        loss = torch.empty(1, device=pred.device)
+        ws = workspace(4096, pred.device)
+        _run("cfun_sobel_edge_loss_fwd", _ptr(pred), _ptr(tgt_index), P, M, ncls, _ptr(loss), _ptr(ws), ws.numel(), _stream())
+        ctx.save_for_backward(pred, tgt_index)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        pred, tgt_index = ctx.saved_tensors
+        P, ncls, M = pred.shape[0], pred.shape[1], pred.shape[2]
+        g = dloss.reshape(1).contiguous().float()
+        dpred = empty_cl(P, ncls, M, M, M, pred.device)
+        nb = lib.cfun_sobel_edge_workspace_size(P, M, ncls)
+        ws = workspace(nb, pred.device)
+        _run("cfun_sobel_edge_loss_bwd", _ptr(pred), _ptr(tgt_index), P, M, ncls, _ptr(g), _ptr(dpred), _ptr(ws), ws.numel(),
+             _stream())
+        return dpred, None
+
+
+def sobel_edge_loss(pred_probs, tgt_index):
+    return SobelEdgeLossFn.apply(pred_probs, tgt_index)
+
+
+# --------------------------------------------------------------------------------------------------------
+# optimizer tail / input molding
+# --------------------------------------------------------------------------------------------------------
+def sumsq_into(flat_grad, acc):
+    _run("cfun_sumsq", _ptr(flat_grad), flat_grad.numel(), _ptr(acc), _stream())
+
+
+def sgd_clip_step(p, g, mom, wd_mask, sumsq, max_norm, lr, momentum, weight_decay):
+    _run("cfun_sgd_clip_step", _ptr(p), _ptr(g), _ptr(mom), _ptr(wd_mask), p.numel(), _ptr(sumsq), float(max_norm),
+         float(lr), float(momentum), float(weight_decay), 0, _stream())
+
+
+def mold_volume_i16(vol_hwd):
+    """int16 [H,W,D] CT volume on device -> molded fp32 [1,1,D,H,W] (model.mold_image + the HWD->DHW transpose)."""
+    _require_cuda(vol_hwd)
+    assert vol_hwd.dtype == torch.int16 and vol_hwd.dim() == 3
+    vol_hwd = vol_hwd.contiguous()
+    H, W, D = vol_hwd.shape
+    out = torch.empty((1, 1, D, H, W), device=vol_hwd.device)
+    acc = torch.empty(2, dtype=torch.float64, device=vol_hwd.device)
+    _run("cfun_mold_volume_i16", _ptr(vol_hwd), H, W, D, _ptr(acc), _ptr(out), _stream())
+    return out

@@ -1,0 +1,7 @@
+"""Drop-in shim: `import mask_branch` from the repository root resolves to the B200-native implementation
+(cfun_b200.mask_branch), so the reference driver heart_main.py (`from config import Config; import model; import utils`,
+reference heart_main.py:15-17) runs against these layers unmodified."""
+from cfun_b200.mask_branch import *  # noqa: F401,F403
+from cfun_b200 import mask_branch as _impl
+
+globals().update({k: v for k, v in vars(_impl).items() if not k.startswith("__")})

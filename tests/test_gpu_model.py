@@ -1,0 +1,113 @@
+"""GPU parity of the CFUN module surface (FPN, RPN, Classifier, Modified3DUNet, whole train step) against golden vectors
+from the unmodified reference and against the CPU oracle, with shared deterministic weights."""
+import numpy as np
+import pytest
+import torch
+
+import cfun_oracle as O
+from detweights import det_state
+from shapes import maskrcnn_shapes
+from synth import golden_step_inputs
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+SMALL = dict(TOP_DOWN_PYRAMID_SIZE=32, RPN_CONV_CHANNELS=48, UNET_MASK_BRANCH_CHANNEL=4, FPN_CLASSIFY_FC_LAYERS_SIZE=16,
+             POOL_SIZE=[4, 4, 4])
+
+
+def build(cfg, seed):
+    from cfun_b200 import model as M
+    net = M.MaskRCNN(cfg, "/tmp/_cfun_test")
+    sd = det_state({k: tuple(v.shape) for k, v in net.state_dict().items()}, seed=seed)
+    net.load_state_dict(sd, strict=True)
+    return net.cuda(), sd
+
+
+@pytest.mark.parametrize("stage", ["beginning", "finetune"])
+def test_layers_match_reference_golden(stage):
+    from cfun_b200 import config as Cf
+    g = load_golden("layers_" + stage)
+    cfg = Cf.heart_config(32, stage, mask_pool=32, anchor_scales=(8, 16), **SMALL)
+    net, sd = build(cfg, 100)
+    assert set(sd) == set(maskrcnn_shapes(fpn=32, rpn=48, unet=4, fc=16, pool=4))
+    net.train()
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    p2, p3 = net.fpn(x)
+    assert rel_err(p2.detach().cpu().numpy(), g["p2"]) < TOL and rel_err(p3.detach().cpu().numpy(), g["p3"]) < TOL
+    (p2.square().sum() + p3.sum()).backward()
+    assert rel_err(net.fpn.P2_conv2.weight.grad.cpu().numpy(), g["g_P2_conv2"]) < TOL
+    assert rel_err(net.fpn.C1[0].weight.grad.cpu().numpy(), g["g_stem"]) < TOL
+    assert rel_err(net.fpn.C2[1].conv2.weight.grad.cpu().numpy(), g["g_C2_1_conv2"]) < TOL
+    assert rel_err(x.grad.cpu().numpy(), g["gx"]) < TOL
+    logits, probs, bbox = net.rpn(p2.detach())
+    assert rel_err(logits.detach().cpu().numpy(), g["rpn_logits"]) < TOL
+    assert rel_err(probs.detach().cpu().numpy(), g["rpn_probs"]) < TOL
+    assert rel_err(bbox.detach().cpu().numpy(), g["rpn_bbox"]) < TOL
+    unet = net.mask.modified_u_net
+    unet.injected_drop = [torch.from_numpy(g["drop%d" % i]) for i in range(5)]
+    net.zero_grad()
+    y = unet(torch.from_numpy(g["crops"]).cuda())
+    assert rel_err(y.detach().flatten()[::13].cpu().numpy(), g["unet_train"]) < TOL
+    w = torch.cos(torch.arange(y.numel(), dtype=torch.float32) * 0.37).view(y.shape).cuda()
+    (y * w).sum().backward()
+    grads = {k: p.grad for k, p in unet.named_parameters()}
+    for name, key in [("conv3d_c1_1", "g_unet_c1_1"), ("conv3d_c3", "g_unet_c3"), ("norm_lrelu_conv_c4.2", "g_unet_nlc4"),
+                      ("conv_norm_lrelu_l4.0", "g_unet_l4"), ("ds2_1x1_conv3d", "g_unet_ds2"), ("out_upscale_conv.1", "g_unet_up")]:
+        gr = grads[name + ".weight"]
+        gr = gr.cpu().numpy() if gr is not None else np.zeros_like(g[key])
+        assert rel_err(gr, g[key]) < 3 * TOL, name
+    unet.eval()
+    y_eval = unet(torch.from_numpy(g["crops"]).cuda())
+    assert rel_err(y_eval.detach().flatten()[::13].cpu().numpy(), g["unet_eval"]) < TOL
+    # classifier tail on given pooled features
+    from cfun_b200 import ops
+    pooled = torch.from_numpy(g["pooled"]).cuda()
+    c = net.classifier
+    t = c.bn1(ops.fc_conv(pooled, c.conv1.weight, c.conv1.bias), relu=True)
+    t = c.bn2(c.conv2(t), relu=True).reshape(-1, 16)
+    assert rel_err(c.linear_class(t).detach().cpu().numpy(), g["cls_logits"]) < TOL
+    assert rel_err(c.linear_bbox(t).view(5, -1, 6).detach().cpu().numpy(), g["cls_bbox"]) < TOL
+
+
+@pytest.mark.parametrize("stage", ["beginning", "finetune"])
+def test_whole_train_step_64_matches_reference_golden(stage):
+    from cfun_b200 import config as Cf
+    g = load_golden("step64_" + stage)
+    cfg = Cf.heart_config(64, stage, mask_pool=32, anchor_scales=(16, 32))
+    net, sd = build(cfg, int(g["seed_weights"]))
+    inp = golden_step_inputs(g)
+    net.mask.modified_u_net.injected_drop = inp["drop"]
+    torch.manual_seed(int(g["seed_perm"]))
+    dev = torch.device("cuda")
+    loss, losses = net.forward_backward(
+        inp["image"].to(dev), None, inp["rpn_match"].to(dev)[None, :, None], inp["rpn_bbox"].to(dev)[None],
+        torch.arange(1, 8).int().to(dev)[None], inp["gt_boxes"].to(dev)[None], inp["gt_masks"].to(dev)[None])
+    got = np.array([float(l) for l in losses])
+    assert np.allclose(got, g["losses"], rtol=5e-4, atol=1e-6), (got, g["losses"])
+    names = list(g["grad_names"])
+    params = dict(net.named_parameters())
+    norms = np.array([float(params[k].grad.norm()) if params[k].grad is not None else 0.0 for k in names])
+    big = g["grad_norms"] > 1e-3 * g["grad_norms"].max()
+    assert np.allclose(norms[big], g["grad_norms"][big], rtol=2e-3), np.abs(norms[big] / g["grad_norms"][big] - 1).max()
+    tot = float(np.sqrt((norms.astype(np.float64) ** 2).sum()))
+    assert abs(tot - float(g["grad_total_norm"])) < 1e-3 * float(g["grad_total_norm"])
+    assert rel_err(net.rpn.conv_shared.weight.grad.flatten()[::811].cpu().numpy(), g["g_rpn_shared"]) < 3 * TOL
+    assert rel_err(net.mask.modified_u_net.conv_norm_lrelu_l4[0].weight.grad.flatten()[::7].cpu().numpy(), g["g_unet_l4"]) < 3 * TOL
+
+
+def test_inference_predict_runs_and_matches_oracle_shapes():
+    from cfun_b200 import config as Cf
+    from cfun_b200 import model as M
+    cfg = Cf.heart_config(64, "beginning", mask_pool=32, anchor_scales=(16, 32), DETECTION_MIN_CONFIDENCE=0.0)
+    net, sd = build(cfg, 200)
+    with torch.no_grad():       # make the binary classifier vote "foreground" so that detections survive
+        net.classifier.linear_class.bias.copy_(torch.tensor([-1.0, 1.0]))
+    g = load_golden("step64_beginning")
+    inp = golden_step_inputs(g)
+    meta = M.compose_image_meta(0, (64, 64, 64, 1), (0, 0, 0, 64, 64, 64), np.zeros(8, dtype=np.int32))[None]
+    with torch.no_grad():
+        det, masks = net.predict([inp["image"].cuda(), meta], "inference")
+    assert det.shape[0] == 1 and det.shape[2] == 8 and masks.shape[2] == 8
+    assert masks.shape[1] == det.shape[1] and masks.shape[3:] == (32, 32, 32)
+    assert torch.isfinite(masks).all()

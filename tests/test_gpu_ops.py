@@ -1,0 +1,309 @@
+"""GPU parity tests for the individual CUDA ops (through the C ABI) against the CPU oracle / torch-CPU fp32."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cfun_oracle as O
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4          # north_star: fp32 conv activations within 1e-4 relative (max|diff| / max|ref|)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    from cfun_b200 import ops as _ops
+    return _ops
+
+
+def cuda(t):
+    return t.cuda()
+
+
+CONV_CASES = [
+    # N, Cin, D, H, W, Cout, k, stride, pad, bias
+    (1, 1, 16, 18, 20, 16, (3, 7, 7), 2, (1, 3, 3), True),      # stem (backbone.py:124)
+    (1, 16, 8, 8, 8, 16, (1, 3, 3), 1, (0, 1, 1), True),        # conv_S
+    (1, 16, 8, 8, 8, 16, (3, 1, 1), 1, (1, 0, 0), True),        # conv_T
+    (1, 16, 8, 10, 12, 64, 1, 2, 0, True),                      # strided 1x1x1 downsample
+    (2, 20, 9, 10, 11, 20, 3, 1, 1, False),                     # U-Net thin conv, ragged extents
+    (2, 20, 12, 12, 12, 40, 3, 2, 1, False),                    # U-Net stride-2
+    (1, 8, 10, 10, 10, 8, 5, 1, 2, False),                      # out_upscale_conv 5^3
+    (1, 32, 6, 6, 6, 2, 1, 1, 0, True),                         # RPN class head
+    (1, 32, 6, 6, 6, 6, 1, 1, 0, True),                         # RPN bbox head
+    (1, 1, 12, 12, 12, 20, 3, 1, 1, False),                     # U-Net first conv (Cin = 1)
+    (1, 48, 8, 8, 8, 80, 3, 1, 1, True),                        # >64 output channels
+    (3, 24, 5, 7, 6, 36, 3, 1, 1, True),                        # odd everything
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv3d_fwd_bwd(ops, case):
+    N, Cin, D, H, W, Cout, k, s, p, bias = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn(N, Cin, D, H, W, generator=g)
+    kk = (k, k, k) if isinstance(k, int) else k
+    w = torch.randn(Cout, Cin, *kk, generator=g) * 0.2
+    b = torch.randn(Cout, generator=g) if bias else None
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True) if bias else None
+    yr = F.conv3d(xr, wr, br, stride=s, padding=p)
+    dy = torch.randn(yr.shape, generator=g)
+    yr.backward(dy)
+    xc, wc = cuda(x).requires_grad_(True), cuda(w).requires_grad_(True)
+    bc = cuda(b).requires_grad_(True) if bias else None
+    yc = ops.conv3d(xc, wc, bc, s, p)
+    assert tuple(yc.shape) == tuple(yr.shape)
+    assert ops.is_cl(yc)
+    yc.backward(cuda(dy))
+    assert rel_err(yc.detach().cpu().numpy(), yr.detach().numpy()) < TOL
+    assert rel_err(xc.grad.cpu().numpy(), xr.grad.numpy()) < TOL
+    assert rel_err(wc.grad.cpu().numpy(), wr.grad.numpy()) < TOL
+    if bias:
+        assert rel_err(bc.grad.cpu().numpy(), br.grad.numpy()) < TOL
+
+
+def test_conv3d_relu_epilogue(ops):
+    g = torch.Generator().manual_seed(3)
+    x, w, b = torch.randn(1, 16, 6, 6, 6, generator=g), torch.randn(24, 16, 3, 3, 3, generator=g) * 0.1, torch.randn(24, generator=g)
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yr = F.relu(F.conv3d(xr, wr, b, padding=1))
+    yr.square().sum().backward()
+    xc, wc = cuda(x).requires_grad_(True), cuda(w).requires_grad_(True)
+    yc = ops.conv3d(xc, wc, cuda(b), 1, 1, relu=True)
+    yc.square().sum().backward()
+    assert rel_err(yc.detach().cpu().numpy(), yr.detach().numpy()) < TOL
+    assert rel_err(xc.grad.cpu().numpy(), xr.grad.numpy()) < TOL
+    assert rel_err(wc.grad.cpu().numpy(), wr.grad.numpy()) < TOL
+
+
+@pytest.mark.parametrize("M,Nout,C,pool", [(12, 128, 8, 6), (5, 16, 32, 4), (40, 24, 4, 5)])
+def test_fc_conv(ops, M, Nout, C, pool):
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(M, C, pool, pool, pool, generator=g)
+    w = torch.randn(Nout, C, pool, pool, pool, generator=g) * 0.05
+    b = torch.randn(Nout, generator=g)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.conv3d(xr, wr, br)
+    xc, wc, bc = cuda(x).requires_grad_(True), cuda(w).requires_grad_(True), cuda(b).requires_grad_(True)
+    yc = ops.fc_conv(xc, wc, bc)
+    assert rel_err(yc.detach().cpu().numpy(), yr.detach().numpy()) < TOL
+    if M <= 16:
+        dy = torch.randn(yr.shape, generator=g)
+        yr.backward(dy)
+        yc.backward(cuda(dy))
+        assert rel_err(xc.grad.cpu().numpy(), xr.grad.numpy()) < TOL
+        assert rel_err(wc.grad.cpu().numpy(), wr.grad.numpy()) < TOL
+        assert rel_err(bc.grad.cpu().numpy(), br.grad.numpy()) < TOL
+
+
+@pytest.mark.parametrize("C,up,use_drop", [(20, 1, False), (40, 2, False), (8, 1, True), (160, 1, True), (320, 2, False)])
+def test_instnorm_lrelu(ops, C, up, use_drop):
+    g = torch.Generator().manual_seed(C + up)
+    N, D, H, W = 2, 5, 6, 7
+    x = torch.randn(N, C, D, H, W, generator=g) * 2 + 0.5
+    drop = ((torch.rand(N, C, generator=g) > 0.6).float() / 0.4) if use_drop else None
+    xr = x.clone().requires_grad_(True)
+    t = xr * drop.view(N, C, 1, 1, 1) if use_drop else xr
+    yr = F.leaky_relu(F.instance_norm(t, eps=1e-5), 0.01)
+    if up == 2:
+        yr = F.interpolate(yr, scale_factor=2, mode="nearest")
+    dy = torch.randn(yr.shape, generator=g)
+    yr.backward(dy)
+    xc = cuda(x).requires_grad_(True)
+    yc = ops.instnorm_lrelu(xc, cuda(drop) if use_drop else None, 1e-5, 0.01, up)
+    yc.backward(cuda(dy))
+    assert rel_err(yc.detach().cpu().numpy(), yr.detach().numpy()) < TOL
+    assert rel_err(xc.grad.cpu().numpy(), xr.grad.numpy()) < 2 * TOL
+
+
+def test_affine_act_residual_and_pool(ops):
+    g = torch.Generator().manual_seed(5)
+    x, r = torch.randn(2, 16, 4, 6, 8, generator=g), torch.randn(2, 16, 4, 6, 8, generator=g)
+    a, b = torch.rand(16, generator=g) + 0.5, torch.randn(16, generator=g)
+    xr, rr = x.clone().requires_grad_(True), r.clone().requires_grad_(True)
+    yr = F.max_pool3d(F.relu(xr * a.view(1, -1, 1, 1, 1) + b.view(1, -1, 1, 1, 1) + rr), 2, 2)
+    dy = torch.randn(yr.shape, generator=g)
+    yr.backward(dy)
+    xc, rc = cuda(x).requires_grad_(True), cuda(r).requires_grad_(True)
+    yc = ops.maxpool2(ops.affine_act(xc, cuda(a), cuda(b), rc, 0.0, 1))
+    yc.backward(cuda(dy))
+    assert rel_err(yc.detach().cpu().numpy(), yr.detach().numpy()) < 1e-6
+    assert rel_err(xc.grad.cpu().numpy(), xr.grad.numpy()) < 1e-6
+    assert rel_err(rc.grad.cpu().numpy(), rr.grad.numpy()) < 1e-6
+    # plain leaky relu and upsample
+    xc2 = cuda(x).requires_grad_(True)
+    y2 = ops.upsample2x(ops.leaky_relu(xc2))
+    xr2 = x.clone().requires_grad_(True)
+    y2r = F.interpolate(F.leaky_relu(xr2, 0.01), scale_factor=2, mode="nearest")
+    dy2 = torch.randn(y2r.shape, generator=g)
+    y2r.backward(dy2); y2.backward(cuda(dy2))
+    assert rel_err(y2.detach().cpu().numpy(), y2r.detach().numpy()) < 1e-6
+    assert rel_err(xc2.grad.cpu().numpy(), xr2.grad.numpy()) < 1e-5
+
+
+def test_roi_crop_resize_matches_golden_and_grads(ops):
+    gd = load_golden("roialign")
+    f2, f3, boxes = torch.from_numpy(gd["f2"]), torch.from_numpy(gd["f3"]), torch.from_numpy(gd["boxes"])
+    pool = tuple(int(p) for p in gd["pool"])
+    lv = ops.roi_level(cuda(boxes))
+    assert np.array_equal(lv.cpu().numpy(), gd["level"] - 2)
+    single = ops.roi_crop_resize(cuda(f2)[None], None, cuda(boxes), None, pool, True)
+    assert rel_err(single.cpu().numpy(), gd["single_level"]) < 1e-5
+    f2c, f3c = cuda(f2)[None].requires_grad_(True), cuda(f3)[None].requires_grad_(True)
+    pooled = ops.roi_crop_resize(f2c, f3c, cuda(boxes), lv, pool, False)
+    assert rel_err(pooled.detach().cpu().numpy(), gd["pooled"]) < 1e-5
+    assert float(pooled[0].abs().max()) == 0.0
+    f2r, f3r = f2.clone().requires_grad_(True), f3.clone().requires_grad_(True)
+    pr = O.pyramid_roi_align(boxes, [f2r, f3r], pool)
+    w = torch.randn(pr.shape, generator=torch.Generator().manual_seed(1))
+    (pr * w).sum().backward()
+    (pooled * cuda(w)).sum().backward()
+    assert rel_err(f2c.grad[0].cpu().numpy(), f2r.grad.numpy()) < 1e-5
+    assert rel_err(f3c.grad[0].cpu().numpy(), f3r.grad.numpy()) < 1e-5
+
+
+def test_sort_desc_total_order(ops):
+    g = torch.Generator().manual_seed(2)
+    for n in (1, 2, 37, 1000, 2048, 2049, 36864, 70000):
+        s = torch.randn(n, generator=g)
+        s[::7] = s[0]           # ties
+        order = ops.sort_desc(cuda(s)).cpu().numpy()
+        assert np.array_equal(order, O.sort_desc(s.numpy())), n
+
+
+@pytest.mark.parametrize("case", ["rand_t7_m50", "rand_t3_all", "rand_t5_m1", "nested_degenerate", "integer_boxes_t3"])
+def test_nms_bit_exact_golden(ops, case):
+    from cfun_b200 import utils as U
+    g = load_golden("nms")
+    keep = U.non_max_suppression(g[case + "/boxes"], g[case + "/scores"], float(g[case + "/thr"]), int(g[case + "/max"]))
+    assert keep.dtype == np.int32 and np.array_equal(keep, g[case + "/keep"])
+    iou = U.compute_iou(g[case + "/boxes"][0], g[case + "/boxes"], None, None)
+    assert np.array_equal(iou.view(np.uint32), g[case + "/iou0"].view(np.uint32))
+
+
+@pytest.mark.parametrize("n,thr,mx", [(3000, 0.7, 500), (3000, 0.3, 3000), (257, 0.5, 64)])
+def test_nms_bit_exact_random(ops, n, thr, mx):
+    from cfun_b200 import utils as U
+    rng = np.random.default_rng(n)
+    c = rng.uniform(0, 256, size=(n, 3)); s = rng.uniform(16, 128, size=(n, 3))
+    b = np.clip(np.concatenate([c - s / 2, c + s / 2], 1), 0, 256).astype(np.float32)
+    sc = rng.uniform(0, 1, size=n).astype(np.float32)
+    assert np.array_equal(U.non_max_suppression(b, sc, thr, mx), O.non_max_suppression(b, sc, thr, mx))
+
+
+def test_decode_clip_and_proposals(ops):
+    from cfun_b200 import model as M
+    g = load_golden("proposal")
+    anchors, probs, deltas = cuda(torch.from_numpy(g["anchors"])), cuda(torch.from_numpy(g["probs"])), cuda(torch.from_numpy(g["deltas"]))
+    dec = M.apply_box_deltas(anchors, deltas * 0.1)
+    assert rel_err(dec.cpu().numpy(), g["decoded"]) < 1e-6       # expf vs torch-CPU exp may differ in the last ulp
+    assert np.array_equal(M.clip_boxes(cuda(torch.from_numpy(g["decoded"])), [0, 0, 0, 64, 64, 64]).cpu().numpy(), g["clipped"])
+
+    class Cfg: PRE_NMS_LIMIT = 1000; IMAGE_SHAPE = g["image_shape"]; RPN_BBOX_STD_DEV = np.array([.1, .1, .1, .2, .2, .2])
+    for key, count in (("rois_training", 500), ("rois_inference", 64)):
+        rois = M.proposal_layer([probs[None], deltas[None]], count, 0.7, anchors, Cfg)[0]
+        assert rois.shape == g[key].shape
+        assert rel_err(rois.cpu().numpy(), g[key]) < 1e-6
+
+
+def test_overlaps_refinement_targets(ops):
+    from cfun_b200 import model as M
+    g = load_golden("dtl")
+    props, gtb = cuda(torch.from_numpy(g["proposals"])), cuda(torch.from_numpy(g["gt_boxes"]))
+    assert np.array_equal(M.bbox_overlaps(props, gtb).cpu().numpy(), g["overlaps"])
+    ref = ops.box_refinement(props[:20], gtb[:1].repeat(20, 1))
+    assert rel_err(ref.cpu().numpy(), g["refinement"]) < 1e-6
+    lab = cuda(torch.from_numpy(g["label"]))
+
+    class Cfg:
+        DETECTION_TARGET_IOU_THRESHOLD = 0.5; TRAIN_ROIS_PER_IMAGE = 15; ROI_POSITIVE_RATIO = 0.33
+        BBOX_STD_DEV = np.array([.1, .1, .1, .2, .2, .2]); MASK_SHAPE = tuple(int(m) for m in g["mask_shape"])
+        DENSE_MASK_TARGETS = True
+    for dense in (True, False):
+        Cfg.DENSE_MASK_TARGETS = dense
+        torch.manual_seed(int(g["seed"]))
+        p_rois, rois, cls, dl, msk = M.detection_target_layer(props[None], torch.arange(1, 8).int().cuda()[None], gtb[None], lab, Cfg)
+        assert np.array_equal(p_rois.cpu().numpy(), g["positive_rois"])
+        assert np.array_equal(rois.cpu().numpy(), g["rois"])
+        assert np.array_equal(cls.cpu().numpy(), g["class_ids"])
+        assert rel_err(dl.cpu().numpy(), g["deltas"]) < 1e-6
+        if dense:
+            assert msk.dtype == torch.float64 and np.array_equal(msk.cpu().numpy().astype(np.uint8), g["masks"])
+        else:
+            assert msk.dtype == torch.int64 and np.array_equal(msk.cpu().numpy(), g["masks"].argmax(1))
+    # the one-hot stack form of gt_masks (reference call shape) gives the same targets
+    onehot = torch.stack([(lab == c) for c in range(8)]).float()
+    torch.manual_seed(int(g["seed"]))
+    out = M.detection_target_layer(props[None], torch.arange(1, 8).int().cuda()[None], gtb[None], onehot[None], Cfg)
+    assert np.array_equal(out[4].cpu().numpy(), g["masks"].argmax(1))
+
+
+def test_refine_detections(ops):
+    from cfun_b200 import model as M
+    g = load_golden("refine")
+
+    class Cfg:
+        RPN_BBOX_STD_DEV = np.array([.1, .1, .1, .2, .2, .2]); IMAGE_SHAPE = (64, 64, 64, 1)
+        DETECTION_MIN_CONFIDENCE = 0.7; DETECTION_NMS_THRESHOLD = 0.3; DETECTION_MAX_INSTANCES = 32
+    det = M.refine_detections(cuda(torch.from_numpy(g["rois"])), cuda(torch.from_numpy(g["probs"])),
+                              cuda(torch.from_numpy(g["deltas"])), [0, 0, 0, 64, 64, 64], Cfg)
+    assert det.shape == g["detections"].shape
+    assert rel_err(det.cpu().numpy(), g["detections"]) < 1e-6
+
+
+def test_sobel_edge_loss_and_other_losses(ops):
+    from cfun_b200 import model as M
+    g = load_golden("losses")
+    lab = torch.from_numpy(g["target_label"])
+    tcls = torch.from_numpy(g["target_class_ids"])
+    mlog = cuda(torch.from_numpy(g["mask_logits"])).requires_grad_(True)
+    mprob = torch.softmax(mlog, 1)
+    mprob.retain_grad()
+    l_mask = M.compute_mrcnn_mask_loss(cuda(lab), cuda(tcls), mlog)
+    l_edge = M.compute_mrcnn_mask_edge_loss(cuda(lab), cuda(tcls), mprob)
+    assert abs(float(l_mask) - float(g["mask_loss"])) < 1e-5 * abs(float(g["mask_loss"]))
+    assert abs(float(l_edge) - float(g["edge_loss"])) < 1e-4 * abs(float(g["edge_loss"]))
+    (g_edge,) = torch.autograd.grad(l_edge.sum(), mprob, retain_graph=True)
+    assert rel_err(g_edge.cpu().numpy(), g["g_edge"]) < TOL
+    (g_mask,) = torch.autograd.grad(l_mask, mlog)
+    assert rel_err(g_mask.cpu().numpy(), g["g_mask"]) < TOL
+    # one-hot float64 target form (the reference's) gives the same numbers
+    onehot = torch.stack([(lab == c) for c in range(8)], 1).double().cuda()
+    assert abs(float(M.compute_mrcnn_mask_edge_loss(onehot, cuda(tcls), mprob)) - float(g["edge_loss"])) < 1e-4 * abs(float(g["edge_loss"]))
+    rmatch = cuda(torch.from_numpy(g["rpn_match"]))
+    assert abs(float(M.compute_rpn_class_loss(rmatch, cuda(torch.from_numpy(g["rpn_logits"])))) - float(g["rpn_class_loss"])) < 1e-5
+    assert abs(float(M.compute_rpn_bbox_loss(cuda(torch.from_numpy(g["rpn_target"])), rmatch, cuda(torch.from_numpy(g["rpn_bbox"])))) - float(g["rpn_bbox_loss"])) < 1e-5
+
+
+def test_mold_volume_and_sgd(ops):
+    rng = np.random.default_rng(0)
+    vol = np.clip(np.round(rng.normal(0, 300, size=(20, 24, 28))), -1024, 3071).astype(np.int16)     # [H,W,D]
+    out = ops.mold_volume_i16(torch.from_numpy(vol).cuda())
+    ref = O.mold_image(vol.astype(np.float32)[..., None]).transpose((3, 2, 0, 1))[None]
+    assert rel_err(out.cpu().numpy(), ref) < 1e-5
+    # fused clip + SGD(momentum, selective weight decay) against torch.optim.SGD + clip_grad_norm_
+    from cfun_b200.dp import FlatSGD
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 4))
+    ref_net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.Linear(16, 4))
+    ref_net.load_state_dict(net.state_dict())
+    net = net.cuda()
+    opt = FlatSGD(net, lr=0.1, momentum=0.9, weight_decay=1e-2, clip_norm=0.5)
+    ropt = torch.optim.SGD(ref_net.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-2)
+    x = torch.randn(5, 8)
+    for it in range(3):
+        opt.zero_grad(); ropt.zero_grad()
+        (net(x.cuda()) ** 2).sum().backward()
+        (ref_net(x) ** 2).sum().backward()
+        torch.nn.utils.clip_grad_norm_(ref_net.parameters(), 0.5)
+        opt.step(); ropt.step()
+    for p, q in zip(net.parameters(), ref_net.parameters()):
+        assert rel_err(p.detach().cpu().numpy(), q.detach().numpy()) < 1e-5
+
+
+def test_product_path_is_cuda_only(ops):
+    with pytest.raises(RuntimeError):
+        ops.conv3d(torch.randn(1, 4, 4, 4, 4), torch.randn(4, 4, 3, 3, 3), None, 1, 1)

@@ -1,0 +1,166 @@
+"""CPU-only tests: C-ABI library loads and exports every declared symbol, checkpoint ABI, host-side logic, and the
+world_size-2 (gloo) data-parallel plumbing.  No CUDA compute is launched here."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import cfun_oracle as O
+from conftest import load_golden, ROOT
+from shapes import maskrcnn_shapes
+
+
+def header_functions():
+    txt = open(os.path.join(ROOT, "include", "cfun_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(cfun_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from cfun_b200 import _lib
+    names = header_functions()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(_lib.lib, n), "libcfun_b200.so does not export %s" % n
+        assert n in _lib.SIGNATURES, "no ctypes signature for %s" % n
+    assert _lib.lib.cfun_version() >= 100
+
+
+def test_sass_is_sm100a_only():
+    from cfun_b200 import _lib
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    if not out:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out
+    assert not re.search(r"sm_(?!100a)\d+", out)
+
+
+def test_checkpoint_abi_matches_reference_table():
+    from cfun_b200 import model as M, config as Cf
+    cfg = Cf.heart_config(64, "beginning", mask_pool=32, anchor_scales=(16, 32))
+    net = M.MaskRCNN(cfg, "/tmp/_cfun_test")
+    sd = net.state_dict()
+    want = maskrcnn_shapes()
+    assert len(sd) == 220 and set(sd) == set(want)
+    for k, shp in want.items():
+        assert tuple(sd[k].shape) == tuple(shp), k
+    trainable = sum(p.numel() for p in net.parameters() if p.requires_grad)
+    assert trainable == 41349586
+    assert all(not p.requires_grad for n, p in net.named_parameters() if ".bn" in n or ".C1.1." in n or "downsample.1" in n)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "cfun_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "cfun_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+    for shim in ("model.py", "utils.py", "backbone.py", "mask_branch.py", "config.py"):
+        assert "oracle" not in open(os.path.join(ROOT, shim)).read()
+
+
+def test_root_shims_expose_reference_names():
+    import model, utils, backbone, mask_branch, config
+    for name in ("MaskRCNN", "FPN", "RPN", "Classifier", "Mask", "proposal_layer", "RoI_Align", "pyramid_roi_align",
+                 "detection_target_layer", "refine_detections", "detection_layer", "apply_box_deltas", "clip_boxes",
+                 "bbox_overlaps", "compute_losses", "compute_mrcnn_mask_edge_loss", "build_rpn_targets", "mold_image",
+                 "compose_image_meta", "parse_image_meta", "compute_backbone_shapes", "Dataset", "log"):
+        assert hasattr(model, name), name
+    for name in ("non_max_suppression", "compute_iou", "box_refinement", "generate_anchors", "generate_pyramid_anchors",
+                 "denorm_boxes_graph", "Dataset", "compute_per_class_mask_iou", "extract_bboxes", "resize_image", "unmold_mask"):
+        assert hasattr(utils, name), name
+    assert hasattr(backbone, "P3D19") and hasattr(backbone, "Bottleneck") and hasattr(backbone, "P3D")
+    assert hasattr(mask_branch, "Modified3DUNet")
+    assert hasattr(config, "Config")
+
+
+def test_anchor_order_matches_reference_golden():
+    from cfun_b200 import utils as U, model as M
+    g = load_golden("anchors")
+
+    class C: BACKBONE_STRIDES = list(g["strides"])
+    shapes = M.compute_backbone_shapes(C, tuple(g["image_shape"]))
+    assert np.array_equal(shapes, g["shapes"])
+    a = U.generate_pyramid_anchors(tuple(g["scales"]), [1], shapes, list(g["strides"]), 1)
+    assert np.array_equal(a, g["anchors"])
+
+
+def test_rpn_targets_match_reference_golden():
+    from cfun_b200 import model as M, config as Cf
+    g = load_golden("step64_beginning")
+    cfg = Cf.heart_config(64, "beginning", mask_pool=32, anchor_scales=(16, 32))
+    anchors = O.generate_pyramid_anchors((16, 32), O.backbone_shapes((64, 64, 64, 1), (8, 16)), (8, 16)).astype(np.float32)
+    lab = g["label"].transpose((2, 0, 1))
+    nz = np.argwhere(lab > 0)
+    gt = np.concatenate([nz.min(0), nz.max(0) + 1])[None].astype(np.int32)
+    np.random.seed(9)
+    match, bbox = M.build_rpn_targets(anchors, gt, cfg)
+    assert np.array_equal(match, g["rpn_match"])
+    assert np.allclose(bbox, g["rpn_bbox"], rtol=1e-6, atol=1e-7)
+
+
+def test_config_is_name_compatible():
+    from cfun_b200 import config as Cf
+    c = Cf.HeartConfig("finetune")
+    assert tuple(c.IMAGE_SHAPE) == (320, 320, 192, 1) and c.MASK_SHAPE == (192, 192, 192) and c.BATCH_SIZE == 1
+    assert Cf.HeartConfig("beginning").MASK_SHAPE == (96, 96, 96)
+    for name in ("PRE_NMS_LIMIT", "UNET_MASK_BRANCH_CHANNEL", "RPN_BBOX_STD_DEV", "DETECTION_TARGET_IOU_THRESHOLD",
+                 "LOSS_WEIGHTS", "TOP_DOWN_PYRAMID_SIZE", "RPN_CONV_CHANNELS", "POST_NMS_ROIS_TRAINING"):
+        assert hasattr(c, name)
+
+
+def test_volume_sharding_is_a_partition():
+    from cfun_b200.dp import shard_volumes
+    for world in (1, 2, 4, 8):
+        got = sorted(sum((shard_volumes(8, r, world) for r in range(world)), []))
+        assert got == list(range(8))
+
+
+WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from cfun_b200.dp import flatten_grads_cpu
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%%s" %% os.environ["MASTER_PORT"], rank=rank, world_size=world)
+torch.manual_seed(0)
+net = torch.nn.Sequential(torch.nn.Conv3d(2, 4, 3, padding=1), torch.nn.Conv3d(4, 2, 1))
+x = torch.randn(1, 2, 6, 6, 6, generator=torch.Generator().manual_seed(100 + rank))       # one volume per rank
+net(x).square().sum().backward()
+local = [p.grad.clone() for p in net.parameters()]
+flat = flatten_grads_cpu(list(net.parameters()))
+dist.all_reduce(flat, op=dist.ReduceOp.SUM)                                                  # the one collective
+# every rank recomputes the other ranks' gradients serially and checks allreduce == sum of per-volume gradients
+tot = [torch.zeros_like(g) for g in local]
+for r in range(world):
+    net.zero_grad(set_to_none=True)
+    xr = torch.randn(1, 2, 6, 6, 6, generator=torch.Generator().manual_seed(100 + r))
+    net(xr).square().sum().backward()
+    for t, p in zip(tot, net.parameters()):
+        t += p.grad
+off = 0
+for t in tot:
+    k = t.numel()
+    assert torch.allclose(flat[off:off + k].view_as(t), t, rtol=1e-5, atol=1e-6), "allreduce != sum of per-volume grads"
+    off += k
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_two_rank_gloo_gradient_allreduce(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % ROOT)
+    port = str(29500 + os.getpid() % 500)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, out
+        assert "ok" in out
