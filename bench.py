@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""Headline benchmark: 256^3 CT volumes/s, forward + backward + clip + SGD step, on N B200 GPUs (BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                   (the reference's own CPU path: the oracle port, host cores)
+
+A "step" is one pass of the hot path over one synthetic 256^3 int16 CT volume (SURVEY.md 8d recipe, HeartConfig at
+256^3, 8 classes, stage 'beginning'): mold -> P3D/FPN -> RPN -> proposals (sort/decode/NMS) -> detection targets ->
+RoI crops -> classifier head + U-Net mask head -> six losses -> backward -> global-norm clip + SGD(momentum).
+`value` is timed with the step's raw inputs already in HBM; `e2e` times the public call
+MaskRCNN.train_step_from_host with pinned host buffers (H2D + D2H of the losses inside the timed region).
+Weak scaling: every rank processes its own volume each step; the only collective is one NCCL all-reduce of the
+flat gradient per step.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FWD_GFLOP_PER_VOLUME = 1314.6        # SURVEY.md 8d / BASELINE.md: H256, 4 positive / 12 RoIs, 'beginning'
+STEP_TFLOP_PER_VOLUME = 3.94
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--image-dim", type=int, default=256)
+    ap.add_argument("--stage", default="beginning")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--conv-algo", default="auto", choices=["auto", "simt", "tc", "tc1"])
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d["bf16_tflops_sustained"],
+                "hbm_gbs": d["hbm_gbs"], "source": "measured"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
+
+
+def bench_weights(shapes, seed):
+    """MaskRCNN.initialize_weights recipe (reference model.py:1306-1319: xavier_uniform conv weights, zero conv bias,
+    N(0, 0.01) linear weights, BN at identity) with a per-tensor generator keyed by (seed, name), so the GPU arm and the
+    CPU reference arm can build bit-identical weights from a seed alone."""
+    import math
+    import zlib
+    import torch
+    sd = {}
+    for k, shp in shapes.items():
+        shp = tuple(shp)
+        g = torch.Generator().manual_seed((seed * 7919 + zlib.crc32(k.encode())) % (2 ** 31 - 1))
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.zeros(shp, dtype=torch.long)
+        elif k.endswith("running_var") or (k.endswith(".weight") and len(shp) == 1):
+            sd[k] = torch.ones(shp)
+        elif k.endswith("running_mean") or k.endswith(".bias"):
+            sd[k] = torch.zeros(shp)
+        elif len(shp) == 5:
+            rf = shp[2] * shp[3] * shp[4]
+            bound = math.sqrt(6.0 / (shp[1] * rf + shp[0] * rf))
+            sd[k] = (torch.rand(shp, generator=g) * 2 - 1) * bound
+        else:
+            sd[k] = torch.randn(shp, generator=g) * 0.01
+    return sd
+
+
+WEIGHT_SEED = 2     # chosen so that the synthetic volume yields 4 positive / 12 sampled RoIs
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.rows = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ---------------------------------------------------------------------------------------------------------
+def cpu_step_runner(image_dim, stage, weight_seed=WEIGHT_SEED):
+    """Returns (fn, cores): fn() runs ONE full train step (forward, 6 losses, backward, clip) of the CPU oracle on a
+    synthetic volume with the same recipe as the GPU arm."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cfun_oracle as O
+    from shapes import maskrcnn_shapes
+    from cfun_b200 import config as Cf
+    from cfun_b200.synth import synth_volume, gt_box_from_label, place_label_cube, label_from_cube
+    import cfun_b200.model as M                      # host-side target builder only (numpy)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    mask_pool = 96 if image_dim >= 128 else 32
+    scales = (64, 128) if image_dim >= 256 else ((32, 64) if image_dim >= 128 else (16, 32))
+    cube = 70 * image_dim // 256
+    cfg = O.Cfg(image_dim=image_dim, stage=stage, mask_pool=mask_pool, anchor_scales=scales)
+    pcfg = Cf.heart_config(image_dim, stage, mask_pool=mask_pool, anchor_scales=scales)
+    sd = bench_weights(maskrcnn_shapes(), weight_seed)
+    trainable = [k for k, v in sd.items() if v.dtype == torch.float32 and "running" not in k and ".bn" not in k
+                 and ".C1.1." not in k and "downsample.1" not in k]
+    anchors = cfg.anchors().numpy()
+    vol, _ = synth_volume(image_dim, 1000, cube)
+    image = torch.from_numpy(np.ascontiguousarray(O.mold_image(vol.astype(np.float32)[..., None]).transpose((3, 2, 0, 1))[None])).float()
+    # label placement from this arm's own proposals (see cfun_b200.synth.place_label_cube)
+    with torch.no_grad():
+        p2, p3 = O.fpn_forward(sd, image)
+        lv = [O.rpn_forward(sd, p) for p in (p2, p3)]
+        rois, _, _ = O.proposal_layer(torch.cat([l[1] for l in lv], 1)[0], torch.cat([l[2] for l in lv], 1)[0],
+                                      cfg.anchors(), cfg.POST_NMS_ROIS_TRAINING, cfg.RPN_NMS_THRESHOLD, cfg.PRE_NMS_LIMIT,
+                                      cfg.IMAGE_SHAPE, cfg.RPN_BBOX_STD_DEV)
+    placed = place_label_cube(rois.numpy(), image_dim)
+    if placed is None:
+        raise RuntimeError("no label placement gives 4 positive RoIs for weight seed %d" % weight_seed)
+    lab = label_from_cube(image_dim, placed[0], placed[1], 1000)
+    boxes = gt_box_from_label(lab, 8)
+    np.random.seed(1000)
+    rpn_match, rpn_bbox = M.build_rpn_targets(anchors, boxes[:1].astype(np.float32), pcfg)
+    labt = lab.transpose((2, 0, 1))
+    gt_masks = torch.from_numpy(np.stack([(labt == c) for c in range(8)]).astype(np.float32))
+    args = (image, torch.from_numpy(rpn_match.astype(np.int32)), torch.from_numpy(rpn_bbox).float(), torch.arange(1, 8).int(),
+            torch.from_numpy(boxes.astype(np.float32)), gt_masks)
+    state = {"pos": None}
+
+    def step():
+        g = torch.Generator().manual_seed(7)
+        torch.manual_seed(77)
+        leaves = {k: sd[k].detach().clone().requires_grad_(True) for k in trainable}
+        sd2 = dict(sd)
+        sd2.update(leaves)
+        # Dropout3d draws for up to 4 positives; the oracle slices them to the actual positive count
+        drop = [(torch.rand(4, c, 1, 1, 1, generator=g) > 0.6).float() / 0.4 for c in (20, 40, 80, 160, 320)]
+        out = O.train_forward(sd2, cfg, *args, drop=drop)
+        out["loss"].sum().backward()
+        torch.nn.utils.clip_grad_norm_(list(leaves.values()), 5.0)
+        state["pos"] = int((out["target_class_ids"] > 0).sum())
+        state["rois"] = int(out["target_class_ids"].shape[0])
+        return out
+
+    return step, cores, state
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step, cores, state = cpu_step_runner(args.image_dim, args.stage)
+    t0 = time.time()
+    warm = min(args.warmup, 1)
+    for _ in range(warm):
+        step()
+    t_first = time.time() - t0 if warm else None
+    budget = 240.0
+    k = args.steps
+    if t_first:
+        k = max(1, min(args.steps, int(budget / max(t_first, 1e-3))))
+    t0 = time.time()
+    for _ in range(k):
+        step()
+    dt = time.time() - t0
+    v = k / dt
+    sample = "%d full %d^3 volume train step(s) (fwd+6 losses+bwd+clip) of the oracle port, torch-CPU fp32, %d threads; %d of %d requested steps timed to bound the run" % (
+        k, args.image_dim, cores, k, args.steps)
+    line = {"impl": "reference", "metric": "ct_volumes_per_sec_fwd_bwd", "value": v, "unit": "volumes/s", "n_gpus": args.gpus,
+            "steps": k, "warmup": warm, "ms_per_step": 1000.0 * dt / k, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "MM-WHS-shape %d^3 synthetic CT, 8-class heart, full train step, stage %s" % (args.image_dim, args.stage),
+                       "positives": state.get("pos"), "rois": state.get("rois")},
+            "cpu_baseline": {"value": v, "unit": "volumes/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def time_kernel(fn, iters=5, flush=None):
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from cfun_b200 import model as M, config as Cf, ops
+    from cfun_b200.synth import StepInputs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (our arm) needs CUDA; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    algo = {"auto": ops.ALGO_AUTO, "simt": ops.ALGO_SIMT, "tc": ops.ALGO_TC, "tc1": ops.ALGO_TC1}[args.conv_algo]
+    ops.set_conv_algo(algo)
+
+    dim = args.image_dim
+    mask_pool = 96 if dim >= 128 else 32
+    scales = (64, 128) if dim >= 256 else ((32, 64) if dim >= 128 else (16, 32))
+    cube = 70 * dim // 256
+    cfg = Cf.heart_config(dim, args.stage, mask_pool=mask_pool, anchor_scales=scales)
+
+    # weights: the reference's own initialisation (MaskRCNN.initialize_weights, bit-identical RNG consumption) from a
+    # per-tensor seeded recipe shared with the CPU arm; label cube placed where the untrained detector's proposals
+    # cluster so that the sampled RoI set is the 4 positives / 12 RoIs the FLOP figure is quoted for
+    from cfun_b200.synth import synth_volume, place_label_cube, label_from_cube
+    net = M.MaskRCNN(cfg, "/tmp/_cfun_bench")
+    net.load_state_dict(bench_weights({k: tuple(v.shape) for k, v in net.state_dict().items()}, WEIGHT_SEED), strict=True)
+    net = net.to(dev)
+    anchors_np = net.anchors.cpu().numpy()
+    pool = []
+    for i in range(1):
+        vol, _ = synth_volume(dim, 1000 + rank * 10007 + i, cube)
+        with torch.no_grad():
+            img = ops.mold_volume_i16(torch.from_numpy(vol).to(dev))
+            rois = net.rpn_proposals(img, "training")[5][0]
+        placed = place_label_cube(rois.cpu().numpy(), dim)
+        if placed is None:
+            raise RuntimeError("no label placement gives 4 positive RoIs (rank %d)" % rank)
+        lab = label_from_cube(dim, placed[0], placed[1], 1000 + i)
+        pool.append(StepInputs(cfg, anchors_np, dim, 1000 + rank * 10007 + i, cube, vol=vol, lab=lab))
+        del img, rois
+    weight_seed = WEIGHT_SEED
+    opt = net.make_optimizer(cfg.LEARNING_RATE)
+    if world > 1:   # identical replicas: broadcast rank 0's parameters once
+        dist.broadcast(opt.flat_param, src=0)
+    dev_inputs = [[t.to(dev) for t in p.tensors()] for p in pool]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -----------------------------------------------------------------------
+    torch.manual_seed(1234 + rank)
+    for i in range(args.warmup):
+        net.train_step_device(opt, *dev_inputs[i % len(dev_inputs)])
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ops.launch_count()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    last = None
+    for i in range(args.steps):
+        last = net.train_step_device(opt, *dev_inputs[i % len(dev_inputs)])
+    e.record()
+    barrier()
+    ms = s.elapsed_time(e)
+    launches = ops.launch_count() - l0
+    clocks = sampler.summary()
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    losses = last.cpu().numpy().tolist()
+    pos, rois = net.last_roi_counts
+
+    # ---- end-to-end timing through the public host call ---------------------------------------------------
+    for i in range(min(args.warmup, 2)):
+        net.train_step_from_host(opt, pool[i % len(pool)])
+    barrier()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s2.record()
+    for i in range(args.steps):
+        out = net.train_step_from_host(opt, pool[i % len(pool)])
+    e2.record()
+    barrier()
+    t2 = torch.tensor([s2.elapsed_time(e2)], device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t2.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * args.steps / (ms / 1000.0)
+    e2e_value = world * args.steps / (ms_e2e / 1000.0)
+    peaks = measured_peaks()
+
+    # ---- roofline of the dominant kernel, measured live with CUDA events on our stream ------------------------
+    from cfun_b200.layers import Conv3d
+    roof = kern = None
+    if dim >= 256:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > L2 (126 MB)
+        conv = Conv3d(40, 40, 3, padding=1, bias=False).to(dev)
+        x = ops.to_cl(torch.randn(4, 40, 96, 96, 96, device=dev))
+        with torch.no_grad():
+            t_dom = time_kernel(lambda: conv(x), flush=flush)
+        fl = 2.0 * 4 * 96 ** 3 * 40 * 40 * 27
+        ach = fl / (t_dom * 1e-3) / 1e12
+        roof = {"kernel": "conv3d fwd 3x3x3 40->40 @ 4x96^3 (mask_branch conv_norm_lrelu_l4.0, largest FLOP share of the step)",
+                "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"] + " bf16 burst",
+                "ms": t_dom, "algorithmic_flop": fl}
+        conv2 = Conv3d(128, 256, 3, padding=1).to(dev)
+        x2 = ops.to_cl(torch.randn(1, 128, 32, 32, 32, device=dev))
+        with torch.no_grad():
+            t_h = time_kernel(lambda: conv2(x2), flush=flush)
+        fl2 = 2.0 * 32 ** 3 * 128 * 256 * 27
+        kern = {"kernel": "conv3d fwd 3x3x3 128->256 @ 32^3 (RPN.conv_shared, north-star headline conv)", "ms": t_h,
+                "achieved_tflops": fl2 / (t_h * 1e-3) / 1e12, "frac_of_bf16_peak": fl2 / (t_h * 1e-3) / 1e12 / peaks["bf16_tflops"]}
+        del flush, x, x2
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            step, cores, st = cpu_step_runner(dim, args.stage)
+            t0 = time.time()
+            step()
+            dt = time.time() - t0
+            cpu = {"value": 1.0 / dt, "unit": "volumes/s", "cores": cores, "kind": "port",
+                   "sample": "1 full %d^3 volume train step (fwd+6 losses+bwd+clip) of the CPU oracle port, torch-CPU fp32, cold "
+                             "(no warm-up), %d positives / %d RoIs" % (dim, st.get("pos"), st.get("rois"))}
+        except Exception as ex:   # never let the baseline leg break the measurement
+            cpu = {"value": None, "unit": "volumes/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
+
+    h2d = pool[0].nbytes()
+    line = {
+        "metric": "ct_volumes_per_sec_fwd_bwd", "value": value, "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "MM-WHS-shape %d^3 synthetic int16 CT, 8-class heart, full train step (fwd+bwd+clip+SGD), stage %s, 1 volume/GPU/step" % (dim, args.stage),
+                   "parallelism": "dp%d" % world, "positives": pos, "rois": rois, "weight_seed": weight_seed,
+                   "conv_algo": args.conv_algo, "l2": "per-step working set (~10 GB of activations) exceeds the 126 MB L2; no explicit flush",
+                   "losses_last_step": losses},
+        "step_tflop": STEP_TFLOP_PER_VOLUME, "achieved_step_tflops": value * STEP_TFLOP_PER_VOLUME / max(world, 1),
+        "step_frac_of_bf16_sustained": value * STEP_TFLOP_PER_VOLUME / max(world, 1) / peaks["bf16_tflops_sustained"],
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": "volumes/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 7 * 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "roofline": roof, "headline_conv": kern, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -35,6 +35,7 @@ _D = C.POINTER(ConvDesc)
 SIGNATURES = {
     "cfun_last_error": (C.c_char_p, []),
     "cfun_version": (_i, []),
+    "cfun_launch_count": (C.c_ulonglong, []),
     "cfun_device_is_sm100": (_i, []),
     "cfun_conv3d_workspace_size": (_sz, [_D, _i, _i]),
     "cfun_conv3d_pick_algo": (_i, [_D, _i]),

@@ -3,6 +3,7 @@
 #include <mutex>
 
 namespace cfun {
+unsigned long long g_launches = 0;
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -25,6 +26,7 @@ int num_sms() {
 
 extern "C" const char* cfun_last_error(void) { return cfun::g_err; }
 extern "C" int cfun_version(void) { return 100; }
+extern "C" unsigned long long cfun_launch_count(void) { return cfun::g_launches; }
 extern "C" int cfun_device_is_sm100(void) {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;

@@ -27,8 +27,11 @@ void set_error(const char* fmt, ...);
     }                                                                                            \
   } while (0)
 
+extern unsigned long long g_launches;  // kernels launched by this library (bench.py "gpu_launches")
+
 #define CFUN_LAUNCH_CHECK()                                                                      \
   do {                                                                                           \
+    ++cfun::g_launches;                                                                          \
     cudaError_t e_ = cudaGetLastError();                                                         \
     if (e_ != cudaSuccess) {                                                                     \
       cfun::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e_)); \

@@ -576,17 +576,9 @@ class MaskRCNN(nn.Module):
             self.train()     # BatchNorm stays frozen/eval regardless (FrozenBatchNorm3d)
         cfg = self.config
 
-        p2_out, p3_out = self.fpn(molded_images)
-        rpn_feature_maps = [p2_out, p3_out]
+        p2_out, p3_out, rpn_class_logits, rpn_class, rpn_bbox, rpn_rois = self.rpn_proposals(molded_images, mode)
         mrcnn_classifier_feature_maps = [p2_out, p3_out]
         mrcnn_mask_feature_maps = [molded_images, molded_images]
-
-        layer_outputs = [self.rpn(p) for p in rpn_feature_maps]
-        rpn_class_logits, rpn_class, rpn_bbox = [torch.cat(list(o), dim=1) for o in zip(*layer_outputs)]
-
-        proposal_count = cfg.POST_NMS_ROIS_TRAINING if mode == "training" else cfg.POST_NMS_ROIS_INFERENCE
-        rpn_rois = proposal_layer([rpn_class, rpn_bbox], proposal_count=proposal_count,
-                                  nms_threshold=cfg.RPN_NMS_THRESHOLD, anchors=self.anchors, config=cfg)
         dev = molded_images.device
         h, w, d = cfg.IMAGE_SHAPE[:3]
         scale = _f32([d, h, w, d, h, w], dev)
@@ -602,6 +594,7 @@ class MaskRCNN(nn.Module):
         gt_boxes = gt_boxes / scale
         p_rois, rois, target_class_ids, target_deltas, target_mask = \
             detection_target_layer(rpn_rois, gt_class_ids, gt_boxes, gt_masks, cfg)
+        self.last_roi_counts = (int(p_rois.shape[0]), int(rois.shape[0]))
         empty = torch.zeros(0, device=dev)
         mrcnn_class_logits = mrcnn_bbox = mrcnn_mask = mrcnn_mask_logits = empty
         if rois.shape[0] > 0:
@@ -610,6 +603,17 @@ class MaskRCNN(nn.Module):
             mrcnn_mask_logits, mrcnn_mask = self.mask(mrcnn_mask_feature_maps, p_rois)
         return [rpn_class_logits, rpn_bbox, target_class_ids, mrcnn_class_logits, target_deltas, mrcnn_bbox, target_mask,
                 mrcnn_mask, mrcnn_mask_logits]
+
+    def rpn_proposals(self, molded_images, mode):
+        """backbone + FPN + RPN on both levels + proposal layer (reference model.py:1409-1437)"""
+        cfg = self.config
+        p2_out, p3_out = self.fpn(molded_images)
+        layer_outputs = [self.rpn(p) for p in (p2_out, p3_out)]
+        rpn_class_logits, rpn_class, rpn_bbox = [torch.cat(list(o), dim=1) for o in zip(*layer_outputs)]
+        proposal_count = cfg.POST_NMS_ROIS_TRAINING if mode == "training" else cfg.POST_NMS_ROIS_INFERENCE
+        rpn_rois = proposal_layer([rpn_class, rpn_bbox], proposal_count=proposal_count,
+                                  nms_threshold=cfg.RPN_NMS_THRESHOLD, anchors=self.anchors, config=cfg)
+        return p2_out, p3_out, rpn_class_logits, rpn_class, rpn_bbox, rpn_rois
 
     def weighted_loss(self, losses):
         w = self.config.LOSS_WEIGHTS
@@ -629,6 +633,25 @@ class MaskRCNN(nn.Module):
         loss = self.weighted_loss(losses)
         loss.sum().backward()
         return loss, losses
+
+    def train_step_device(self, optimizer, vol_i16, label_hwd, rpn_match, rpn_bbox, gt_boxes, gt_class_ids):
+        """One optimizer step on one volume whose raw inputs are already on the device: mold (int16 -> normalised fp32,
+        HWD -> DHW), forward, six losses, backward, global-norm clip + SGD.  Returns the 7 loss scalars as one tensor
+        (total first) without synchronising."""
+        image = ops.mold_volume_i16(vol_i16)
+        label = label_hwd.permute(2, 0, 1).to(torch.int32).contiguous()
+        optimizer.zero_grad()
+        loss, losses = self.forward_backward(image, None, rpn_match.view(1, -1, 1), rpn_bbox.unsqueeze(0),
+                                             gt_class_ids.unsqueeze(0), gt_boxes.unsqueeze(0), label)
+        optimizer.step()
+        return torch.stack([loss.detach().reshape(())] + [l.detach().reshape(()) for l in losses])
+
+    def train_step_from_host(self, optimizer, step_inputs):
+        """The end-to-end call: pinned host buffers of one volume -> H2D -> train_step_device -> D2H of the 7 losses."""
+        dev = self.anchors.device
+        args = [t.to(dev, non_blocking=True) for t in step_inputs.tensors()]
+        out = self.train_step_device(optimizer, *args)
+        return out.cpu()
 
     # -- inference ------------------------------------------------------------------------------------------
     def detect(self, images):

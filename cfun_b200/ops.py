@@ -24,6 +24,11 @@ def call_count():
     return _calls["n"]
 
 
+def launch_count():
+    """CUDA kernels launched by libcfun_b200.so so far in this process"""
+    return int(lib.cfun_launch_count())
+
+
 def _require_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:

@@ -31,6 +31,8 @@ extern "C" {
 
 const char* cfun_last_error(void);
 int cfun_version(void);
+/* number of CUDA kernels this library has launched so far in this process */
+unsigned long long cfun_launch_count(void);
 /* 1 when the current device is compute capability 10.x (tcgen05 / TMA paths usable). */
 int cfun_device_is_sm100(void);
 

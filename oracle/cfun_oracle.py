@@ -471,7 +471,7 @@ def unet_forward(sd, x, stage="beginning", drop=None, prefix="mask.modified_u_ne
     w = lambda n: sd[prefix + "." + n + ".weight"]
     c3 = lambda n, t, s=1: F.conv3d(t, w(n), None, stride=s, padding=1)
     c1 = lambda n, t: F.conv3d(t, w(n), None)
-    dp = (lambda i, t: t) if drop is None else (lambda i, t: t * drop[i])
+    dp = (lambda i, t: t) if drop is None else (lambda i, t: t * drop[i][:t.shape[0]])
     out = c3("conv3d_c1_1", x)
     res = out
     out = c3("conv3d_c1_2", _lrelu(out))
@@ -579,7 +579,7 @@ def mrcnn_mask_edge_loss(target_masks, target_class_ids, pred_masks):
     the literal range(7); target rows are taken as target_masks[:P, 1:]."""
     if target_class_ids.numel() == 0:
         return torch.zeros(1)
-    kernel = sobel_bank()
+    kernel = sobel_bank().to(pred_masks.dtype)
     pos = torch.nonzero(target_class_ids > 0)[:, 0]
     P = pos.shape[0]
     y_true = target_masks[:P, 1:]
@@ -587,7 +587,7 @@ def mrcnn_mask_edge_loss(target_masks, target_class_ids, pred_masks):
     loss = torch.zeros(1)
     for i in range(P):
         for j in range(7):
-            gt = F.conv3d(y_true[i, j][None, None].float(), kernel)
+            gt = F.conv3d(y_true[i, j][None, None].to(pred_masks.dtype), kernel)
             gp = F.conv3d(y_pred[i, j][None, None], kernel)
             mt = torch.sqrt(gt[:, 0] ** 2 + gt[:, 1] ** 2 + gt[:, 0] ** 2)
             mp = torch.sqrt(gp[:, 0] ** 2 + gp[:, 1] ** 2 + gp[:, 0] ** 2)

@@ -1,0 +1,39 @@
+"""TEST INFRASTRUCTURE: float64 run of the oracle on the golden 64^3 step -> tests/golden/step64_fp64.npz.
+
+The deepest U-Net weight gradients are ill-conditioned in fp32 (the reference's own torch-CPU fp32 result differs from
+the float64 result by ~2.5e-3 relative on mask.modified_u_net.conv_norm_lrelu_l4.0.weight), so the GPU parity test
+bounds the CUDA path's distance to the float64 value by the reference's own distance instead of a flat 1e-4."""
+import os
+import sys
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import cfun_oracle as O  # noqa: E402
+from detweights import det_state  # noqa: E402
+from shapes import maskrcnn_shapes  # noqa: E402
+from synth import golden_step_inputs  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+out = {}
+for stage in ("beginning", "finetune"):
+    g = dict(np.load(os.path.join(GOLD, "step64_%s.npz" % stage)))
+    sd = det_state(maskrcnn_shapes(), seed=int(g["seed_weights"]))
+    sd = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    cfg = O.Cfg(image_dim=64, stage=stage, mask_pool=32, anchor_scales=(16, 32))
+    inp = golden_step_inputs(g)
+    keys = ["mask.modified_u_net.conv_norm_lrelu_l4.0.weight", "rpn.conv_shared.weight"]
+    leaves = {k: sd[k].clone().requires_grad_(True) for k in keys}
+    sd2 = dict(sd)
+    sd2.update(leaves)
+    torch.manual_seed(int(g["seed_perm"]))
+    res = O.train_forward(sd2, cfg, inp["image"].double(), inp["rpn_match"], inp["rpn_bbox"].double(), torch.arange(1, 8).int(),
+                          inp["gt_boxes"].double(), inp["gt_masks"].double(), drop=[d.double() for d in inp["drop"]])
+    res["loss"].sum().backward()
+    out[stage + "/g_unet_l4"] = leaves[keys[0]].grad.flatten()[::7].numpy()
+    out[stage + "/g_rpn_shared"] = leaves[keys[1]].grad.flatten()[::811].numpy()
+    out[stage + "/losses"] = np.array([float(l) for l in res["losses"]])
+    d = np.abs(g["g_unet_l4"] - out[stage + "/g_unet_l4"]).max() / np.abs(out[stage + "/g_unet_l4"]).max()
+    print(stage, "reference fp32 vs fp64 on g_unet_l4:", d)
+np.savez_compressed(os.path.join(GOLD, "step64_fp64.npz"), **out)

@@ -93,7 +93,14 @@ def test_whole_train_step_64_matches_reference_golden(stage):
     tot = float(np.sqrt((norms.astype(np.float64) ** 2).sum()))
     assert abs(tot - float(g["grad_total_norm"])) < 1e-3 * float(g["grad_total_norm"])
     assert rel_err(net.rpn.conv_shared.weight.grad.flatten()[::811].cpu().numpy(), g["g_rpn_shared"]) < 3 * TOL
-    assert rel_err(net.mask.modified_u_net.conv_norm_lrelu_l4[0].weight.grad.flatten()[::7].cpu().numpy(), g["g_unet_l4"]) < 3 * TOL
+    # The deepest U-Net weight gradient is ill-conditioned in fp32: the reference's own torch-CPU fp32 value is 2.1e-3 ..
+    # 2.5e-3 (relative) away from the float64 value (oracle/gen_fp64_yardstick.py).  Bound the CUDA path by the same
+    # yardstick: no further from float64 than 3x the reference's own distance.
+    y = load_golden("step64_fp64")
+    got_l4 = net.mask.modified_u_net.conv_norm_lrelu_l4[0].weight.grad.flatten()[::7].cpu().numpy()
+    ref_dist = rel_err(g["g_unet_l4"], y[stage + "/g_unet_l4"])
+    assert rel_err(got_l4, y[stage + "/g_unet_l4"]) < 3 * ref_dist + TOL, (rel_err(got_l4, y[stage + "/g_unet_l4"]), ref_dist)
+    assert rel_err(net.rpn.conv_shared.weight.grad.flatten()[::811].cpu().numpy(), y[stage + "/g_rpn_shared"]) < 3 * TOL
 
 
 def test_inference_predict_runs_and_matches_oracle_shapes():
