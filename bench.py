@@ -294,8 +294,10 @@ def run_ours(args):
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     last = None
+    roi_counts = []
     for i in range(args.steps):
         last = net.train_step_device(opt, *dev_inputs[i % len(dev_inputs)])
+        roi_counts.append(list(net.last_roi_counts))
     e.record()
     barrier()
     ms = s.elapsed_time(e)
@@ -375,7 +377,7 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "MM-WHS-shape %d^3 synthetic int16 CT, 8-class heart, full train step (fwd+bwd+clip+SGD), stage %s, 1 volume/GPU/step" % (dim, args.stage),
-                   "parallelism": "dp%d" % world, "positives": pos, "rois": rois, "weight_seed": weight_seed,
+                   "parallelism": "dp%d" % world, "positives": pos, "rois": rois, "roi_counts_per_timed_step": roi_counts, "weight_seed": weight_seed,
                    "conv_algo": args.conv_algo, "l2": "per-step working set (~10 GB of activations) exceeds the 126 MB L2; no explicit flush",
                    "losses_last_step": losses},
         "step_tflop": STEP_TFLOP_PER_VOLUME, "achieved_step_tflops": value * STEP_TFLOP_PER_VOLUME / max(world, 1),

@@ -1,11 +1,559 @@
-// tcgen05 implicit-GEMM conv3d (placeholder until the kernel lands: reports "unsupported" so AUTO picks SIMT).
+// tcgen05 implicit-GEMM 3-D convolution for sm_100a (stride 1, any odd/even kernel, arbitrary zero padding).
+//
+//   y[m, co] = sum_{tap, ci} x[m + tap - pad, ci] * w[co, ci, tap]        m = one output voxel
+//
+// Design (im2col-free, DESIGN.md "conv_tc"):
+//   * operands are split-bf16 pairs: v = hi + lo with hi = bf16(v), lo = bf16(v - hi); the product is accumulated as
+//     hi*hi + lo*hi + hi*lo in the fp32 TMEM accumulator (3 MMAs per K-chunk, relative error ~2^-16, inside the 1e-4
+//     parity bar that a single bf16 or tf32 pass misses); `nsplit = 1` runs hi*hi only (fast mode, not parity grade);
+//   * one CTA owns a 128-voxel output box (Dt x Ht x Wt) times BN <= 256 output channels; for every kernel tap and every
+//     16-channel K-chunk the TMA loads the *shifted* input box (16 ch x Wt x Ht x Dt) straight out of the NDHWC tensor,
+//     out-of-bounds coordinates are zero-filled by the TMA unit = the conv's zero padding, no halo code, no im2col buffer;
+//     the 27 re-reads of the input tile hit L2, HBM sees each activation once;
+//   * smem tiles are K-major, SWIZZLE_32B (row = 16 bf16 = 32 B = exactly one UMMA K step), descriptors per chunk;
+//   * warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread tcgen05.mma issuer, warps 2..5 = epilogue
+//     (tcgen05.ld 32x32b -> bias / ReLU -> coalesced fp32 NDHWC stores); full/empty mbarrier ring between TMA and MMA,
+//     tcgen05.commit releases smem stages and publishes the accumulator.
+// The data gradient of a stride-1 conv is the same kernel on dy with spatially flipped, (ci,co)-transposed weights and
+// pad' = k-1-pad.
 #include "common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <mutex>
+
 namespace cfun {
-bool tc_supported(const cfun_conv3d_desc*, int) { return false; }
-size_t tc_workspace(const cfun_conv3d_desc*, int) { return 0; }
-int tc_conv_fwd(const cfun_conv3d_desc*, const float*, const float*, const float*, float*, int, int, void*, size_t, cudaStream_t) { return CFUN_ERR_INVALID; }
-int tc_conv_bwd_data(const cfun_conv3d_desc*, const float*, const float*, float*, int, void*, size_t, cudaStream_t) { return CFUN_ERR_INVALID; }
-int tc_conv_bwd_weight(const cfun_conv3d_desc*, const float*, const float*, float*, float*, int, void*, size_t, cudaStream_t) { return CFUN_ERR_INVALID; }
-int cfun_pack_split_bf16_impl() { return 0; }
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must surface as a trapped kernel (an error the host sees), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+    if (spin > (1u << 24)) {
+      printf("cfun conv_tc: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_32B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, SM100 "version 1"):
+//   rows of 32 B, 8-row groups 256 B apart (SBO), LBO field = 1 (unused for a single 32 B K-slab)
+__device__ __forceinline__ uint64_t make_desc_sw32(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;            // leading byte offset (>>4)
+  d |= (uint64_t)(256 >> 4) << 32;   // stride byte offset (>>4)
+  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+  d |= (uint64_t)6 << 61;            // layout type SWIZZLE_32B
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TC_KCH = 4;            // 16-channel K chunks per pipeline stage
+constexpr int TC_A_BYTES = 128 * 32; // one A operand part per chunk
+constexpr int TC_THREADS = 192;
+
+struct TcParams {
+  int N, Do, Ho, Wo, Cout;
+  int kD, kH, kW, pD, pH, pW;
+  int CPC;           // K chunks per tap (= Cp / 16)
+  int BN;            // output channels per CTA (multiple of 16, <= 256)
+  int Dt, Ht, Wt;    // output box per CTA, Dt*Ht*Wt == 128
+  int tilesD, tilesH, tilesW;
+  int nsplit;        // 3: hi*hi + lo*hi + hi*lo ; 1: hi*hi
+  int stages;
+  int tmem_cols;
+  int epi;
+  const float* bias;
+  float* y;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+               const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: barriers first (small), then the stage ring aligned to 1024
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* tmem_full_bar = empty_bar + 8;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint8_t* ring = smem_raw + 1024 + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-aligned in the shared window
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int b_bytes = p.BN * 32;
+  const int parts = p.nsplit == 3 ? 2 : 1;
+  const int chunk_bytes = parts * (TC_A_BYTES + b_bytes);
+  const int stage_bytes = TC_KCH * chunk_bytes;
+  const int taps = p.kD * p.kH * p.kW;
+  const int total_chunks = taps * p.CPC;
+  const int nstage_iters = (total_chunks + TC_KCH - 1) / TC_KCH;
+
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tw = t % p.tilesW; t /= p.tilesW;
+  const int th = t % p.tilesH; t /= p.tilesH;
+  const int td = t % p.tilesD; t /= p.tilesD;
+  const int n = t;
+  const int d0 = td * p.Dt, h0 = th * p.Ht, w0 = tw * p.Wt;
+  const int n0 = blockIdx.y * p.BN;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_ah);
+    prefetch_tmap(&map_bh);
+    if (p.nsplit == 3) { prefetch_tmap(&map_al); prefetch_tmap(&map_bl); }
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int q = 0;
+      for (int it = 0; it < nstage_iters; ++it) {
+        const int slot = it % p.stages;
+        const uint32_t ph = (uint32_t)((it / p.stages) & 1);
+        mbar_wait(&empty_bar[slot], ph ^ 1u);
+        const int nch = min(TC_KCH, total_chunks - q);
+        mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)(nch * chunk_bytes));
+        uint8_t* sbase = ring + (size_t)slot * stage_bytes;
+        for (int c = 0; c < nch; ++c, ++q) {
+          const int tap = q / p.CPC;
+          const int cc = q - tap * p.CPC;
+          const int khw = p.kH * p.kW;
+          const int kd = tap / khw;
+          const int r = tap - kd * khw;
+          const int kh = r / p.kW;
+          const int kw = r - kh * p.kW;
+          uint8_t* cb = sbase + (size_t)c * chunk_bytes;
+          const int xc = cc * 16, xw = w0 + kw - p.pW, xh = h0 + kh - p.pH, xd = d0 + kd - p.pD;
+          tma_load_5d(&map_ah, &full_bar[slot], cb, xc, xw, xh, xd, n);
+          tma_load_3d(&map_bh, &full_bar[slot], cb + parts * TC_A_BYTES, xc, n0, tap);
+          if (parts == 2) {
+            tma_load_5d(&map_al, &full_bar[slot], cb + TC_A_BYTES, xc, xw, xh, xd, n);
+            tma_load_3d(&map_bl, &full_bar[slot], cb + 2 * TC_A_BYTES + b_bytes, xc, n0, tap);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      int q = 0;
+      uint32_t acc = 0;
+      for (int it = 0; it < nstage_iters; ++it) {
+        const int slot = it % p.stages;
+        const uint32_t ph = (uint32_t)((it / p.stages) & 1);
+        mbar_wait(&full_bar[slot], ph);
+        tc_fence_after();
+        const int nch = min(TC_KCH, total_chunks - q);
+        const uint32_t sbase = smem_u32(ring + (size_t)slot * stage_bytes);
+        for (int c = 0; c < nch; ++c, ++q) {
+          const uint32_t cb = sbase + (uint32_t)(c * chunk_bytes);
+          const uint64_t a_hi = make_desc_sw32(cb);
+          const uint64_t b_hi = make_desc_sw32(cb + parts * TC_A_BYTES);
+          umma_bf16(tmem_base, a_hi, b_hi, idesc, acc);
+          acc = 1;
+          if (parts == 2) {
+            const uint64_t a_lo = make_desc_sw32(cb + TC_A_BYTES);
+            const uint64_t b_lo = make_desc_sw32(cb + 2 * TC_A_BYTES + b_bytes);
+            umma_bf16(tmem_base, a_lo, b_hi, idesc, 1);
+            umma_bf16(tmem_base, a_hi, b_lo, idesc, 1);
+          }
+        }
+        umma_commit(&empty_bar[slot]);   // frees the smem stage once the MMAs above have consumed it
+      }
+      umma_commit(tmem_full_bar);        // accumulator complete
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;          // row of the 128-row tile == voxel inside the box
+    const int lw = row % p.Wt;
+    const int lh = (row / p.Wt) % p.Ht;
+    const int ld = row / (p.Wt * p.Ht);
+    const int od = d0 + ld, oh = h0 + lh, ow = w0 + lw;
+    const bool vox_ok = od < p.Do && oh < p.Ho && ow < p.Wo;
+    float* yrow = p.y + ((((long long)n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * (long long)p.Cout;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const bool vec = (p.Cout & 3) == 0;
+    for (int j = 0; j < p.BN; j += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)j, r);
+      tmem_ld_wait();
+      if (vox_ok) {
+        const int c0 = n0 + j;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float f = __uint_as_float(r[i]);
+          if ((p.epi & CFUN_EPI_BIAS) && c0 + i < p.Cout) f += __ldg(p.bias + c0 + i);
+          if (p.epi & CFUN_EPI_RELU) f = fmaxf(f, 0.f);
+          v[i] = f;
+        }
+        if (vec && c0 + 16 <= p.Cout) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(yrow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < p.Cout) yrow[c0 + i] = v[i];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// operand packing
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// x [rows, C] fp32 -> hi/lo [rows, Cp] bf16 (channels >= C zero)
+__global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                                       __nv_bfloat16* __restrict__ lo, long long rows, int C, int Cp) {
+  const int G = Cp / 8;
+  const long long total = rows * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    const long long r = i / G;
+    const int c0 = g * 8;
+    float v[8];
+    if (c0 + 8 <= C && (C & 3) == 0) {
+      float4 a = __ldg(reinterpret_cast<const float4*>(x + r * C + c0));
+      float4 b = __ldg(reinterpret_cast<const float4*>(x + r * C + c0 + 4));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c0 + j < C) ? __ldg(x + r * C + c0 + j) : 0.f;
+    }
+    __align__(16) __nv_bfloat16 h[8];
+    __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split_bf16(v[j], h[j], l[j]);
+    *reinterpret_cast<uint4*>(hi + r * Cp + c0) = *reinterpret_cast<const uint4*>(h);
+    if (lo) *reinterpret_cast<uint4*>(lo + r * Cp + c0) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
+// w (Cout, Cin, taps) fp32 -> [tap][Np][Kp] hi/lo.  mode 0 (forward): row = co, k = ci, tap as is.
+// mode 1 (data gradient): row = ci, k = co, tap mirrored (kD-1-kd, kH-1-kh, kW-1-kw).
+__global__ void __launch_bounds__(256) pack_w_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                                        __nv_bfloat16* __restrict__ lo, int Cout, int Cin, int kD, int kH,
+                                                        int kW, int Np, int Kp, int mode) {
+  const int taps = kD * kH * kW;
+  const long long total = (long long)taps * Np * Kp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kp);
+    long long r = i / Kp;
+    const int row = (int)(r % Np);
+    const int tap = (int)(r / Np);
+    float v = 0.f;
+    int co, ci, st = tap;
+    if (mode == 0) { co = row; ci = k; }
+    else {
+      co = k; ci = row;
+      int kd = tap / (kH * kW), rr = tap % (kH * kW), kh = rr / kW, kw = rr % kW;
+      st = ((kD - 1 - kd) * kH + (kH - 1 - kh)) * kW + (kW - 1 - kw);
+    }
+    if (co < Cout && ci < Cin) v = w[((long long)co * Cin + ci) * taps + st];
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct TcPlan {
+  // the conv this plan executes (already in "forward" form: source tensor, weights [tap][Np][Kp], target tensor)
+  int N, Cs, Ds, Hs, Ws;     // source (K channels)
+  int Ct, Dt_, Ht_, Wt_;     // target dims (output channels, spatial)
+  int kD, kH, kW, pD, pH, pW;
+  int Kp, Np, BN, ntiles_n;
+  int bd, bh, bw;            // output box
+  int tilesD, tilesH, tilesW;
+  size_t off_ah, off_al, off_bh, off_bl, total;
+};
+
+static void pick_box(int Do, int Ho, int Wo, int& bd, int& bh, int& bw) {
+  static const int cand[][3] = {{4, 4, 8}, {2, 8, 8}, {8, 4, 4}, {4, 8, 4}, {8, 2, 8}, {2, 4, 16}, {4, 2, 16}, {1, 8, 16},
+                                {8, 8, 2}, {1, 16, 8}, {16, 1, 8}, {2, 2, 32}, {1, 4, 32}, {4, 1, 32}, {16, 8, 1}, {8, 16, 1},
+                                {2, 16, 4}, {16, 2, 4}, {1, 2, 64}, {2, 1, 64}, {1, 1, 128}, {32, 4, 1}, {4, 32, 1}, {16, 4, 2}, {4, 16, 2}};
+  long long best = -1;
+  for (auto& c : cand) {
+    long long vol = cdiv(Do, c[0]) * c[0] * cdiv(Ho, c[1]) * c[1] * cdiv(Wo, c[2]) * c[2];
+    if (best < 0 || vol < best) { best = vol; bd = c[0]; bh = c[1]; bw = c[2]; }
+  }
+}
+
+static bool make_plan(const cfun_conv3d_desc* d, int pass, TcPlan& pl) {
+  if (!d || d->sD != 1 || d->sH != 1 || d->sW != 1) return false;
+  pl.N = d->N;
+  pl.kD = d->kD; pl.kH = d->kH; pl.kW = d->kW;
+  if (pass == CFUN_PASS_FWD) {
+    pl.Cs = d->Cin; pl.Ds = d->Din; pl.Hs = d->Hin; pl.Ws = d->Win;
+    pl.Ct = d->Cout; pl.Dt_ = d->Dout; pl.Ht_ = d->Hout; pl.Wt_ = d->Wout;
+    pl.pD = d->pD; pl.pH = d->pH; pl.pW = d->pW;
+  } else if (pass == CFUN_PASS_BWD_DATA) {
+    pl.Cs = d->Cout; pl.Ds = d->Dout; pl.Hs = d->Hout; pl.Ws = d->Wout;
+    pl.Ct = d->Cin; pl.Dt_ = d->Din; pl.Ht_ = d->Hin; pl.Wt_ = d->Win;
+    pl.pD = d->kD - 1 - d->pD; pl.pH = d->kH - 1 - d->pH; pl.pW = d->kW - 1 - d->pW;
+    if (pl.pD < 0 || pl.pH < 0 || pl.pW < 0) return false;
+  } else {
+    return false;
+  }
+  pl.Kp = (int)align_up((size_t)pl.Cs, 16);
+  pl.Np = (int)align_up((size_t)pl.Ct, 16);
+  pl.ntiles_n = (int)cdiv(pl.Np, 256);
+  pl.BN = (int)align_up((size_t)cdiv(pl.Np, pl.ntiles_n), 16);
+  pick_box(pl.Dt_, pl.Ht_, pl.Wt_, pl.bd, pl.bh, pl.bw);
+  pl.tilesD = (int)cdiv(pl.Dt_, pl.bd); pl.tilesH = (int)cdiv(pl.Ht_, pl.bh); pl.tilesW = (int)cdiv(pl.Wt_, pl.bw);
+  const size_t rows = (size_t)pl.N * pl.Ds * pl.Hs * pl.Ws;
+  const size_t act = align_up(rows * pl.Kp * 2, 1024);
+  const size_t wgt = align_up((size_t)pl.kD * pl.kH * pl.kW * (size_t)(pl.BN * pl.ntiles_n) * pl.Kp * 2, 1024);
+  pl.off_ah = 0; pl.off_al = act; pl.off_bh = 2 * act; pl.off_bl = 2 * act + wgt; pl.total = 2 * act + 2 * wgt + 2048;
+  return true;
+}
+
+bool tc_supported(const cfun_conv3d_desc* d, int pass) {
+  static int sm100 = -1;
+  if (sm100 < 0) sm100 = cfun_device_is_sm100();
+  if (!sm100 || !get_encode()) return false;
+  TcPlan pl;
+  if (!make_plan(d, pass, pl)) return false;
+  const int taps = pl.kD * pl.kH * pl.kW;
+  if (taps < 27) return false;                       // pointwise / P3D factorised convs stay on CUDA cores
+  if (pl.Cs < 16 || (pl.Cs & 3) || pl.Ct < 8) return false;
+  if ((long long)pl.N * pl.Dt_ * pl.Ht_ * pl.Wt_ < 2048) return false;
+  if (pl.ntiles_n > 8) return false;
+  return true;
+}
+
+size_t tc_workspace(const cfun_conv3d_desc* d, int pass) {
+  TcPlan pl;
+  if (!make_plan(d, pass, pl)) return 0;
+  return pl.total;
+}
+
+static int encode_act_map(CUtensorMap* m, void* base, const TcPlan& pl) {
+  cuuint64_t dims[5] = {(cuuint64_t)pl.Kp, (cuuint64_t)pl.Ws, (cuuint64_t)pl.Hs, (cuuint64_t)pl.Ds, (cuuint64_t)pl.N};
+  cuuint64_t strides[4] = {(cuuint64_t)pl.Kp * 2, (cuuint64_t)pl.Ws * pl.Kp * 2, (cuuint64_t)pl.Hs * pl.Ws * pl.Kp * 2,
+                           (cuuint64_t)pl.Ds * pl.Hs * pl.Ws * pl.Kp * 2};
+  cuuint32_t box[5] = {16, (cuuint32_t)pl.bw, (cuuint32_t)pl.bh, (cuuint32_t)pl.bd, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations) failed: %d", (int)r); return CFUN_ERR_CUDA; }
+  return CFUN_OK;
+}
+
+static int encode_w_map(CUtensorMap* m, void* base, const TcPlan& pl) {
+  const int rows = pl.BN * pl.ntiles_n;
+  cuuint64_t dims[3] = {(cuuint64_t)pl.Kp, (cuuint64_t)rows, (cuuint64_t)(pl.kD * pl.kH * pl.kW)};
+  cuuint64_t strides[2] = {(cuuint64_t)pl.Kp * 2, (cuuint64_t)rows * pl.Kp * 2};
+  cuuint32_t box[3] = {16, (cuuint32_t)pl.BN, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return CFUN_ERR_CUDA; }
+  return CFUN_OK;
+}
+
+static int run_tc(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
+                  int nsplit, void* ws, size_t ws_bytes, cudaStream_t st) {
+  TcPlan pl;
+  CFUN_CHECK_ARG(make_plan(d, pass, pl));
+  CFUN_CHECK_ARG(src && w && dst && ws);
+  CFUN_CHECK_ARG(get_encode() != nullptr);
+  const size_t base = align_up((size_t)ws, 1024);
+  if (ws_bytes < pl.total || base + pl.total - 2048 > (size_t)ws + ws_bytes) { set_error("conv3d tc: workspace too small"); return CFUN_ERR_WORKSPACE; }
+  __nv_bfloat16* ah = reinterpret_cast<__nv_bfloat16*>(base + pl.off_ah);
+  __nv_bfloat16* al = reinterpret_cast<__nv_bfloat16*>(base + pl.off_al);
+  __nv_bfloat16* bh = reinterpret_cast<__nv_bfloat16*>(base + pl.off_bh);
+  __nv_bfloat16* bl = reinterpret_cast<__nv_bfloat16*>(base + pl.off_bl);
+  const bool split = nsplit == 3;
+  const long long rows = (long long)pl.N * pl.Ds * pl.Hs * pl.Ws;
+  {
+    long long total = rows * (pl.Kp / 8);
+    pack_act_kernel<<<(unsigned)std::min<long long>(cdiv(total, 256), 32LL * num_sms()), 256, 0, st>>>(src, ah, split ? al : nullptr, rows, pl.Cs, pl.Kp);
+    CFUN_LAUNCH_CHECK();
+    const int Nrows = pl.BN * pl.ntiles_n;
+    long long wt = (long long)pl.kD * pl.kH * pl.kW * Nrows * pl.Kp;
+    pack_w_tc_kernel<<<(unsigned)std::min<long long>(cdiv(wt, 256), 8LL * num_sms()), 256, 0, st>>>(
+        w, bh, split ? bl : nullptr, d->Cout, d->Cin, d->kD, d->kH, d->kW, Nrows, pl.Kp, pass == CFUN_PASS_BWD_DATA ? 1 : 0);
+    CFUN_LAUNCH_CHECK();
+  }
+  CUtensorMap mah, mal, mbh, mbl;
+  int rc;
+  if ((rc = encode_act_map(&mah, ah, pl)) != CFUN_OK) return rc;
+  if ((rc = encode_act_map(&mal, split ? al : ah, pl)) != CFUN_OK) return rc;
+  if ((rc = encode_w_map(&mbh, bh, pl)) != CFUN_OK) return rc;
+  if ((rc = encode_w_map(&mbl, split ? bl : bh, pl)) != CFUN_OK) return rc;
+
+  TcParams p;
+  p.N = pl.N; p.Do = pl.Dt_; p.Ho = pl.Ht_; p.Wo = pl.Wt_; p.Cout = pl.Ct;
+  p.kD = pl.kD; p.kH = pl.kH; p.kW = pl.kW; p.pD = pl.pD; p.pH = pl.pH; p.pW = pl.pW;
+  p.CPC = pl.Kp / 16;
+  p.BN = pl.BN;
+  p.Dt = pl.bd; p.Ht = pl.bh; p.Wt = pl.bw;
+  p.tilesD = pl.tilesD; p.tilesH = pl.tilesH; p.tilesW = pl.tilesW;
+  p.nsplit = split ? 3 : 1;
+  const int parts = split ? 2 : 1;
+  const size_t stage_bytes = (size_t)TC_KCH * parts * (TC_A_BYTES + pl.BN * 32);
+  int stages = (int)std::min<size_t>(8, (200 * 1024) / stage_bytes);
+  CFUN_CHECK_ARG(stages >= 2);
+  p.stages = stages;
+  int cols = 32;
+  while (cols < pl.BN) cols <<= 1;
+  p.tmem_cols = cols;
+  p.epi = epi;
+  p.bias = bias;
+  p.y = dst;
+  const size_t smem = 1024 + stages * stage_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)((long long)pl.N * pl.tilesD * pl.tilesH * pl.tilesW), (unsigned)pl.ntiles_n);
+  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(mah, mal, mbh, mbl, p);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
+int tc_conv_fwd(const cfun_conv3d_desc* d, const float* x, const float* w, const float* bias, float* y, int epi, int nsplit,
+                void* ws, size_t ws_bytes, cudaStream_t st) {
+  CFUN_CHECK_ARG(!(epi & CFUN_EPI_BIAS) || bias);
+  return run_tc(d, CFUN_PASS_FWD, x, w, bias, y, epi, nsplit, ws, ws_bytes, st);
+}
+
+int tc_conv_bwd_data(const cfun_conv3d_desc* d, const float* dy, const float* w, float* dx, int nsplit, void* ws,
+                     size_t ws_bytes, cudaStream_t st) {
+  return run_tc(d, CFUN_PASS_BWD_DATA, dy, w, nullptr, dx, 0, nsplit, ws, ws_bytes, st);
+}
+
+int tc_conv_bwd_weight(const cfun_conv3d_desc*, const float*, const float*, float*, float*, int, void*, size_t, cudaStream_t) {
+  set_error("tcgen05 weight-gradient kernel not available for this shape");
+  return CFUN_ERR_INVALID;
+}
+
 }  // namespace cfun
-extern "C" int cfun_pack_split_bf16(const float*, void*, void*, long long, int, int, void*) { return CFUN_ERR_INVALID; }
+
+extern "C" int cfun_pack_split_bf16(const float* x, void* hi, void* lo, long long rows, int C, int Cpad, void* stream) {
+  using namespace cfun;
+  CFUN_CHECK_ARG(x && hi && rows >= 0 && C > 0 && Cpad >= C && Cpad % 8 == 0);
+  if (rows == 0) return CFUN_OK;
+  long long total = rows * (Cpad / 8);
+  pack_act_kernel<<<(unsigned)std::min<long long>(cdiv(total, 256), 32LL * num_sms()), 256, 0, as_stream(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), rows, C, Cpad);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}

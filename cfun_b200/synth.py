@@ -68,12 +68,21 @@ def _iou_many(boxes, cands):
     return inter / (vc + vb - inter + 1e-9)
 
 
+def _final_gt_box(center, side, dim):
+    """label cube (start, L) and the GT box load_image_gt derives from it (+5 % margin, floor / ceil, clipped)"""
+    L = int(round(side / 1.1))
+    start = np.clip(np.round(center - L / 2.0).astype(int), 0, dim - L)
+    lo = np.floor(np.maximum(0, start - 0.05 * L))
+    hi = np.ceil(np.minimum(dim, start + L + 0.05 * L))
+    return start, L, np.concatenate([lo, hi]).astype(np.float64)
+
+
 def place_label_cube(rois_norm, dim, want=4, sides=(72, 80, 88, 96, 104), margin=0.03):
     """With random-init weights and a noise volume the RPN's proposals are unrelated to any fixed label, so a centred
     cube usually yields zero positive RoIs and the U-Net (92 % of the step's FLOPs) never runs.  The benchmark therefore
-    places the synthetic label cube where the untrained detector's proposals cluster: the GT box that maximises the
-    number of proposals with IoU >= 0.5 (at least `want`, none within `margin` of the threshold).  Returns the label
-    cube (start, side) in voxels such that its +5 % GT box (reference model.py:1063-1075) is the chosen box."""
+    places the synthetic label cube where the untrained detector's proposals cluster: the cube whose GT box (as
+    load_image_gt derives it, reference model.py:1058-1075) has the most proposals with IoU >= 0.5 (at least `want`, none
+    within `margin` of the threshold).  Returns (start_zyx, side, n_positive_candidates) or None."""
     boxes = np.asarray(rois_norm, dtype=np.float64) * dim
     ctr = 0.5 * (boxes[:, :3] + boxes[:, 3:])
     cents = [ctr]
@@ -81,11 +90,11 @@ def place_label_cube(rois_norm, dim, want=4, sides=(72, 80, 88, 96, 104), margin
     nn = np.argsort(d2, axis=1)
     for k in (2, 4, 8):
         cents.append(ctr[nn[:, :k]].mean(axis=1))
-    cents = np.concatenate(cents, 0)
+    cents = np.unique(np.round(np.concatenate(cents, 0)), axis=0)
     best = None
     for s in sides:
-        c = np.clip(np.round(cents), s / 2 + 1, dim - s / 2 - 1)
-        cand = np.concatenate([c - s / 2, c + s / 2], axis=1)
+        finals = [_final_gt_box(c, s, dim) for c in cents]
+        cand = np.stack([f[2] for f in finals])
         iou = _iou_many(boxes, cand)
         npos = (iou >= 0.5 + margin).sum(1)
         amb = ((iou > 0.5 - margin) & (iou < 0.5 + margin)).sum(1)
@@ -95,15 +104,10 @@ def place_label_cube(rois_norm, dim, want=4, sides=(72, 80, 88, 96, 104), margin
         score = np.where(ok, npos + iou.max(1) * 0.5, -1)
         i = int(np.argmax(score))
         if best is None or score[i] > best[0]:
-            best = (score[i], cand[i], int(npos[i]))
+            best = (score[i], finals[i][0], finals[i][1], int(npos[i]))
     if best is None:
         return None
-    gt = best[1]
-    # invert the 5 % margin: label extent L with floor(a - .05 L) .. ceil(a + 1.05 L) ~= gt
-    side = int(round((gt[3] - gt[0]) / 1.1))
-    start = np.round(0.5 * (gt[:3] + gt[3:]) - side / 2).astype(int)
-    start = np.clip(start, 0, dim - side)
-    return start, side, best[2]
+    return best[1], best[2], best[3]
 
 
 def label_from_cube(dim, start_zyx, side, seed):

@@ -180,3 +180,28 @@ def test_whole_step_64(stage):
     assert np.array_equal(out["target_class_ids"].numpy(), g["target_class_ids"])
     assert abs(norm - float(g["grad_total_norm"])) < 1e-3 * float(g["grad_total_norm"])
     assert rel_err(out["rpn_class_logits"][::37].detach().numpy(), g["rpn_class_logits"]) < 1e-4
+
+
+def test_c_restatement_of_nms_agrees_with_numpy_oracle_and_goldens():
+    import ctypes, os, subprocess
+    from conftest import ROOT
+    so = os.path.join(ROOT, "oracle", "_ref", "libcfun_boxes_ref.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    lib = ctypes.CDLL(so)
+    lib.cfun_ref_nms.restype = ctypes.c_int
+    g = load_golden("nms")
+
+    def c_nms(b, s, thr, mx):
+        b = np.ascontiguousarray(b, dtype=np.float32); s = np.ascontiguousarray(s, dtype=np.float32)
+        keep = np.zeros(max(mx, 1), dtype=np.int32)
+        n = lib.cfun_ref_nms(b.ctypes.data_as(ctypes.c_void_p), s.ctypes.data_as(ctypes.c_void_p), b.shape[0],
+                             ctypes.c_float(thr), mx, keep.ctypes.data_as(ctypes.c_void_p))
+        return keep[:n]
+    for case in ("rand_t7_m50", "rand_t3_all", "nested_degenerate", "integer_boxes_t3"):
+        assert np.array_equal(c_nms(g[case + "/boxes"], g[case + "/scores"], float(g[case + "/thr"]), int(g[case + "/max"])), g[case + "/keep"])
+    rng = np.random.default_rng(5)
+    c = rng.uniform(0, 256, size=(4000, 3)); s = rng.uniform(16, 128, size=(4000, 3))
+    b = np.clip(np.concatenate([c - s / 2, c + s / 2], 1), 0, 256).astype(np.float32)
+    sc = rng.uniform(0, 1, size=4000).astype(np.float32)
+    assert np.array_equal(c_nms(b, sc, 0.7, 500), O.non_max_suppression(b, sc, 0.7, 500))
