@@ -13,6 +13,7 @@ int simt_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float*
 int simt_bias_grad(const float* dy, long long M, int C, float* dbias, cudaStream_t st);
 
 bool tc_supported(const cfun_conv3d_desc* d, int pass);
+bool tc_preferred(const cfun_conv3d_desc* d, int pass);
 size_t tc_workspace(const cfun_conv3d_desc* d, int pass);
 int tc_conv_fwd(const cfun_conv3d_desc* d, const float* x, const float* w, const float* bias, float* y, int epi, int nsplit,
                 void* ws, size_t ws_bytes, cudaStream_t st);
@@ -25,7 +26,7 @@ static int resolve(const cfun_conv3d_desc* d, int pass, int algo) {
   if (algo == CFUN_CONV_ALGO_AUTO) {
     const char* e = getenv("CFUN_CONV_ALGO");  // "simt" pins the CUDA-core path (debug / A-B measurements)
     if (e && e[0] == 's') return CFUN_CONV_ALGO_SIMT;
-    return tc_supported(d, pass) ? CFUN_CONV_ALGO_TC : CFUN_CONV_ALGO_SIMT;
+    return tc_preferred(d, pass) ? CFUN_CONV_ALGO_TC : CFUN_CONV_ALGO_SIMT;
   }
   return algo;
 }

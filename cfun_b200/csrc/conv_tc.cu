@@ -16,96 +16,11 @@
 //     tcgen05.commit releases smem stages and publishes the accumulator.
 // The data gradient of a stride-1 conv is the same kernel on dy with spatially flipped, (ci,co)-transposed weights and
 // pad' = k-1-pad.
-#include "common.cuh"
-#include <cuda.h>
-#include <cuda_bf16.h>
+#include "tc_ptx.cuh"
 #include <mutex>
+#include <cstdlib>
 
 namespace cfun {
-
-// ---------------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a pipeline bug must surface as a trapped kernel (an error the host sees), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-    if (spin > (1u << 24)) {
-      printf("cfun conv_tc: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_32B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, SM100 "version 1"):
 //   rows of 32 B, 8-row groups 256 B apart (SBO), LBO field = 1 (unused for a single 32 B K-slab)
@@ -293,11 +208,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
 // ---------------------------------------------------------------------------------------------------------
 // operand packing
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(v);
-  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-}
-
 // x [rows, C] fp32 -> hi/lo [rows, Cp] bf16 (channels >= C zero)
 __global__ void __launch_bounds__(256) pack_act_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                                                        __nv_bfloat16* __restrict__ lo, long long rows, int C, int Cp) {
@@ -356,11 +266,7 @@ __global__ void __launch_bounds__(256) pack_w_tc_kernel(const float* __restrict_
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
+EncodeTiledFn get_tensor_map_encoder() {
   static EncodeTiledFn fn = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -423,21 +329,35 @@ static bool make_plan(const cfun_conv3d_desc* d, int pass, TcPlan& pl) {
   return true;
 }
 
+bool tc_wgrad_supported(const cfun_conv3d_desc* d);
+size_t tc_wgrad_workspace(const cfun_conv3d_desc* d);
+
 bool tc_supported(const cfun_conv3d_desc* d, int pass) {
   static int sm100 = -1;
   if (sm100 < 0) sm100 = cfun_device_is_sm100();
-  if (!sm100 || !get_encode()) return false;
+  if (!sm100 || !get_tensor_map_encoder()) return false;
+  if (pass == CFUN_PASS_BWD_WEIGHT) {
+    const char* e = getenv("CFUN_TC_WGRAD");     // "0" keeps the weight gradient on CUDA cores (A/B measurements)
+    if (e && e[0] == '0') return false;
+    return tc_wgrad_supported(d);
+  }
   TcPlan pl;
   if (!make_plan(d, pass, pl)) return false;
   const int taps = pl.kD * pl.kH * pl.kW;
   if (taps < 27) return false;                       // pointwise / P3D factorised convs stay on CUDA cores
   if (pl.Cs < 16 || (pl.Cs & 3) || pl.Ct < 8) return false;
-  if ((long long)pl.N * pl.Dt_ * pl.Ht_ * pl.Wt_ < 2048) return false;
   if (pl.ntiles_n > 8) return false;
   return true;
 }
 
+// heuristic used by CFUN_CONV_ALGO_AUTO: tensor cores only where the launch is big enough to pay for the operand packing
+bool tc_preferred(const cfun_conv3d_desc* d, int pass) {
+  if (!tc_supported(d, pass)) return false;
+  return (long long)d->N * d->Dout * d->Hout * d->Wout >= 2048;
+}
+
 size_t tc_workspace(const cfun_conv3d_desc* d, int pass) {
+  if (pass == CFUN_PASS_BWD_WEIGHT) return tc_wgrad_workspace(d);
   TcPlan pl;
   if (!make_plan(d, pass, pl)) return 0;
   return pl.total;
@@ -449,7 +369,7 @@ static int encode_act_map(CUtensorMap* m, void* base, const TcPlan& pl) {
                            (cuuint64_t)pl.Ds * pl.Hs * pl.Ws * pl.Kp * 2};
   cuuint32_t box[5] = {16, (cuuint32_t)pl.bw, (cuuint32_t)pl.bh, (cuuint32_t)pl.bd, 1};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = get_tensor_map_encoder()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activations) failed: %d", (int)r); return CFUN_ERR_CUDA; }
   return CFUN_OK;
@@ -461,7 +381,7 @@ static int encode_w_map(CUtensorMap* m, void* base, const TcPlan& pl) {
   cuuint64_t strides[2] = {(cuuint64_t)pl.Kp * 2, (cuuint64_t)rows * pl.Kp * 2};
   cuuint32_t box[3] = {16, (cuuint32_t)pl.BN, 1};
   cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = get_tensor_map_encoder()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r); return CFUN_ERR_CUDA; }
   return CFUN_OK;
@@ -472,7 +392,7 @@ static int run_tc(const cfun_conv3d_desc* d, int pass, const float* src, const f
   TcPlan pl;
   CFUN_CHECK_ARG(make_plan(d, pass, pl));
   CFUN_CHECK_ARG(src && w && dst && ws);
-  CFUN_CHECK_ARG(get_encode() != nullptr);
+  CFUN_CHECK_ARG(get_tensor_map_encoder() != nullptr);
   const size_t base = align_up((size_t)ws, 1024);
   if (ws_bytes < pl.total || base + pl.total - 2048 > (size_t)ws + ws_bytes) { set_error("conv3d tc: workspace too small"); return CFUN_ERR_WORKSPACE; }
   __nv_bfloat16* ah = reinterpret_cast<__nv_bfloat16*>(base + pl.off_ah);
@@ -538,11 +458,6 @@ int tc_conv_fwd(const cfun_conv3d_desc* d, const float* x, const float* w, const
 int tc_conv_bwd_data(const cfun_conv3d_desc* d, const float* dy, const float* w, float* dx, int nsplit, void* ws,
                      size_t ws_bytes, cudaStream_t st) {
   return run_tc(d, CFUN_PASS_BWD_DATA, dy, w, nullptr, dx, 0, nsplit, ws, ws_bytes, st);
-}
-
-int tc_conv_bwd_weight(const cfun_conv3d_desc*, const float*, const float*, float*, float*, int, void*, size_t, cudaStream_t) {
-  set_error("tcgen05 weight-gradient kernel not available for this shape");
-  return CFUN_ERR_INVALID;
 }
 
 }  // namespace cfun

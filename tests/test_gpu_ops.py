@@ -314,7 +314,7 @@ def test_product_path_is_cuda_only(ops):
 # ---------------------------------------------------------------------------------------------------------
 TC_CASES = [
     # N, Cin, D, H, W, Cout, k, pad, bias, relu
-    (2, 20, 12, 12, 12, 20, 3, 1, False, False),       # U-Net thin conv: Cin 20 -> K padded to 32, N = 32
+    (2, 20, 12, 12, 16, 20, 3, 1, False, False),       # U-Net thin conv: Cin 20 -> K padded to 32, N = 32
     (1, 40, 16, 16, 24, 40, 3, 1, False, False),
     (1, 80, 9, 10, 11, 40, 3, 1, False, False),        # ragged extents: overhanging boxes, TMA zero fill
     (1, 128, 16, 16, 16, 256, 3, 1, True, True),       # RPN.conv_shared shape family, fused bias + ReLU
@@ -331,16 +331,18 @@ def test_conv3d_tcgen05_fwd_dgrad(ops, case):
     x = torch.randn(N, Cin, D, H, W, generator=g)
     w = torch.randn(Cout, Cin, k, k, k, generator=g) * (1.0 / (Cin * k ** 3) ** 0.5)
     b = torch.randn(Cout, generator=g) if bias else None
-    xr = x.clone().requires_grad_(True)
-    yr = F.conv3d(xr, w, b, padding=p)
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yr = F.conv3d(xr, wr, b, padding=p)
     if relu:
         yr = F.relu(yr)
     dy = torch.randn(yr.shape, generator=g)
     yr.backward(dy)
+    # the weight gradient kernel needs W % 8 == 0 (TMA stride rule) and Cin <= 256; otherwise only fwd + dgrad run on TC
+    wgrad_tc = (W % 8 == 0) and ((W + 2 * p - k + 1) % 8 == 0) and Cin <= 256
     ops.set_conv_algo(ops.ALGO_TC)
     try:
         xc = x.cuda().requires_grad_(True)
-        wc = w.cuda()          # no weight grad requested: only fwd + data gradient run (both on tensor cores)
+        wc = w.cuda().requires_grad_(wgrad_tc)
         yc = ops.conv3d(xc, wc, b.cuda() if bias else None, 1, p, relu=relu)
         yc.backward(dy.cuda())
         torch.cuda.synchronize()
@@ -348,6 +350,8 @@ def test_conv3d_tcgen05_fwd_dgrad(ops, case):
         ops.set_conv_algo(ops.ALGO_AUTO)
     assert rel_err(yc.detach().cpu().numpy(), yr.detach().numpy()) < TOL
     assert rel_err(xc.grad.cpu().numpy(), xr.grad.numpy()) < TOL
+    if wgrad_tc:
+        assert rel_err(wc.grad.cpu().numpy(), wr.grad.numpy()) < TOL
 
 
 def test_conv3d_tcgen05_single_pass_is_fast_mode_only(ops):

@@ -63,6 +63,29 @@ def main():
     x4 = torch.randn(1, 128, 16, 16, 16)
     run("random 128->256 bias relu", x4, torch.randn(256, 128, 3, 3, 3) * 0.02, torch.randn(256), relu=True)
     run("single pass 128->256", x4, torch.randn(256, 128, 3, 3, 3) * 0.02, algo=ops.ALGO_TC1)
+    # weight gradient on tensor cores vs torch
+    for (N, Ci, S, Co, k, pd) in [(2, 20, 16, 20, 3, 1), (1, 40, 16, 40, 3, 1), (1, 128, 16, 256, 3, 1), (1, 32, 16, 24, 3, 0), (1, 80, 24, 40, 3, 1), (1, 16, 32, 16, 5, 2)]:
+        x = torch.randn(N, Ci, S, S, S)
+        w = (torch.randn(Co, Ci, k, k, k) * 0.05).requires_grad_(True)
+        b = torch.randn(Co).requires_grad_(True)
+        y = F.conv3d(x, w, b, padding=pd)
+        dy = torch.randn(y.shape)
+        y.backward(dy)
+        for algo, nm in ((ops.ALGO_TC, "tc"), (ops.ALGO_SIMT, "simt")):
+            ops.set_conv_algo(algo)
+            try:
+                wc = w.detach().cuda().requires_grad_(True)
+                bc = b.detach().cuda().requires_grad_(True)
+                yc = ops.conv3d(x.cuda(), wc, bc, 1, pd)
+                yc.backward(dy.cuda())
+                torch.cuda.synchronize()
+                e = float((wc.grad.cpu() - w.grad).abs().max() / w.grad.abs().max())
+                eb = float((bc.grad.cpu() - b.grad).abs().max() / b.grad.abs().max())
+                print("wgrad %-5s N%d %d->%d @%d^3 k%d: rel_err dw %.3e db %.3e" % (nm, N, Ci, Co, S, k, e, eb))
+            except Exception as ex:
+                print("wgrad", nm, (N, Ci, S, Co, k), "EXC", ex)
+            finally:
+                ops.set_conv_algo(ops.ALGO_AUTO)
     # timing
     import time
     for (N, Ci, S, Co) in [(4, 40, 96, 40), (1, 128, 32, 256), (4, 20, 96, 20), (4, 80, 48, 80)]:
@@ -79,7 +102,13 @@ def main():
                 e.record(); torch.cuda.synchronize()
                 ms = s.elapsed_time(e) / 3
                 fl = 2.0 * N * S ** 3 * Ci * Co * 27
-                print("time %-6s N%d %d->%d @%d^3: %.3f ms  %.1f TFLOP/s (incl. pack)" % (nm, N, Ci, Co, S, ms, fl / ms / 1e9))
+                print("time %-6s N%d %d->%d @%d^3: fwd %.3f ms  %.1f TFLOP/s (incl. pack)" % (nm, N, Ci, Co, S, ms, fl / ms / 1e9))
+                xg = x.clone().requires_grad_(True); wg = w.clone().requires_grad_(True)
+                yy = ops.conv3d(xg, wg, None, 1, 1); gy = torch.randn_like(yy); torch.cuda.synchronize()
+                s.record()
+                yy.backward(gy)
+                e.record(); torch.cuda.synchronize()
+                print("     %-6s bwd (dgrad+wgrad) %.3f ms" % (nm, s.elapsed_time(e)))
             except Exception as ex:
                 print("time", nm, "EXC", ex)
             finally:
