@@ -106,7 +106,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
       for (int it = 0; it < nstage_iters; ++it) {
         const int slot = it % p.stages;
         const uint32_t ph = (uint32_t)((it / p.stages) & 1);
-        mbar_wait(&empty_bar[slot], ph ^ 1u);
+        mbar_wait(&empty_bar[slot], ph ^ 1u, 10);
         const int nch = min(TC_KCH, total_chunks - q);
         mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)(nch * chunk_bytes));
         uint8_t* sbase = ring + (size_t)slot * stage_bytes;
@@ -138,7 +138,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
       for (int it = 0; it < nstage_iters; ++it) {
         const int slot = it % p.stages;
         const uint32_t ph = (uint32_t)((it / p.stages) & 1);
-        mbar_wait(&full_bar[slot], ph);
+        mbar_wait(&full_bar[slot], ph, 20);
         tc_fence_after();
         const int nch = min(TC_KCH, total_chunks - q);
         const uint32_t sbase = smem_u32(ring + (size_t)slot * stage_bytes);
@@ -169,7 +169,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     const int od = d0 + ld, oh = h0 + lh, ow = w0 + lw;
     const bool vox_ok = od < p.Do && oh < p.Ho && ow < p.Wo;
     float* yrow = p.y + ((((long long)n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * (long long)p.Cout;
-    mbar_wait(tmem_full_bar, 0);
+    mbar_wait(tmem_full_bar, 0, 30);
     tc_fence_after();
     const bool vec = (p.Cout & 3) == 0;
     for (int j = 0; j < p.BN; j += 16) {
@@ -294,7 +294,9 @@ static void pick_box(int Do, int Ho, int Wo, int& bd, int& bh, int& bw) {
                                 {8, 8, 2}, {1, 16, 8}, {16, 1, 8}, {2, 2, 32}, {1, 4, 32}, {4, 1, 32}, {16, 8, 1}, {8, 16, 1},
                                 {2, 16, 4}, {16, 2, 4}, {1, 2, 64}, {2, 1, 64}, {1, 1, 128}, {32, 4, 1}, {4, 32, 1}, {16, 4, 2}, {4, 16, 2}};
   long long best = -1;
+  bd = bh = bw = 0;
   for (auto& c : cand) {
+    if (c[0] > Do || c[1] > Ho || c[2] > Wo) continue;   // the TMA box never exceeds the tensor extent
     long long vol = cdiv(Do, c[0]) * c[0] * cdiv(Ho, c[1]) * c[1] * cdiv(Wo, c[2]) * c[2];
     if (best < 0 || vol < best) { best = vol; bd = c[0]; bh = c[1]; bw = c[2]; }
   }
@@ -320,7 +322,8 @@ static bool make_plan(const cfun_conv3d_desc* d, int pass, TcPlan& pl) {
   pl.Np = (int)align_up((size_t)pl.Ct, 16);
   pl.ntiles_n = (int)cdiv(pl.Np, 256);
   pl.BN = (int)align_up((size_t)cdiv(pl.Np, pl.ntiles_n), 16);
-  pick_box(pl.Dt_, pl.Ht_, pl.Wt_, pl.bd, pl.bh, pl.bw);
+  pick_box(std::min(pl.Dt_, pl.Ds), std::min(pl.Ht_, pl.Hs), std::min(pl.Wt_, pl.Ws), pl.bd, pl.bh, pl.bw);
+  if (pl.bd == 0) return false;
   pl.tilesD = (int)cdiv(pl.Dt_, pl.bd); pl.tilesH = (int)cdiv(pl.Ht_, pl.bh); pl.tilesW = (int)cdiv(pl.Wt_, pl.bw);
   const size_t rows = (size_t)pl.N * pl.Ds * pl.Hs * pl.Ws;
   const size_t act = align_up(rows * pl.Kp * 2, 1024);
@@ -470,5 +473,28 @@ extern "C" int cfun_pack_split_bf16(const float* x, void* hi, void* lo, long lon
   pack_act_kernel<<<(unsigned)std::min<long long>(cdiv(total, 256), 32LL * num_sms()), 256, 0, as_stream(stream)>>>(
       x, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), rows, C, Cpad);
   CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
+namespace cfun {
+int tc_debug_read_wgrad(int* out8);
+int tc_debug_read_conv(int* out8) {
+  int z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  CFUN_CUDA(cudaMemcpyFromSymbol(out8, g_tc_debug, sizeof(z)));
+  CFUN_CUDA(cudaMemcpyToSymbol(g_tc_debug, z, sizeof(z)));
+  return CFUN_OK;
+}
+}  // namespace cfun
+
+// debugging aid: {site+1 (0 = no time-out), blockIdx.x, blockIdx.y, threadIdx.x, parity, spins}; reading resets it.
+extern "C" int cfun_tc_debug_status(int* out8_host) {
+  using namespace cfun;
+  if (cudaDeviceSynchronize() != cudaSuccess) { set_error("cfun_tc_debug_status: device in error state"); return CFUN_ERR_CUDA; }
+  int a[8], b[8];
+  int rc = tc_debug_read_conv(a);
+  if (rc != CFUN_OK) return rc;
+  rc = tc_debug_read_wgrad(b);
+  if (rc != CFUN_OK) return rc;
+  for (int i = 0; i < 8; ++i) out8_host[i] = a[0] ? a[i] : b[i];
   return CFUN_OK;
 }

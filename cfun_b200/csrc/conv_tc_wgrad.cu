@@ -13,6 +13,7 @@
 // tcgen05 prices M = 64 and M = 128 identically.
 // Operands are split-bf16 pairs, accumulated as hi*hi + lo*hi + hi*lo (see conv_tc.cu).
 #include "tc_ptx.cuh"
+#include <cstdlib>
 
 namespace cfun {
 
@@ -30,11 +31,21 @@ struct WgParams {
   long long slabs_total;         // N*Do*Ho*kt_per_line
   long long slabs_per_cta;
   float* dw;                     // (Cout, Cin, taps) fp32, zero-initialised
+  int debug_skip;                // bring-up aid (CFUN_WG_DEBUG): 1 no TMA, 2 no MMA, 4 no epilogue
+};
+
+// TMA requires the innermost box coordinate to be 16-byte aligned, so the +-1 voxel shifts along w (the K axis here)
+// cannot be expressed as box coordinates: the pack pass materialises kW copies of X, copy kw pre-shifted by kw - pW along
+// w, and the kernel picks the map of its tap's kw.  Shifts along h and d stay plain (outer-dimension) coordinates.
+constexpr int WG_MAX_KW = 5;
+struct alignas(64) XMaps {
+  CUtensorMap hi[WG_MAX_KW];
+  CUtensorMap lo[WG_MAX_KW];
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid_constant__ CUtensorMap map_yl,
-                     const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, const WgParams p) {
+                     const __grid_constant__ XMaps xmaps, const WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* empty_bar = full_bar + 8;
@@ -56,7 +67,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid_co
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_yh);
-    prefetch_tmap(&map_xh);
+    prefetch_tmap(&xmaps.hi[0]);
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
@@ -72,13 +83,14 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid_co
       for (int it = 0; it < niter; ++it) {
         const int slot = it % p.stages;
         const uint32_t ph = (uint32_t)((it / p.stages) & 1);
-        mbar_wait(&empty_bar[slot], ph ^ 1u);
+        mbar_wait(&empty_bar[slot], ph ^ 1u, 110);
         long long s = s_beg + it;
         const int kt = (int)(s % p.kt_per_line); s /= p.kt_per_line;
         const int h = (int)(s % p.Ho); s /= p.Ho;
         const int d = (int)(s % p.Do);
         const int n = (int)(s / p.Do);
         const int w0 = kt * p.Wk;
+        if (p.debug_skip & 1) { mbar_arrive_expect_tx(&full_bar[slot], 0); continue; }
         mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)(parts * (a_bytes + ntap * p.Npad * p.swz)));
         uint8_t* sb = ring + (size_t)slot * stage_bytes;
         tma_load_5d(&map_yh, &full_bar[slot], sb, w0, h, d, n, m0);
@@ -88,9 +100,9 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid_co
         for (int t = 0; t < ntap; ++t) {
           const int tap = tap0 + t;
           const int kd = tap / khw, r = tap - kd * khw, kh = r / p.kW, kw = r - kh * p.kW;
-          const int xw = w0 + kw - p.pW, xh = h + kh - p.pH, xd = d + kd - p.pD;
-          tma_load_5d(&map_xh, &full_bar[slot], bb + (size_t)(t * parts) * b_bytes, xw, xh, xd, n, 0);
-          if (parts == 2) tma_load_5d(&map_xl, &full_bar[slot], bb + (size_t)(t * parts + 1) * b_bytes, xw, xh, xd, n, 0);
+          const int xh = h + kh - p.pH, xd = d + kd - p.pD;
+          tma_load_5d(&xmaps.hi[kw], &full_bar[slot], bb + (size_t)(t * parts) * b_bytes, w0, xh, xd, n, 0);
+          if (parts == 2) tma_load_5d(&xmaps.lo[kw], &full_bar[slot], bb + (size_t)(t * parts + 1) * b_bytes, w0, xh, xd, n, 0);
         }
       }
     }
@@ -101,12 +113,12 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid_co
       for (int it = 0; it < niter; ++it) {
         const int slot = it % p.stages;
         const uint32_t ph = (uint32_t)((it / p.stages) & 1);
-        mbar_wait(&full_bar[slot], ph);
+        mbar_wait(&full_bar[slot], ph, 120);
         tc_fence_after();
         const uint32_t sb = smem_u32(ring + (size_t)slot * stage_bytes);
         const uint32_t bb = sb + parts * a_bytes;
         const uint32_t acc = it > 0 ? 1u : 0u;
-        for (int t = 0; t < ntap; ++t) {
+        for (int t = 0; t < ntap && !(p.debug_skip & 2); ++t) {
           const uint32_t dcol = tmem_base + (uint32_t)(t * p.Npad);
           for (int ks = 0; ks < ksteps; ++ks) {
             const uint32_t koff = (uint32_t)(ks * 32);   // 16 bf16 along K inside the swizzled row
@@ -128,9 +140,9 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid_co
   } else {
     const int quad = warp & 3;
     const int co = m0 + quad * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
+    mbar_wait(tmem_full_bar, 0, 130);
     tc_fence_after();
-    if (niter > 0) {
+    if (niter > 0 && !(p.debug_skip & 4)) {
       for (int t = 0; t < ntap; ++t) {
         const int tap = tap0 + t;
         for (int j = 0; j < p.Npad; j += 16) {
@@ -180,15 +192,50 @@ __global__ void __launch_bounds__(256) pack_transpose_kernel(const float* __rest
   }
 }
 
+// X [N*D*H rows of W voxels, C] fp32 -> kW channel-major copies [kw][C][N*D*H][Wo] with copy kw holding x[.., w + kw - pW, c]
+// (zero outside [0, W)); Wo = output width, so every copy is aligned to the dY lines.
+__global__ void __launch_bounds__(256) pack_transpose_shift_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                                                   __nv_bfloat16* __restrict__ lo, long long lines, int W, int Wo,
+                                                                   int C, int kW, int pW) {
+  __shared__ float tile[32][33];
+  const long long line = blockIdx.x;                 // (n, d, h) line index of X
+  const int wt = blockIdx.y;
+  const int w0 = wt * 32 - pW;                       // first source voxel of copy kw = 0 (may be negative)
+  const int c0 = blockIdx.z * 32;
+  // stage 32 + (kW - 1) source voxels? keep it simple: one tile per kw
+  for (int kw = 0; kw < kW; ++kw) {
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+      int w = w0 + j + kw;
+      int c = c0 + threadIdx.x;
+      tile[j][threadIdx.x] = (w >= 0 && w < W && c < C) ? __ldg(x + (line * W + w) * C + c) : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+      int c = c0 + j;
+      int wo = wt * 32 + threadIdx.x;
+      if (c < C && wo < Wo) {
+        __nv_bfloat16 h, l;
+        split_bf16(tile[threadIdx.x][j], h, l);
+        long long o = (((long long)kw * C + c) * lines + line) * Wo + wo;
+        hi[o] = h;
+        if (lo) lo[o] = l;
+      }
+    }
+  }
+}
+
 struct WgPlan {
   int Wk, swz, T, ngroups, mtiles, Npad, stages, tmem_cols;
   size_t off_yh, off_yl, off_xh, off_xl, total;
-  long long rows_y, rows_x;
+  long long rows_y, rows_x, lines_x;
+  size_t copy_elems;
 };
 
 static bool make_wg_plan(const cfun_conv3d_desc* d, WgPlan& pl) {
   if (!d || d->sD != 1 || d->sH != 1 || d->sW != 1) return false;
-  if ((d->Wout & 7) || (d->Win & 7)) return false;      // TMA row stride must be a multiple of 16 B
+  if (d->Wout & 7) return false;                        // TMA row stride must be a multiple of 16 B
+  if (d->kW > WG_MAX_KW) return false;
   if (d->Cin > 256) return false;
   pl.Wk = (d->Wout % 64 == 0) ? 64 : ((d->Wout % 32 == 0) ? 32 : 16);
   pl.swz = pl.Wk * 2;
@@ -211,7 +258,9 @@ static bool make_wg_plan(const cfun_conv3d_desc* d, WgPlan& pl) {
   pl.rows_y = (long long)d->N * d->Dout * d->Hout * d->Wout;
   pl.rows_x = (long long)d->N * d->Din * d->Hin * d->Win;
   const size_t ybytes = align_up((size_t)pl.rows_y * d->Cout * 2, 1024);
-  const size_t xbytes = align_up((size_t)pl.rows_x * d->Cin * 2, 1024);
+  pl.lines_x = (long long)d->N * d->Din * d->Hin;
+  pl.copy_elems = (size_t)d->Cin * pl.lines_x * d->Wout;          // one pre-shifted copy of X (one part)
+  const size_t xbytes = align_up(pl.copy_elems * 2 * d->kW, 1024);
   pl.off_yh = 0; pl.off_yl = ybytes; pl.off_xh = 2 * ybytes; pl.off_xl = 2 * ybytes + xbytes;
   pl.total = 2 * ybytes + 2 * xbytes + 2048;
   return true;
@@ -260,17 +309,22 @@ int tc_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* d
   __nv_bfloat16* xl = reinterpret_cast<__nv_bfloat16*>(base + pl.off_xl);
   pack_transpose_kernel<<<dim3((unsigned)cdiv(pl.rows_y, 32), (unsigned)cdiv(d->Cout, 32)), dim3(32, 8), 0, st>>>(dy, yh, split ? yl : nullptr, pl.rows_y, d->Cout);
   CFUN_LAUNCH_CHECK();
-  pack_transpose_kernel<<<dim3((unsigned)cdiv(pl.rows_x, 32), (unsigned)cdiv(d->Cin, 32)), dim3(32, 8), 0, st>>>(x, xh, split ? xl : nullptr, pl.rows_x, d->Cin);
+  pack_transpose_shift_kernel<<<dim3((unsigned)pl.lines_x, (unsigned)cdiv(d->Wout, 32), (unsigned)cdiv(d->Cin, 32)), dim3(32, 8), 0, st>>>(
+      x, xh, split ? xl : nullptr, pl.lines_x, d->Win, d->Wout, d->Cin, d->kW, d->pW);
   CFUN_LAUNCH_CHECK();
   const int taps = d->kD * d->kH * d->kW;
   CFUN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * d->Cin * taps, st));
 
-  CUtensorMap myh, myl, mxh, mxl;
+  CUtensorMap myh, myl;
+  XMaps xm;
   int rc;
   if ((rc = encode_cmajor_map(&myh, yh, d->Wout, d->Hout, d->Dout, d->N, d->Cout, pl.Wk, 128, pl.swz)) != CFUN_OK) return rc;
   if ((rc = encode_cmajor_map(&myl, split ? yl : yh, d->Wout, d->Hout, d->Dout, d->N, d->Cout, pl.Wk, 128, pl.swz)) != CFUN_OK) return rc;
-  if ((rc = encode_cmajor_map(&mxh, xh, d->Win, d->Hin, d->Din, d->N, d->Cin, pl.Wk, pl.Npad, pl.swz)) != CFUN_OK) return rc;
-  if ((rc = encode_cmajor_map(&mxl, split ? xl : xh, d->Win, d->Hin, d->Din, d->N, d->Cin, pl.Wk, pl.Npad, pl.swz)) != CFUN_OK) return rc;
+  for (int kw = 0; kw < WG_MAX_KW; ++kw) {
+    const int k = kw < d->kW ? kw : 0;
+    if ((rc = encode_cmajor_map(&xm.hi[kw], xh + (size_t)k * pl.copy_elems, d->Wout, d->Hin, d->Din, d->N, d->Cin, pl.Wk, pl.Npad, pl.swz)) != CFUN_OK) return rc;
+    if ((rc = encode_cmajor_map(&xm.lo[kw], (split ? xl : xh) + (size_t)k * pl.copy_elems, d->Wout, d->Hin, d->Din, d->N, d->Cin, pl.Wk, pl.Npad, pl.swz)) != CFUN_OK) return rc;
+  }
 
   WgParams p;
   p.N = d->N; p.Do = d->Dout; p.Ho = d->Hout; p.Wo = d->Wout;
@@ -289,6 +343,7 @@ int tc_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* d
   p.slabs_per_cta = cdiv(p.slabs_total, ctas);
   ctas = cdiv(p.slabs_total, p.slabs_per_cta);
   p.dw = dw;
+  { const char* e = getenv("CFUN_WG_DEBUG"); p.debug_skip = e ? atoi(e) : 0; }
   const int parts = split ? 2 : 1;
   const int b_bytes = (int)align_up((size_t)pl.Npad * pl.swz, 1024);
   const size_t stage_bytes = (size_t)parts * (128 * pl.swz + pl.T * b_bytes);
@@ -299,9 +354,16 @@ int tc_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* d
     attr_set = true;
   }
   dim3 grid((unsigned)ctas, (unsigned)pl.ngroups, (unsigned)pl.mtiles);
-  conv_tc_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(myh, myl, mxh, mxl, p);
+  conv_tc_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(myh, myl, xm, p);
   CFUN_LAUNCH_CHECK();
   if (dbias) return simt_bias_grad(dy, pl.rows_y, d->Cout, dbias, st);
+  return CFUN_OK;
+}
+
+int tc_debug_read_wgrad(int* out8) {
+  int z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  CFUN_CUDA(cudaMemcpyFromSymbol(out8, g_tc_debug, sizeof(z)));
+  CFUN_CUDA(cudaMemcpyToSymbol(g_tc_debug, z, sizeof(z)));
   return CFUN_OK;
 }
 

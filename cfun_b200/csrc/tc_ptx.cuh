@@ -33,12 +33,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline bug must surface as a trapped kernel (an error the host sees), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// Bounded wait: a pipeline bug must surface as a reported error, never as a hung GPU.  On time-out the first offender
+// records (site, block, thread, parity) in g_tc_debug and every later wait falls through immediately, so the kernel
+// drains and terminates; the host reads the record with cfun_tc_debug_status().
+static __device__ int g_tc_debug[8];   // one copy per translation unit (no -rdc); each TU exports a reader
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int site = 0) {
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-    if (spin > (1u << 24)) {
-      printf("cfun conv_tc: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, parity);
-      __trap();
+    if (spin > (1u << 22) || *((volatile int*)&g_tc_debug[0]) != 0) {
+      if (atomicCAS(&g_tc_debug[0], 0, site + 1) == 0) {
+        g_tc_debug[1] = (int)blockIdx.x; g_tc_debug[2] = (int)blockIdx.y; g_tc_debug[3] = (int)threadIdx.x;
+        g_tc_debug[4] = (int)parity; g_tc_debug[5] = (int)spin;
+      }
+      return;
     }
   }
 }

@@ -493,6 +493,42 @@ class Dataset(torch.utils.data.Dataset):
 
 
 # ---------------------------------------------------------------------------------------------------------
+#  Heads + head losses as one static-shape callable (CUDA-graph capturable: no host syncs, no dynamic shapes)
+# ---------------------------------------------------------------------------------------------------------
+class HeadsTail(nn.Module):
+    """classifier head + mask head + their four losses for a fixed (P positives, R RoIs) split, positives first
+    (the layout detection_target_layer produces).  Numerically the same ops as Classifier / Mask / compute_*_loss; the
+    only difference is that the positive rows are addressed as [:P] instead of through torch.nonzero, which lets
+    torch.cuda.make_graphed_callables capture forward and backward (about 1500 of the step's kernel launches)."""
+
+    def __init__(self, classifier, mask, stage):
+        super().__init__()
+        self.classifier = classifier
+        self.mask = mask
+        self.stage = stage
+
+    def forward(self, p2, p3, image, rois, p_rois, class_ids, deltas, mask_index, d0, d1, d2, d3, d4):
+        P = p_rois.shape[0]
+        unet = self.mask.modified_u_net
+        saved = unet.injected_drop
+        unet.injected_drop = [d0, d1, d2, d3, d4] if unet.training and unet.use_dropout else None
+        try:
+            c_logits, _, c_bbox = self.classifier([p2, p3], rois)
+            m_logits, m_probs = self.mask([image, image], p_rois)
+        finally:
+            unet.injected_drop = saved
+        binary = (class_ids > 0).long()
+        l_cls = F.cross_entropy(c_logits, binary)
+        l_box = F.smooth_l1_loss(c_bbox[:P, 1, :], deltas[:P])
+        l_mask = F.cross_entropy(m_logits, mask_index)
+        if self.stage == 'finetune':
+            l_edge = ops.sobel_edge_loss(m_probs, mask_index).reshape(())
+        else:
+            l_edge = torch.zeros((), device=p2.device)
+        return torch.stack([l_cls, l_box, l_mask, l_edge])
+
+
+# ---------------------------------------------------------------------------------------------------------
 #  MaskRCNN
 # ---------------------------------------------------------------------------------------------------------
 LOSS_NAMES = ["rpn_class_loss", "rpn_bbox_loss", "mrcnn_class_loss", "mrcnn_bbox_loss", "mrcnn_mask_loss",
@@ -510,6 +546,9 @@ class MaskRCNN(nn.Module):
         self.model_dir = model_dir
         self.build(config=config, test_flag=test_flag)
         self.initialize_weights()
+        self._graphed_tails = None
+        self.graph_kernel_counts = {}
+        self.graph_replays = {}
 
     def build(self, config, test_flag=False):
         h, w, d = config.IMAGE_SHAPE[:3]
@@ -528,6 +567,8 @@ class MaskRCNN(nn.Module):
                                      config.FPN_CLASSIFY_FC_LAYERS_SIZE, test_flag)
         self.mask = Mask(1, config.MASK_POOL_SIZE, config.NUM_CLASSES, config.UNET_MASK_BRANCH_CHANNEL, config.STAGE,
                          test_flag)
+        # not registered as a sub-module (would duplicate state_dict keys): shares classifier / mask by reference
+        object.__setattr__(self, "_tail", HeadsTail(self.classifier, self.mask, config.STAGE))
         if not config.TRAIN_BN:
             for m in self.modules():
                 if isinstance(m, nn.BatchNorm3d):
@@ -624,15 +665,68 @@ class MaskRCNN(nn.Module):
 
     def forward_backward(self, images, image_metas, rpn_match, rpn_bbox, gt_class_ids, gt_boxes, gt_masks):
         """One volume: predict('training') -> compute_losses -> weighted sum -> backward (reference model.py:1622-1640).
-        Returns (total loss tensor, list of the six loss tensors); gradients accumulate into .grad."""
-        outs = self.predict([images, image_metas, gt_class_ids, gt_boxes, gt_masks], mode='training')
-        rpn_class_logits, rpn_pred_bbox, target_class_ids, mrcnn_class_logits, target_deltas, mrcnn_bbox, target_mask, \
-            mrcnn_mask, mrcnn_mask_logits = outs
-        losses = compute_losses(rpn_match, rpn_bbox, rpn_class_logits, rpn_pred_bbox, target_class_ids, mrcnn_class_logits,
-                                target_deltas, mrcnn_bbox, target_mask, mrcnn_mask, mrcnn_mask_logits, self.config.STAGE)
+        Returns (total loss tensor, list of the six loss tensors); gradients accumulate into .grad.
+        Same arithmetic as predict() + compute_losses(); the heads and their losses go through HeadsTail so that they can
+        be replayed as CUDA graphs (enable_graphs)."""
+        self.train()
+        cfg = self.config
+        dev = images.device
+        p2, p3, rpn_class_logits, rpn_class, rpn_pred_bbox, rpn_rois = self.rpn_proposals(images, 'training')
+        h, w, d = cfg.IMAGE_SHAPE[:3]
+        scale = _f32([d, h, w, d, h, w], dev)
+        p_rois, rois, target_class_ids, target_deltas, target_mask = \
+            detection_target_layer(rpn_rois, gt_class_ids, gt_boxes / scale, gt_masks, cfg)
+        P, R = int(p_rois.shape[0]), int(rois.shape[0])
+        self.last_roi_counts = (P, R)
+        rpn_class_loss = compute_rpn_class_loss(rpn_match, rpn_class_logits)
+        rpn_bbox_loss = compute_rpn_bbox_loss(rpn_bbox, rpn_match, rpn_pred_bbox)
+        zero = _zero_loss(rpn_class_logits)
+        if P > 0:
+            if target_mask.dim() == 5:
+                target_mask = torch.argmax(target_mask.long(), dim=1)
+            unet = self.mask.modified_u_net
+            drops = unet._drop_masks(P, dev)
+            if drops[0] is None:
+                drops = [torch.ones((P, unet.base_n_filter * m), device=dev) for m in (1, 2, 4, 8, 16)]
+            tail = self._graphed_tails.get((P, R), self._tail) if self._graphed_tails is not None else self._tail
+            if self._graphed_tails is not None and (P, R) not in self._graphed_tails:
+                tail = self._capture_tail(P, R, p2, p3, images, rois, p_rois, target_class_ids, target_deltas, target_mask, drops)
+            if self._graphed_tails is not None:
+                self.graph_replays[(P, R)] = self.graph_replays.get((P, R), 0) + 1
+            hl = tail(p2, p3, images, rois.detach(), p_rois.detach(), target_class_ids, target_deltas, target_mask, *drops)
+            head_losses = [hl[0].reshape(1), hl[1].reshape(1), hl[2].reshape(1), hl[3].reshape(1)]
+        elif R > 0:
+            c_logits, _, c_bbox = self.classifier([p2, p3], rois)
+            binary = (target_class_ids > 0).long()
+            head_losses = [compute_mrcnn_class_loss(binary, c_logits), compute_mrcnn_bbox_loss(target_deltas, binary, c_bbox), zero, zero]
+        else:
+            head_losses = [zero, zero, zero, zero]
+        losses = [rpn_class_loss, rpn_bbox_loss] + head_losses
         loss = self.weighted_loss(losses)
         loss.sum().backward()
         return loss, losses
+
+    # -- CUDA graphs for the heads ----------------------------------------------------------------------------
+    def enable_graphs(self, on=True):
+        """Replay classifier + mask heads + their losses (forward and backward) as CUDA graphs, one pair per (P, R) RoI
+        split, captured lazily on first use.  Call after the optimizer has re-homed the parameters (FlatSGD) and after one
+        eager step (so that the conv workspace has reached its final size)."""
+        self._graphed_tails = {} if on else None
+        self.graph_kernel_counts = {}
+        self.graph_replays = {}
+
+    def _capture_tail(self, P, R, *sample):
+        from .ops import launch_count
+        p2, p3, images, rois, p_rois, tcls, tdel, tmask, drops = sample
+        args = (p2.detach().clone().requires_grad_(True), p3.detach().clone().requires_grad_(True), images.detach().clone(),
+                rois.detach().clone(), p_rois.detach().clone(), tcls.clone(), tdel.clone(), tmask.clone()) + \
+            tuple(dm.clone() for dm in drops)
+        n0 = launch_count()
+        graphed = torch.cuda.make_graphed_callables(self._tail, args, num_warmup_iters=1)
+        # kernels per replay (forward + backward): launches during capture = (1 warm-up + 1 capture) iterations
+        self.graph_kernel_counts[(P, R)] = (launch_count() - n0) // 2
+        self._graphed_tails[(P, R)] = graphed
+        return graphed
 
     def train_step_device(self, optimizer, vol_i16, label_hwd, rpn_match, rpn_bbox, gt_boxes, gt_class_ids):
         """One optimizer step on one volume whose raw inputs are already on the device: mold (int16 -> normalised fp32,

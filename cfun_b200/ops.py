@@ -24,6 +24,14 @@ def call_count():
     return _calls["n"]
 
 
+def tc_debug_status():
+    """(site, blockIdx.x, blockIdx.y, threadIdx.x, parity, spins) of the first tcgen05 pipeline wait that timed out, or None"""
+    buf = (C.c_int * 8)()
+    check(lib.cfun_tc_debug_status(buf), "cfun_tc_debug_status")
+    vals = list(buf)
+    return None if vals[0] == 0 else tuple(vals[:6])
+
+
 def launch_count():
     """CUDA kernels launched by libcfun_b200.so so far in this process"""
     return int(lib.cfun_launch_count())

@@ -111,6 +111,9 @@ int cfun_instnorm_bwd_apply(const float* x, const float* a, const float* b, cons
 int cfun_maxpool2_fwd(const float* x, float* y, int N, int D, int H, int W, int C, void* stream);
 int cfun_maxpool2_bwd(const float* x, const float* y, const float* dy, float* dx, int N, int D, int H, int W, int C,
                       void* stream);
+/* debugging aid for the tcgen05 pipelines: out[0] != 0 means an mbarrier wait timed out (out[0]-1 = wait site,
+ * out[1..5] = blockIdx.x, blockIdx.y, threadIdx.x, parity, spins).  Synchronises the device; reading resets the record. */
+int cfun_tc_debug_status(int* out8_host);
 /* split fp32 -> (hi, lo) bf16 pairs, channel-padded NDHWC, the operand format of the tcgen05 convs */
 int cfun_pack_split_bf16(const float* x, void* hi, void* lo, long long rows, int C, int Cpad, void* stream);
 

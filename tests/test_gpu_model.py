@@ -118,3 +118,36 @@ def test_inference_predict_runs_and_matches_oracle_shapes():
     assert det.shape[0] == 1 and det.shape[2] == 8 and masks.shape[2] == 8
     assert masks.shape[1] == det.shape[1] and masks.shape[3:] == (32, 32, 32)
     assert torch.isfinite(masks).all()
+
+
+def test_cuda_graph_heads_match_eager():
+    """enable_graphs(): the heads + head losses replayed as CUDA graphs give the same losses and gradients as eager."""
+    from cfun_b200 import config as Cf
+    g = load_golden("step64_beginning")
+    cfg = Cf.heart_config(64, "beginning", mask_pool=32, anchor_scales=(16, 32))
+    net, sd = build(cfg, int(g["seed_weights"]))
+    inp = golden_step_inputs(g)
+    net.mask.modified_u_net.injected_drop = inp["drop"]
+    dev = torch.device("cuda")
+    args = (inp["image"].to(dev), None, inp["rpn_match"].to(dev)[None, :, None], inp["rpn_bbox"].to(dev)[None],
+            torch.arange(1, 8).int().to(dev)[None], inp["gt_boxes"].to(dev)[None], inp["gt_masks"].to(dev)[None])
+
+    def run():
+        net.zero_grad(set_to_none=True)
+        torch.manual_seed(int(g["seed_perm"]))
+        loss, losses = net.forward_backward(*args)
+        torch.cuda.synchronize()
+        grads = {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
+        return np.array([float(l) for l in losses]), grads
+
+    l_eager, g_eager = run()
+    net.enable_graphs()
+    l_cap, g_cap = run()          # captures (and computes)
+    l_rep, g_rep = run()          # replays
+    assert np.allclose(l_eager, g["losses"], rtol=5e-4, atol=1e-6)
+    for l, gr in ((l_cap, g_cap), (l_rep, g_rep)):
+        assert np.allclose(l, l_eager, rtol=1e-5, atol=1e-7), (l, l_eager)
+        for k in ("rpn.conv_shared.weight", "classifier.conv1.weight", "mask.modified_u_net.conv_norm_lrelu_l4.0.weight",
+                  "mask.modified_u_net.conv3d_c1_1.weight", "fpn.P2_conv2.weight"):
+            assert rel_err(gr[k].cpu().numpy(), g_eager[k].cpu().numpy()) < 1e-4, k
+    assert net.graph_replays[(1, 3)] >= 2 and net.graph_kernel_counts[(1, 3)] > 100
