@@ -36,4 +36,26 @@ for stage in ("beginning", "finetune"):
     out[stage + "/losses"] = np.array([float(l) for l in res["losses"]])
     d = np.abs(g["g_unet_l4"] - out[stage + "/g_unet_l4"]).max() / np.abs(out[stage + "/g_unet_l4"]).max()
     print(stage, "reference fp32 vs fp64 on g_unet_l4:", d)
+
+# U-Net layer-level gradients of the reduced-width golden model (tests/golden/layers_*.npz), float64
+names = ["conv3d_c1_1", "conv3d_c3", "norm_lrelu_conv_c4.2", "conv_norm_lrelu_l4.0", "ds2_1x1_conv3d", "out_upscale_conv.1"]
+keys = ["g_unet_c1_1", "g_unet_c3", "g_unet_nlc4", "g_unet_l4", "g_unet_ds2", "g_unet_up"]
+for stage in ("beginning", "finetune"):
+    g = dict(np.load(os.path.join(GOLD, "layers_%s.npz" % stage)))
+    sd = det_state(maskrcnn_shapes(fpn=32, rpn=48, unet=4, fc=16, pool=4, num_classes=8), seed=100)
+    sd = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    pre = "mask.modified_u_net."
+    leaves = {pre + n + ".weight": sd[pre + n + ".weight"].clone().requires_grad_(True) for n in names}
+    sd2 = dict(sd)
+    sd2.update(leaves)
+    drop = [torch.from_numpy(g["drop%d" % i]).double() for i in range(5)]
+    y = O.unet_forward(sd2, torch.from_numpy(g["crops"]).double(), stage, drop)
+    w = torch.cos(torch.arange(y.numel(), dtype=torch.float32) * 0.37).view(y.shape).double()
+    (y * w).sum().backward()
+    for n, k in zip(names, keys):
+        gr = leaves[pre + n + ".weight"].grad
+        out["layers_%s/%s" % (stage, k)] = gr.numpy() if gr is not None else np.zeros_like(g[k], dtype=np.float64)
+        den = np.abs(out["layers_%s/%s" % (stage, k)]).max()
+        if den > 0:
+            print(stage, k, "reference fp32 vs fp64:", np.abs(g[k] - out["layers_%s/%s" % (stage, k)]).max() / den)
 np.savez_compressed(os.path.join(GOLD, "step64_fp64.npz"), **out)

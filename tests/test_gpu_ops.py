@@ -319,7 +319,7 @@ TC_CASES = [
     (1, 80, 9, 10, 11, 40, 3, 1, False, False),        # ragged extents: overhanging boxes, TMA zero fill
     (1, 128, 16, 16, 16, 256, 3, 1, True, True),       # RPN.conv_shared shape family, fused bias + ReLU
     (1, 16, 12, 12, 12, 320, 3, 1, True, False),       # two N tiles of 160
-    (1, 32, 10, 10, 10, 8, 5, 2, False, False),        # 5^3 kernel (out_upscale_conv family)
+    (1, 32, 10, 10, 16, 16, 5, 2, False, False),       # 5^3 kernel (out_upscale_conv family)
     (1, 48, 8, 8, 20, 24, 3, 0, True, False),          # no padding
 ]
 
@@ -333,9 +333,12 @@ def test_conv3d_tcgen05_fwd_dgrad(ops, case):
     b = torch.randn(Cout, generator=g) if bias else None
     xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
     yr = F.conv3d(xr, wr, b, padding=p)
-    if relu:
-        yr = F.relu(yr)
     dy = torch.randn(yr.shape, generator=g)
+    if relu:
+        # the ReLU mask is decided by pre-activations that differ by ~1e-5 between the two paths; keep the comparison
+        # well-posed by zeroing the incoming gradient wherever the pre-activation is within 1e-3 of the kink
+        dy = dy * (yr.detach().abs() > 1e-3).float()
+        yr = F.relu(yr)
     yr.backward(dy)
     # the weight gradient kernel needs W % 8 == 0 (TMA stride rule) and Cin <= 256; otherwise only fwd + dgrad run on TC
     wgrad_tc = (W % 8 == 0) and ((W + 2 * p - k + 1) % 8 == 0) and Cin <= 256
