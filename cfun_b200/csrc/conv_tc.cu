@@ -334,6 +334,11 @@ static bool make_plan(const cfun_conv3d_desc* d, int pass, TcPlan& pl) {
 
 bool tc_wgrad_supported(const cfun_conv3d_desc* d);
 size_t tc_wgrad_workspace(const cfun_conv3d_desc* d);
+bool hl_supported(const cfun_conv3d_desc* d, int pass);
+size_t hl_workspace(const cfun_conv3d_desc* d, int pass);
+int hl_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
+            int nsplit, void* ws, size_t ws_bytes, cudaStream_t st);
+int tc_debug_read_halo(int* out8);
 
 bool tc_supported(const cfun_conv3d_desc* d, int pass) {
   static int sm100 = -1;
@@ -361,6 +366,7 @@ bool tc_preferred(const cfun_conv3d_desc* d, int pass) {
 
 size_t tc_workspace(const cfun_conv3d_desc* d, int pass) {
   if (pass == CFUN_PASS_BWD_WEIGHT) return tc_wgrad_workspace(d);
+  if (hl_supported(d, pass)) return hl_workspace(d, pass);
   TcPlan pl;
   if (!make_plan(d, pass, pl)) return 0;
   return pl.total;
@@ -455,11 +461,13 @@ static int run_tc(const cfun_conv3d_desc* d, int pass, const float* src, const f
 int tc_conv_fwd(const cfun_conv3d_desc* d, const float* x, const float* w, const float* bias, float* y, int epi, int nsplit,
                 void* ws, size_t ws_bytes, cudaStream_t st) {
   CFUN_CHECK_ARG(!(epi & CFUN_EPI_BIAS) || bias);
+  if (hl_supported(d, CFUN_PASS_FWD)) return hl_conv(d, CFUN_PASS_FWD, x, w, bias, y, epi, nsplit, ws, ws_bytes, st);
   return run_tc(d, CFUN_PASS_FWD, x, w, bias, y, epi, nsplit, ws, ws_bytes, st);
 }
 
 int tc_conv_bwd_data(const cfun_conv3d_desc* d, const float* dy, const float* w, float* dx, int nsplit, void* ws,
                      size_t ws_bytes, cudaStream_t st) {
+  if (hl_supported(d, CFUN_PASS_BWD_DATA)) return hl_conv(d, CFUN_PASS_BWD_DATA, dy, w, nullptr, dx, 0, nsplit, ws, ws_bytes, st);
   return run_tc(d, CFUN_PASS_BWD_DATA, dy, w, nullptr, dx, 0, nsplit, ws, ws_bytes, st);
 }
 
@@ -490,11 +498,13 @@ int tc_debug_read_conv(int* out8) {
 extern "C" int cfun_tc_debug_status(int* out8_host) {
   using namespace cfun;
   if (cudaDeviceSynchronize() != cudaSuccess) { set_error("cfun_tc_debug_status: device in error state"); return CFUN_ERR_CUDA; }
-  int a[8], b[8];
+  int a[8], b[8], c[8];
   int rc = tc_debug_read_conv(a);
   if (rc != CFUN_OK) return rc;
   rc = tc_debug_read_wgrad(b);
   if (rc != CFUN_OK) return rc;
-  for (int i = 0; i < 8; ++i) out8_host[i] = a[0] ? a[i] : b[i];
+  rc = tc_debug_read_halo(c);
+  if (rc != CFUN_OK) return rc;
+  for (int i = 0; i < 8; ++i) out8_host[i] = a[0] ? a[i] : (b[0] ? b[i] : c[i]);
   return CFUN_OK;
 }

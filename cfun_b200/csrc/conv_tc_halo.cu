@@ -1,0 +1,400 @@
+// tcgen05 3x3x3 / stride 1 / pad 1 convolution with the input halo resident in shared memory (thin-channel layers).
+//
+// conv_tc.cu re-loads the shifted input box from L2 for every tap, which makes thin convs (Cin <= 64: the top levels of
+// the U-Net mask branch, 92 % of the step's FLOPs) L2-bandwidth bound: 27 x 8 KB of activations per 128-voxel tile.
+// Here one CTA tile is a 1 x 16 x 8 slab of output voxels; its 3 x 18 x 10 input halo is loaded ONCE per tile and the 27
+// taps are 27 *views* of it, expressed purely through the UMMA shared-memory descriptor:
+//   * activations are packed "group-planar": [Kp/8 groups][N*(D+2)][H][W][8 ch] split-bf16 (zero planes at d = -1, D), so a
+//     TMA box (80 elements = 10 voxels x 8 ch, 18 rows, 3 planes) lands as one plane of 16-byte rows per 8-channel group;
+//   * with the un-swizzled ("interleave") K-major canonical layout ((8,n),2):((1,SBO),LBO) a 128-row operand is 16 groups of 8
+//     consecutive 16-byte rows; rows = w (contiguous), groups = h lines (SBO = 10*16 B), the second 8-channel half of a K=16
+//     step is the next plane (LBO = plane size), and tap (kd,kh,kw) is just start address + ((kd*18 + kh)*10 + kw)*16;
+//   * every inner TMA coordinate is a multiple of 8 elements (16 B), the alignment rule the weight-gradient kernel ran into.
+// Weights stream through a 3-stage ring as contiguous 16-B-row planes (one stage = one K-chunk x one kd plane of 9 taps).
+// Persistent CTAs, TMEM accumulator double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1; the halo ring
+// is per K-chunk, so chunk c of tile i+1 loads while chunks c+1.. of tile i are still being consumed.
+// Split-bf16 x3 arithmetic as in conv_tc.cu.  The data gradient is the same kernel with flipped / transposed weights.
+#include "tc_ptx.cuh"
+#include <cstdlib>
+
+namespace cfun {
+
+constexpr int HL_THREADS = 192;
+constexpr int HL_HT = 16, HL_WT = 8;                 // output slab 1 x 16 x 8
+constexpr int HL_HH = HL_HT + 2, HL_WH = HL_WT + 2;  // halo 3 x 18 x 10
+constexpr int HL_PLANE = 3 * HL_HH * HL_WH * 16;     // 8640 B: one 8-channel group, one part
+constexpr int HL_MAX_CPC = 4;                        // Kp <= 64
+constexpr int HL_BSTAGES = 3;
+
+__device__ __forceinline__ uint64_t make_desc_interleave(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell); layout type 0 = no swizzle
+  return d;
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct HlParams {
+  int N, D, H, W, Cout;       // output extents == input extents (pad 1, stride 1)
+  int CPC;                    // K chunks of 16 channels
+  int Npad;                   // MMA N
+  int tilesH, tilesW;
+  long long ntiles;
+  int nsplit;
+  int tmem_cols;
+  int epi;
+  const float* bias;
+  float* y;
+  const uint8_t* wpack;       // [chunk][kd][part][tap9][kgroup2][Npad][8] bf16
+};
+
+__global__ void __launch_bounds__(HL_THREADS, 1)
+conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_l, const HlParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_raw);       // [HL_MAX_CPC]
+  uint64_t* a_empty = a_full + HL_MAX_CPC;
+  uint64_t* b_full = a_empty + HL_MAX_CPC;                        // [HL_BSTAGES]
+  uint64_t* b_empty = b_full + HL_BSTAGES;
+  uint64_t* t_full = b_empty + HL_BSTAGES;                        // [2]
+  uint64_t* t_empty = t_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint8_t* base = smem_raw + 1024 + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int parts = p.nsplit == 3 ? 2 : 1;
+  const int a_slot_bytes = parts * 2 * HL_PLANE;                  // one K chunk: 2 channel groups x parts
+  const int b_part_bytes = 9 * 2 * p.Npad * 16;
+  const int b_stage_bytes = parts * b_part_bytes;
+  uint8_t* a_ring = base;
+  uint8_t* b_ring = base + (size_t)p.CPC * a_slot_bytes;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_h);
+    if (parts == 2) prefetch_tmap(&map_l);
+    for (int i = 0; i < p.CPC; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < HL_BSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== producer: halo (TMA tensor) + weights (bulk) =====================
+    if (lane == 0) {
+      uint32_t bcount = 0;
+      int local = 0;
+      for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++local) {
+        long long t = tile;
+        const int wb = (int)(t % p.tilesW); t /= p.tilesW;
+        const int hb = (int)(t % p.tilesH); t /= p.tilesH;
+        const int d = (int)(t % p.D);
+        const int n = (int)(t / p.D);
+        const int c_w = (wb * HL_WT - 1) * 8;          // inner coordinate in elements (multiple of 8 -> 16 B aligned)
+        const int c_h = hb * HL_HT - 1;
+        const int c_nd = n * (p.D + 2) + d;            // padded plane index of d-1
+        for (int c = 0; c < p.CPC; ++c) {
+          mbar_wait(&a_empty[c], (uint32_t)((local & 1) ^ 1), 210);
+          mbar_arrive_expect_tx(&a_full[c], (uint32_t)(parts * 2 * HL_PLANE));
+          uint8_t* slot = a_ring + (size_t)c * a_slot_bytes;
+          for (int g = 0; g < 2; ++g) {
+            tma_load_4d(&map_h, &a_full[c], slot + g * HL_PLANE, c_w, c_h, c_nd, 2 * c + g);
+            if (parts == 2) tma_load_4d(&map_l, &a_full[c], slot + (2 + g) * HL_PLANE, c_w, c_h, c_nd, 2 * c + g);
+          }
+          for (int kd = 0; kd < 3; ++kd, ++bcount) {
+            const int st = (int)(bcount % HL_BSTAGES);
+            mbar_wait(&b_empty[st], (uint32_t)(((bcount / HL_BSTAGES) & 1) ^ 1), 220);
+            mbar_arrive_expect_tx(&b_full[st], (uint32_t)b_stage_bytes);
+            const uint8_t* src = p.wpack + ((size_t)(c * 3 + kd)) * (size_t)(parts * b_part_bytes);
+            bulk_load(b_ring + (size_t)st * b_stage_bytes, src, (uint32_t)b_part_bytes, &b_full[st]);
+            if (parts == 2) bulk_load(b_ring + (size_t)st * b_stage_bytes + b_part_bytes, src + b_part_bytes, (uint32_t)b_part_bytes, &b_full[st]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_ring);
+      uint32_t bcount = 0;
+      int local = 0;
+      for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++local) {
+        const int buf = local & 1;
+        mbar_wait(&t_empty[buf], (uint32_t)(((local >> 1) & 1) ^ 1), 230);
+        tc_fence_after();
+        const uint32_t dcol = tmem_base + (uint32_t)(buf * p.Npad);
+        uint32_t acc = 0;
+        for (int c = 0; c < p.CPC; ++c) {
+          mbar_wait(&a_full[c], (uint32_t)(local & 1), 240);
+          tc_fence_after();
+          const uint32_t aslot = a_base + (uint32_t)(c * a_slot_bytes);
+          for (int kd = 0; kd < 3; ++kd, ++bcount) {
+            const int st = (int)(bcount % HL_BSTAGES);
+            mbar_wait(&b_full[st], (uint32_t)((bcount / HL_BSTAGES) & 1), 250);
+            tc_fence_after();
+            const uint32_t bst = b_base + (uint32_t)(st * b_stage_bytes);
+#pragma unroll 1
+            for (int t9 = 0; t9 < 9; ++t9) {
+              const int kh = t9 / 3, kw = t9 - kh * 3;
+              const uint32_t aoff = (uint32_t)(((kd * HL_HH + kh) * HL_WH + kw) * 16);
+              const uint64_t a_hi = make_desc_interleave(aslot + aoff, HL_PLANE, HL_WH * 16);
+              const uint64_t b_hi = make_desc_interleave(bst + (uint32_t)(t9 * 2 * p.Npad * 16), (uint32_t)(p.Npad * 16), 128);
+              umma_bf16(dcol, a_hi, b_hi, idesc, acc);
+              acc = 1;
+              if (parts == 2) {
+                const uint64_t a_lo = make_desc_interleave(aslot + 2 * HL_PLANE + aoff, HL_PLANE, HL_WH * 16);
+                const uint64_t b_lo = make_desc_interleave(bst + (uint32_t)b_part_bytes + (uint32_t)(t9 * 2 * p.Npad * 16), (uint32_t)(p.Npad * 16), 128);
+                umma_bf16(dcol, a_lo, b_hi, idesc, 1);
+                umma_bf16(dcol, a_hi, b_lo, idesc, 1);
+              }
+            }
+            umma_commit(&b_empty[st]);
+          }
+          umma_commit(&a_empty[c]);
+        }
+        umma_commit(&t_full[buf]);
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int lh = row >> 3, lw = row & 7;
+    const bool vec = (p.Cout & 3) == 0;
+    int local = 0;
+    for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++local) {
+      long long t = tile;
+      const int wb = (int)(t % p.tilesW); t /= p.tilesW;
+      const int hb = (int)(t % p.tilesH); t /= p.tilesH;
+      const int d = (int)(t % p.D);
+      const int n = (int)(t / p.D);
+      const int oh = hb * HL_HT + lh, ow = wb * HL_WT + lw;
+      const bool ok = oh < p.H && ow < p.W;
+      float* yrow = p.y + ((((long long)n * p.D + d) * p.H + oh) * p.W + ow) * (long long)p.Cout;
+      const int buf = local & 1;
+      mbar_wait(&t_full[buf], (uint32_t)((local >> 1) & 1), 260);
+      tc_fence_after();
+      for (int j = 0; j < p.Npad; j += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.Npad + j), r);
+        tmem_ld_wait();
+        if (ok) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float f = __uint_as_float(r[i]);
+            if ((p.epi & CFUN_EPI_BIAS) && j + i < p.Cout) f += __ldg(p.bias + j + i);
+            if (p.epi & CFUN_EPI_RELU) f = fmaxf(f, 0.f);
+            v[i] = f;
+          }
+          if (vec && j + 16 <= p.Cout) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(yrow + j + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (j + i < p.Cout) yrow[j + i] = v[i];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[buf]);     // 4 epilogue warps -> barrier count 4
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// x fp32 NDHWC [N,D,H,W,C] -> group-planar split bf16 [Kp/8][N*(D+2)][H][W][8]; d-planes 0 and D+1 of every sample are zero
+__global__ void __launch_bounds__(256) pack_act_gp_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                                          __nv_bfloat16* __restrict__ lo, int N, int D, int H, int W, int C, int G) {
+  const long long HW = (long long)H * W;
+  const long long vox_p = (long long)N * (D + 2) * HW;      // padded voxel count per group
+  const long long total = vox_p * G;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pv = i % vox_p;
+    const int g = (int)(i / vox_p);
+    const long long plane = pv / HW;                        // n*(D+2) + d'
+    const int dp = (int)(plane % (D + 2));
+    const int n = (int)(plane / (D + 2));
+    __align__(16) __nv_bfloat16 h[8];
+    __align__(16) __nv_bfloat16 l[8];
+    if (dp == 0 || dp == D + 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { h[j] = __float2bfloat16_rn(0.f); l[j] = h[j]; }
+    } else {
+      const long long src = (((long long)n * D + (dp - 1)) * HW + (pv % HW)) * C + g * 8;
+      float v[8];
+      if (g * 8 + 8 <= C && (C & 3) == 0) {
+        float4 a = __ldg(reinterpret_cast<const float4*>(x + src));
+        float4 b = __ldg(reinterpret_cast<const float4*>(x + src + 4));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (g * 8 + j < C) ? __ldg(x + src + j) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split_bf16(v[j], h[j], l[j]);
+    }
+    *reinterpret_cast<uint4*>(hi + i * 8) = *reinterpret_cast<const uint4*>(h);
+    if (lo) *reinterpret_cast<uint4*>(lo + i * 8) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
+// w (Cout, Cin, 27) fp32 -> [chunk][kd][part][tap9][kgroup2][Npad][8] bf16.  mode 1 = data gradient (rows = ci, k = co,
+// taps mirrored).
+__global__ void __launch_bounds__(256) pack_w_halo_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout,
+                                                          int Cin, int Npad, int CPC, int parts, int mode) {
+  const long long total = (long long)CPC * 3 * parts * 9 * 2 * Npad * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int e = (int)(r % 8); r /= 8;
+    const int row = (int)(r % Npad); r /= Npad;
+    const int kg = (int)(r % 2); r /= 2;
+    const int t9 = (int)(r % 9); r /= 9;
+    const int part = (int)(r % parts); r /= parts;
+    const int kd = (int)(r % 3); r /= 3;
+    const int c = (int)r;
+    const int k = c * 16 + kg * 8 + e;
+    int tap = kd * 9 + t9;
+    int co, ci;
+    if (mode == 0) { co = row; ci = k; }
+    else { co = k; ci = row; tap = 26 - tap; }
+    float v = 0.f;
+    if (co < Cout && ci < Cin) v = w[((long long)co * Cin + ci) * 27 + tap];
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    out[i] = part == 0 ? h : l;
+  }
+}
+
+struct HlPlan {
+  int Cs, Ct, N, D, H, W, Kp, G, CPC, Npad, tmem_cols;
+  size_t off_ah, off_al, off_w, total, act_bytes, w_bytes, smem;
+};
+
+static bool make_hl_plan(const cfun_conv3d_desc* d, int pass, HlPlan& pl) {
+  if (!d || d->sD != 1 || d->sH != 1 || d->sW != 1) return false;
+  if (d->kD != 3 || d->kH != 3 || d->kW != 3 || d->pD != 1 || d->pH != 1 || d->pW != 1) return false;
+  if (pass == CFUN_PASS_FWD) { pl.Cs = d->Cin; pl.Ct = d->Cout; }
+  else if (pass == CFUN_PASS_BWD_DATA) { pl.Cs = d->Cout; pl.Ct = d->Cin; }
+  else return false;
+  pl.N = d->N; pl.D = d->Din; pl.H = d->Hin; pl.W = d->Win;
+  if (pl.H < 8 || pl.W < 8) return false;
+  if ((long long)pl.W * 8 > 0x7fffffffLL) return false;
+  pl.Kp = (int)align_up((size_t)pl.Cs, 16);
+  pl.G = pl.Kp / 8;
+  pl.CPC = pl.Kp / 16;
+  if (pl.CPC > HL_MAX_CPC) return false;
+  pl.Npad = (int)align_up((size_t)pl.Ct, 16);
+  if (pl.Npad > 256) return false;
+  int cols = 32;
+  while (cols < 2 * pl.Npad) cols <<= 1;
+  pl.tmem_cols = cols;
+  const size_t a_bytes = (size_t)pl.CPC * 2 * 2 * HL_PLANE;
+  const size_t b_bytes = (size_t)HL_BSTAGES * 2 * 9 * 2 * pl.Npad * 16;
+  pl.smem = 2048 + a_bytes + b_bytes;
+  if (pl.smem > 225 * 1024) return false;
+  pl.act_bytes = align_up((size_t)pl.G * pl.N * (pl.D + 2) * pl.H * pl.W * 16, 1024);
+  pl.w_bytes = align_up((size_t)pl.CPC * 3 * 2 * 9 * 2 * pl.Npad * 16, 1024);
+  pl.off_ah = 0; pl.off_al = pl.act_bytes; pl.off_w = 2 * pl.act_bytes;
+  pl.total = 2 * pl.act_bytes + pl.w_bytes + 2048;
+  return true;
+}
+
+bool hl_supported(const cfun_conv3d_desc* d, int pass) {
+  const char* e = getenv("CFUN_TC_HALO");       // "0" disables the halo kernel (A/B measurements)
+  if (e && e[0] == '0') return false;
+  HlPlan pl;
+  if (!make_hl_plan(d, pass, pl)) return false;
+  return pl.Cs >= 16 && (pl.Cs & 3) == 0 && pl.Ct >= 8;
+}
+size_t hl_workspace(const cfun_conv3d_desc* d, int pass) {
+  HlPlan pl;
+  return make_hl_plan(d, pass, pl) ? pl.total : 0;
+}
+
+int hl_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
+            int nsplit, void* ws, size_t ws_bytes, cudaStream_t st) {
+  HlPlan pl;
+  CFUN_CHECK_ARG(make_hl_plan(d, pass, pl));
+  CFUN_CHECK_ARG(src && w && dst && ws && get_tensor_map_encoder());
+  const size_t base = align_up((size_t)ws, 1024);
+  if (ws_bytes < pl.total || base + pl.total - 2048 > (size_t)ws + ws_bytes) { set_error("conv3d halo: workspace too small"); return CFUN_ERR_WORKSPACE; }
+  const bool split = nsplit == 3;
+  const int parts = split ? 2 : 1;
+  __nv_bfloat16* ah = reinterpret_cast<__nv_bfloat16*>(base + pl.off_ah);
+  __nv_bfloat16* al = reinterpret_cast<__nv_bfloat16*>(base + pl.off_al);
+  __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(base + pl.off_w);
+  {
+    long long total = (long long)pl.G * pl.N * (pl.D + 2) * pl.H * pl.W;
+    pack_act_gp_kernel<<<(unsigned)std::min<long long>(cdiv(total, 256), 32LL * num_sms()), 256, 0, st>>>(src, ah, split ? al : nullptr, pl.N, pl.D, pl.H, pl.W, pl.Cs, pl.G);
+    CFUN_LAUNCH_CHECK();
+    long long wt = (long long)pl.CPC * 3 * parts * 9 * 2 * pl.Npad * 8;
+    pack_w_halo_kernel<<<(unsigned)std::min<long long>(cdiv(wt, 256), 4LL * num_sms()), 256, 0, st>>>(w, wp, d->Cout, d->Cin, pl.Npad, pl.CPC, parts, pass == CFUN_PASS_BWD_DATA ? 1 : 0);
+    CFUN_LAUNCH_CHECK();
+  }
+  CUtensorMap mh, ml;
+  for (int part = 0; part < 2; ++part) {
+    void* b = part == 0 ? (void*)ah : (void*)(split ? al : ah);
+    cuuint64_t dims[4] = {(cuuint64_t)pl.W * 8, (cuuint64_t)pl.H, (cuuint64_t)pl.N * (pl.D + 2), (cuuint64_t)pl.G};
+    cuuint64_t strides[3] = {(cuuint64_t)pl.W * 16, (cuuint64_t)pl.H * pl.W * 16, (cuuint64_t)pl.N * (pl.D + 2) * pl.H * pl.W * 16};
+    cuuint32_t box[4] = {HL_WH * 8, HL_HH, 3, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = get_tensor_map_encoder()(part == 0 ? &mh : &ml, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, b, dims, strides, box, es,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(halo) failed: %d", (int)r); return CFUN_ERR_CUDA; }
+  }
+  HlParams p;
+  p.N = pl.N; p.D = pl.D; p.H = pl.H; p.W = pl.W; p.Cout = pl.Ct;
+  p.CPC = pl.CPC; p.Npad = pl.Npad;
+  p.tilesH = (int)cdiv(pl.H, HL_HT); p.tilesW = (int)cdiv(pl.W, HL_WT);
+  p.ntiles = (long long)pl.N * pl.D * p.tilesH * p.tilesW;
+  p.nsplit = split ? 3 : 1;
+  p.tmem_cols = pl.tmem_cols;
+  p.epi = epi; p.bias = bias; p.y = dst;
+  p.wpack = reinterpret_cast<const uint8_t*>(wp);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const unsigned grid = (unsigned)std::min<long long>(p.ntiles, num_sms());
+  conv_tc_halo_kernel<<<grid, HL_THREADS, pl.smem, st>>>(mh, ml, p);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
+int tc_debug_read_halo(int* out8) {
+  int z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  CFUN_CUDA(cudaMemcpyFromSymbol(out8, g_tc_debug, sizeof(z)));
+  CFUN_CUDA(cudaMemcpyToSymbol(g_tc_debug, z, sizeof(z)));
+  return CFUN_OK;
+}
+
+}  // namespace cfun

@@ -324,6 +324,22 @@ TC_CASES = [
 ]
 
 
+HALO_CASES = [
+    (2, 20, 12, 20, 16, 20, 3, 1, False, False),       # thin U-Net conv: K 20 -> 32 (2 chunks), N = 32
+    (1, 40, 5, 33, 24, 40, 3, 1, True, True),          # K 48 (3 chunks), ragged H (3 slabs, last overhangs), bias + ReLU
+    (1, 64, 4, 16, 8, 24, 3, 1, False, False),         # K 64 (4 chunks), exactly one slab per plane
+    (3, 16, 3, 9, 11, 64, 3, 1, True, False),          # box larger than the map, W not a multiple of 8
+]
+
+
+@pytest.mark.parametrize("halo", ["1", "0"])
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_conv3d_tcgen05_halo_kernel_vs_tap_reload_kernel(ops, case, halo, monkeypatch):
+    """the halo-resident kernel (conv_tc_halo.cu) and the per-tap reload kernel (conv_tc.cu) both match fp32"""
+    monkeypatch.setenv("CFUN_TC_HALO", halo)
+    test_conv3d_tcgen05_fwd_dgrad(ops, case)
+
+
 @pytest.mark.parametrize("case", TC_CASES)
 def test_conv3d_tcgen05_fwd_dgrad(ops, case):
     N, Cin, D, H, W, Cout, k, p, bias, relu = case

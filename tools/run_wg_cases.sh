@@ -1,4 +1,7 @@
 #!/bin/bash
-for c in "1 128 16 16 16 128 3 1" "1 128 16 16 16 256 3 1" "1 32 16 16 32 32 3 1" "1 64 8 8 64 64 3 1" "2 20 16 16 16 20 3 1" "1 40 16 16 16 40 3 1" "1 80 24 24 24 40 3 1" "1 16 32 32 32 16 5 2" "1 48 8 8 24 24 3 0"; do
-  timeout 120 python tools/wg_case.py $c 2>&1 | grep -E "CASE" | head -3
+# N Ci D H W Co k pad [mode]
+for c in "1 16 16 16 16 16 3 1" "1 16 16 16 16 8 3 1" "1 16 16 16 16 16 3 1 fwd" "1 16 16 16 16 8 3 1 fwd"; do
+  for h in 1 0; do
+    CFUN_TC_HALO=$h timeout 120 python tools/wg_case.py $c 2>&1 | grep -E "CASE \[" | sed "s/^/halo=$h /" | head -2
+  done
 done
