@@ -18,6 +18,8 @@ struct ConvGeo {
   int Ct, Dt, Ht, Wt;     // target tensor (one GEMM row per target voxel)
   int kD, kH, kW, sD, sH, sW, pD, pH, pW;
   int Ktot;  // taps * Cs
+  int cls;   // 1: rows are ordered by stride-parity class (strided data gradient), see row_to_voxel()
+  long long Mc;  // rows per parity class
   int ldb;   // leading dimension of the packed weight matrix
   long long M;
 };
@@ -37,6 +39,36 @@ __device__ __forceinline__ bool src_coord(int t, int k, int s, int p, int size_s
     out = q;
     return q < size_src;
   }
+}
+
+// GEMM row -> target voxel.  For a strided data gradient the rows are grouped by the parity class of the input voxel
+// ((td+pD)%s, (th+pH)%s, (tw+pW)%s with s = 2): all rows of a class share the same set of contributing taps (1/8 of the
+// 27 on average), so a block whose rows sit in one class can skip the other taps' K-chunks altogether.
+__device__ __forceinline__ void row_to_voxel(const ConvGeo& g, long long m, int& n, int& td, int& th, int& tw) {
+  if (!g.cls) {
+    tw = (int)(m % g.Wt); m /= g.Wt;
+    th = (int)(m % g.Ht); m /= g.Ht;
+    td = (int)(m % g.Dt); m /= g.Dt;
+    n = (int)m;
+  } else {
+    const int c = (int)(m / g.Mc);
+    long long r = m % g.Mc;
+    const int Wq = g.Wt >> 1, Hq = g.Ht >> 1, Dq = g.Dt >> 1;
+    tw = 2 * (int)(r % Wq) + (c & 1); r /= Wq;
+    th = 2 * (int)(r % Hq) + ((c >> 1) & 1); r /= Hq;
+    td = 2 * (int)(r % Dq) + ((c >> 2) & 1); r /= Dq;
+    n = (int)r;
+  }
+}
+// does K-chunk kt (16 consecutive kk) touch a tap that can contribute to parity class c?
+__device__ __forceinline__ bool chunk_live(const ConvGeo& g, int kt, int c) {
+  const int t0 = (kt * 16) / g.Cs, t1 = min((kt * 16 + 15) / g.Cs, g.kD * g.kH * g.kW - 1);
+  const int khw = g.kH * g.kW;
+  for (int t = t0; t <= t1; ++t) {
+    const int kd = t / khw, r = t - kd * khw, kh = r / g.kW, kw = r - kh * g.kW;
+    if ((((c >> 2) & 1) + g.pD - kd) % 2 == 0 && (((c >> 1) & 1) + g.pH - kh) % 2 == 0 && ((c & 1) + g.pW - kw) % 2 == 0) return true;
+  }
+  return false;
 }
 
 // address (in floats) of source element for target voxel (n,td,th,tw) and reduction index kk; -1 when it is padding
@@ -86,12 +118,12 @@ __global__ void __launch_bounds__(256) igemm_kernel(ConvGeo g, const float* __re
   const long long am = m0 + arow;
   const bool arow_ok = am < g.M;
   int an = 0, atd = 0, ath = 0, atw = 0;
-  if (arow_ok) {
-    long long t = am;
-    atw = (int)(t % g.Wt); t /= g.Wt;
-    ath = (int)(t % g.Ht); t /= g.Ht;
-    atd = (int)(t % g.Dt); t /= g.Dt;
-    an = (int)t;
+  if (arow_ok) row_to_voxel(g, am, an, atd, ath, atw);
+  // block-uniform parity class (strided dgrad only): -1 = rows of several classes, no K-chunk skipping
+  int bcls = -1;
+  if (MODE == 1 && g.cls) {
+    const long long mlast = min(g.M - 1, m0 + BM - 1);
+    if (m0 / g.Mc == mlast / g.Mc) bcls = (int)(m0 / g.Mc);
   }
   // B loader
   const int bk = (tid * BPT) / BN;
@@ -148,12 +180,18 @@ __global__ void __launch_bounds__(256) igemm_kernel(ConvGeo g, const float* __re
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
   const int nk = (g.Ktot + BK - 1) / BK;
-  load_tile(0);
-  store_tile(0);
+  auto next_live = [&](int k) {
+    if (MODE == 1 && bcls >= 0)
+      while (k < nk && !chunk_live(g, k, bcls)) ++k;
+    return k;
+  };
+  int kt = next_live(0);
+  if (kt < nk) { load_tile(kt); store_tile(0); }
   __syncthreads();
-  for (int kt = 0; kt < nk; ++kt) {
-    const int buf = kt & 1;
-    if (kt + 1 < nk) load_tile(kt + 1);
+  int buf = 0;
+  while (kt < nk) {
+    const int kn = next_live(kt + 1);
+    if (kn < nk) load_tile(kn);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
       float a[TM], b[TN];
@@ -172,8 +210,10 @@ __global__ void __launch_bounds__(256) igemm_kernel(ConvGeo g, const float* __re
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
-    if (kt + 1 < nk) store_tile(buf ^ 1);
+    if (kn < nk) store_tile(buf ^ 1);
     __syncthreads();
+    buf ^= 1;
+    kt = kn;
   }
 
   const bool vec_out = (g.Ct % 4 == 0);
@@ -181,6 +221,11 @@ __global__ void __launch_bounds__(256) igemm_kernel(ConvGeo g, const float* __re
   for (int i = 0; i < TM; ++i) {
     long long m = m0 + ty * TM + i;
     if (m >= g.M) continue;
+    if (g.cls) {   // parity-class row order -> real voxel index
+      int n, td, th, tw;
+      row_to_voxel(g, m, n, td, th, tw);
+      m = (((long long)n * g.Dt + td) * g.Ht + th) * g.Wt + tw;
+    }
     float* orow = dst + m * g.Ct;
     int c = col0 + tx * TN;
     float v[TN];
@@ -410,6 +455,12 @@ static bool make_geo(const cfun_conv3d_desc* d, int pass, ConvGeo& g) {
   g.Ktot = (int)kt;
   g.ldb = (int)align_up((size_t)g.Ct, 64);
   g.M = (long long)g.N * g.Dt * g.Ht * g.Wt;
+  g.cls = 0;
+  g.Mc = g.M;
+  if (pass == CFUN_PASS_BWD_DATA && d->sD == 2 && d->sH == 2 && d->sW == 2 && (g.Dt % 2 == 0) && (g.Ht % 2 == 0) && (g.Wt % 2 == 0)) {
+    g.cls = 1;
+    g.Mc = g.M / 8;
+  }
   return true;
 }
 

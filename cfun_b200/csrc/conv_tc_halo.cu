@@ -22,7 +22,8 @@ namespace cfun {
 constexpr int HL_THREADS = 192;
 constexpr int HL_HT = 16, HL_WT = 8;                 // output slab 1 x 16 x 8
 constexpr int HL_HH = HL_HT + 2, HL_WH = HL_WT + 2;  // halo 3 x 18 x 10
-constexpr int HL_PLANE = 3 * HL_HH * HL_WH * 16;     // 8640 B: one 8-channel group, one part
+constexpr int HL_PLANE_DATA = 3 * HL_HH * HL_WH * 16;   // 8640 B: one 8-channel group, one part
+constexpr int HL_PLANE = (HL_PLANE_DATA + 127) / 128 * 128;   // 8704: plane pitch (TMA smem destinations are 128 B aligned)
 constexpr int HL_MAX_CPC = 4;                        // Kp <= 64
 constexpr int HL_BSTAGES = 3;
 
@@ -113,7 +114,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
         const int c_nd = n * (p.D + 2) + d;            // padded plane index of d-1
         for (int c = 0; c < p.CPC; ++c) {
           mbar_wait(&a_empty[c], (uint32_t)((local & 1) ^ 1), 210);
-          mbar_arrive_expect_tx(&a_full[c], (uint32_t)(parts * 2 * HL_PLANE));
+          mbar_arrive_expect_tx(&a_full[c], (uint32_t)(parts * 2 * HL_PLANE_DATA));
           uint8_t* slot = a_ring + (size_t)c * a_slot_bytes;
           for (int g = 0; g < 2; ++g) {
             tma_load_4d(&map_h, &a_full[c], slot + g * HL_PLANE, c_w, c_h, c_nd, 2 * c + g);

@@ -170,7 +170,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid_co
 
 // fp32 NDHWC [rows, C] -> channel-major split bf16 [C][rows] (32x32 smem-tiled transpose)
 __global__ void __launch_bounds__(256) pack_transpose_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
-                                                             __nv_bfloat16* __restrict__ lo, long long rows, int C) {
+                                                             __nv_bfloat16* __restrict__ lo, long long rows, int C,
+                                                             long long pitch) {
   __shared__ float tile[32][33];
   const long long r0 = (long long)blockIdx.x * 32;
   const int c0 = blockIdx.y * 32;
@@ -186,8 +187,8 @@ __global__ void __launch_bounds__(256) pack_transpose_kernel(const float* __rest
     if (c < C && r < rows) {
       __nv_bfloat16 h, l;
       split_bf16(tile[threadIdx.x][j], h, l);
-      hi[(long long)c * rows + r] = h;
-      if (lo) lo[(long long)c * rows + r] = l;
+      hi[(long long)c * pitch + r] = h;
+      if (lo) lo[(long long)c * pitch + r] = l;
     }
   }
 }
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(256) pack_transpose_kernel(const float* __rest
 // (zero outside [0, W)); Wo = output width, so every copy is aligned to the dY lines.
 __global__ void __launch_bounds__(256) pack_transpose_shift_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                                                                    __nv_bfloat16* __restrict__ lo, long long lines, int W, int Wo,
-                                                                   int C, int kW, int pW) {
+                                                                   int C, int kW, int pW, long long pitch) {
   __shared__ float tile[32][33];
   const long long line = blockIdx.x;                 // (n, d, h) line index of X
   const int wt = blockIdx.y;
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(256) pack_transpose_shift_kernel(const float* 
       if (c < C && wo < Wo) {
         __nv_bfloat16 h, l;
         split_bf16(tile[threadIdx.x][j], h, l);
-        long long o = (((long long)kw * C + c) * lines + line) * Wo + wo;
+        long long o = ((long long)kw * C + c) * pitch + line * Wo + wo;
         hi[o] = h;
         if (lo) lo[o] = l;
       }
@@ -229,6 +230,7 @@ struct WgPlan {
   int Wk, swz, T, ngroups, mtiles, Npad, stages, tmem_cols;
   size_t off_yh, off_yl, off_xh, off_xl, total;
   long long rows_y, rows_x, lines_x;
+  long long pitch_y, pitch_x;   // channel-plane pitch (elements): padded so that planes do not alias in L2
   size_t copy_elems;
 };
 
@@ -257,9 +259,14 @@ static bool make_wg_plan(const cfun_conv3d_desc* d, WgPlan& pl) {
   if (pl.stages < 2) return false;
   pl.rows_y = (long long)d->N * d->Dout * d->Hout * d->Wout;
   pl.rows_x = (long long)d->N * d->Din * d->Hin * d->Win;
-  const size_t ybytes = align_up((size_t)pl.rows_y * d->Cout * 2, 1024);
+  // The planes of consecutive channels are read by consecutive rows of every TMA box; an un-padded pitch is a multiple of
+  // large powers of two for the usual extents (4 x 96^3 x 2 B = 27 x 256 KiB) and makes all rows of a box camp on the
+  // same L2 slices.  17 x 128 B of padding per plane spreads them.
+  pl.pitch_y = pl.rows_y + 1088;
+  const size_t ybytes = align_up((size_t)pl.pitch_y * d->Cout * 2, 1024);
   pl.lines_x = (long long)d->N * d->Din * d->Hin;
-  pl.copy_elems = (size_t)d->Cin * pl.lines_x * d->Wout;          // one pre-shifted copy of X (one part)
+  pl.pitch_x = pl.lines_x * d->Wout + 1088;
+  pl.copy_elems = (size_t)d->Cin * pl.pitch_x;                    // one pre-shifted copy of X (one part)
   const size_t xbytes = align_up(pl.copy_elems * 2 * d->kW, 1024);
   pl.off_yh = 0; pl.off_yl = ybytes; pl.off_xh = 2 * ybytes; pl.off_xl = 2 * ybytes + xbytes;
   pl.total = 2 * ybytes + 2 * xbytes + 2048;
@@ -280,9 +287,10 @@ size_t tc_wgrad_workspace(const cfun_conv3d_desc* d) {
   return pl.total;
 }
 
-static int encode_cmajor_map(CUtensorMap* m, void* base, int W, int H, int D, int N, int C, int Wk, int rows, int swz) {
+static int encode_cmajor_map(CUtensorMap* m, void* base, int W, int H, int D, int N, int C, int Wk, int rows, int swz,
+                             long long pitch) {
   cuuint64_t dims[5] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)C};
-  cuuint64_t strides[4] = {(cuuint64_t)W * 2, (cuuint64_t)H * W * 2, (cuuint64_t)D * H * W * 2, (cuuint64_t)N * D * H * W * 2};
+  cuuint64_t strides[4] = {(cuuint64_t)W * 2, (cuuint64_t)H * W * 2, (cuuint64_t)D * H * W * 2, (cuuint64_t)pitch * 2};
   cuuint32_t box[5] = {(cuuint32_t)Wk, 1, 1, 1, (cuuint32_t)rows};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -307,10 +315,10 @@ int tc_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* d
   __nv_bfloat16* yl = reinterpret_cast<__nv_bfloat16*>(base + pl.off_yl);
   __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(base + pl.off_xh);
   __nv_bfloat16* xl = reinterpret_cast<__nv_bfloat16*>(base + pl.off_xl);
-  pack_transpose_kernel<<<dim3((unsigned)cdiv(pl.rows_y, 32), (unsigned)cdiv(d->Cout, 32)), dim3(32, 8), 0, st>>>(dy, yh, split ? yl : nullptr, pl.rows_y, d->Cout);
+  pack_transpose_kernel<<<dim3((unsigned)cdiv(pl.rows_y, 32), (unsigned)cdiv(d->Cout, 32)), dim3(32, 8), 0, st>>>(dy, yh, split ? yl : nullptr, pl.rows_y, d->Cout, pl.pitch_y);
   CFUN_LAUNCH_CHECK();
   pack_transpose_shift_kernel<<<dim3((unsigned)pl.lines_x, (unsigned)cdiv(d->Wout, 32), (unsigned)cdiv(d->Cin, 32)), dim3(32, 8), 0, st>>>(
-      x, xh, split ? xl : nullptr, pl.lines_x, d->Win, d->Wout, d->Cin, d->kW, d->pW);
+      x, xh, split ? xl : nullptr, pl.lines_x, d->Win, d->Wout, d->Cin, d->kW, d->pW, pl.pitch_x);
   CFUN_LAUNCH_CHECK();
   const int taps = d->kD * d->kH * d->kW;
   CFUN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * d->Cin * taps, st));
@@ -318,12 +326,12 @@ int tc_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* d
   CUtensorMap myh, myl;
   XMaps xm;
   int rc;
-  if ((rc = encode_cmajor_map(&myh, yh, d->Wout, d->Hout, d->Dout, d->N, d->Cout, pl.Wk, 128, pl.swz)) != CFUN_OK) return rc;
-  if ((rc = encode_cmajor_map(&myl, split ? yl : yh, d->Wout, d->Hout, d->Dout, d->N, d->Cout, pl.Wk, 128, pl.swz)) != CFUN_OK) return rc;
+  if ((rc = encode_cmajor_map(&myh, yh, d->Wout, d->Hout, d->Dout, d->N, d->Cout, pl.Wk, 128, pl.swz, pl.pitch_y)) != CFUN_OK) return rc;
+  if ((rc = encode_cmajor_map(&myl, split ? yl : yh, d->Wout, d->Hout, d->Dout, d->N, d->Cout, pl.Wk, 128, pl.swz, pl.pitch_y)) != CFUN_OK) return rc;
   for (int kw = 0; kw < WG_MAX_KW; ++kw) {
     const int k = kw < d->kW ? kw : 0;
-    if ((rc = encode_cmajor_map(&xm.hi[kw], xh + (size_t)k * pl.copy_elems, d->Wout, d->Hin, d->Din, d->N, d->Cin, pl.Wk, pl.Npad, pl.swz)) != CFUN_OK) return rc;
-    if ((rc = encode_cmajor_map(&xm.lo[kw], (split ? xl : xh) + (size_t)k * pl.copy_elems, d->Wout, d->Hin, d->Din, d->N, d->Cin, pl.Wk, pl.Npad, pl.swz)) != CFUN_OK) return rc;
+    if ((rc = encode_cmajor_map(&xm.hi[kw], xh + (size_t)k * pl.copy_elems, d->Wout, d->Hin, d->Din, d->N, d->Cin, pl.Wk, pl.Npad, pl.swz, pl.pitch_x)) != CFUN_OK) return rc;
+    if ((rc = encode_cmajor_map(&xm.lo[kw], (split ? xl : xh) + (size_t)k * pl.copy_elems, d->Wout, d->Hin, d->Din, d->N, d->Cin, pl.Wk, pl.Npad, pl.swz, pl.pitch_x)) != CFUN_OK) return rc;
   }
 
   WgParams p;
