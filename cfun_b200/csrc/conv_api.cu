@@ -26,6 +26,8 @@ static int resolve(const cfun_conv3d_desc* d, int pass, int algo) {
   if (algo == CFUN_CONV_ALGO_AUTO) {
     const char* e = getenv("CFUN_CONV_ALGO");  // "simt" pins the CUDA-core path (debug / A-B measurements)
     if (e && e[0] == 's') return CFUN_CONV_ALGO_SIMT;
+    const char* m = getenv("CFUN_TC_PASSES");   // bit mask of passes allowed on tensor cores (1 fwd, 2 dgrad, 4 wgrad)
+    if (m && !((atoi(m) >> pass) & 1)) return CFUN_CONV_ALGO_SIMT;
     return tc_preferred(d, pass) ? CFUN_CONV_ALGO_TC : CFUN_CONV_ALGO_SIMT;
   }
   return algo;
