@@ -339,6 +339,7 @@ size_t hl_workspace(const cfun_conv3d_desc* d, int pass);
 int hl_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
             int nsplit, void* ws, size_t ws_bytes, cudaStream_t st);
 int tc_debug_read_halo(int* out8);
+int tc_debug_read_hw(int* out8);
 
 bool tc_supported(const cfun_conv3d_desc* d, int pass) {
   static int sm100 = -1;
@@ -505,6 +506,9 @@ extern "C" int cfun_tc_debug_status(int* out8_host) {
   if (rc != CFUN_OK) return rc;
   rc = tc_debug_read_halo(c);
   if (rc != CFUN_OK) return rc;
-  for (int i = 0; i < 8; ++i) out8_host[i] = a[0] ? a[i] : (b[0] ? b[i] : c[i]);
+  int e[8];
+  rc = tc_debug_read_hw(e);
+  if (rc != CFUN_OK) return rc;
+  for (int i = 0; i < 8; ++i) out8_host[i] = a[0] ? a[i] : (b[0] ? b[i] : (c[0] ? c[i] : e[i]));
   return CFUN_OK;
 }

@@ -293,6 +293,14 @@ __global__ void __launch_bounds__(256) pack_w_halo_kernel(const float* __restric
   }
 }
 
+// host-side launcher so that other translation units (conv_tc_wgrad_halo.cu) can reuse the group-planar pack
+int launch_pack_act_gp(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int C, int G, cudaStream_t st) {
+  long long total = (long long)G * N * (D + 2) * H * W;
+  pack_act_gp_kernel<<<(unsigned)std::min<long long>(cdiv(total, 256), 32LL * num_sms()), 256, 0, st>>>(x, hi, lo, N, D, H, W, C, G);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
 struct HlPlan {
   int Cs, Ct, N, D, H, W, Kp, G, CPC, Npad, tmem_cols;
   size_t off_ah, off_al, off_w, total, act_bytes, w_bytes, smem;

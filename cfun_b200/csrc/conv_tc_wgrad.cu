@@ -273,7 +273,13 @@ static bool make_wg_plan(const cfun_conv3d_desc* d, WgPlan& pl) {
   return true;
 }
 
+bool hw_supported(const cfun_conv3d_desc* d);
+size_t hw_workspace(const cfun_conv3d_desc* d);
+int hw_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, float* dbias, int nsplit,
+                       void* ws, size_t ws_bytes, cudaStream_t st);
+
 bool tc_wgrad_supported(const cfun_conv3d_desc* d) {
+  if (hw_supported(d)) return true;
   WgPlan pl;
   if (!make_wg_plan(d, pl)) return false;
   if (d->kD * d->kH * d->kW < 27) return false;
@@ -282,6 +288,7 @@ bool tc_wgrad_supported(const cfun_conv3d_desc* d) {
 }
 
 size_t tc_wgrad_workspace(const cfun_conv3d_desc* d) {
+  if (hw_supported(d)) return hw_workspace(d);
   WgPlan pl;
   if (!make_wg_plan(d, pl)) return 0;
   return pl.total;
@@ -305,6 +312,7 @@ int simt_bias_grad(const float* dy, long long M, int C, float* dbias, cudaStream
 
 int tc_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, float* dbias, int nsplit,
                        void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (hw_supported(d)) return hw_conv_bwd_weight(d, x, dy, dw, dbias, nsplit, ws, ws_bytes, st);
   WgPlan pl;
   CFUN_CHECK_ARG(make_wg_plan(d, pl));
   CFUN_CHECK_ARG(x && dy && dw && ws && get_tensor_map_encoder());
