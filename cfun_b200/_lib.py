@@ -39,6 +39,7 @@ SIGNATURES = {
     "cfun_device_is_sm100": (_i, []),
     "cfun_conv3d_workspace_size": (_sz, [_D, _i, _i]),
     "cfun_conv3d_pick_algo": (_i, [_D, _i]),
+    "cfun_conv3d_supported": (_i, [_D, _i, _i]),
     "cfun_conv3d_fwd": (_i, [_D, _p, _p, _p, _p, _i, _i, _p, _sz, _p]),
     "cfun_conv3d_bwd_data": (_i, [_D, _p, _p, _p, _i, _p, _sz, _p]),
     "cfun_conv3d_bwd_weight": (_i, [_D, _p, _p, _p, _p, _i, _p, _sz, _p]),

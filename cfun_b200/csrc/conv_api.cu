@@ -36,6 +36,12 @@ static int resolve(const cfun_conv3d_desc* d, int pass, int algo) {
 
 using namespace cfun;
 
+extern "C" int cfun_conv3d_supported(const cfun_conv3d_desc* d, int pass, int algo) {
+  if (!d) return 0;
+  if (algo == CFUN_CONV_ALGO_SIMT || algo == CFUN_CONV_ALGO_AUTO) return 1;
+  return tc_supported(d, pass) ? 1 : 0;
+}
+
 extern "C" int cfun_conv3d_pick_algo(const cfun_conv3d_desc* d, int pass) { return resolve(d, pass, CFUN_CONV_ALGO_AUTO); }
 
 extern "C" size_t cfun_conv3d_workspace_size(const cfun_conv3d_desc* d, int pass, int algo) {

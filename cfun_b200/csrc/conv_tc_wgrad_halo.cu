@@ -199,12 +199,13 @@ static bool make_hw_plan(const cfun_conv3d_desc* d, HwPlan& pl) {
   if (cols > 512) return false;
   pl.tmem_cols = cols;
   const int gy = std::min(pl.Gy_total, 16);
-  // M = 128 reads 16 channel-group planes of the dY tile region; keep all of them inside the stage
-  const size_t stage = 2 * ((size_t)16 * HW_YP + (size_t)pl.Gx * HW_XP);
-  (void)gy;
-  pl.stages = (int)std::min<size_t>(4, (200 * 1024) / stage);
+  const size_t stage = 2 * ((size_t)gy * HW_YP + (size_t)pl.Gx * HW_XP);
+  // M = 128 makes the MMA read 16 channel-group planes from the dY tile base; the planes beyond the real ones only feed
+  // accumulator rows that are never read back, but they must lie inside the allocation: 36 KB of slack after the ring
+  const size_t slack = 36 * 1024;
+  pl.stages = (int)std::min<size_t>(4, (224 * 1024 - 2048 - slack) / stage);
   if (pl.stages < 2) return false;
-  pl.smem = 2048 + pl.stages * stage;
+  pl.smem = 2048 + pl.stages * stage + slack;
   pl.act_y = align_up((size_t)pl.Gy_total * d->N * (d->Dout + 2) * d->Hout * d->Wout * 16, 1024);
   pl.act_x = align_up((size_t)pl.Gx * d->N * (d->Din + 2) * d->Hin * d->Win * 16, 1024);
   pl.off_yh = 0; pl.off_yl = pl.act_y; pl.off_xh = 2 * pl.act_y; pl.off_xl = 2 * pl.act_y + pl.act_x;

@@ -112,6 +112,11 @@ def _conv_desc(x_shape, w_shape, stride, padding):
     return ConvDesc(N, Cin, D, H, W, Cout, Do, Ho, Wo, kD, kH, kW, s[0], s[1], s[2], p[0], p[1], p[2])
 
 
+def conv3d_supported(x_shape, w_shape, stride, padding, pass_id, algo):
+    d = _conv_desc(tuple(x_shape), tuple(w_shape), stride, padding)
+    return bool(lib.cfun_conv3d_supported(C.byref(d), pass_id, algo))
+
+
 _default_algo = {"algo": ALGO_AUTO}
 
 

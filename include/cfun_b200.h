@@ -64,6 +64,8 @@ typedef struct {
 size_t cfun_conv3d_workspace_size(const cfun_conv3d_desc* d, int pass, int algo);
 /* which algorithm AUTO resolves to for (desc, pass): one of CFUN_CONV_ALGO_{SIMT,TC} */
 int cfun_conv3d_pick_algo(const cfun_conv3d_desc* d, int pass);
+/* 1 when `algo` can execute (desc, pass) on the current device */
+int cfun_conv3d_supported(const cfun_conv3d_desc* d, int pass, int algo);
 int cfun_conv3d_fwd(const cfun_conv3d_desc* d, const float* x, const float* w, const float* bias, float* y,
                     int epi_flags, int algo, void* ws, size_t ws_bytes, void* stream);
 int cfun_conv3d_bwd_data(const cfun_conv3d_desc* d, const float* dy, const float* w, float* dx, int algo, void* ws,

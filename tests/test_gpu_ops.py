@@ -356,11 +356,8 @@ def test_conv3d_tcgen05_fwd_dgrad(ops, case):
         dy = dy * (yr.detach().abs() > 1e-3).float()
         yr = F.relu(yr)
     yr.backward(dy)
-    # the weight gradient kernel needs W % 8 == 0 (TMA stride rule) and Cin <= 256; otherwise only fwd + dgrad run on TC
-    import os
-    halo_ok = (k == 3 and p == 1 and Cin >= 16 and Cin % 4 == 0 and Cout % 4 == 0 and Cin <= 256 and min(H, W) >= 8
-               and os.environ.get("CFUN_TC_HALO", "1") != "0")          # conv_tc_wgrad_halo.cu: any W
-    wgrad_tc = halo_ok or ((W % 8 == 0) and ((W + 2 * p - k + 1) % 8 == 0) and Cin <= 256)
+    # the weight gradient runs on tensor cores where a kernel supports the shape; otherwise only fwd + dgrad do
+    wgrad_tc = ops.conv3d_supported(x.shape, w.shape, 1, p, ops.PASS_BWD_WEIGHT, ops.ALGO_TC)
     ops.set_conv_algo(ops.ALGO_TC)
     try:
         xc = x.cuda().requires_grad_(True)

@@ -108,7 +108,16 @@ def main():
                 s.record()
                 yy.backward(gy)
                 e.record(); torch.cuda.synchronize()
-                print("     %-6s bwd (dgrad+wgrad) %.3f ms" % (nm, s.elapsed_time(e)))
+                print("     %-6s bwd (dgrad+wgrad) %.3f ms  debug_status %s" % (nm, s.elapsed_time(e), ops.tc_debug_status()))
+                if algo == ops.ALGO_TC:
+                    ref_w = wg.grad.clone()
+                    ops.set_conv_algo(ops.ALGO_SIMT)
+                    xg2 = x.clone().requires_grad_(True); wg2 = w.clone().requires_grad_(True)
+                    ops.conv3d(xg2, wg2, None, 1, 1).backward(gy)
+                    torch.cuda.synchronize()
+                    print("     full-size check vs CUDA-core path: dw rel %.2e  dx rel %.2e" % (
+                        float((ref_w - wg2.grad).abs().max() / wg2.grad.abs().max()),
+                        float((xg.grad - xg2.grad).abs().max() / xg2.grad.abs().max())))
             except Exception as ex:
                 print("time", nm, "EXC", ex)
             finally:
