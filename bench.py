@@ -261,17 +261,21 @@ def run_ours(args):
     net = net.to(dev)
     anchors_np = net.anchors.cpu().numpy()
     pool = []
-    for i in range(1):
-        vol, _ = synth_volume(dim, 1000 + rank * 10007 + i, cube)
+    vol_seed = None
+    for attempt in range(32):       # a volume whose untrained proposals admit a 4-positive label placement (off the clock)
+        vol_seed = 1000 + rank * 10007 + attempt
+        vol, _ = synth_volume(dim, vol_seed, cube)
         with torch.no_grad():
             img = ops.mold_volume_i16(torch.from_numpy(vol).to(dev))
             rois = net.rpn_proposals(img, "training")[5][0]
         placed = place_label_cube(rois.cpu().numpy(), dim)
-        if placed is None:
-            raise RuntimeError("no label placement gives 4 positive RoIs (rank %d)" % rank)
-        lab = label_from_cube(dim, placed[0], placed[1], 1000 + i)
-        pool.append(StepInputs(cfg, anchors_np, dim, 1000 + rank * 10007 + i, cube, vol=vol, lab=lab))
         del img, rois
+        if placed is not None:
+            lab = label_from_cube(dim, placed[0], placed[1], vol_seed)
+            pool.append(StepInputs(cfg, anchors_np, dim, vol_seed, cube, vol=vol, lab=lab))
+            break
+    if not pool:
+        raise RuntimeError("no synthetic volume admits a 4-positive label placement (rank %d)" % rank)
     weight_seed = WEIGHT_SEED
     opt = net.make_optimizer(cfg.LEARNING_RATE)
     if world > 1:   # identical replicas: broadcast rank 0's parameters once
@@ -395,7 +399,7 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "MM-WHS-shape %d^3 synthetic int16 CT, 8-class heart, full train step (fwd+bwd+clip+SGD), stage %s, 1 volume/GPU/step" % (dim, args.stage),
-                   "parallelism": "dp%d" % world, "positives": pos, "rois": rois, "roi_counts_per_timed_step": roi_counts, "weight_seed": weight_seed,
+                   "parallelism": "dp%d" % world, "positives": pos, "rois": rois, "roi_counts_per_timed_step": roi_counts, "weight_seed": weight_seed, "volume_seed": vol_seed,
                    "conv_algo": args.conv_algo, "cuda_graphs": (not args.no_graphs), "l2": "per-step working set (~10 GB of activations) exceeds the 126 MB L2; no explicit flush",
                    "losses_last_step": losses},
         "step_tflop": STEP_TFLOP_PER_VOLUME, "achieved_step_tflops": value * STEP_TFLOP_PER_VOLUME / max(world, 1),
