@@ -29,7 +29,19 @@ def _digest():
 
 
 def build(force=False, verbose=False):
+    """Idempotent and safe under concurrent callers (one rank per GPU imports the package at the same time): an
+    exclusive file lock serialises the build, objects go to a private directory and the library is renamed into place."""
+    import fcntl
     os.makedirs(LIBDIR, exist_ok=True)
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force, verbose):
     stamp = os.path.join(LIBDIR, "build.sha256")
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
@@ -53,8 +65,10 @@ def build(force=False, verbose=False):
         fh.write("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed; see messages above")
-    subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs +
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs +
                           ["-lcudart_static", "-ldl", "-lrt", "-lpthread"])
+    os.replace(tmp, LIB)
     with open(stamp, "w") as fh:
         fh.write(dig)
     if verbose:

@@ -13,7 +13,11 @@
 // Weights stream through a 3-stage ring as contiguous 16-B-row planes (one stage = one K-chunk x one kd plane of 9 taps).
 // Persistent CTAs, TMEM accumulator double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1; the halo ring
 // is per K-chunk, so chunk c of tile i+1 loads while chunks c+1.. of tile i are still being consumed.
-// Split-bf16 x3 arithmetic as in conv_tc.cu.  The data gradient is the same kernel with flipped / transposed weights.
+// Split-bf16 x3 arithmetic as in conv_tc.cu, issued as TWO MMAs per (tap, K-chunk): the weight tile holds the hi rows and
+// the lo rows back to back, so  A_hi x [B_hi ; B_lo]  is one N = 2*Npad instruction (hi*hi and hi*lo land in adjacent
+// accumulator column ranges, summed in the epilogue) and  A_lo x B_hi  a second N = Npad instruction.  The kernel is
+// shared-memory-bandwidth bound on the 4 KB A operand (ncu: tensor pipe 27 % active, SM throughput 74 %), and this reads A
+// twice instead of three times.  The data gradient is the same kernel with flipped / transposed weights.
 #include "tc_ptx.cuh"
 #include <cstdlib>
 
@@ -61,7 +65,7 @@ struct HlParams {
   int epi;
   const float* bias;
   float* y;
-  const uint8_t* wpack;       // [chunk][kd][part][tap9][kgroup2][Npad][8] bf16
+  const uint8_t* wpack;       // [chunk][kd][tap9][kgroup2][part][Npad][8] bf16 (hi rows, then lo rows)
 };
 
 __global__ void __launch_bounds__(HL_THREADS, 1)
@@ -79,8 +83,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int parts = p.nsplit == 3 ? 2 : 1;
   const int a_slot_bytes = parts * 2 * HL_PLANE;                  // one K chunk: 2 channel groups x parts
-  const int b_part_bytes = 9 * 2 * p.Npad * 16;
-  const int b_stage_bytes = parts * b_part_bytes;
+  const int nrows = parts * p.Npad;                               // weight rows per K-group: hi rows then lo rows
+  const int b_stage_bytes = 9 * 2 * nrows * 16;
   uint8_t* a_ring = base;
   uint8_t* b_ring = base + (size_t)p.CPC * a_slot_bytes;
 
@@ -124,9 +128,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
             const int st = (int)(bcount % HL_BSTAGES);
             mbar_wait(&b_empty[st], (uint32_t)(((bcount / HL_BSTAGES) & 1) ^ 1), 220);
             mbar_arrive_expect_tx(&b_full[st], (uint32_t)b_stage_bytes);
-            const uint8_t* src = p.wpack + ((size_t)(c * 3 + kd)) * (size_t)(parts * b_part_bytes);
-            bulk_load(b_ring + (size_t)st * b_stage_bytes, src, (uint32_t)b_part_bytes, &b_full[st]);
-            if (parts == 2) bulk_load(b_ring + (size_t)st * b_stage_bytes + b_part_bytes, src + b_part_bytes, (uint32_t)b_part_bytes, &b_full[st]);
+            const uint8_t* src = p.wpack + ((size_t)(c * 3 + kd)) * (size_t)b_stage_bytes;
+            bulk_load(b_ring + (size_t)st * b_stage_bytes, src, (uint32_t)b_stage_bytes, &b_full[st]);
           }
         }
       }
@@ -134,7 +137,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc_n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc_2n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nrows >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_ring);
       uint32_t bcount = 0;
       int local = 0;
@@ -142,7 +146,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
         const int buf = local & 1;
         mbar_wait(&t_empty[buf], (uint32_t)(((local >> 1) & 1) ^ 1), 230);
         tc_fence_after();
-        const uint32_t dcol = tmem_base + (uint32_t)(buf * p.Npad);
+        const uint32_t dcol = tmem_base + (uint32_t)(buf * nrows);
         uint32_t acc = 0;
         for (int c = 0; c < p.CPC; ++c) {
           mbar_wait(&a_full[c], (uint32_t)(local & 1), 240);
@@ -158,15 +162,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
               const int kh = t9 / 3, kw = t9 - kh * 3;
               const uint32_t aoff = (uint32_t)(((kd * HL_HH + kh) * HL_WH + kw) * 16);
               const uint64_t a_hi = make_desc_interleave(aslot + aoff, HL_PLANE, HL_WH * 16);
-              const uint64_t b_hi = make_desc_interleave(bst + (uint32_t)(t9 * 2 * p.Npad * 16), (uint32_t)(p.Npad * 16), 128);
-              umma_bf16(dcol, a_hi, b_hi, idesc, acc);
-              acc = 1;
+              const uint64_t b_all = make_desc_interleave(bst + (uint32_t)(t9 * 2 * nrows * 16), (uint32_t)(nrows * 16), 128);
+              umma_bf16(dcol, a_hi, b_all, idesc_2n, acc);      // [hi*hi | hi*lo] into columns [0,N) and [N,2N)
               if (parts == 2) {
                 const uint64_t a_lo = make_desc_interleave(aslot + 2 * HL_PLANE + aoff, HL_PLANE, HL_WH * 16);
-                const uint64_t b_lo = make_desc_interleave(bst + (uint32_t)b_part_bytes + (uint32_t)(t9 * 2 * p.Npad * 16), (uint32_t)(p.Npad * 16), 128);
-                umma_bf16(dcol, a_lo, b_hi, idesc, 1);
-                umma_bf16(dcol, a_hi, b_lo, idesc, 1);
+                umma_bf16(dcol, a_lo, b_all, idesc_n, 1);       // lo*hi: the same tile, first Npad rows only
               }
+              acc = 1;
             }
             umma_commit(&b_empty[st]);
           }
@@ -195,14 +197,16 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
       mbar_wait(&t_full[buf], (uint32_t)((local >> 1) & 1), 260);
       tc_fence_after();
       for (int j = 0; j < p.Npad; j += 16) {
-        uint32_t r[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.Npad + j), r);
+        uint32_t r[16], r2[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * nrows + j), r);
+        if (parts == 2) tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * nrows + p.Npad + j), r2);
         tmem_ld_wait();
         if (ok) {
           float v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             float f = __uint_as_float(r[i]);
+            if (parts == 2) f += __uint_as_float(r2[i]);
             if ((p.epi & CFUN_EPI_BIAS) && j + i < p.Cout) f += __ldg(p.bias + j + i);
             if (p.epi & CFUN_EPI_RELU) f = fmaxf(f, 0.f);
             v[i] = f;
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(256) pack_act_gp_kernel(const float* __restric
   }
 }
 
-// w (Cout, Cin, 27) fp32 -> [chunk][kd][part][tap9][kgroup2][Npad][8] bf16.  mode 1 = data gradient (rows = ci, k = co,
+// w (Cout, Cin, 27) fp32 -> [chunk][kd][tap9][kgroup2][part][Npad][8] bf16.  mode 1 = data gradient (rows = ci, k = co,
 // taps mirrored).
 __global__ void __launch_bounds__(256) pack_w_halo_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout,
                                                           int Cin, int Npad, int CPC, int parts, int mode) {
@@ -275,9 +279,9 @@ __global__ void __launch_bounds__(256) pack_w_halo_kernel(const float* __restric
     long long r = i;
     const int e = (int)(r % 8); r /= 8;
     const int row = (int)(r % Npad); r /= Npad;
+    const int part = (int)(r % parts); r /= parts;
     const int kg = (int)(r % 2); r /= 2;
     const int t9 = (int)(r % 9); r /= 9;
-    const int part = (int)(r % parts); r /= parts;
     const int kd = (int)(r % 3); r /= 3;
     const int c = (int)r;
     const int k = c * 16 + kg * 8 + e;
@@ -320,9 +324,9 @@ static bool make_hl_plan(const cfun_conv3d_desc* d, int pass, HlPlan& pl) {
   pl.CPC = pl.Kp / 16;
   if (pl.CPC > HL_MAX_CPC) return false;
   pl.Npad = (int)align_up((size_t)pl.Ct, 16);
-  if (pl.Npad > 256) return false;
+  if (pl.Npad > 128) return false;                         // [hi | lo] accumulator pairs, double buffered: 4 * Npad <= 512
   int cols = 32;
-  while (cols < 2 * pl.Npad) cols <<= 1;
+  while (cols < 4 * pl.Npad) cols <<= 1;
   pl.tmem_cols = cols;
   const size_t a_bytes = (size_t)pl.CPC * 2 * 2 * HL_PLANE;
   const size_t b_bytes = (size_t)HL_BSTAGES * 2 * 9 * 2 * pl.Npad * 16;
