@@ -347,6 +347,23 @@ def run_ours(args):
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     ms_e2e = float(t2.item())
 
+    if args.profile_calls and rank == 0:   # off the clock: one eager step with per-library-call CUDA-event timing
+        net.enable_graphs(False)
+        ops.profile_start()
+        run_step(net.train_step_device, *dev_inputs[0])
+        rows = ops.profile_stop()
+        agg = {}
+        for name, tag, t in rows:
+            a = agg.setdefault((name, tag), [0, 0.0])
+            a[0] += 1
+            a[1] += t
+        tot = sum(t for _, _, t in rows)
+        with open(args.profile_calls, "w") as f:
+            f.write("# library calls of one eager train step, CUDA-event time per call (includes inter-call gaps on the stream)\n")
+            f.write("# total %.2f ms over %d calls\n" % (tot, len(rows)))
+            for (name, tag), (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                f.write("%8.3f ms %5.1f%% x%-4d %s %s\n" % (t, 100 * t / tot, n, name, tag))
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

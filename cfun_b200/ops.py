@@ -86,8 +86,36 @@ def workspace(nbytes, device):
     return buf
 
 
-def _run(name, *args):
+_prof = {"on": False, "rows": []}
+
+
+def profile_start():
+    """Per-call device timing of every library call (CUDA events on the current stream); for tools/, never for bench."""
+    _prof["on"], _prof["rows"] = True, []
+
+
+def profile_stop():
+    """-> list of (entry point, tag, milliseconds); tag carries the conv geometry and the algorithm picked."""
+    _prof["on"] = False
+    torch.cuda.synchronize()
+    return [(n, t, a.elapsed_time(b)) for n, t, a, b in _prof["rows"]]
+
+
+def _conv_tag(d, pass_id, algo):
+    picked = lib.cfun_conv3d_pick_algo(C.byref(d), pass_id) if algo == ALGO_AUTO else algo
+    return "N%d %d->%d in%dx%dx%d k%d%d%d s%d%d%d algo%d" % (d.N, d.Cin, d.Cout, d.Din, d.Hin, d.Win, d.kD, d.kH, d.kW,
+                                                          d.sD, d.sH, d.sW, picked)
+
+
+def _run(name, *args, tag=""):
     _calls["n"] += 1
+    if _prof["on"]:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        check(getattr(lib, name)(*args), name)
+        b.record()
+        _prof["rows"].append((name, tag, a, b))
+        return
     check(getattr(lib, name)(*args), name)
 
 
@@ -137,7 +165,8 @@ class Conv3dFn(Function):
         ws_bytes = lib.cfun_conv3d_workspace_size(C.byref(d), PASS_FWD, algo)
         ws = workspace(ws_bytes, x.device)
         epi = (EPI_BIAS if b is not None else 0) | (EPI_RELU if relu else 0)
-        _run("cfun_conv3d_fwd", C.byref(d), _ptr(x), _ptr(w), _ptr(b), _ptr(y), epi, algo, _ptr(ws), ws.numel(), _stream())
+        _run("cfun_conv3d_fwd", C.byref(d), _ptr(x), _ptr(w), _ptr(b), _ptr(y), epi, algo, _ptr(ws), ws.numel(), _stream(),
+             tag=_conv_tag(d, PASS_FWD, algo) if _prof["on"] else "")
         ctx.d = d
         ctx.relu = relu
         ctx.has_bias = b is not None
@@ -157,14 +186,15 @@ class Conv3dFn(Function):
             dx = empty_cl(d.N, d.Cin, d.Din, d.Hin, d.Win, dy.device)
             ws_bytes = lib.cfun_conv3d_workspace_size(C.byref(d), PASS_BWD_DATA, ctx.algo)
             ws = workspace(ws_bytes, dy.device)
-            _run("cfun_conv3d_bwd_data", C.byref(d), _ptr(dy), _ptr(w), _ptr(dx), ctx.algo, _ptr(ws), ws.numel(), _stream())
+            _run("cfun_conv3d_bwd_data", C.byref(d), _ptr(dy), _ptr(w), _ptr(dx), ctx.algo, _ptr(ws), ws.numel(), _stream(),
+                 tag=_conv_tag(d, PASS_BWD_DATA, ctx.algo) if _prof["on"] else "")
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw = torch.empty_like(w)
             db = torch.empty(d.Cout, device=dy.device) if ctx.has_bias else None
             ws_bytes = lib.cfun_conv3d_workspace_size(C.byref(d), PASS_BWD_WEIGHT, ctx.algo)
             ws = workspace(ws_bytes, dy.device)
             _run("cfun_conv3d_bwd_weight", C.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), ctx.algo, _ptr(ws),
-                 ws.numel(), _stream())
+                 ws.numel(), _stream(), tag=_conv_tag(d, PASS_BWD_WEIGHT, ctx.algo) if _prof["on"] else "")
         return dx, dw, db, None, None, None
 
 
