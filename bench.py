@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--image-dim", type=int, default=256)
     ap.add_argument("--stage", default="beginning")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-calls", default=None, help="write a per-library-call timing table of one eager step here")
     ap.add_argument("--conv-algo", default="auto", choices=["auto", "simt", "tc", "tc1"])
     ap.add_argument("--no-graphs", action="store_true", help="run the heads eagerly instead of as CUDA graphs")
     return ap.parse_args()
