@@ -722,7 +722,11 @@ class MaskRCNN(nn.Module):
                 rois.detach().clone(), p_rois.detach().clone(), tcls.clone(), tdel.clone(), tmask.clone()) + \
             tuple(dm.clone() for dm in drops)
         n0 = launch_count()
-        graphed = torch.cuda.make_graphed_callables(self._tail, args, num_warmup_iters=1, allow_unused_input=True)
+        # make_graphed_callables patches an nn.Module's forward in place: capture a fresh HeadsTail per RoI split (it only
+        # references the shared classifier / mask modules) so that self._tail stays the eager path
+        fresh = HeadsTail(self.classifier, self.mask, self.config.STAGE)
+        fresh.train(self.training)
+        graphed = torch.cuda.make_graphed_callables(fresh, args, num_warmup_iters=1, allow_unused_input=True)
         # kernels per replay (forward + backward): launches during capture = (1 warm-up + 1 capture) iterations
         self.graph_kernel_counts[(P, R)] = (launch_count() - n0) // 2
         self._graphed_tails[(P, R)] = graphed
