@@ -130,9 +130,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, elected lane issues: tc_ptx.cuh "issue-rate note") ==========
+    {
+      const uint32_t leader = elect_one();
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t hiword = (uint32_t)(make_desc_sw32(0) >> 32);
+      const uint32_t lbo1 = 1u << 16;
       int q = 0;
       uint32_t acc = 0;
       for (int it = 0; it < nstage_iters; ++it) {
@@ -142,22 +145,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
         tc_fence_after();
         const int nch = min(TC_KCH, total_chunks - q);
         const uint32_t sbase = smem_u32(ring + (size_t)slot * stage_bytes);
-        for (int c = 0; c < nch; ++c, ++q) {
-          const uint32_t cb = sbase + (uint32_t)(c * chunk_bytes);
-          const uint64_t a_hi = make_desc_sw32(cb);
-          const uint64_t b_hi = make_desc_sw32(cb + parts * TC_A_BYTES);
-          umma_bf16(tmem_base, a_hi, b_hi, idesc, acc);
-          acc = 1;
-          if (parts == 2) {
-            const uint64_t a_lo = make_desc_sw32(cb + TC_A_BYTES);
-            const uint64_t b_lo = make_desc_sw32(cb + 2 * TC_A_BYTES + b_bytes);
-            umma_bf16(tmem_base, a_lo, b_hi, idesc, 1);
-            umma_bf16(tmem_base, a_hi, b_lo, idesc, 1);
+#pragma unroll
+        for (int c = 0; c < TC_KCH; ++c) {
+          if (c < nch) {
+            const uint32_t cb = ((sbase + (uint32_t)(c * chunk_bytes)) >> 4) | lbo1;
+            const uint64_t a_hi = desc_join(hiword, cb);
+            const uint64_t b_hi = desc_join(hiword, cb + (uint32_t)((parts * TC_A_BYTES) >> 4));
+            if (leader) {
+              umma_bf16(tmem_base, a_hi, b_hi, idesc, acc);
+              if (parts == 2) {
+                const uint64_t a_lo = desc_join(hiword, cb + (uint32_t)(TC_A_BYTES >> 4));
+                const uint64_t b_lo = desc_join(hiword, cb + (uint32_t)((2 * TC_A_BYTES + b_bytes) >> 4));
+                umma_bf16_acc(tmem_base, a_lo, b_hi, idesc);
+                umma_bf16_acc(tmem_base, a_hi, b_lo, idesc);
+              }
+            }
+            acc = 1;
           }
         }
-        umma_commit(&empty_bar[slot]);   // frees the smem stage once the MMAs above have consumed it
+        q += nch;
+        if (leader) umma_commit(&empty_bar[slot]);   // frees the smem stage once the MMAs above have consumed it
+        __syncwarp();
       }
-      umma_commit(tmem_full_bar);        // accumulator complete
+      if (leader) umma_commit(tmem_full_bar);        // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> global =====================
@@ -340,6 +351,7 @@ int hl_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* 
             int nsplit, void* ws, size_t ws_bytes, cudaStream_t st);
 int tc_debug_read_halo(int* out8);
 int tc_debug_read_hw(int* out8);
+int tc_debug_read_ds(int* out8);
 
 bool tc_supported(const cfun_conv3d_desc* d, int pass) {
   static int sm100 = -1;
@@ -509,6 +521,9 @@ extern "C" int cfun_tc_debug_status(int* out8_host) {
   int e[8];
   rc = tc_debug_read_hw(e);
   if (rc != CFUN_OK) return rc;
-  for (int i = 0; i < 8; ++i) out8_host[i] = a[0] ? a[i] : (b[0] ? b[i] : (c[0] ? c[i] : e[i]));
+  int f[8];
+  rc = tc_debug_read_ds(f);
+  if (rc != CFUN_OK) return rc;
+  for (int i = 0; i < 8; ++i) out8_host[i] = a[0] ? a[i] : (b[0] ? b[i] : (c[0] ? c[i] : (e[0] ? e[i] : f[i])));
   return CFUN_OK;
 }

@@ -135,11 +135,17 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, elected lane issues: tc_ptx.cuh "issue-rate note") ==========
+    {
+      const uint32_t leader = elect_one();
       const uint32_t idesc_n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t idesc_2n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nrows >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_ring);
+      // descriptor = constant high word (SBO, version) | low word (start address >> 4, LBO >> 4 in bits 16..29)
+      const uint32_t a_hiword = (uint32_t)(make_desc_interleave(0, HL_PLANE, HL_WH * 16) >> 32);
+      const uint32_t b_hiword = (uint32_t)(make_desc_interleave(0, (uint32_t)(nrows * 16), 128) >> 32);
+      const uint32_t a_lbo = (uint32_t)(HL_PLANE >> 4) << 16, b_lbo = (uint32_t)nrows << 16;
+      const uint32_t b_tap = (uint32_t)(2 * nrows);                 // 16-byte rows per tap in a weight stage
       uint32_t bcount = 0;
       int local = 0;
       for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++local) {
@@ -151,30 +157,34 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
         for (int c = 0; c < p.CPC; ++c) {
           mbar_wait(&a_full[c], (uint32_t)(local & 1), 240);
           tc_fence_after();
-          const uint32_t aslot = a_base + (uint32_t)(c * a_slot_bytes);
+          const uint32_t a_hi0 = ((a_base + (uint32_t)(c * a_slot_bytes)) >> 4) | a_lbo;
+          const uint32_t a_lo0 = a_hi0 + (uint32_t)((2 * HL_PLANE) >> 4);
           for (int kd = 0; kd < 3; ++kd, ++bcount) {
             const int st = (int)(bcount % HL_BSTAGES);
             mbar_wait(&b_full[st], (uint32_t)((bcount / HL_BSTAGES) & 1), 250);
             tc_fence_after();
-            const uint32_t bst = b_base + (uint32_t)(st * b_stage_bytes);
-#pragma unroll 1
+            const uint32_t b0 = ((b_base + (uint32_t)(st * b_stage_bytes)) >> 4) | b_lbo;
+            const uint32_t a_kd = (uint32_t)(kd * HL_HH * HL_WH);
+#pragma unroll
             for (int t9 = 0; t9 < 9; ++t9) {
-              const int kh = t9 / 3, kw = t9 - kh * 3;
-              const uint32_t aoff = (uint32_t)(((kd * HL_HH + kh) * HL_WH + kw) * 16);
-              const uint64_t a_hi = make_desc_interleave(aslot + aoff, HL_PLANE, HL_WH * 16);
-              const uint64_t b_all = make_desc_interleave(bst + (uint32_t)(t9 * 2 * nrows * 16), (uint32_t)(nrows * 16), 128);
-              umma_bf16(dcol, a_hi, b_all, idesc_2n, acc);      // [hi*hi | hi*lo] into columns [0,N) and [N,2N)
-              if (parts == 2) {
-                const uint64_t a_lo = make_desc_interleave(aslot + 2 * HL_PLANE + aoff, HL_PLANE, HL_WH * 16);
-                umma_bf16(dcol, a_lo, b_all, idesc_n, 1);       // lo*hi: the same tile, first Npad rows only
+              const uint32_t aoff = a_kd + (uint32_t)((t9 / 3) * HL_WH + (t9 % 3));     // halo row of tap (kd, kh, kw)
+              const uint64_t a_hi = desc_join(a_hiword, a_hi0 + aoff);
+              const uint64_t b_all = desc_join(b_hiword, b0 + (uint32_t)t9 * b_tap);
+              if (leader) {
+                if (t9 == 0) umma_bf16(dcol, a_hi, b_all, idesc_2n, acc);   // [hi*hi | hi*lo] into columns [0,N) and [N,2N)
+                else umma_bf16_acc(dcol, a_hi, b_all, idesc_2n);
+                if (parts == 2) umma_bf16_acc(dcol, desc_join(a_hiword, a_lo0 + aoff), b_all, idesc_n);   // lo*hi: first Npad rows only
               }
-              acc = 1;
             }
-            umma_commit(&b_empty[st]);
+            acc = 1;
+            if (leader) umma_commit(&b_empty[st]);
+            __syncwarp();
           }
-          umma_commit(&a_empty[c]);
+          if (leader) umma_commit(&a_empty[c]);
+          __syncwarp();
         }
-        umma_commit(&t_full[buf]);
+        if (leader) umma_commit(&t_full[buf]);
+        __syncwarp();
       }
     }
   } else {

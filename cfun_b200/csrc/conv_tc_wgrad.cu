@@ -107,36 +107,47 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);
-      const int ksteps = p.Wk / 16;
-      for (int it = 0; it < niter; ++it) {
-        const int slot = it % p.stages;
-        const uint32_t ph = (uint32_t)((it / p.stages) & 1);
-        mbar_wait(&full_bar[slot], ph, 120);
-        tc_fence_after();
-        const uint32_t sb = smem_u32(ring + (size_t)slot * stage_bytes);
-        const uint32_t bb = sb + parts * a_bytes;
-        const uint32_t acc = it > 0 ? 1u : 0u;
-        for (int t = 0; t < ntap && !(p.debug_skip & 2); ++t) {
-          const uint32_t dcol = tmem_base + (uint32_t)(t * p.Npad);
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t koff = (uint32_t)(ks * 32);   // 16 bf16 along K inside the swizzled row
-            const uint64_t a_hi = make_desc_kmajor(sb + koff, p.swz);
-            const uint64_t b_hi = make_desc_kmajor(bb + (uint32_t)((t * parts) * b_bytes) + koff, p.swz);
-            umma_bf16(dcol, a_hi, b_hi, idesc, (acc | (uint32_t)(ks > 0)));
-            if (parts == 2) {
-              const uint64_t a_lo = make_desc_kmajor(sb + a_bytes + koff, p.swz);
-              const uint64_t b_lo = make_desc_kmajor(bb + (uint32_t)((t * parts + 1) * b_bytes) + koff, p.swz);
-              umma_bf16(dcol, a_lo, b_hi, idesc, 1);
-              umma_bf16(dcol, a_hi, b_lo, idesc, 1);
+    // warp-uniform issue loop, elected lane issues (tc_ptx.cuh "issue-rate note")
+    const uint32_t leader = elect_one();
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t hiword = (uint32_t)(make_desc_kmajor(0, p.swz) >> 32);
+    const uint32_t lbo1 = 1u << 16;
+    const int ksteps = p.Wk / 16;
+    for (int it = 0; it < niter; ++it) {
+      const int slot = it % p.stages;
+      const uint32_t ph = (uint32_t)((it / p.stages) & 1);
+      mbar_wait(&full_bar[slot], ph, 120);
+      tc_fence_after();
+      const uint32_t sb = (smem_u32(ring + (size_t)slot * stage_bytes) >> 4) | lbo1;
+      const uint32_t bb = sb + (uint32_t)((parts * a_bytes) >> 4);
+      const uint32_t acc = it > 0 ? 1u : 0u;
+      for (int t = 0; t < ntap && !(p.debug_skip & 2); ++t) {
+        const uint32_t dcol = tmem_base + (uint32_t)(t * p.Npad);
+        const uint32_t bt = bb + (uint32_t)(((t * parts) * b_bytes) >> 4);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          if (ks < ksteps) {
+            const uint32_t koff = (uint32_t)(ks * 2);   // 16 bf16 (32 B) along K inside the swizzled row
+            const uint64_t a_hi = desc_join(hiword, sb + koff);
+            const uint64_t b_hi = desc_join(hiword, bt + koff);
+            if (leader) {
+              if (ks == 0) umma_bf16(dcol, a_hi, b_hi, idesc, acc);
+              else umma_bf16_acc(dcol, a_hi, b_hi, idesc);
+              if (parts == 2) {
+                const uint64_t a_lo = desc_join(hiword, sb + (uint32_t)(a_bytes >> 4) + koff);
+                const uint64_t b_lo = desc_join(hiword, bt + (uint32_t)(b_bytes >> 4) + koff);
+                umma_bf16_acc(dcol, a_lo, b_hi, idesc);
+                umma_bf16_acc(dcol, a_hi, b_lo, idesc);
+              }
             }
           }
         }
-        umma_commit(&empty_bar[slot]);
       }
-      umma_commit(tmem_full_bar);
+      if (leader) umma_commit(&empty_bar[slot]);
+      __syncwarp();
     }
+    if (leader) umma_commit(tmem_full_bar);
+    __syncwarp();
   } else {
     const int quad = warp & 3;
     const int co = m0 + quad * 32 + lane;
@@ -273,13 +284,17 @@ static bool make_wg_plan(const cfun_conv3d_desc* d, WgPlan& pl) {
   return true;
 }
 
+bool ds_supported(const cfun_conv3d_desc* d);     // conv_tc_wgrad_ds.cu (d-stacked, thin channels)
+size_t ds_workspace(const cfun_conv3d_desc* d);
+int ds_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, float* dbias, int nsplit,
+                       void* ws, size_t ws_bytes, cudaStream_t st);
 bool hw_supported(const cfun_conv3d_desc* d);
 size_t hw_workspace(const cfun_conv3d_desc* d);
 int hw_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, float* dbias, int nsplit,
                        void* ws, size_t ws_bytes, cudaStream_t st);
 
 bool tc_wgrad_supported(const cfun_conv3d_desc* d) {
-  if (hw_supported(d)) return true;
+  if (ds_supported(d) || hw_supported(d)) return true;
   WgPlan pl;
   if (!make_wg_plan(d, pl)) return false;
   if (d->kD * d->kH * d->kW < 27) return false;
@@ -288,6 +303,7 @@ bool tc_wgrad_supported(const cfun_conv3d_desc* d) {
 }
 
 size_t tc_wgrad_workspace(const cfun_conv3d_desc* d) {
+  if (ds_supported(d)) return ds_workspace(d);
   if (hw_supported(d)) return hw_workspace(d);
   WgPlan pl;
   if (!make_wg_plan(d, pl)) return 0;
@@ -312,6 +328,7 @@ int simt_bias_grad(const float* dy, long long M, int C, float* dbias, cudaStream
 
 int tc_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, float* dbias, int nsplit,
                        void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (ds_supported(d)) return ds_conv_bwd_weight(d, x, dy, dw, dbias, nsplit, ws, ws_bytes, st);
   if (hw_supported(d)) return hw_conv_bwd_weight(d, x, dy, dw, dbias, nsplit, ws, ws_bytes, st);
   WgPlan pl;
   CFUN_CHECK_ARG(make_wg_plan(d, pl));

@@ -84,6 +84,29 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Issue-rate note (tools/umma_bench.cu, B200): one tcgen05.mma M=128 K=16 costs max(N/2, 32 + N/4) cycles in the tensor
+// pipe (A fetch 4 KB + B fetch N*32 B at 128 B/clk from shared memory, independent of layout / swizzle).  A lone thread
+// that rebuilds 64-bit descriptors per instruction issues one MMA per ~65-100 cycles and starves the pipe for N < 256:
+// issuer loops therefore run warp-uniform (all 32 lanes execute the address arithmetic, so it lives in uniform
+// registers), keep the descriptor high words constant, add 16-byte offsets to the low word, and only the elected lane
+// executes the tcgen05 instructions.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t p;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t desc_join(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
+// accumulate = compile-time true: no predicate set-up instruction
+__device__ __forceinline__ void umma_bf16_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
