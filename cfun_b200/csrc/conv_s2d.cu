@@ -1,0 +1,165 @@
+// Stride-2 3x3x3 / pad 1 convolutions (the four down-sampling convs of the U-Net context pathway, mask_branch.py:33-52)
+// on the tensor-core path, by space-to-depth:
+//
+//   y[o] = sum_{k in 0..2} x[2 o + k - 1] w[k]   per axis;   write 2 o + k - 1 = 2 (o + s) + q  with parity q in {0,1}:
+//       k = 0 -> (s,q) = (-1,1),   k = 1 -> (0,0),   k = 2 -> (0,1),   (s,q) = (-1,0) never occurs.
+//
+// So with X'[n, (qd,qh,qw,ci), d', h', w'] = X[n, ci, 2d'+qd, 2h'+qh, 2w'+qw]  (8 Cin channels, half the extent) the
+// strided conv IS a stride-1, 2x2x2-tap, pad-1 convolution of X' whose weights W'[co, (q,ci), k'] hold the 27 original
+// taps and 37 structural zeros (k' = s + 1).  Forward, data gradient and weight gradient of that dense stride-1 problem
+// run on the existing tcgen05 implicit-GEMM kernels (conv_tc.cu / conv_tc_wgrad.cu); the 64/27 extra MMA work is cheap
+// next to the CUDA-core kernels it replaces (20->40 @ 96^3 data gradient: 4.3 ms -> see DESIGN.md).
+// The permutations X <-> X' are pure fp32 copies (NDHWC rows of Cin floats move as a block); when 8 Cin exceeds the
+// weight-gradient kernel's 256-channel limit X' is written as P parity-group tensors of 8 Cin / P channels.
+#include "common.cuh"
+
+namespace cfun {
+
+bool tc_capable(const cfun_conv3d_desc* d, int pass);          // conv_tc.cu: geometry check without the size policy
+size_t tc_workspace(const cfun_conv3d_desc* d, int pass);
+int tc_conv_fwd(const cfun_conv3d_desc* d, const float* x, const float* w, const float* bias, float* y, int epi, int nsplit,
+                void* ws, size_t ws_bytes, cudaStream_t st);
+int tc_conv_bwd_data(const cfun_conv3d_desc* d, const float* dy, const float* w, float* dx, int nsplit, void* ws,
+                     size_t ws_bytes, cudaStream_t st);
+int tc_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, float* dbias, int nsplit,
+                       void* ws, size_t ws_bytes, cudaStream_t st);
+int simt_bias_grad(const float* dy, long long M, int C, float* dbias, cudaStream_t st);
+
+// X (N,D,H,W,C) -> P tensors (N,D/2,H/2,W/2, 8C/P); parity class q = (qd*2+qh)*2+qw lives in tensor q / (8/P), channel
+// block q % (8/P).  inverse = true copies the other way (the data gradient's dX' -> dX).
+template <bool INV>
+__global__ void __launch_bounds__(256) s2d_kernel(float* __restrict__ x, float* __restrict__ xp, int N, int D, int H, int W, int C,
+                                                  int P) {
+  const int c4 = C >> 2;
+  const long long total = (long long)N * D * H * W * c4;
+  const int qpt = 8 / P;                                  // parity classes per output tensor
+  const long long rows_half = (long long)N * (D / 2) * (H / 2) * (W / 2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % c4);
+    long long r = i / c4;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H); r /= H;
+    const int d = (int)(r % D);
+    const int n = (int)(r / D);
+    const int q = ((d & 1) * 2 + (h & 1)) * 2 + (w & 1);
+    const long long row2 = (((long long)n * (D / 2) + (d >> 1)) * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1);
+    float4* src = reinterpret_cast<float4*>(x) + i;
+    float4* dst = reinterpret_cast<float4*>(xp + ((long long)(q / qpt) * rows_half + row2) * (long long)(qpt * C) + (q % qpt) * C) + cc;
+    if (INV) *src = *dst;
+    else *dst = *src;
+  }
+}
+
+// W (Cout, Cin, 27) -> P tensors (Cout, 8Cin/P, 8) with structural zeros; inverse gathers dW' back into dW
+template <bool INV>
+__global__ void __launch_bounds__(256) w_s2d_kernel(float* __restrict__ w, float* __restrict__ wp, int Cout, int Cin, int P) {
+  const int qpt = 8 / P;
+  const long long total = (long long)Cout * 8 * Cin * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int kp = (int)(i % 8);                          // k' = (k'd, k'h, k'w)
+    long long r = i / 8;
+    const int ci = (int)(r % Cin); r /= Cin;
+    const int q = (int)(r % 8);
+    const int co = (int)(r / 8);
+    int k[3];
+    bool live = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int ka = (kp >> (2 - a)) & 1, qa = (q >> (2 - a)) & 1;
+      if (ka == 0) { live = live && qa == 1; k[a] = 0; }
+      else k[a] = qa ? 2 : 1;
+    }
+    const long long o = ((long long)(q / qpt) * Cout + co) * (long long)(qpt * Cin) * 8 + ((long long)(q % qpt) * Cin + ci) * 8 + kp;
+    const long long s = ((long long)co * Cin + ci) * 27 + (k[0] * 3 + k[1]) * 3 + k[2];
+    if (INV) { if (live) w[s] = wp[o]; }
+    else wp[o] = live ? w[s] : 0.f;
+  }
+}
+
+struct S2dPlan {
+  cfun_conv3d_desc d2;       // the stride-1 2x2x2 problem (Cin' = 8 Cin / P per tensor for the weight gradient)
+  int P;
+  size_t act, wgt, inner, total;
+};
+
+static bool make_s2d_plan(const cfun_conv3d_desc* d, int pass, S2dPlan& pl) {
+  if (!d) return false;
+  if (d->sD != 2 || d->sH != 2 || d->sW != 2 || d->kD != 3 || d->kH != 3 || d->kW != 3 || d->pD != 1 || d->pH != 1 || d->pW != 1) return false;
+  if ((d->Din | d->Hin | d->Win) & 1) return false;
+  if (d->Dout != d->Din / 2 || d->Hout != d->Hin / 2 || d->Wout != d->Win / 2) return false;
+  if (d->Cin & 3) return false;
+  pl.P = 1;
+  if (pass == CFUN_PASS_BWD_WEIGHT) while (8 * d->Cin / pl.P > 256 && pl.P < 8) pl.P *= 2;
+  cfun_conv3d_desc& e = pl.d2;
+  e = *d;
+  e.Cin = 8 * d->Cin / pl.P;
+  e.Din = d->Din / 2; e.Hin = d->Hin / 2; e.Win = d->Win / 2;
+  e.kD = e.kH = e.kW = 2;
+  e.sD = e.sH = e.sW = 1;
+  e.pD = e.pH = e.pW = 1;
+  if (!tc_capable(&e, pass)) return false;
+  pl.act = align_up((size_t)d->N * d->Din * d->Hin * d->Win * d->Cin * 4, 1024);
+  pl.wgt = align_up((size_t)d->Cout * 8 * d->Cin * 8 * 4, 1024);
+  pl.inner = tc_workspace(&e, pass);
+  pl.total = pl.act + pl.wgt + pl.inner + 2048;
+  return pl.inner > 0;
+}
+
+bool s2d_supported(const cfun_conv3d_desc* d, int pass) {
+  const char* e = getenv("CFUN_TC_S2D");           // "0" keeps strided convs on CUDA cores (A/B measurements)
+  if (e && e[0] == '0') return false;
+  // weight gradient: the channel-major repack of the 8x wider X' costs more than the CUDA-core kernel it would replace
+  // (20->40 @ 96^3: 1.48 ms vs 1.38 ms); opt-in with CFUN_TC_S2D=w
+  if (pass == CFUN_PASS_BWD_WEIGHT && !(e && e[0] == 'w')) return false;
+  S2dPlan pl;
+  return make_s2d_plan(d, pass, pl);
+}
+size_t s2d_workspace(const cfun_conv3d_desc* d, int pass) {
+  S2dPlan pl;
+  return make_s2d_plan(d, pass, pl) ? pl.total : 0;
+}
+
+static inline unsigned grid_for(long long total) { return (unsigned)std::min<long long>(cdiv(total, 256), 32LL * num_sms()); }
+
+int s2d_conv(const cfun_conv3d_desc* d, int pass, const float* a, const float* b, const float* bias, float* out, float* dbias,
+             int epi, int nsplit, void* ws, size_t ws_bytes, cudaStream_t st) {
+  S2dPlan pl;
+  CFUN_CHECK_ARG(make_s2d_plan(d, pass, pl));
+  CFUN_CHECK_ARG(a && b && out && ws);
+  const size_t base = align_up((size_t)ws, 1024);
+  if (ws_bytes < pl.total || base + pl.total - 2048 > (size_t)ws + ws_bytes) { set_error("conv3d s2d: workspace too small"); return CFUN_ERR_WORKSPACE; }
+  float* xp = reinterpret_cast<float*>(base);
+  float* wp = reinterpret_cast<float*>(base + pl.act);
+  void* inner = reinterpret_cast<void*>(base + pl.act + pl.wgt);
+  const long long xtotal = (long long)d->N * d->Din * d->Hin * d->Win * (d->Cin >> 2);
+  const long long wtotal = (long long)d->Cout * 8 * d->Cin * 8;
+  int rc;
+  if (pass == CFUN_PASS_FWD) {                     // a = x, b = w
+    s2d_kernel<false><<<grid_for(xtotal), 256, 0, st>>>(const_cast<float*>(a), xp, d->N, d->Din, d->Hin, d->Win, d->Cin, 1);
+    CFUN_LAUNCH_CHECK();
+    w_s2d_kernel<false><<<grid_for(wtotal), 256, 0, st>>>(const_cast<float*>(b), wp, d->Cout, d->Cin, 1);
+    CFUN_LAUNCH_CHECK();
+    return tc_conv_fwd(&pl.d2, xp, wp, bias, out, epi, nsplit, inner, pl.inner, st);
+  }
+  if (pass == CFUN_PASS_BWD_DATA) {                // a = dy, b = w, out = dx
+    w_s2d_kernel<false><<<grid_for(wtotal), 256, 0, st>>>(const_cast<float*>(b), wp, d->Cout, d->Cin, 1);
+    CFUN_LAUNCH_CHECK();
+    if ((rc = tc_conv_bwd_data(&pl.d2, a, wp, xp, nsplit, inner, pl.inner, st)) != CFUN_OK) return rc;
+    s2d_kernel<true><<<grid_for(xtotal), 256, 0, st>>>(out, xp, d->N, d->Din, d->Hin, d->Win, d->Cin, 1);
+    CFUN_LAUNCH_CHECK();
+    return CFUN_OK;
+  }
+  // weight gradient: a = x, b = dy, out = dw
+  s2d_kernel<false><<<grid_for(xtotal), 256, 0, st>>>(const_cast<float*>(a), xp, d->N, d->Din, d->Hin, d->Win, d->Cin, pl.P);
+  CFUN_LAUNCH_CHECK();
+  const size_t xslice = (size_t)d->N * pl.d2.Din * pl.d2.Hin * pl.d2.Win * pl.d2.Cin;
+  const size_t wslice = (size_t)d->Cout * pl.d2.Cin * 8;
+  for (int s = 0; s < pl.P; ++s)
+    if ((rc = tc_conv_bwd_weight(&pl.d2, xp + s * xslice, b, wp + s * wslice, nullptr, nsplit, inner, pl.inner, st)) != CFUN_OK) return rc;
+  w_s2d_kernel<true><<<grid_for(wtotal), 256, 0, st>>>(out, wp, d->Cout, d->Cin, pl.P);
+  CFUN_LAUNCH_CHECK();
+  if (dbias) return simt_bias_grad(b, (long long)d->N * d->Dout * d->Hout * d->Wout, d->Cout, dbias, st);
+  return CFUN_OK;
+}
+
+}  // namespace cfun

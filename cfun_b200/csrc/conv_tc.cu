@@ -45,7 +45,7 @@ struct TcParams {
   int kD, kH, kW, pD, pH, pW;
   int CPC;           // K chunks per tap (= Cp / 16)
   int BN;            // output channels per CTA (multiple of 16, <= 256)
-  int Dt, Ht, Wt;    // output box per CTA, Dt*Ht*Wt == 128
+  int Nt, Dt, Ht, Wt;    // output box per CTA, Nt*Dt*Ht*Wt == 128 (Nt > 1 only for volumes smaller than a tile)
   int tilesD, tilesH, tilesW;
   int nsplit;        // 3: hi*hi + lo*hi + hi*lo ; 1: hi*hi
   int stages;
@@ -81,7 +81,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
   const int tw = t % p.tilesW; t /= p.tilesW;
   const int th = t % p.tilesH; t /= p.tilesH;
   const int td = t % p.tilesD; t /= p.tilesD;
-  const int n = t;
+  const int n = t * p.Nt;            // first sample of the box
   const int d0 = td * p.Dt, h0 = th * p.Ht, w0 = tw * p.Wt;
   const int n0 = blockIdx.y * p.BN;
 
@@ -176,10 +176,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     const int row = quad * 32 + lane;          // row of the 128-row tile == voxel inside the box
     const int lw = row % p.Wt;
     const int lh = (row / p.Wt) % p.Ht;
-    const int ld = row / (p.Wt * p.Ht);
+    const int ld = (row / (p.Wt * p.Ht)) % p.Dt;
+    const int on = n + row / (p.Wt * p.Ht * p.Dt);
     const int od = d0 + ld, oh = h0 + lh, ow = w0 + lw;
-    const bool vox_ok = od < p.Do && oh < p.Ho && ow < p.Wo;
-    float* yrow = p.y + ((((long long)n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * (long long)p.Cout;
+    const bool vox_ok = on < p.N && od < p.Do && oh < p.Ho && ow < p.Wo;
+    float* yrow = p.y + ((((long long)on * p.Do + od) * p.Ho + oh) * p.Wo + ow) * (long long)p.Cout;
     mbar_wait(tmem_full_bar, 0, 30);
     tc_fence_after();
     const bool vec = (p.Cout & 3) == 0;
@@ -295,22 +296,27 @@ struct TcPlan {
   int Ct, Dt_, Ht_, Wt_;     // target dims (output channels, spatial)
   int kD, kH, kW, pD, pH, pW;
   int Kp, Np, BN, ntiles_n;
-  int bd, bh, bw;            // output box
-  int tilesD, tilesH, tilesW;
+  int bn, bd, bh, bw;        // output box (bn samples x bd x bh x bw voxels = 128 rows)
+  int tilesN, tilesD, tilesH, tilesW;
   size_t off_ah, off_al, off_bh, off_bl, total;
 };
 
-static void pick_box(int Do, int Ho, int Wo, int& bd, int& bh, int& bw) {
-  static const int cand[][3] = {{4, 4, 8}, {2, 8, 8}, {8, 4, 4}, {4, 8, 4}, {8, 2, 8}, {2, 4, 16}, {4, 2, 16}, {1, 8, 16},
-                                {8, 8, 2}, {1, 16, 8}, {16, 1, 8}, {2, 2, 32}, {1, 4, 32}, {4, 1, 32}, {16, 8, 1}, {8, 16, 1},
-                                {2, 16, 4}, {16, 2, 4}, {1, 2, 64}, {2, 1, 64}, {1, 1, 128}, {32, 4, 1}, {4, 32, 1}, {16, 4, 2}, {4, 16, 2}};
+// 128-row output box = bn samples x bd x bh x bw voxels, every extent a power of two not larger than the tensor's (the
+// TMA box never exceeds the tensor extent); minimises the padded volume, then prefers one sample per box and wide rows.
+// bn > 1 lets volumes smaller than 128 voxels per sample (the 6^3 bottom of the U-Net) use the tensor-core path.
+static void pick_box(int N, int Do, int Ho, int Wo, int& bn, int& bd, int& bh, int& bw) {
   long long best = -1;
-  bd = bh = bw = 0;
-  for (auto& c : cand) {
-    if (c[0] > Do || c[1] > Ho || c[2] > Wo) continue;   // the TMA box never exceeds the tensor extent
-    long long vol = cdiv(Do, c[0]) * c[0] * cdiv(Ho, c[1]) * c[1] * cdiv(Wo, c[2]) * c[2];
-    if (best < 0 || vol < best) { best = vol; bd = c[0]; bh = c[1]; bw = c[2]; }
-  }
+  int best_pref = -1;
+  bn = bd = bh = bw = 0;
+  for (int n = 1; n <= 128 && n <= N; n <<= 1)
+    for (int a = 1; n * a <= 128 && a <= Do; a <<= 1)
+      for (int b = 1; n * a * b <= 128 && b <= Ho; b <<= 1) {
+        const int c = 128 / (n * a * b);
+        if (n * a * b * c != 128 || c > Wo) continue;
+        const long long vol = cdiv(N, n) * n * cdiv(Do, a) * a * cdiv(Ho, b) * b * cdiv(Wo, c) * c;
+        const int pref = (n == 1 ? 1000 : 0) + (c >= 8 ? 100 : 0) - abs(a - b) - abs(b - c);
+        if (best < 0 || vol < best || (vol == best && pref > best_pref)) { best = vol; best_pref = pref; bn = n; bd = a; bh = b; bw = c; }
+      }
 }
 
 static bool make_plan(const cfun_conv3d_desc* d, int pass, TcPlan& pl) {
@@ -333,8 +339,9 @@ static bool make_plan(const cfun_conv3d_desc* d, int pass, TcPlan& pl) {
   pl.Np = (int)align_up((size_t)pl.Ct, 16);
   pl.ntiles_n = (int)cdiv(pl.Np, 256);
   pl.BN = (int)align_up((size_t)cdiv(pl.Np, pl.ntiles_n), 16);
-  pick_box(std::min(pl.Dt_, pl.Ds), std::min(pl.Ht_, pl.Hs), std::min(pl.Wt_, pl.Ws), pl.bd, pl.bh, pl.bw);
+  pick_box(pl.N, std::min(pl.Dt_, pl.Ds), std::min(pl.Ht_, pl.Hs), std::min(pl.Wt_, pl.Ws), pl.bn, pl.bd, pl.bh, pl.bw);
   if (pl.bd == 0) return false;
+  pl.tilesN = (int)cdiv(pl.N, pl.bn);
   pl.tilesD = (int)cdiv(pl.Dt_, pl.bd); pl.tilesH = (int)cdiv(pl.Ht_, pl.bh); pl.tilesW = (int)cdiv(pl.Wt_, pl.bw);
   const size_t rows = (size_t)pl.N * pl.Ds * pl.Hs * pl.Ws;
   const size_t act = align_up(rows * pl.Kp * 2, 1024);
@@ -353,10 +360,28 @@ int tc_debug_read_halo(int* out8);
 int tc_debug_read_hw(int* out8);
 int tc_debug_read_ds(int* out8);
 
+bool wg_capable(const cfun_conv3d_desc* d);   // conv_tc_wgrad.cu
+bool s2d_supported(const cfun_conv3d_desc* d, int pass);   // conv_s2d.cu: stride-2 3^3 convs by space-to-depth
+size_t s2d_workspace(const cfun_conv3d_desc* d, int pass);
+int s2d_conv(const cfun_conv3d_desc* d, int pass, const float* a, const float* b, const float* bias, float* out, float* dbias,
+             int epi, int nsplit, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// geometry / alignment capability of the generic tcgen05 kernels, without the "is it worth it" policy of tc_supported
+bool tc_capable(const cfun_conv3d_desc* d, int pass) {
+  if (pass == CFUN_PASS_BWD_WEIGHT) return wg_capable(d);
+  TcPlan pl;
+  if (!make_plan(d, pass, pl)) return false;
+  if (pl.Cs < 16 || (pl.Cs & 3) || pl.Ct < 8) return false;
+  if (pl.ntiles_n > 8) return false;
+  const size_t stage_bytes = (size_t)TC_KCH * 2 * (TC_A_BYTES + pl.BN * 32);
+  return (200 * 1024) / stage_bytes >= 2;
+}
+
 bool tc_supported(const cfun_conv3d_desc* d, int pass) {
   static int sm100 = -1;
   if (sm100 < 0) sm100 = cfun_device_is_sm100();
   if (!sm100 || !get_tensor_map_encoder()) return false;
+  if (d && d->sD == 2 && s2d_supported(d, pass)) return true;
   if (pass == CFUN_PASS_BWD_WEIGHT) {
     const char* e = getenv("CFUN_TC_WGRAD");     // "0" keeps the weight gradient on CUDA cores (A/B measurements)
     if (e && e[0] == '0') return false;
@@ -374,10 +399,13 @@ bool tc_supported(const cfun_conv3d_desc* d, int pass) {
 // heuristic used by CFUN_CONV_ALGO_AUTO: tensor cores only where the launch is big enough to pay for the operand packing
 bool tc_preferred(const cfun_conv3d_desc* d, int pass) {
   if (!tc_supported(d, pass)) return false;
-  return (long long)d->N * d->Dout * d->Hout * d->Wout >= 2048;
+  const long long vox = (long long)d->N * d->Dout * d->Hout * d->Wout;
+  const double flop = 2.0 * (double)vox * d->Cin * d->Cout * d->kD * d->kH * d->kW;
+  return vox >= 2048 || flop >= 5e8;      // the 6^3 x 320-channel bottom of the U-Net is tiny in voxels, not in work
 }
 
 size_t tc_workspace(const cfun_conv3d_desc* d, int pass) {
+  if (d && d->sD == 2) return s2d_workspace(d, pass);
   if (pass == CFUN_PASS_BWD_WEIGHT) return tc_wgrad_workspace(d);
   if (hl_supported(d, pass)) return hl_workspace(d, pass);
   TcPlan pl;
@@ -389,7 +417,7 @@ static int encode_act_map(CUtensorMap* m, void* base, const TcPlan& pl) {
   cuuint64_t dims[5] = {(cuuint64_t)pl.Kp, (cuuint64_t)pl.Ws, (cuuint64_t)pl.Hs, (cuuint64_t)pl.Ds, (cuuint64_t)pl.N};
   cuuint64_t strides[4] = {(cuuint64_t)pl.Kp * 2, (cuuint64_t)pl.Ws * pl.Kp * 2, (cuuint64_t)pl.Hs * pl.Ws * pl.Kp * 2,
                            (cuuint64_t)pl.Ds * pl.Hs * pl.Ws * pl.Kp * 2};
-  cuuint32_t box[5] = {16, (cuuint32_t)pl.bw, (cuuint32_t)pl.bh, (cuuint32_t)pl.bd, 1};
+  cuuint32_t box[5] = {16, (cuuint32_t)pl.bw, (cuuint32_t)pl.bh, (cuuint32_t)pl.bd, (cuuint32_t)pl.bn};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUresult r = get_tensor_map_encoder()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -445,7 +473,7 @@ static int run_tc(const cfun_conv3d_desc* d, int pass, const float* src, const f
   p.kD = pl.kD; p.kH = pl.kH; p.kW = pl.kW; p.pD = pl.pD; p.pH = pl.pH; p.pW = pl.pW;
   p.CPC = pl.Kp / 16;
   p.BN = pl.BN;
-  p.Dt = pl.bd; p.Ht = pl.bh; p.Wt = pl.bw;
+  p.Nt = pl.bn; p.Dt = pl.bd; p.Ht = pl.bh; p.Wt = pl.bw;
   p.tilesD = pl.tilesD; p.tilesH = pl.tilesH; p.tilesW = pl.tilesW;
   p.nsplit = split ? 3 : 1;
   const int parts = split ? 2 : 1;
@@ -465,7 +493,7 @@ static int run_tc(const cfun_conv3d_desc* d, int pass, const float* src, const f
     CFUN_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  dim3 grid((unsigned)((long long)pl.N * pl.tilesD * pl.tilesH * pl.tilesW), (unsigned)pl.ntiles_n);
+  dim3 grid((unsigned)((long long)pl.tilesN * pl.tilesD * pl.tilesH * pl.tilesW), (unsigned)pl.ntiles_n);
   conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(mah, mal, mbh, mbl, p);
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;
@@ -474,12 +502,14 @@ static int run_tc(const cfun_conv3d_desc* d, int pass, const float* src, const f
 int tc_conv_fwd(const cfun_conv3d_desc* d, const float* x, const float* w, const float* bias, float* y, int epi, int nsplit,
                 void* ws, size_t ws_bytes, cudaStream_t st) {
   CFUN_CHECK_ARG(!(epi & CFUN_EPI_BIAS) || bias);
+  if (d->sD == 2) return s2d_conv(d, CFUN_PASS_FWD, x, w, bias, y, nullptr, epi, nsplit, ws, ws_bytes, st);
   if (hl_supported(d, CFUN_PASS_FWD)) return hl_conv(d, CFUN_PASS_FWD, x, w, bias, y, epi, nsplit, ws, ws_bytes, st);
   return run_tc(d, CFUN_PASS_FWD, x, w, bias, y, epi, nsplit, ws, ws_bytes, st);
 }
 
 int tc_conv_bwd_data(const cfun_conv3d_desc* d, const float* dy, const float* w, float* dx, int nsplit, void* ws,
                      size_t ws_bytes, cudaStream_t st) {
+  if (d->sD == 2) return s2d_conv(d, CFUN_PASS_BWD_DATA, dy, w, nullptr, dx, nullptr, 0, nsplit, ws, ws_bytes, st);
   if (hl_supported(d, CFUN_PASS_BWD_DATA)) return hl_conv(d, CFUN_PASS_BWD_DATA, dy, w, nullptr, dx, 0, nsplit, ws, ws_bytes, st);
   return run_tc(d, CFUN_PASS_BWD_DATA, dy, w, nullptr, dx, 0, nsplit, ws, ws_bytes, st);
 }

@@ -22,7 +22,8 @@ constexpr int WG_THREADS = 192;
 struct WgParams {
   int N, Do, Ho, Wo;             // dY spatial extents
   int kD, kH, kW, pD, pH, pW;
-  int Cout, Cin, taps;
+  int Cout, Cin, taps;           // Cin = input channels of this launch's slice
+  int ci0, Cin_total;            // slice offset / full channel count (dW addressing)
   int Npad;                      // MMA N (Cin tile rounded up to 16)
   int Wk, swz;                   // K slab (voxels) and its byte width (Wk*2 = swizzle width)
   int kt_per_line;               // ceil(Wo / Wk)
@@ -164,7 +165,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid_co
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int ci = j + i;
-              if (ci < p.Cin) atomicAdd(p.dw + ((long long)co * p.Cin + ci) * p.taps + tap, __uint_as_float(r[i]));
+              if (ci < p.Cin) atomicAdd(p.dw + ((long long)co * p.Cin_total + p.ci0 + ci) * p.taps + tap, __uint_as_float(r[i]));
             }
           }
         }
@@ -204,11 +205,12 @@ __global__ void __launch_bounds__(256) pack_transpose_kernel(const float* __rest
   }
 }
 
-// X [N*D*H rows of W voxels, C] fp32 -> kW channel-major copies [kw][C][N*D*H][Wo] with copy kw holding x[.., w + kw - pW, c]
-// (zero outside [0, W)); Wo = output width, so every copy is aligned to the dY lines.
+// X [N*D*H rows of W voxels, C] fp32 -> kW channel-major copies [kw][C][N*D*H][Wp] with copy kw holding x[.., w + kw - pW, c]
+// (zero outside [0, W)); Wp = output width rounded up to the TMA row granularity, so every copy is aligned to the dY lines.
 __global__ void __launch_bounds__(256) pack_transpose_shift_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                                                                    __nv_bfloat16* __restrict__ lo, long long lines, int W, int Wo,
                                                                    int C, int kW, int pW, long long pitch) {
+  // (Wo here is the padded line pitch Wp of the packed copies)
   __shared__ float tile[32][33];
   const long long line = blockIdx.x;                 // (n, d, h) line index of X
   const int wt = blockIdx.y;
@@ -239,6 +241,8 @@ __global__ void __launch_bounds__(256) pack_transpose_shift_kernel(const float* 
 
 struct WgPlan {
   int Wk, swz, T, ngroups, mtiles, Npad, stages, tmem_cols;
+  int slices, Cs;               // input channels are processed in `slices` launches of Cs channels (MMA N <= 256)
+  int Wp;                       // packed line pitch: Wout, or Wout rounded up to 16 when it is not a multiple of 8
   size_t off_yh, off_yl, off_xh, off_xl, total;
   long long rows_y, rows_x, lines_x;
   long long pitch_y, pitch_x;   // channel-plane pitch (elements): padded so that planes do not alias in L2
@@ -247,12 +251,15 @@ struct WgPlan {
 
 static bool make_wg_plan(const cfun_conv3d_desc* d, WgPlan& pl) {
   if (!d || d->sD != 1 || d->sH != 1 || d->sW != 1) return false;
-  if (d->Wout & 7) return false;                        // TMA row stride must be a multiple of 16 B
+  pl.Wp = (d->Wout & 7) ? (int)align_up((size_t)d->Wout, 16) : d->Wout;   // TMA row stride must be a multiple of 16 B
   if (d->kW > WG_MAX_KW) return false;
-  if (d->Cin > 256) return false;
-  pl.Wk = (d->Wout % 64 == 0) ? 64 : ((d->Wout % 32 == 0) ? 32 : 16);
+  if (d->Cin > 512) return false;
+  pl.slices = d->Cin > 256 ? 2 : 1;
+  if (d->Cin % pl.slices) return false;
+  pl.Cs = d->Cin / pl.slices;
+  pl.Wk = (pl.Wp % 64 == 0) ? 64 : ((pl.Wp % 32 == 0) ? 32 : 16);
   pl.swz = pl.Wk * 2;
-  pl.Npad = (int)align_up((size_t)d->Cin, 16);
+  pl.Npad = (int)align_up((size_t)pl.Cs, 16);
   const int taps = d->kD * d->kH * d->kW;
   pl.T = std::min(taps, 512 / pl.Npad);
   // keep a stage (dY tile + T shifted X tiles, hi+lo) within ~100 KB so that two stages fit
@@ -268,7 +275,7 @@ static bool make_wg_plan(const cfun_conv3d_desc* d, WgPlan& pl) {
   const size_t stage = 2 * (size_t)(128 * pl.swz + pl.T * b_bytes);
   pl.stages = (int)std::min<size_t>(4, (200 * 1024) / stage);
   if (pl.stages < 2) return false;
-  pl.rows_y = (long long)d->N * d->Dout * d->Hout * d->Wout;
+  pl.rows_y = (long long)d->N * d->Dout * d->Hout * pl.Wp;
   pl.rows_x = (long long)d->N * d->Din * d->Hin * d->Win;
   // The planes of consecutive channels are read by consecutive rows of every TMA box; an un-padded pitch is a multiple of
   // large powers of two for the usual extents (4 x 96^3 x 2 B = 27 x 256 KiB) and makes all rows of a box camp on the
@@ -276,7 +283,7 @@ static bool make_wg_plan(const cfun_conv3d_desc* d, WgPlan& pl) {
   pl.pitch_y = pl.rows_y + 1088;
   const size_t ybytes = align_up((size_t)pl.pitch_y * d->Cout * 2, 1024);
   pl.lines_x = (long long)d->N * d->Din * d->Hin;
-  pl.pitch_x = pl.lines_x * d->Wout + 1088;
+  pl.pitch_x = pl.lines_x * pl.Wp + 1088;
   pl.copy_elems = (size_t)d->Cin * pl.pitch_x;                    // one pre-shifted copy of X (one part)
   const size_t xbytes = align_up(pl.copy_elems * 2 * d->kW, 1024);
   pl.off_yh = 0; pl.off_yl = ybytes; pl.off_xh = 2 * ybytes; pl.off_xl = 2 * ybytes + xbytes;
@@ -292,6 +299,16 @@ bool hw_supported(const cfun_conv3d_desc* d);
 size_t hw_workspace(const cfun_conv3d_desc* d);
 int hw_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, float* dbias, int nsplit,
                        void* ws, size_t ws_bytes, cudaStream_t st);
+
+int s2d_conv(const cfun_conv3d_desc* d, int pass, const float* a, const float* b, const float* bias, float* out, float* dbias,
+             int epi, int nsplit, void* ws, size_t ws_bytes, cudaStream_t st);   // conv_s2d.cu
+
+// capability of the generic channel-major kernel without the size policy (used by the space-to-depth path)
+bool wg_capable(const cfun_conv3d_desc* d) {
+  WgPlan pl;
+  if (!make_wg_plan(d, pl)) return false;
+  return d->Cin >= 16 && d->Cout >= 8;
+}
 
 bool tc_wgrad_supported(const cfun_conv3d_desc* d) {
   if (ds_supported(d) || hw_supported(d)) return true;
@@ -328,6 +345,7 @@ int simt_bias_grad(const float* dy, long long M, int C, float* dbias, cudaStream
 
 int tc_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, float* dbias, int nsplit,
                        void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (d->sD == 2) return s2d_conv(d, CFUN_PASS_BWD_WEIGHT, x, dy, nullptr, dw, dbias, 0, nsplit, ws, ws_bytes, st);
   if (ds_supported(d)) return ds_conv_bwd_weight(d, x, dy, dw, dbias, nsplit, ws, ws_bytes, st);
   if (hw_supported(d)) return hw_conv_bwd_weight(d, x, dy, dw, dbias, nsplit, ws, ws_bytes, st);
   WgPlan pl;
@@ -340,31 +358,31 @@ int tc_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* d
   __nv_bfloat16* yl = reinterpret_cast<__nv_bfloat16*>(base + pl.off_yl);
   __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(base + pl.off_xh);
   __nv_bfloat16* xl = reinterpret_cast<__nv_bfloat16*>(base + pl.off_xl);
-  pack_transpose_kernel<<<dim3((unsigned)cdiv(pl.rows_y, 32), (unsigned)cdiv(d->Cout, 32)), dim3(32, 8), 0, st>>>(dy, yh, split ? yl : nullptr, pl.rows_y, d->Cout, pl.pitch_y);
+  if (pl.Wp == d->Wout) {
+    pack_transpose_kernel<<<dim3((unsigned)cdiv(pl.rows_y, 32), (unsigned)cdiv(d->Cout, 32)), dim3(32, 8), 0, st>>>(dy, yh, split ? yl : nullptr, pl.rows_y, d->Cout, pl.pitch_y);
+  } else {   // padded lines: the line-aware kernel with one un-shifted copy writes zeros into [Wout, Wp)
+    const long long lines_y = (long long)d->N * d->Dout * d->Hout;
+    pack_transpose_shift_kernel<<<dim3((unsigned)lines_y, (unsigned)cdiv(pl.Wp, 32), (unsigned)cdiv(d->Cout, 32)), dim3(32, 8), 0, st>>>(
+        dy, yh, split ? yl : nullptr, lines_y, d->Wout, pl.Wp, d->Cout, 1, 0, pl.pitch_y);
+  }
   CFUN_LAUNCH_CHECK();
-  pack_transpose_shift_kernel<<<dim3((unsigned)pl.lines_x, (unsigned)cdiv(d->Wout, 32), (unsigned)cdiv(d->Cin, 32)), dim3(32, 8), 0, st>>>(
-      x, xh, split ? xl : nullptr, pl.lines_x, d->Win, d->Wout, d->Cin, d->kW, d->pW, pl.pitch_x);
+  pack_transpose_shift_kernel<<<dim3((unsigned)pl.lines_x, (unsigned)cdiv(pl.Wp, 32), (unsigned)cdiv(d->Cin, 32)), dim3(32, 8), 0, st>>>(
+      x, xh, split ? xl : nullptr, pl.lines_x, d->Win, pl.Wp, d->Cin, d->kW, d->pW, pl.pitch_x);
   CFUN_LAUNCH_CHECK();
   const int taps = d->kD * d->kH * d->kW;
   CFUN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * d->Cin * taps, st));
 
   CUtensorMap myh, myl;
-  XMaps xm;
   int rc;
-  if ((rc = encode_cmajor_map(&myh, yh, d->Wout, d->Hout, d->Dout, d->N, d->Cout, pl.Wk, 128, pl.swz, pl.pitch_y)) != CFUN_OK) return rc;
-  if ((rc = encode_cmajor_map(&myl, split ? yl : yh, d->Wout, d->Hout, d->Dout, d->N, d->Cout, pl.Wk, 128, pl.swz, pl.pitch_y)) != CFUN_OK) return rc;
-  for (int kw = 0; kw < WG_MAX_KW; ++kw) {
-    const int k = kw < d->kW ? kw : 0;
-    if ((rc = encode_cmajor_map(&xm.hi[kw], xh + (size_t)k * pl.copy_elems, d->Wout, d->Hin, d->Din, d->N, d->Cin, pl.Wk, pl.Npad, pl.swz, pl.pitch_x)) != CFUN_OK) return rc;
-    if ((rc = encode_cmajor_map(&xm.lo[kw], (split ? xl : xh) + (size_t)k * pl.copy_elems, d->Wout, d->Hin, d->Din, d->N, d->Cin, pl.Wk, pl.Npad, pl.swz, pl.pitch_x)) != CFUN_OK) return rc;
-  }
+  if ((rc = encode_cmajor_map(&myh, yh, pl.Wp, d->Hout, d->Dout, d->N, d->Cout, pl.Wk, 128, pl.swz, pl.pitch_y)) != CFUN_OK) return rc;
+  if ((rc = encode_cmajor_map(&myl, split ? yl : yh, pl.Wp, d->Hout, d->Dout, d->N, d->Cout, pl.Wk, 128, pl.swz, pl.pitch_y)) != CFUN_OK) return rc;
 
   WgParams p;
   p.N = d->N; p.Do = d->Dout; p.Ho = d->Hout; p.Wo = d->Wout;
   p.kD = d->kD; p.kH = d->kH; p.kW = d->kW; p.pD = d->pD; p.pH = d->pH; p.pW = d->pW;
-  p.Cout = d->Cout; p.Cin = d->Cin; p.taps = taps;
+  p.Cout = d->Cout; p.Cin = pl.Cs; p.Cin_total = d->Cin; p.taps = taps;
   p.Npad = pl.Npad; p.Wk = pl.Wk; p.swz = pl.swz;
-  p.kt_per_line = (int)cdiv(d->Wout, pl.Wk);
+  p.kt_per_line = (int)cdiv(pl.Wp, pl.Wk);      // Wp = 8: one 16-wide slab per line, the upper half is TMA zero fill
   p.T = pl.T;
   p.nsplit = split ? 3 : 1;
   p.stages = pl.stages;
@@ -387,9 +405,19 @@ int tc_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* d
     attr_set = true;
   }
   dim3 grid((unsigned)ctas, (unsigned)pl.ngroups, (unsigned)pl.mtiles);
-  conv_tc_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(myh, myl, xm, p);
-  CFUN_LAUNCH_CHECK();
-  if (dbias) return simt_bias_grad(dy, pl.rows_y, d->Cout, dbias, st);
+  for (int sl = 0; sl < pl.slices; ++sl) {       // channel slices of X (MMA N <= 256): channel planes are contiguous in the pack
+    XMaps xm;
+    const size_t coff = (size_t)sl * pl.Cs * pl.pitch_x;
+    for (int kw = 0; kw < WG_MAX_KW; ++kw) {
+      const int k = kw < d->kW ? kw : 0;
+      if ((rc = encode_cmajor_map(&xm.hi[kw], xh + (size_t)k * pl.copy_elems + coff, pl.Wp, d->Hin, d->Din, d->N, pl.Cs, pl.Wk, pl.Npad, pl.swz, pl.pitch_x)) != CFUN_OK) return rc;
+      if ((rc = encode_cmajor_map(&xm.lo[kw], (split ? xl : xh) + (size_t)k * pl.copy_elems + coff, pl.Wp, d->Hin, d->Din, d->N, pl.Cs, pl.Wk, pl.Npad, pl.swz, pl.pitch_x)) != CFUN_OK) return rc;
+    }
+    p.ci0 = sl * pl.Cs;
+    conv_tc_wgrad_kernel<<<grid, WG_THREADS, smem, st>>>(myh, myl, xm, p);
+    CFUN_LAUNCH_CHECK();
+  }
+  if (dbias) return simt_bias_grad(dy, (long long)d->N * d->Dout * d->Hout * d->Wout, d->Cout, dbias, st);
   return CFUN_OK;
 }
 

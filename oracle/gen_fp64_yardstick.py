@@ -24,7 +24,8 @@ for stage in ("beginning", "finetune"):
     cfg = O.Cfg(image_dim=64, stage=stage, mask_pool=32, anchor_scales=(16, 32))
     inp = golden_step_inputs(g)
     keys = ["mask.modified_u_net.conv_norm_lrelu_l4.0.weight", "rpn.conv_shared.weight"]
-    leaves = {k: sd[k].clone().requires_grad_(True) for k in keys}
+    names = [str(k) for k in g["grad_names"]]
+    leaves = {k: sd[k].clone().requires_grad_(True) for k in set(keys) | set(names)}
     sd2 = dict(sd)
     sd2.update(leaves)
     torch.manual_seed(int(g["seed_perm"]))
@@ -34,6 +35,11 @@ for stage in ("beginning", "finetune"):
     out[stage + "/g_unet_l4"] = leaves[keys[0]].grad.flatten()[::7].numpy()
     out[stage + "/g_rpn_shared"] = leaves[keys[1]].grad.flatten()[::811].numpy()
     out[stage + "/losses"] = np.array([float(l) for l in res["losses"]])
+    # float64 norm of every parameter gradient, in the order of the fp32 golden's grad_names: the yardstick for the
+    # whole-step gradient check (how far is the reference's own fp32 arithmetic from the exact value, per tensor)
+    out[stage + "/grad_norms64"] = np.array([float(leaves[k].grad.norm()) if leaves[k].grad is not None else 0.0 for k in names])
+    big = g["grad_norms"] > 1e-3 * g["grad_norms"].max()
+    print(stage, "reference fp32 vs fp64 grad norms, worst relative:", np.abs(g["grad_norms"][big] / out[stage + "/grad_norms64"][big] - 1).max())
     d = np.abs(g["g_unet_l4"] - out[stage + "/g_unet_l4"]).max() / np.abs(out[stage + "/g_unet_l4"]).max()
     print(stage, "reference fp32 vs fp64 on g_unet_l4:", d)
 
