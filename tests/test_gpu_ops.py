@@ -373,6 +373,49 @@ def test_conv3d_tcgen05_fwd_dgrad(ops, case):
         assert rel_err(wc.grad.cpu().numpy(), wr.grad.numpy()) < TOL
 
 
+NEW_TC_CASES = [
+    # N, Cin, D, H, W, Cout, k, stride, pad, what it covers
+    (1, 20, 16, 16, 16, 40, 3, 2, 1, "stride 2 by space-to-depth (conv_s2d.cu), fwd + dgrad"),
+    (2, 40, 8, 12, 16, 80, 3, 2, 1, "stride 2, ragged half extents"),
+    (4, 64, 6, 6, 6, 48, 3, 1, 1, "6^3 volume: batch-dim boxes (bn = 4) in conv_tc.cu, padded lines in the wgrad pack"),
+    (3, 32, 4, 4, 4, 32, 3, 1, 1, "4^3 volume, N not a multiple of the box"),
+    (1, 320, 12, 12, 12, 24, 3, 1, 1, "Cin 320: two channel slices in conv_tc_wgrad.cu, W = 12 padded to 16"),
+    (2, 24, 5, 18, 10, 40, 3, 1, 1, "d-stacked wgrad (conv_tc_wgrad_ds.cu): 3 + 5 channel groups, ragged slabs"),
+    (1, 80, 6, 16, 16, 80, 3, 1, 1, "d-stacked wgrad: two M tiles of 5 groups, two tap groups"),
+    (2, 16, 2, 8, 8, 16, 3, 1, 1, "d-stacked wgrad: two channel groups, D smaller than the 3-plane stack"),
+]
+
+
+@pytest.mark.parametrize("case", NEW_TC_CASES, ids=[c[-1].split(":")[0].split(",")[0] + "_%d" % i for i, c in enumerate(NEW_TC_CASES)])
+def test_conv3d_tcgen05_strided_tiny_and_stacked_wgrad(ops, case):
+    N, Cin, D, H, W, Cout, k, st, p, _ = case
+    g = torch.Generator().manual_seed(sum(case[:9]))
+    x = torch.randn(N, Cin, D, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, k, generator=g) * (1.0 / (Cin * k ** 3) ** 0.5)
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    yr = F.conv3d(xr, wr, None, stride=st, padding=p)
+    dy = torch.randn(yr.shape, generator=g)
+    yr.backward(dy)
+    sup = [ops.conv3d_supported(x.shape, w.shape, st, p, ps, ops.ALGO_TC) for ps in (ops.PASS_FWD, ops.PASS_BWD_DATA, ops.PASS_BWD_WEIGHT)]
+    assert sup[0] and sup[1], "the tensor-core path must take this shape"
+    ops.set_conv_algo(ops.ALGO_TC)
+    try:
+        xc = x.cuda().requires_grad_(True)
+        wc = w.cuda().requires_grad_(sup[2])
+        yc = ops.conv3d(xc, wc, None, st, p)
+        yc.backward(dy.cuda())
+        torch.cuda.synchronize()
+        assert ops.tc_debug_status() is None
+    finally:
+        ops.set_conv_algo(ops.ALGO_AUTO)
+    assert rel_err(yc.detach().cpu().numpy(), yr.detach().numpy()) < TOL
+    assert rel_err(xc.grad.cpu().numpy(), xr.grad.numpy()) < TOL
+    if st == 1:
+        assert sup[2], "stride-1 3^3 weight gradients run on tensor cores"
+    if sup[2]:
+        assert rel_err(wc.grad.cpu().numpy(), wr.grad.numpy()) < TOL
+
+
 def test_conv3d_tcgen05_single_pass_is_fast_mode_only(ops):
     g = torch.Generator().manual_seed(9)
     x = torch.randn(1, 64, 12, 12, 12, generator=g)
