@@ -148,7 +148,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
 #pragma unroll
         for (int c = 0; c < TC_KCH; ++c) {
           if (c < nch) {
-            const uint32_t cb = ((sbase + (uint32_t)(c * chunk_bytes)) >> 4) | lbo1;
+            const uint32_t cb = desc_addr(sbase + (uint32_t)(c * chunk_bytes)) | lbo1;
             const uint64_t a_hi = desc_join(hiword, cb);
             const uint64_t b_hi = desc_join(hiword, cb + (uint32_t)((parts * TC_A_BYTES) >> 4));
             if (leader) {
@@ -352,6 +352,11 @@ static bool make_plan(const cfun_conv3d_desc* d, int pass, TcPlan& pl) {
 
 bool tc_wgrad_supported(const cfun_conv3d_desc* d);
 size_t tc_wgrad_workspace(const cfun_conv3d_desc* d);
+bool hx_supported(const cfun_conv3d_desc* d, int pass);     // conv_tc_hx.cu: halo-resident, cluster-multicast weights
+size_t hx_workspace(const cfun_conv3d_desc* d, int pass);
+int hx_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
+            int nsplit, void* ws, size_t ws_bytes, cudaStream_t st);
+int tc_debug_read_hx(int* out8);
 bool hl_supported(const cfun_conv3d_desc* d, int pass);
 size_t hl_workspace(const cfun_conv3d_desc* d, int pass);
 int hl_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
@@ -387,6 +392,7 @@ bool tc_supported(const cfun_conv3d_desc* d, int pass) {
     if (e && e[0] == '0') return false;
     return tc_wgrad_supported(d);
   }
+  if (hx_supported(d, pass)) return true;
   TcPlan pl;
   if (!make_plan(d, pass, pl)) return false;
   const int taps = pl.kD * pl.kH * pl.kW;
@@ -407,6 +413,7 @@ bool tc_preferred(const cfun_conv3d_desc* d, int pass) {
 size_t tc_workspace(const cfun_conv3d_desc* d, int pass) {
   if (d && d->sD == 2) return s2d_workspace(d, pass);
   if (pass == CFUN_PASS_BWD_WEIGHT) return tc_wgrad_workspace(d);
+  if (hx_supported(d, pass)) return hx_workspace(d, pass);
   if (hl_supported(d, pass)) return hl_workspace(d, pass);
   TcPlan pl;
   if (!make_plan(d, pass, pl)) return 0;
@@ -503,6 +510,7 @@ int tc_conv_fwd(const cfun_conv3d_desc* d, const float* x, const float* w, const
                 void* ws, size_t ws_bytes, cudaStream_t st) {
   CFUN_CHECK_ARG(!(epi & CFUN_EPI_BIAS) || bias);
   if (d->sD == 2) return s2d_conv(d, CFUN_PASS_FWD, x, w, bias, y, nullptr, epi, nsplit, ws, ws_bytes, st);
+  if (hx_supported(d, CFUN_PASS_FWD)) return hx_conv(d, CFUN_PASS_FWD, x, w, bias, y, epi, nsplit, ws, ws_bytes, st);
   if (hl_supported(d, CFUN_PASS_FWD)) return hl_conv(d, CFUN_PASS_FWD, x, w, bias, y, epi, nsplit, ws, ws_bytes, st);
   return run_tc(d, CFUN_PASS_FWD, x, w, bias, y, epi, nsplit, ws, ws_bytes, st);
 }
@@ -510,6 +518,7 @@ int tc_conv_fwd(const cfun_conv3d_desc* d, const float* x, const float* w, const
 int tc_conv_bwd_data(const cfun_conv3d_desc* d, const float* dy, const float* w, float* dx, int nsplit, void* ws,
                      size_t ws_bytes, cudaStream_t st) {
   if (d->sD == 2) return s2d_conv(d, CFUN_PASS_BWD_DATA, dy, w, nullptr, dx, nullptr, 0, nsplit, ws, ws_bytes, st);
+  if (hx_supported(d, CFUN_PASS_BWD_DATA)) return hx_conv(d, CFUN_PASS_BWD_DATA, dy, w, nullptr, dx, 0, nsplit, ws, ws_bytes, st);
   if (hl_supported(d, CFUN_PASS_BWD_DATA)) return hl_conv(d, CFUN_PASS_BWD_DATA, dy, w, nullptr, dx, 0, nsplit, ws, ws_bytes, st);
   return run_tc(d, CFUN_PASS_BWD_DATA, dy, w, nullptr, dx, 0, nsplit, ws, ws_bytes, st);
 }
@@ -551,9 +560,11 @@ extern "C" int cfun_tc_debug_status(int* out8_host) {
   int e[8];
   rc = tc_debug_read_hw(e);
   if (rc != CFUN_OK) return rc;
-  int f[8];
+  int f[8], g[8];
   rc = tc_debug_read_ds(f);
   if (rc != CFUN_OK) return rc;
-  for (int i = 0; i < 8; ++i) out8_host[i] = a[0] ? a[i] : (b[0] ? b[i] : (c[0] ? c[i] : (e[0] ? e[i] : f[i])));
+  rc = tc_debug_read_hx(g);
+  if (rc != CFUN_OK) return rc;
+  for (int i = 0; i < 8; ++i) out8_host[i] = a[0] ? a[i] : (b[0] ? b[i] : (c[0] ? c[i] : (e[0] ? e[i] : (f[0] ? f[i] : g[i]))));
   return CFUN_OK;
 }

@@ -157,13 +157,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
         for (int c = 0; c < p.CPC; ++c) {
           mbar_wait(&a_full[c], (uint32_t)(local & 1), 240);
           tc_fence_after();
-          const uint32_t a_hi0 = ((a_base + (uint32_t)(c * a_slot_bytes)) >> 4) | a_lbo;
+          const uint32_t a_hi0 = desc_addr(a_base + (uint32_t)(c * a_slot_bytes)) | a_lbo;
           const uint32_t a_lo0 = a_hi0 + (uint32_t)((2 * HL_PLANE) >> 4);
           for (int kd = 0; kd < 3; ++kd, ++bcount) {
             const int st = (int)(bcount % HL_BSTAGES);
             mbar_wait(&b_full[st], (uint32_t)((bcount / HL_BSTAGES) & 1), 250);
             tc_fence_after();
-            const uint32_t b0 = ((b_base + (uint32_t)(st * b_stage_bytes)) >> 4) | b_lbo;
+            const uint32_t b0 = desc_addr(b_base + (uint32_t)(st * b_stage_bytes)) | b_lbo;
             const uint32_t a_kd = (uint32_t)(kd * HL_HH * HL_WH);
 #pragma unroll
             for (int t9 = 0; t9 < 9; ++t9) {

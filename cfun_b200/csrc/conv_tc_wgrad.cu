@@ -119,7 +119,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid_co
       const uint32_t ph = (uint32_t)((it / p.stages) & 1);
       mbar_wait(&full_bar[slot], ph, 120);
       tc_fence_after();
-      const uint32_t sb = (smem_u32(ring + (size_t)slot * stage_bytes) >> 4) | lbo1;
+      const uint32_t sb = desc_addr(smem_u32(ring + (size_t)slot * stage_bytes)) | lbo1;
       const uint32_t bb = sb + (uint32_t)((parts * a_bytes) >> 4);
       const uint32_t acc = it > 0 ? 1u : 0u;
       for (int t = 0; t < ntap && !(p.debug_skip & 2); ++t) {

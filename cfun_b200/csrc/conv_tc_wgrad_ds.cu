@@ -121,9 +121,9 @@ conv_tc_wgrad_ds_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid
       mbar_wait(&full_bar[slot], (uint32_t)((it / p.stages) & 1), 420);
       tc_fence_after();
       const uint32_t sb = smem_u32(ring + (size_t)slot * p.stage_bytes);
-      const uint32_t y_hi = (sb >> 4) | a_lbo, y_lo = ((sb + (uint32_t)p.y_bytes) >> 4) | a_lbo;
-      const uint32_t x_hi = ((sb + (uint32_t)(parts * p.y_bytes)) >> 4) | b_lbo;
-      const uint32_t x_lo = ((sb + (uint32_t)(parts * p.y_bytes + p.x_bytes)) >> 4) | b_lbo;
+      const uint32_t y_hi = desc_addr(sb) | a_lbo, y_lo = desc_addr(sb + (uint32_t)p.y_bytes) | a_lbo;
+      const uint32_t x_hi = desc_addr(sb + (uint32_t)(parts * p.y_bytes)) | b_lbo;
+      const uint32_t x_lo = desc_addr(sb + (uint32_t)(parts * p.y_bytes + p.x_bytes)) | b_lbo;
       const uint32_t first = it == 0 ? 0u : 1u;
 #pragma unroll 1
       for (int t = 0; t < nt9; ++t) {

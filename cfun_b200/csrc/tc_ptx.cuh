@@ -95,6 +95,10 @@ __device__ __forceinline__ uint32_t elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(p));
   return p;
 }
+// start-address field of a shared-memory matrix descriptor: (address >> 4) in 14 bits.  The mask matters inside a
+// thread-block cluster, where the shared-window address of CTA rank r carries r in its upper bits (they would spill into
+// the LBO field of a hoisted low word).
+__device__ __forceinline__ uint32_t desc_addr(uint32_t saddr) { return (saddr & 0x3FFFFu) >> 4; }
 __device__ __forceinline__ uint64_t desc_join(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
 // accumulate = compile-time true: no predicate set-up instruction
 __device__ __forceinline__ void umma_bf16_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {

@@ -25,6 +25,8 @@ SMALL = [(1, 16, 16, 16, 3, 1, 1), (2, 24, 20, 40, 3, 1, 1), (1, 40, 24, 20, 3, 
          (1, 16, 48, 24, 3, 2, 1)]
 TINY = [(4, 320, 6, 320, 3, 1, 1), (4, 320, 12, 320, 3, 1, 1), (4, 160, 12, 160, 3, 1, 1), (4, 320, 12, 160, 3, 1, 1),
         (4, 160, 12, 320, 3, 2, 1), (2, 32, 6, 48, 3, 1, 1), (3, 16, 5, 16, 3, 1, 1), (1, 64, 12, 32, 3, 1, 1)]
+HX = [(1, 16, 16, 16, 3, 1, 1), (2, 24, 20, 40, 3, 1, 1), (1, 80, 16, 80, 3, 1, 1), (1, 48, 17, 44, 3, 1, 1), (1, 32, 16, 160, 3, 1, 1),
+      (1, 128, 16, 256, 3, 1, 1), (1, 320, 8, 320, 3, 1, 1), (3, 20, 9, 20, 3, 1, 1)]
 STRIDED = [(4, 20, 96, 40, 3, 2, 1), (4, 40, 48, 80, 3, 2, 1), (4, 80, 24, 160, 3, 2, 1), (4, 160, 12, 320, 3, 2, 1)]
 
 
@@ -47,7 +49,7 @@ def med(fn, flush, iters=5):
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "unet"
     passes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["fwd", "dgrad", "wgrad"]
-    cases = {"unet": UNET, "small": SMALL, "all": SMALL + UNET, "strided": STRIDED, "tiny": TINY}[which]
+    cases = {"unet": UNET, "small": SMALL, "all": SMALL + UNET, "strided": STRIDED, "hx": HX, "tiny": TINY}[which]
     dev = torch.device("cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for (N, Ci, S, Co, k, st, pd) in cases:
