@@ -350,8 +350,10 @@ static bool make_hl_plan(const cfun_conv3d_desc* d, int pass, HlPlan& pl) {
 }
 
 bool hl_supported(const cfun_conv3d_desc* d, int pass) {
-  const char* e = getenv("CFUN_TC_HALO");       // "0" disables the halo kernel (A/B measurements)
+  const char* e = getenv("CFUN_TC_HALO");       // "0" disables the halo kernels (A/B measurements)
   if (e && e[0] == '0') return false;
+  const char* x = getenv("CFUN_TC_HX");         // "only": route every supported shape through conv_tc_hx.cu instead
+  if (x && x[0] == 'o') return false;
   HlPlan pl;
   if (!make_hl_plan(d, pass, pl)) return false;
   return pl.Cs >= 16 && (pl.Cs & 3) == 0 && pl.Ct >= 8;

@@ -19,7 +19,7 @@
 
 namespace cfun {
 
-constexpr int HX_THREADS = 192;
+constexpr int HX_THREADS = 224;      // warp 0: halo producer, 1: MMA issuer, 2..5: epilogue, 6: weight producer
 constexpr int HX_HT = 16, HX_WT = 8, HX_HH = 18, HX_WH = 10;
 constexpr int HX_PLANE_DATA = 3 * HX_HH * HX_WH * 16;                 // 8640 B: one 8-channel group, one part
 constexpr int HX_PLANE = (HX_PLANE_DATA + 127) / 128 * 128;          // 8704
@@ -90,6 +90,7 @@ struct HxParams {
   const uint8_t* wpack;       // [ntile][chunk][kd][tap9][kgroup2][part][Npad][8] bf16 (hi rows, then lo rows)
 };
 
+template <int TPS>   // taps per weight stage: 9 (one kd plane) or 3 (one (kd, kh) row) -- compile-time so the issue loop is straight-line
 __global__ void __launch_bounds__(HX_THREADS, 1)
 conv_tc_hx_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_l, const HxParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -108,7 +109,7 @@ conv_tc_hx_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
   const int nrows = parts * p.Npad;                               // weight rows per K group: hi rows then lo rows
   uint8_t* a_ring = base;
   uint8_t* b_ring = base + (size_t)HX_ASLOTS * a_slot_bytes;
-  const int spc = 27 / p.TPS;                                     // weight stages per K chunk
+  constexpr int spc = 27 / TPS;                                   // weight stages per K chunk
   const uint32_t rank = p.cluster > 1 ? cluster_ctarank() : 0u;
   const uint16_t cmask = (uint16_t)((1u << p.cluster) - 1u);
   const uint16_t self_mask = (uint16_t)(1u << rank);
@@ -129,10 +130,10 @@ conv_tc_hx_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== producer: halo (TMA tensor) + weights (bulk, multicast across the cluster) =====================
+    // ===================== halo producer (TMA tensor): runs up to HX_ASLOTS chunks ahead, independent of the weight ring =========
     if (lane == 0) {
-      uint32_t bcount = 0, acount = 0;
-      const uint32_t slice = (uint32_t)(p.b_stage_bytes / p.cluster);
+      int slot = 0;
+      uint32_t ph = 0;
       for (int nt = 0; nt < p.ntn; ++nt) {
         for (int it = 0; it < p.iters; ++it) {
           long long t = (long long)blockIdx.x + (long long)it * gridDim.x;
@@ -144,25 +145,36 @@ conv_tc_hx_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
           const int c_w = (wb * HX_WT - 1) * 8;                 // inner coordinate in elements (multiple of 8 -> 16 B aligned)
           const int c_h = hb * HX_HT - 1;
           const int c_nd = n * (p.D + 2) + d;                   // padded plane index of d-1
-          for (int c = 0; c < p.CPC; ++c, ++acount) {
-            const int slot = (int)(acount % HX_ASLOTS);
-            mbar_wait(&a_empty[slot], (uint32_t)(((acount / HX_ASLOTS) & 1) ^ 1), 510);
+          for (int c = 0; c < p.CPC; ++c) {
+            mbar_wait(&a_empty[slot], ph ^ 1u, 510);
             mbar_arrive_expect_tx(&a_full[slot], (uint32_t)(parts * 2 * HX_PLANE_DATA));
             uint8_t* sl = a_ring + (size_t)slot * a_slot_bytes;
             for (int g = 0; g < 2; ++g) {
               hx_tma_4d(&map_h, &a_full[slot], sl + g * HX_PLANE, c_w, c_h, c_nd, 2 * c + g);
               if (parts == 2) hx_tma_4d(&map_l, &a_full[slot], sl + (2 + g) * HX_PLANE, c_w, c_h, c_nd, 2 * c + g);
             }
-            for (int s = 0; s < spc; ++s, ++bcount) {
-              const int st = (int)(bcount % p.bstages);
-              mbar_wait(&b_empty[st], (uint32_t)(((bcount / p.bstages) & 1) ^ 1), 520);
-              mbar_arrive_expect_tx(&b_full[st], (uint32_t)p.b_stage_bytes);
-              const uint8_t* src = p.wpack + ((size_t)(nt * p.CPC + c) * spc + s) * (size_t)p.b_stage_bytes + (size_t)rank * slice;
-              uint8_t* dst = b_ring + (size_t)st * p.b_stage_bytes + (size_t)rank * slice;
-              if (p.cluster > 1 && !(p.debug & 1)) hx_bulk_load_mc(dst, src, slice, &b_full[st], cmask);
-              else if (p.cluster > 1) hx_bulk_load(dst - (size_t)rank * slice, src - (size_t)rank * slice, (uint32_t)p.b_stage_bytes, &b_full[st]);
-              else hx_bulk_load(dst, src, slice, &b_full[st]);
-            }
+            if (++slot == HX_ASLOTS) { slot = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ===================== weight producer (bulk copies, multicast across the cluster) =====================
+    if (lane == 0) {
+      const uint32_t slice = (uint32_t)(p.b_stage_bytes / p.cluster);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int nt = 0; nt < p.ntn; ++nt) {
+        for (int it = 0; it < p.iters; ++it) {
+          const uint8_t* src = p.wpack + (size_t)nt * p.CPC * spc * (size_t)p.b_stage_bytes + (size_t)rank * slice;
+          for (int q = 0; q < p.CPC * spc; ++q, src += p.b_stage_bytes) {
+            mbar_wait(&b_empty[st], ph ^ 1u, 520);
+            mbar_arrive_expect_tx(&b_full[st], (uint32_t)p.b_stage_bytes);
+            uint8_t* dst = b_ring + (size_t)st * p.b_stage_bytes + (size_t)rank * slice;
+            if (p.cluster > 1 && !(p.debug & 1)) hx_bulk_load_mc(dst, src, slice, &b_full[st], cmask);
+            else if (p.cluster > 1) hx_bulk_load(dst - (size_t)rank * slice, src - (size_t)rank * slice, (uint32_t)p.b_stage_bytes, &b_full[st]);
+            else hx_bulk_load(dst, src, slice, &b_full[st]);
+            if (++st == p.bstages) { st = 0; ph ^= 1u; }
           }
         }
       }
@@ -177,7 +189,8 @@ conv_tc_hx_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
     const uint32_t b_hiword = (uint32_t)(make_desc_il(0, (uint32_t)(nrows * 16), 128) >> 32);
     const uint32_t a_lbo = (uint32_t)(HX_PLANE >> 4) << 16, b_lbo = (uint32_t)nrows << 16;
     const uint32_t b_tap = (uint32_t)(2 * nrows);                 // 16-byte rows per tap in a weight stage
-    uint32_t bcount = 0, acount = 0;
+    int slot = 0, st = 0;
+    uint32_t aph = 0, bph = 0;
     int local = 0;
     for (int nt = 0; nt < p.ntn; ++nt) {
       for (int it = 0; it < p.iters; ++it, ++local) {
@@ -186,22 +199,20 @@ conv_tc_hx_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
         tc_fence_after();
         const uint32_t dcol = tmem_base + (uint32_t)(buf * nrows);
         uint32_t acc = 0;
-        for (int c = 0; c < p.CPC; ++c, ++acount) {
-          const int slot = (int)(acount % HX_ASLOTS);
-          mbar_wait(&a_full[slot], (uint32_t)((acount / HX_ASLOTS) & 1), 540);
+        for (int c = 0; c < p.CPC; ++c) {
+          mbar_wait(&a_full[slot], aph, 540);
           tc_fence_after();
           const uint32_t a_hi0 = desc_addr(a_base + (uint32_t)(slot * a_slot_bytes)) | a_lbo;
           const uint32_t a_lo0 = a_hi0 + (uint32_t)((2 * HX_PLANE) >> 4);
-          for (int s = 0; s < spc; ++s, ++bcount) {
-            const int st = (int)(bcount % p.bstages);
-            mbar_wait(&b_full[st], (uint32_t)((bcount / p.bstages) & 1), 550);
+          for (int s = 0; s < spc; ++s) {
+            mbar_wait(&b_full[st], bph, 550);
             tc_fence_after();
             const uint32_t b0 = desc_addr(b_base + (uint32_t)(st * p.b_stage_bytes)) | b_lbo;
-            const int tap0 = s * p.TPS;                           // first tap (0..26) of this stage
+            const int tap0 = s * TPS;                             // first tap (0..26) of this stage
             const uint32_t a_s = (uint32_t)((tap0 / 9) * HX_HH * HX_WH + ((tap0 % 9) / 3) * HX_WH);   // halo row of (kd, kh0)
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              if (t < p.TPS) {
+            for (int t = 0; t < TPS; ++t) {
+              {
                 const uint32_t aoff = a_s + (uint32_t)((t / 3) * HX_WH + (t % 3));
                 const uint64_t a_hi = desc_join(a_hiword, a_hi0 + aoff);
                 const uint64_t b_all = desc_join(b_hiword, b0 + (uint32_t)t * b_tap);
@@ -218,16 +229,18 @@ conv_tc_hx_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
               else umma_commit(&b_empty[st]);
             }
             __syncwarp();
+            if (++st == p.bstages) { st = 0; bph ^= 1u; }
           }
           // inside a cluster the commits name their target CTA(s) by mask
           if (leader) { if (p.cluster > 1) hx_commit_mc(&a_empty[slot], self_mask); else umma_commit(&a_empty[slot]); }
           __syncwarp();
+          if (++slot == HX_ASLOTS) { slot = 0; aph ^= 1u; }
         }
         if (leader) { if (p.cluster > 1) hx_commit_mc(&t_full[buf], self_mask); else umma_commit(&t_full[buf]); }
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp < 6) {
     // ===================== epilogue =====================
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
@@ -390,13 +403,17 @@ size_t hx_workspace(const cfun_conv3d_desc* d, int pass) {
 }
 
 // cluster size and grid: the largest cluster (4, 2, 1) whose co-resident CTA count covers >= 90 % of the SMs
-static void pick_cluster(size_t smem, long long ntiles, int& cluster, int& grid) {
+static void pick_cluster(size_t smem, long long ntiles, size_t w_pass_bytes, int& cluster, int& grid) {
   static int cached_cluster = 0, cached_grid = 0;
   static size_t cached_smem = 0;
+  // Multicast halves / quarters the weight bytes pulled from L2.  Measured on B200 it is time-neutral at 2 CTAs and ~10 %
+  // slower at 4 (fewer co-resident CTAs, lock-step coupling), so the default is pairs, and only where a pass over the
+  // weights is large (>= 512 KB per tile); CFUN_HX_CLUSTER=1|2|4 forces a size.
   const char* e = getenv("CFUN_HX_CLUSTER");
-  const int forced = e ? atoi(e) : 0;
-  if (cached_cluster == 0 || cached_smem != smem) {
-    cached_cluster = 1; cached_grid = num_sms(); cached_smem = smem;
+  const int forced = e ? atoi(e) : (w_pass_bytes >= (512u << 10) ? 2 : 1);
+  static int cached_forced = -1;
+  if (cached_cluster == 0 || cached_smem != smem || cached_forced != forced) {
+    cached_cluster = 1; cached_grid = num_sms(); cached_smem = smem; cached_forced = forced;
     for (int cl = 4; cl >= 2; cl >>= 1) {
       if (forced && cl != forced) continue;
       cudaLaunchConfig_t cfg = {};
@@ -408,7 +425,7 @@ static void pick_cluster(size_t smem, long long ntiles, int& cluster, int& grid)
       at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       int nclusters = 0;
-      if (cudaOccupancyMaxActiveClusters(&nclusters, conv_tc_hx_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (cudaOccupancyMaxActiveClusters(&nclusters, conv_tc_hx_kernel<9>, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
       const int g = std::min(nclusters * cl, num_sms() / cl * cl);
       if (g * 10 >= num_sms() * 9 || forced) { cached_cluster = cl; cached_grid = g; break; }
     }
@@ -440,7 +457,8 @@ int hx_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* 
   }
   static bool attr_set = false;
   if (!attr_set) {     // before the occupancy query of pick_cluster
-    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_hx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_hx_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_hx_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   CUtensorMap mh, ml;
@@ -467,7 +485,7 @@ int hx_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* 
   p.TPS = pl.TPS; p.bstages = pl.bstages;
   p.b_stage_bytes = split ? pl.b_stage_bytes : pl.b_stage_bytes / 2;
   int cluster, grid;
-  pick_cluster(pl.smem, p.ntiles, cluster, grid);
+  pick_cluster(pl.smem, p.ntiles, (size_t)pl.CPC * 27 * 2 * (2 * pl.Npad) * 16, cluster, grid);
   p.cluster = cluster;
   { const char* e = getenv("CFUN_HX_DEBUG"); p.debug = e ? atoi(e) : 0; }
   p.iters = (int)cdiv(p.ntiles, grid);
@@ -481,7 +499,8 @@ int hx_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* 
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel, mh, ml, p));
+  if (pl.TPS == 9) CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<9>, mh, ml, p));
+  else CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<3>, mh, ml, p));
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;
 }
