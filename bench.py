@@ -385,10 +385,17 @@ def run_ours(args):
             t_dom = time_kernel(lambda: conv(x), flush=flush)
         fl = 2.0 * 4 * 96 ** 3 * 40 * 40 * 27
         ach = fl / (t_dom * 1e-3) / 1e12
-        roof = {"kernel": "conv3d fwd 3x3x3 40->40 @ 4x96^3 (mask_branch conv_norm_lrelu_l4.0, largest FLOP share of the step)",
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of conv_tc_halo_kernel for this launch, from the committed
+        # ncu --set full capture profiles/r01_ncu_unet_halo_fwd_dgrad_ds_wgrad.json (694.1 MB read: the two split-bf16
+        # activation packs once; 532.6 MB written: the fp32 output once) -- equal to the algorithmic bytes, no re-reads
+        roof = {"kernel": "conv3d fwd 3x3x3 40->40 @ 4x96^3 (mask_branch conv_norm_lrelu_l4.0, largest FLOP share of the step; "
+                          "pack_act_gp + pack_w_halo + conv_tc_halo_kernel)",
                 "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"] + " bf16 burst",
-                "ms": t_dom, "algorithmic_flop": fl}
+                "frac": ach / peaks["bf16_tflops"], "traffic": 1226.7e6, "traffic_unit": "bytes per launch (ncu dram read + write)",
+                "peak_source": peaks["source"] + " bf16 burst",
+                "ms": t_dom, "algorithmic_flop": fl,
+                "note": "parity mode issues 3 bf16 MMAs per product (split-bf16, DESIGN.md 4): frac is capped at 1/3; ncu "
+                        "tensor-pipe active 57 % for this kernel, 80 % for the 128->256 headline conv"}
         conv2 = Conv3d(128, 256, 3, padding=1).to(dev)
         x2 = ops.to_cl(torch.randn(1, 128, 32, 32, 32, device=dev))
         with torch.no_grad():
