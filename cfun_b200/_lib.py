@@ -43,6 +43,10 @@ SIGNATURES = {
     "cfun_conv3d_fwd": (_i, [_D, _p, _p, _p, _p, _i, _i, _p, _sz, _p]),
     "cfun_conv3d_bwd_data": (_i, [_D, _p, _p, _p, _i, _p, _sz, _p]),
     "cfun_conv3d_bwd_weight": (_i, [_D, _p, _p, _p, _p, _i, _p, _sz, _p]),
+    "cfun_conv3d_pack_bytes": (_sz, [_D]),
+    "cfun_conv3d_bwd_fused_workspace_size": (_sz, [_D]),
+    "cfun_conv3d_fwd_keep_pack": (_i, [_D, _p, _p, _p, _p, _i, _p, _sz, _p, _sz, _p]),
+    "cfun_conv3d_bwd_fused": (_i, [_D, _p, _sz, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "cfun_fc_fwd": (_i, [_i, _i, _ll, _p, _p, _p, _p, _p]),
     "cfun_fc_bwd_data": (_i, [_i, _i, _ll, _p, _p, _p, _p]),
     "cfun_fc_bwd_weight": (_i, [_i, _i, _ll, _p, _p, _p, _p, _p]),

@@ -1,0 +1,105 @@
+// Fused backward of the 3x3x3 / stride-1 tensor-core convolutions.
+//
+// The halo-family kernels (conv_tc_halo.cu, conv_tc_hx.cu, conv_tc_wgrad_ds.cu) all consume the same operand format: a
+// group-planar split-bf16 pack [C/8][N*(D+2)][H][W][8ch] (hi and lo).  A train step used to write it four times per conv
+// (forward: X; data gradient: dY; weight gradient: X and dY again), ~0.3 ms per 40-channel 96^3 tensor each time.  Here
+//   * cfun_conv3d_fwd_keep_pack   runs the forward and leaves the X pack in a caller-owned buffer,
+//   * cfun_conv3d_bwd_fused       packs dY once and feeds it to the data-gradient kernel AND (with the kept X pack) to the
+//                                 d-stacked weight-gradient kernel.
+// Replaces the same nn.Conv3d forward / autograd backward as cfun_conv3d_{fwd,bwd_data,bwd_weight} (mask_branch.py:23-89,
+// model.py:131-148,713 and loss.backward() at model.py:1640) for the shapes where all three passes run on these kernels.
+#include "common.cuh"
+#include <cuda_bf16.h>
+#include <cstdlib>
+
+namespace cfun {
+bool hl_supported(const cfun_conv3d_desc* d, int pass);
+bool hx_supported(const cfun_conv3d_desc* d, int pass);
+bool ds_supported(const cfun_conv3d_desc* d);
+size_t hl_pack_bytes(const cfun_conv3d_desc* d, int pass);
+size_t hx_pack_bytes(const cfun_conv3d_desc* d, int pass);
+size_t tc_workspace(const cfun_conv3d_desc* d, int pass);
+int hl_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
+               int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st);
+int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
+               int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st);
+int ds_bwd_weight_packed(const cfun_conv3d_desc* d, __nv_bfloat16* yh, __nv_bfloat16* yl, int gy_pack, __nv_bfloat16* xh,
+                         __nv_bfloat16* xl, float* dw, cudaStream_t st);
+int launch_pack_act_gp(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int C, int G,
+                       cudaStream_t st);
+int simt_bias_grad(const float* dy, long long M, int C, float* dbias, cudaStream_t st);
+
+static bool fused_ok(const cfun_conv3d_desc* d) {
+  const char* e = getenv("CFUN_CONV_FUSED");      // "0": separate fwd / dgrad / wgrad calls (A/B measurements)
+  if (e && e[0] == '0') return false;
+  if (!d) return false;
+  for (int pass = 0; pass < 3; ++pass)
+    if (cfun_conv3d_pick_algo(d, pass) != CFUN_CONV_ALGO_TC) return false;
+  if (!hl_supported(d, CFUN_PASS_FWD) && !hx_supported(d, CFUN_PASS_FWD)) return false;
+  if (!hl_supported(d, CFUN_PASS_BWD_DATA) && !hx_supported(d, CFUN_PASS_BWD_DATA)) return false;
+  return ds_supported(d);
+}
+static size_t act_bytes(const cfun_conv3d_desc* d, int pass) {
+  return hl_supported(d, pass) ? hl_pack_bytes(d, pass) : hx_pack_bytes(d, pass);
+}
+static int run_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
+                    void* ws, size_t ws_bytes, __nv_bfloat16* hi, __nv_bfloat16* lo, bool ready, cudaStream_t st) {
+  if (hl_supported(d, pass)) return hl_conv_ex(d, pass, src, w, bias, dst, epi, 3, ws, ws_bytes, hi, lo, ready, st);
+  return hx_conv_ex(d, pass, src, w, bias, dst, epi, 3, ws, ws_bytes, hi, lo, ready, st);
+}
+}  // namespace cfun
+
+using namespace cfun;
+
+extern "C" size_t cfun_conv3d_pack_bytes(const cfun_conv3d_desc* d) {
+  if (!fused_ok(d)) return 0;
+  return 2 * act_bytes(d, CFUN_PASS_FWD);
+}
+
+extern "C" size_t cfun_conv3d_bwd_fused_workspace_size(const cfun_conv3d_desc* d) {
+  if (!fused_ok(d)) return 0;
+  return 2 * act_bytes(d, CFUN_PASS_BWD_DATA) + tc_workspace(d, CFUN_PASS_BWD_DATA) + 4096;
+}
+
+extern "C" int cfun_conv3d_fwd_keep_pack(const cfun_conv3d_desc* d, const float* x, const float* w, const float* bias, float* y,
+                                         int epi_flags, void* xpack, size_t xpack_bytes, void* ws, size_t ws_bytes, void* stream) {
+  CFUN_CHECK_ARG(fused_ok(d));
+  CFUN_CHECK_ARG(x && w && y && xpack && ws);
+  CFUN_CHECK_ARG(!(epi_flags & CFUN_EPI_BIAS) || bias);
+  const size_t act = act_bytes(d, CFUN_PASS_FWD);
+  CFUN_CHECK_ARG(xpack_bytes >= 2 * act && ((size_t)xpack & 127) == 0);
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(xpack);
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(xpack) + act);
+  return run_conv(d, CFUN_PASS_FWD, x, w, bias, y, epi_flags, ws, ws_bytes, hi, lo, false, as_stream(stream));
+}
+
+extern "C" int cfun_conv3d_bwd_fused(const cfun_conv3d_desc* d, const void* xpack, size_t xpack_bytes, const float* dy,
+                                     const float* w, float* dx, float* dw, float* dbias, void* ws, size_t ws_bytes, void* stream) {
+  CFUN_CHECK_ARG(fused_ok(d));
+  CFUN_CHECK_ARG(dy && w && ws && (dx || dw || dbias));
+  cudaStream_t st = as_stream(stream);
+  const size_t act_y = act_bytes(d, CFUN_PASS_BWD_DATA);
+  const size_t inner = tc_workspace(d, CFUN_PASS_BWD_DATA);
+  const size_t base = align_up((size_t)ws, 1024);
+  if (base + 2 * act_y + inner > (size_t)ws + ws_bytes) { set_error("conv3d fused backward: workspace too small"); return CFUN_ERR_WORKSPACE; }
+  __nv_bfloat16* yh = reinterpret_cast<__nv_bfloat16*>(base);
+  __nv_bfloat16* yl = reinterpret_cast<__nv_bfloat16*>(base + act_y);
+  void* iws = reinterpret_cast<void*>(base + 2 * act_y);
+  const int gy = (int)align_up((size_t)d->Cout, 16) / 8;
+  int rc;
+  if (dx || dw) {
+    if ((rc = launch_pack_act_gp(dy, yh, yl, d->N, d->Dout, d->Hout, d->Wout, d->Cout, gy, st)) != CFUN_OK) return rc;
+  }
+  if (dx) {
+    if ((rc = run_conv(d, CFUN_PASS_BWD_DATA, nullptr, w, nullptr, dx, 0, iws, ws_bytes - (2 * act_y + (base - (size_t)ws)), yh, yl, true, st)) != CFUN_OK) return rc;
+  }
+  if (dw) {
+    const size_t act_x = act_bytes(d, CFUN_PASS_FWD);
+    CFUN_CHECK_ARG(xpack && xpack_bytes >= 2 * act_x);
+    __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(xpack));
+    __nv_bfloat16* xl = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(const_cast<void*>(xpack)) + act_x);
+    if ((rc = ds_bwd_weight_packed(d, yh, yl, gy, xh, xl, dw, st)) != CFUN_OK) return rc;
+  }
+  if (dbias) return simt_bias_grad(dy, (long long)d->N * d->Dout * d->Hout * d->Wout, d->Cout, dbias, st);
+  return CFUN_OK;
+}

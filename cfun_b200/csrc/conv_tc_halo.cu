@@ -363,22 +363,36 @@ size_t hl_workspace(const cfun_conv3d_desc* d, int pass) {
   return make_hl_plan(d, pass, pl) ? pl.total : 0;
 }
 
+// ext_hi / ext_lo (optional): caller-owned buffers for the split-bf16 activation pack (pl.act_bytes each, see
+// hl_pack_bytes); ext_ready = the pack is already in them (fused backward, forward pack kept for the weight gradient).
+int hl_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
+               int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st);
 int hl_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
             int nsplit, void* ws, size_t ws_bytes, cudaStream_t st) {
+  return hl_conv_ex(d, pass, src, w, bias, dst, epi, nsplit, ws, ws_bytes, nullptr, nullptr, false, st);
+}
+size_t hl_pack_bytes(const cfun_conv3d_desc* d, int pass) {
+  HlPlan pl;
+  return make_hl_plan(d, pass, pl) ? pl.act_bytes : 0;
+}
+int hl_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
+               int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st) {
   HlPlan pl;
   CFUN_CHECK_ARG(make_hl_plan(d, pass, pl));
-  CFUN_CHECK_ARG(src && w && dst && ws && get_tensor_map_encoder());
+  CFUN_CHECK_ARG((src || ext_ready) && w && dst && ws && get_tensor_map_encoder());
   const size_t base = align_up((size_t)ws, 1024);
   if (ws_bytes < pl.total || base + pl.total - 2048 > (size_t)ws + ws_bytes) { set_error("conv3d halo: workspace too small"); return CFUN_ERR_WORKSPACE; }
   const bool split = nsplit == 3;
   const int parts = split ? 2 : 1;
-  __nv_bfloat16* ah = reinterpret_cast<__nv_bfloat16*>(base + pl.off_ah);
-  __nv_bfloat16* al = reinterpret_cast<__nv_bfloat16*>(base + pl.off_al);
+  __nv_bfloat16* ah = ext_hi ? ext_hi : reinterpret_cast<__nv_bfloat16*>(base + pl.off_ah);
+  __nv_bfloat16* al = ext_hi ? ext_lo : reinterpret_cast<__nv_bfloat16*>(base + pl.off_al);
   __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(base + pl.off_w);
   {
-    long long total = (long long)pl.G * pl.N * (pl.D + 2) * pl.H * pl.W;
-    pack_act_gp_kernel<<<(unsigned)std::min<long long>(cdiv(total, 256), 32LL * num_sms()), 256, 0, st>>>(src, ah, split ? al : nullptr, pl.N, pl.D, pl.H, pl.W, pl.Cs, pl.G);
-    CFUN_LAUNCH_CHECK();
+    if (!(ext_hi && ext_ready)) {
+      long long total = (long long)pl.G * pl.N * (pl.D + 2) * pl.H * pl.W;
+      pack_act_gp_kernel<<<(unsigned)std::min<long long>(cdiv(total, 256), 32LL * num_sms()), 256, 0, st>>>(src, ah, split ? al : nullptr, pl.N, pl.D, pl.H, pl.W, pl.Cs, pl.G);
+      CFUN_LAUNCH_CHECK();
+    }
     long long wt = (long long)pl.CPC * 3 * parts * 9 * 2 * pl.Npad * 8;
     pack_w_halo_kernel<<<(unsigned)std::min<long long>(cdiv(wt, 256), 4LL * num_sms()), 256, 0, st>>>(w, wp, d->Cout, d->Cin, pl.Npad, pl.CPC, parts, pass == CFUN_PASS_BWD_DATA ? 1 : 0);
     CFUN_LAUNCH_CHECK();

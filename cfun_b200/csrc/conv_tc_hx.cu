@@ -436,20 +436,32 @@ static void pick_cluster(size_t smem, long long ntiles, size_t w_pass_bytes, int
   if (ntiles < grid) grid = (int)(cdiv(ntiles, cluster) * cluster);
 }
 
+int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
+               int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st);
 int hx_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
             int nsplit, void* ws, size_t ws_bytes, cudaStream_t st) {
+  return hx_conv_ex(d, pass, src, w, bias, dst, epi, nsplit, ws, ws_bytes, nullptr, nullptr, false, st);
+}
+size_t hx_pack_bytes(const cfun_conv3d_desc* d, int pass) {
+  HxPlan pl;
+  return make_hx_plan(d, pass, pl) ? pl.act_bytes : 0;
+}
+// ext_hi / ext_lo: see hl_conv_ex (conv_tc_halo.cu)
+int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
+               int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st) {
   HxPlan pl;
   CFUN_CHECK_ARG(make_hx_plan(d, pass, pl));
-  CFUN_CHECK_ARG(src && w && dst && ws && get_tensor_map_encoder());
+  CFUN_CHECK_ARG((src || ext_ready) && w && dst && ws && get_tensor_map_encoder());
   const size_t base = align_up((size_t)ws, 1024);
   if (ws_bytes < pl.total || base + pl.total - 2048 > (size_t)ws + ws_bytes) { set_error("conv3d hx: workspace too small"); return CFUN_ERR_WORKSPACE; }
   const bool split = nsplit == 3;
   const int parts = split ? 2 : 1;
-  __nv_bfloat16* ah = reinterpret_cast<__nv_bfloat16*>(base + pl.off_ah);
-  __nv_bfloat16* al = reinterpret_cast<__nv_bfloat16*>(base + pl.off_al);
+  __nv_bfloat16* ah = ext_hi ? ext_hi : reinterpret_cast<__nv_bfloat16*>(base + pl.off_ah);
+  __nv_bfloat16* al = ext_hi ? ext_lo : reinterpret_cast<__nv_bfloat16*>(base + pl.off_al);
   __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(base + pl.off_w);
   int rc;
-  if ((rc = launch_pack_act_gp(src, ah, split ? al : nullptr, pl.N, pl.D, pl.H, pl.W, pl.Cs, pl.G, st)) != CFUN_OK) return rc;
+  if (!(ext_hi && ext_ready))
+    if ((rc = launch_pack_act_gp(src, ah, split ? al : nullptr, pl.N, pl.D, pl.H, pl.W, pl.Cs, pl.G, st)) != CFUN_OK) return rc;
   {
     long long wt = (long long)pl.ntn * pl.CPC * 3 * parts * 9 * 2 * pl.Npad * 8;
     pack_w_hx_kernel<<<(unsigned)std::min<long long>(cdiv(wt, 256), 4LL * num_sms()), 256, 0, st>>>(w, wp, d->Cout, d->Cin, pl.Npad, pl.ntn, pl.CPC, parts, pass == CFUN_PASS_BWD_DATA ? 1 : 0);

@@ -269,13 +269,15 @@ static int encode_gp_map_ds(CUtensorMap* m, void* base, int W, int H, long long 
 }
 
 // yh/yl/xh/xl: group-planar split-bf16 packs (pack_act_gp) of dY (Gy_total groups) and X (Gx groups)
+// gy_pack: channel groups the dY pack was written with (>= Gy_total; the fused backward shares the data gradient's pack,
+// whose group count is rounded up to a multiple of 2 -- the extra group is zeros)
 int ds_launch(const cfun_conv3d_desc* d, const DsPlan& pl, __nv_bfloat16* yh, __nv_bfloat16* yl, __nv_bfloat16* xh,
-              __nv_bfloat16* xl, float* dw, bool split, cudaStream_t st) {
+              __nv_bfloat16* xl, float* dw, bool split, int gy_pack, cudaStream_t st) {
   CUtensorMap myh, myl, mxh, mxl;
   int rc;
   const long long planes = (long long)d->N * (d->Din + 2);
-  if ((rc = encode_gp_map_ds(&myh, yh, d->Wout, d->Hout, planes, pl.Gy_total, DS_WT * 8, DS_HT, 3, pl.Gt)) != CFUN_OK) return rc;
-  if ((rc = encode_gp_map_ds(&myl, split ? yl : yh, d->Wout, d->Hout, planes, pl.Gy_total, DS_WT * 8, DS_HT, 3, pl.Gt)) != CFUN_OK) return rc;
+  if ((rc = encode_gp_map_ds(&myh, yh, d->Wout, d->Hout, planes, gy_pack, DS_WT * 8, DS_HT, 3, pl.Gt)) != CFUN_OK) return rc;
+  if ((rc = encode_gp_map_ds(&myl, split ? yl : yh, d->Wout, d->Hout, planes, gy_pack, DS_WT * 8, DS_HT, 3, pl.Gt)) != CFUN_OK) return rc;
   if ((rc = encode_gp_map_ds(&mxh, xh, d->Win, d->Hin, planes, pl.Gx, DS_WH * 8, DS_HH, 1, pl.Gx)) != CFUN_OK) return rc;
   if ((rc = encode_gp_map_ds(&mxl, split ? xl : xh, d->Win, d->Hin, planes, pl.Gx, DS_WH * 8, DS_HH, 1, pl.Gx)) != CFUN_OK) return rc;
 
@@ -320,10 +322,21 @@ int ds_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* d
   if ((prc = launch_pack_act_gp(dy, yh, split ? yl : nullptr, d->N, d->Dout, d->Hout, d->Wout, d->Cout, pl.Gy_total, st)) != CFUN_OK) return prc;
   if ((prc = launch_pack_act_gp(x, xh, split ? xl : nullptr, d->N, d->Din, d->Hin, d->Win, d->Cin, pl.Gx, st)) != CFUN_OK) return prc;
   CFUN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * d->Cin * 27, st));
-  int rc = ds_launch(d, pl, yh, yl, xh, xl, dw, split, st);
+  int rc = ds_launch(d, pl, yh, yl, xh, xl, dw, split, pl.Gy_total, st);
   if (rc != CFUN_OK) return rc;
   if (dbias) return simt_bias_grad(dy, (long long)d->N * d->Dout * d->Hout * d->Wout, d->Cout, dbias, st);
   return CFUN_OK;
+}
+
+// weight gradient from ready-made packs (fused backward): xh/xl = forward's X pack (align16(Cin)/8 groups), yh/yl = the data
+// gradient's dY pack (gy_pack groups)
+int ds_bwd_weight_packed(const cfun_conv3d_desc* d, __nv_bfloat16* yh, __nv_bfloat16* yl, int gy_pack, __nv_bfloat16* xh,
+                         __nv_bfloat16* xl, float* dw, cudaStream_t st) {
+  DsPlan pl;
+  CFUN_CHECK_ARG(make_ds_plan(d, pl));
+  CFUN_CHECK_ARG(yh && yl && xh && xl && dw && gy_pack >= pl.Gy_total);
+  CFUN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * d->Cin * 27, st));
+  return ds_launch(d, pl, yh, yl, xh, xl, dw, true, gy_pack, st);
 }
 
 int tc_debug_read_ds(int* out8) {

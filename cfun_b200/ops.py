@@ -165,13 +165,24 @@ class Conv3dFn(Function):
         ws_bytes = lib.cfun_conv3d_workspace_size(C.byref(d), PASS_FWD, algo)
         ws = workspace(ws_bytes, x.device)
         epi = (EPI_BIAS if b is not None else 0) | (EPI_RELU if relu else 0)
-        _run("cfun_conv3d_fwd", C.byref(d), _ptr(x), _ptr(w), _ptr(b), _ptr(y), epi, algo, _ptr(ws), ws.numel(), _stream(),
-             tag=_conv_tag(d, PASS_FWD, algo) if _prof["on"] else "")
+        # Fused backward (conv_fused.cu): where all three passes run on the halo-family tcgen05 kernels, the forward keeps its
+        # split-bf16 pack of x for the weight gradient, and the backward packs dy once for both gradients.
+        pack_bytes = lib.cfun_conv3d_pack_bytes(C.byref(d)) if (algo == ALGO_AUTO and ctx.needs_input_grad[1]) else 0
+        xpack = None
+        if pack_bytes:
+            xpack = torch.empty(pack_bytes, dtype=torch.uint8, device=x.device)
+            _run("cfun_conv3d_fwd_keep_pack", C.byref(d), _ptr(x), _ptr(w), _ptr(b), _ptr(y), epi, _ptr(xpack), xpack.numel(),
+                 _ptr(ws), ws.numel(), _stream(), tag=_conv_tag(d, PASS_FWD, algo) if _prof["on"] else "")
+        else:
+            _run("cfun_conv3d_fwd", C.byref(d), _ptr(x), _ptr(w), _ptr(b), _ptr(y), epi, algo, _ptr(ws), ws.numel(), _stream(),
+                 tag=_conv_tag(d, PASS_FWD, algo) if _prof["on"] else "")
         ctx.d = d
         ctx.relu = relu
         ctx.has_bias = b is not None
         ctx.algo = algo
-        ctx.save_for_backward(x, w, y if relu else None)
+        ctx.fused = xpack is not None
+        # the fused backward reads x only through its pack
+        ctx.save_for_backward(xpack if xpack is not None else x, w, y if relu else None)
         return y
 
     @staticmethod
@@ -182,6 +193,19 @@ class Conv3dFn(Function):
         if ctx.relu:
             dy = to_cl(torch.where(y > 0, dy, torch.zeros((), device=dy.device)))
         dx = dw = db = None
+        if ctx.fused:
+            xpack = x
+            if ctx.needs_input_grad[0]:
+                dx = empty_cl(d.N, d.Cin, d.Din, d.Hin, d.Win, dy.device)
+            if ctx.needs_input_grad[1]:
+                dw = torch.empty_like(w)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                db = torch.empty(d.Cout, device=dy.device)
+            ws_bytes = lib.cfun_conv3d_bwd_fused_workspace_size(C.byref(d))
+            ws = workspace(ws_bytes, dy.device)
+            _run("cfun_conv3d_bwd_fused", C.byref(d), _ptr(xpack), xpack.numel(), _ptr(dy), _ptr(w), _ptr(dx), _ptr(dw), _ptr(db),
+                 _ptr(ws), ws.numel(), _stream(), tag=_conv_tag(d, PASS_BWD_WEIGHT, ctx.algo) if _prof["on"] else "")
+            return dx, dw, db, None, None, None
         if ctx.needs_input_grad[0]:
             dx = empty_cl(d.N, d.Cin, d.Din, d.Hin, d.Win, dy.device)
             ws_bytes = lib.cfun_conv3d_workspace_size(C.byref(d), PASS_BWD_DATA, ctx.algo)

@@ -74,6 +74,20 @@ int cfun_conv3d_bwd_data(const cfun_conv3d_desc* d, const float* dy, const float
 int cfun_conv3d_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, float* dbias,
                            int algo, void* ws, size_t ws_bytes, void* stream);
 
+/* Fused backward for the 3x3x3 / stride-1 convs whose three passes run on the halo-family tcgen05 kernels (the U-Net
+ * mask branch mask_branch.py:23-89, FPN smoothing model.py:133-134, RPN.conv_shared model.py:713): the split-bf16 operand
+ * pack of X written by the forward is kept for the weight gradient, and dY is packed once for both gradients.
+ *   cfun_conv3d_pack_bytes            bytes of the X pack the caller must own (0 = shape not eligible, use the calls above)
+ *   cfun_conv3d_fwd_keep_pack         = cfun_conv3d_fwd, leaving the pack in xpack (128-byte aligned)
+ *   cfun_conv3d_bwd_fused             = cfun_conv3d_bwd_data (dx may be NULL) + cfun_conv3d_bwd_weight (dw / dbias may be NULL)
+ * Forward workspace: cfun_conv3d_workspace_size(d, CFUN_PASS_FWD, CFUN_CONV_ALGO_AUTO). */
+size_t cfun_conv3d_pack_bytes(const cfun_conv3d_desc* d);
+size_t cfun_conv3d_bwd_fused_workspace_size(const cfun_conv3d_desc* d);
+int cfun_conv3d_fwd_keep_pack(const cfun_conv3d_desc* d, const float* x, const float* w, const float* bias, float* y,
+                              int epi_flags, void* xpack, size_t xpack_bytes, void* ws, size_t ws_bytes, void* stream);
+int cfun_conv3d_bwd_fused(const cfun_conv3d_desc* d, const void* xpack, size_t xpack_bytes, const float* dy, const float* w,
+                          float* dx, float* dw, float* dbias, void* ws, size_t ws_bytes, void* stream);
+
 /* Classifier.conv1 (model.py:758): a kernel-size == input-size conv, i.e. a [M,K]x[Nout,K]^T product with
  * K = Cin*kD*kH*kW (221184) and M = #RoIs (12).  x is NCDHW-contiguous [M,K]; w is [Nout,K]. */
 int cfun_fc_fwd(int M, int Nout, long long K, const float* x, const float* w, const float* bias, float* y, void* stream);
