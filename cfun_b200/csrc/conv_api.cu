@@ -22,6 +22,11 @@ int tc_conv_bwd_data(const cfun_conv3d_desc* d, const float* dy, const float* w,
 int tc_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, float* dbias, int nsplit,
                        void* ws, size_t ws_bytes, cudaStream_t st);
 
+// conv_c1.cu: direct CUDA-core kernels for single-channel inputs (stem, first U-Net conv); part of the SIMT algorithm
+bool c1_supported(const cfun_conv3d_desc* d, int pass);
+int c1_conv_fwd(const cfun_conv3d_desc* d, const float* x, const float* w, const float* bias, float* y, int epi, cudaStream_t st);
+int c1_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, float* dbias, cudaStream_t st);
+
 static int resolve(const cfun_conv3d_desc* d, int pass, int algo) {
   if (algo == CFUN_CONV_ALGO_AUTO) {
     const char* e = getenv("CFUN_CONV_ALGO");  // "simt" pins the CUDA-core path (debug / A-B measurements)
@@ -55,6 +60,7 @@ extern "C" int cfun_conv3d_fwd(const cfun_conv3d_desc* d, const float* x, const 
                                int epi_flags, int algo, void* ws, size_t ws_bytes, void* stream) {
   CFUN_CHECK_ARG(d != nullptr);
   int a = resolve(d, CFUN_PASS_FWD, algo);
+  if (a == CFUN_CONV_ALGO_SIMT && c1_supported(d, CFUN_PASS_FWD)) return c1_conv_fwd(d, x, w, bias, y, epi_flags, as_stream(stream));
   if (a == CFUN_CONV_ALGO_SIMT) return simt_conv_fwd(d, x, w, bias, y, epi_flags, ws, ws_bytes, as_stream(stream));
   CFUN_CHECK_ARG(tc_supported(d, CFUN_PASS_FWD));
   return tc_conv_fwd(d, x, w, bias, y, epi_flags, a == CFUN_CONV_ALGO_TC1 ? 1 : 3, ws, ws_bytes, as_stream(stream));
@@ -73,6 +79,7 @@ extern "C" int cfun_conv3d_bwd_weight(const cfun_conv3d_desc* d, const float* x,
                                       int algo, void* ws, size_t ws_bytes, void* stream) {
   CFUN_CHECK_ARG(d != nullptr);
   int a = resolve(d, CFUN_PASS_BWD_WEIGHT, algo);
+  if (a == CFUN_CONV_ALGO_SIMT && c1_supported(d, CFUN_PASS_BWD_WEIGHT)) return c1_conv_bwd_weight(d, x, dy, dw, dbias, as_stream(stream));
   if (a == CFUN_CONV_ALGO_SIMT) return simt_conv_bwd_weight(d, x, dy, dw, dbias, ws, ws_bytes, as_stream(stream));
   CFUN_CHECK_ARG(tc_supported(d, CFUN_PASS_BWD_WEIGHT));
   return tc_conv_bwd_weight(d, x, dy, dw, dbias, a == CFUN_CONV_ALGO_TC1 ? 1 : 3, ws, ws_bytes, as_stream(stream));
