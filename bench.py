@@ -81,35 +81,65 @@ WEIGHT_SEED = 2     # chosen so that the synthetic volume yields
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled during the timed region (B200_PROFILING.md recipe).  NVML in-process (one
+    call takes microseconds, so even a 250 ms timed region gets tens of samples); `nvidia-smi` as the fallback."""
+
+    HW_SLOWDOWN, SW_POWER_CAP, SW_THERMAL, HW_THERMAL = 0x8, 0x4, 0x20, 0x40
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
         self.stop_flag = threading.Event()
-        self.rows = []
+        self.rows = []          # (sm_mhz, sm_max_mhz, set of reason names)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    def sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+            mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+            try:
+                bits = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            except Exception:
+                bits = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            names = {nm for nm, b in (("hw_slowdown", self.HW_SLOWDOWN), ("hw_thermal_slowdown", self.HW_THERMAL),
+                                      ("sw_thermal_slowdown", self.SW_THERMAL), ("sw_power_cap", self.SW_POWER_CAP)) if bits & b}
+            self.rows.append((int(sm), int(mx), names))
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        c = [v.strip() for v in out.split(",")]
+        if len(c) >= 6 and c[0].isdigit():
+            names = {nm for nm, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[2:6])
+                     if v.lower().startswith("active")}
+            self.rows.append((int(c[0]), int(c[1]) if c[1].isdigit() else None, names))
+
+    def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                self.sample()
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.01 if self.nvml is not None else 0.2)
 
     def summary(self):
         self.stop_flag.set()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        sm = sorted(r[0] for r in self.rows)
+        mx = [r[1] for r in self.rows if r[1]]
+        reasons = sorted({n for r in self.rows for n in r[2]})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -332,11 +362,11 @@ def run_ours(args):
         roi_counts.append(list(net.last_roi_counts))
     e.record()
     barrier()
+    clocks = sampler.summary()          # samples cover exactly the timed region (GPU busy from s to e)
     ms = s.elapsed_time(e)
     launches = ops.launch_count() - l0
     for key, cnt in net.graph_replays.items():          # kernels inside replayed graphs are not seen by the launch hook
         launches += (cnt - replays0.get(key, 0)) * net.graph_kernel_counts.get(key, 0)
-    clocks = sampler.summary()
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
