@@ -44,7 +44,8 @@ __device__ __forceinline__ void tma_load_4d_ds(const CUtensorMap* map, uint64_t*
 struct DsParams {
   int N, D, H, W, Cout, Cin;
   int Gt;                     // dY channel groups per M tile (<= 5)
-  int Gx;                     // X channel groups (Npad / 8)
+  int Gx;                     // X channel groups of this launch's Cin slice (Npad / 8)
+  int ci0;                    // first input channel of the slice (dW addressing); X groups start at ci0 / 8
   int Npad;                   // MMA N
   int T9, ng9;                // (kh,kw) taps per CTA, number of tap groups
   int tilesH, tilesW;
@@ -104,7 +105,7 @@ conv_tc_wgrad_ds_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid
           tma_load_4d_ds(part == 0 ? &map_yh : &map_yl, &full_bar[slot], sb + (size_t)part * p.y_bytes, wb * DS_WT * 8,
                          hb * DS_HT, plane0, g0);
           tma_load_4d_ds(part == 0 ? &map_xh : &map_xl, &full_bar[slot], sb + (size_t)parts * p.y_bytes + (size_t)part * p.x_bytes,
-                         (wb * DS_WT - 1) * 8, hb * DS_HT - 1, plane0 + 1, 0);
+                         (wb * DS_WT - 1) * 8, hb * DS_HT - 1, plane0 + 1, p.ci0 >> 3);
         }
       }
     }
@@ -174,7 +175,7 @@ conv_tc_wgrad_ds_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid
           if (row_ok) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const int ci = j + i;
+              const int ci = p.ci0 + j + i;
               if (ci < p.Cin) atomicAdd(p.dw + ((long long)co * p.Cin + ci) * 27 + tap, __uint_as_float(r[i]));
             }
           }
@@ -192,6 +193,7 @@ conv_tc_wgrad_ds_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid
 
 struct DsPlan {
   int Gy_total, Gt, Gx, Npad, T9, ng9, mtiles, stages, tmem_cols;
+  int Gx_total, slices;        // input channels are processed in `slices` launches of Gx groups (MMA N = 8 Gx <= 128)
   int y_bytes, x_bytes, stage_bytes;
   size_t act_y, act_x, off_yh, off_yl, off_xh, off_xl, total, smem;
 };
@@ -201,9 +203,12 @@ static bool make_ds_plan(const cfun_conv3d_desc* d, DsPlan& pl) {
   if (d->kD != 3 || d->kH != 3 || d->kW != 3 || d->pD != 1 || d->pH != 1 || d->pW != 1) return false;
   if (d->Hin < 8 || d->Win < 8) return false;
   pl.Gy_total = (int)cdiv(d->Cout, 8);
-  pl.Gx = (int)align_up((size_t)d->Cin, 16) / 8;
+  pl.Gx_total = (int)align_up((size_t)d->Cin, 16) / 8;
+  // wide inputs: slices of <= 80 channels (10 groups) keep two pipeline stages of X planes + 3 dY planes in shared memory
+  pl.slices = pl.Gx_total <= 10 ? 1 : (int)cdiv(pl.Gx_total, 10);
+  pl.Gx = (int)align_up((size_t)cdiv(pl.Gx_total, pl.slices), 2);
   pl.Npad = pl.Gx * 8;
-  if (pl.Npad > 128) return false;
+  if (pl.Npad > 128 || pl.slices > 8) return false;
   pl.T9 = std::min(9, 512 / pl.Npad);
   pl.ng9 = (int)cdiv(9, pl.T9);
   pl.T9 = (int)cdiv(9, pl.ng9);
@@ -235,7 +240,7 @@ static bool make_ds_plan(const cfun_conv3d_desc* d, DsPlan& pl) {
   pl.Gt = (int)cdiv(pl.Gy_total, pl.mtiles);
   pl.y_bytes = pl.Gt * 3 * DS_YP;
   pl.act_y = align_up((size_t)pl.Gy_total * d->N * (d->Dout + 2) * d->Hout * d->Wout * 16, 1024);
-  pl.act_x = align_up((size_t)pl.Gx * d->N * (d->Din + 2) * d->Hin * d->Win * 16, 1024);
+  pl.act_x = align_up((size_t)pl.Gx_total * d->N * (d->Din + 2) * d->Hin * d->Win * 16, 1024);
   pl.off_yh = 0; pl.off_yl = pl.act_y; pl.off_xh = 2 * pl.act_y; pl.off_xl = 2 * pl.act_y + pl.act_x;
   pl.total = 2 * pl.act_y + 2 * pl.act_x + 2048;
   return true;
@@ -278,8 +283,8 @@ int ds_launch(const cfun_conv3d_desc* d, const DsPlan& pl, __nv_bfloat16* yh, __
   const long long planes = (long long)d->N * (d->Din + 2);
   if ((rc = encode_gp_map_ds(&myh, yh, d->Wout, d->Hout, planes, gy_pack, DS_WT * 8, DS_HT, 3, pl.Gt)) != CFUN_OK) return rc;
   if ((rc = encode_gp_map_ds(&myl, split ? yl : yh, d->Wout, d->Hout, planes, gy_pack, DS_WT * 8, DS_HT, 3, pl.Gt)) != CFUN_OK) return rc;
-  if ((rc = encode_gp_map_ds(&mxh, xh, d->Win, d->Hin, planes, pl.Gx, DS_WH * 8, DS_HH, 1, pl.Gx)) != CFUN_OK) return rc;
-  if ((rc = encode_gp_map_ds(&mxl, split ? xl : xh, d->Win, d->Hin, planes, pl.Gx, DS_WH * 8, DS_HH, 1, pl.Gx)) != CFUN_OK) return rc;
+  if ((rc = encode_gp_map_ds(&mxh, xh, d->Win, d->Hin, planes, pl.Gx_total, DS_WH * 8, DS_HH, 1, pl.Gx)) != CFUN_OK) return rc;
+  if ((rc = encode_gp_map_ds(&mxl, split ? xl : xh, d->Win, d->Hin, planes, pl.Gx_total, DS_WH * 8, DS_HH, 1, pl.Gx)) != CFUN_OK) return rc;
 
   DsParams p;
   p.N = d->N; p.D = d->Din; p.H = d->Hin; p.W = d->Win; p.Cout = d->Cout; p.Cin = d->Cin;
@@ -301,8 +306,11 @@ int ds_launch(const cfun_conv3d_desc* d, const DsPlan& pl, __nv_bfloat16* yh, __
     attr_set = true;
   }
   dim3 grid((unsigned)ctas, (unsigned)pl.ng9, (unsigned)pl.mtiles);
-  conv_tc_wgrad_ds_kernel<<<grid, DS_THREADS, pl.smem, st>>>(myh, myl, mxh, mxl, p);
-  CFUN_LAUNCH_CHECK();
+  for (int sl = 0; sl < pl.slices; ++sl) {     // groups beyond Gx_total in the last slice are TMA zero fill
+    p.ci0 = sl * pl.Gx * 8;
+    conv_tc_wgrad_ds_kernel<<<grid, DS_THREADS, pl.smem, st>>>(myh, myl, mxh, mxl, p);
+    CFUN_LAUNCH_CHECK();
+  }
   return CFUN_OK;
 }
 
@@ -320,7 +328,7 @@ int ds_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* d
   __nv_bfloat16* xl = reinterpret_cast<__nv_bfloat16*>(base + pl.off_xl);
   int prc;
   if ((prc = launch_pack_act_gp(dy, yh, split ? yl : nullptr, d->N, d->Dout, d->Hout, d->Wout, d->Cout, pl.Gy_total, st)) != CFUN_OK) return prc;
-  if ((prc = launch_pack_act_gp(x, xh, split ? xl : nullptr, d->N, d->Din, d->Hin, d->Win, d->Cin, pl.Gx, st)) != CFUN_OK) return prc;
+  if ((prc = launch_pack_act_gp(x, xh, split ? xl : nullptr, d->N, d->Din, d->Hin, d->Win, d->Cin, pl.Gx_total, st)) != CFUN_OK) return prc;
   CFUN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * d->Cin * 27, st));
   int rc = ds_launch(d, pl, yh, yl, xh, xl, dw, split, pl.Gy_total, st);
   if (rc != CFUN_OK) return rc;

@@ -28,6 +28,8 @@ TINY = [(4, 320, 6, 320, 3, 1, 1), (4, 320, 12, 320, 3, 1, 1), (4, 160, 12, 160,
 HX = [(1, 16, 16, 16, 3, 1, 1), (2, 24, 20, 40, 3, 1, 1), (1, 80, 16, 80, 3, 1, 1), (1, 48, 17, 44, 3, 1, 1), (1, 32, 16, 160, 3, 1, 1),
       (1, 128, 16, 256, 3, 1, 1), (1, 320, 8, 320, 3, 1, 1), (3, 20, 9, 20, 3, 1, 1)]
 C1 = [(1, 1, 256, 16, (3, 7, 7), 2, (1, 3, 3)), (4, 1, 96, 20, 3, 1, 1), (1, 1, 40, 16, (3, 7, 7), 2, (1, 3, 3)), (2, 1, 21, 20, 3, 1, 1)]
+WIDE = [(4, 160, 24, 160, 3, 1, 1), (4, 160, 24, 80, 3, 1, 1), (4, 320, 12, 320, 3, 1, 1), (4, 320, 12, 160, 3, 1, 1), (1, 128, 32, 256, 3, 1, 1),
+        (1, 176, 9, 24, 3, 1, 1), (1, 128, 32, 128, 3, 1, 1), (1, 96, 16, 48, 3, 1, 1)]
 STRIDED = [(4, 20, 96, 40, 3, 2, 1), (4, 40, 48, 80, 3, 2, 1), (4, 80, 24, 160, 3, 2, 1), (4, 160, 12, 320, 3, 2, 1)]
 
 
@@ -50,7 +52,7 @@ def med(fn, flush, iters=5):
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "unet"
     passes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["fwd", "dgrad", "wgrad"]
-    cases = {"unet": UNET, "small": SMALL, "all": SMALL + UNET, "strided": STRIDED, "c1": C1, "hx": HX, "tiny": TINY}[which]
+    cases = {"unet": UNET, "small": SMALL, "all": SMALL + UNET, "strided": STRIDED, "wide": WIDE, "c1": C1, "hx": HX, "tiny": TINY}[which]
     dev = torch.device("cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for (N, Ci, S, Co, k, st, pd) in cases:
