@@ -24,6 +24,12 @@ int tc_conv_bwd_data(const cfun_conv3d_desc* d, const float* dy, const float* w,
 int tc_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, float* dbias, int nsplit,
                        void* ws, size_t ws_bytes, cudaStream_t st);
 int simt_bias_grad(const float* dy, long long M, int C, float* dbias, cudaStream_t st);
+bool ds_masked_supported(const cfun_conv3d_desc* d, int tap_mask);          // conv_tc_wgrad_ds.cu
+size_t ds_masked_workspace(const cfun_conv3d_desc* d, int tap_mask);
+int ds_conv_bwd_weight_masked(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, int tap_mask, int kd_mask,
+                              void* ws, size_t ws_bytes, cudaStream_t st);
+constexpr int S2D_TAPMASK = 0x1B;     // (kh,kw) in {0,1}^2 -> kh*3+kw in {0,1,3,4}
+constexpr int S2D_KDMASK = 0x3;       // kd in {0,1}
 
 // X (N,D,H,W,C) -> P tensors (N,D/2,H/2,W/2, 8C/P); parity class q = (qd*2+qh)*2+qw lives in tensor q / (8/P), channel
 // block q % (8/P).  inverse = true copies the other way (the data gradient's dX' -> dX).
@@ -76,6 +82,26 @@ __global__ void __launch_bounds__(256) w_s2d_kernel(float* __restrict__ w, float
   }
 }
 
+// dW3 (Cout, 8 Cin, 27) of the embedding 3^3 kernel (only the taps with kd,kh,kw in {0,1} are filled) -> dW (Cout, Cin, 27)
+__global__ void __launch_bounds__(256) w_s2d3_gather_kernel(const float* __restrict__ w3, float* __restrict__ w, int Cout, int Cin) {
+  const long long total = (long long)Cout * Cin * 27;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int tap = (int)(i % 27);
+    long long r = i / 27;
+    const int ci = (int)(r % Cin);
+    const int co = (int)(r / Cin);
+    const int k[3] = {tap / 9, (tap / 3) % 3, tap % 3};
+    int q = 0, t3 = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {          // k = 0 -> (k',q) = (0,1); k = 1 -> (1,0); k = 2 -> (1,1)
+      const int kp = k[a] == 0 ? 0 : 1, qa = k[a] == 1 ? 0 : 1;
+      q = q * 2 + qa;
+      t3 = t3 * 3 + kp;
+    }
+    w[i] = w3[((long long)co * 8 * Cin + (long long)q * Cin + ci) * 27 + t3];
+  }
+}
+
 struct S2dPlan {
   cfun_conv3d_desc d2;       // the stride-1 2x2x2 problem (Cin' = 8 Cin / P per tensor for the weight gradient)
   int P;
@@ -89,16 +115,25 @@ static bool make_s2d_plan(const cfun_conv3d_desc* d, int pass, S2dPlan& pl) {
   if (d->Dout != d->Din / 2 || d->Hout != d->Hin / 2 || d->Wout != d->Win / 2) return false;
   if (d->Cin & 3) return false;
   pl.P = 1;
-  if (pass == CFUN_PASS_BWD_WEIGHT) while (8 * d->Cin / pl.P > 256 && pl.P < 8) pl.P *= 2;
   cfun_conv3d_desc& e = pl.d2;
   e = *d;
-  e.Cin = 8 * d->Cin / pl.P;
+  e.Cin = 8 * d->Cin;
   e.Din = d->Din / 2; e.Hin = d->Hin / 2; e.Win = d->Win / 2;
-  e.kD = e.kH = e.kW = 2;
   e.sD = e.sH = e.sW = 1;
   e.pD = e.pH = e.pW = 1;
-  if (!tc_capable(&e, pass)) return false;
   pl.act = align_up((size_t)d->N * d->Din * d->Hin * d->Win * d->Cin * 4, 1024);
+  if (pass == CFUN_PASS_BWD_WEIGHT) {
+    // weight gradient: the 2x2x2 kernel is the {0,1}^3 corner of a 3x3x3 / pad-1 kernel -> masked d-stacked kernel
+    e.kD = e.kH = e.kW = 3;
+    if (8 * d->Cin > 320) return false;       // >= 8 channel slices: the CUDA-core kernel wins (80->160: 0.27 vs 0.34 ms)
+    if (!ds_masked_supported(&e, S2D_TAPMASK)) return false;
+    pl.wgt = align_up((size_t)d->Cout * 8 * d->Cin * 27 * 4, 1024);
+    pl.inner = ds_masked_workspace(&e, S2D_TAPMASK);
+    pl.total = pl.act + pl.wgt + pl.inner + 2048;
+    return pl.inner > 0;
+  }
+  e.kD = e.kH = e.kW = 2;
+  if (!tc_capable(&e, pass)) return false;
   pl.wgt = align_up((size_t)d->Cout * 8 * d->Cin * 8 * 4, 1024);
   pl.inner = tc_workspace(&e, pass);
   pl.total = pl.act + pl.wgt + pl.inner + 2048;
@@ -108,9 +143,7 @@ static bool make_s2d_plan(const cfun_conv3d_desc* d, int pass, S2dPlan& pl) {
 bool s2d_supported(const cfun_conv3d_desc* d, int pass) {
   const char* e = getenv("CFUN_TC_S2D");           // "0" keeps strided convs on CUDA cores (A/B measurements)
   if (e && e[0] == '0') return false;
-  // weight gradient: the channel-major repack of the 8x wider X' costs more than the CUDA-core kernel it would replace
-  // (20->40 @ 96^3: 1.48 ms vs 1.38 ms); opt-in with CFUN_TC_S2D=w
-  if (pass == CFUN_PASS_BWD_WEIGHT && !(e && e[0] == 'w')) return false;
+  if (pass == CFUN_PASS_BWD_WEIGHT && e && e[0] == 'n') return false;      // "nw": forward / data gradient only
   S2dPlan pl;
   return make_s2d_plan(d, pass, pl);
 }
@@ -150,14 +183,14 @@ int s2d_conv(const cfun_conv3d_desc* d, int pass, const float* a, const float* b
     return CFUN_OK;
   }
   // weight gradient: a = x, b = dy, out = dw
-  s2d_kernel<false><<<grid_for(xtotal), 256, 0, st>>>(const_cast<float*>(a), xp, d->N, d->Din, d->Hin, d->Win, d->Cin, pl.P);
+  s2d_kernel<false><<<grid_for(xtotal), 256, 0, st>>>(const_cast<float*>(a), xp, d->N, d->Din, d->Hin, d->Win, d->Cin, 1);
   CFUN_LAUNCH_CHECK();
-  const size_t xslice = (size_t)d->N * pl.d2.Din * pl.d2.Hin * pl.d2.Win * pl.d2.Cin;
-  const size_t wslice = (size_t)d->Cout * pl.d2.Cin * 8;
-  for (int s = 0; s < pl.P; ++s)
-    if ((rc = tc_conv_bwd_weight(&pl.d2, xp + s * xslice, b, wp + s * wslice, nullptr, nsplit, inner, pl.inner, st)) != CFUN_OK) return rc;
-  w_s2d_kernel<true><<<grid_for(wtotal), 256, 0, st>>>(out, wp, d->Cout, d->Cin, pl.P);
-  CFUN_LAUNCH_CHECK();
+  if ((rc = ds_conv_bwd_weight_masked(&pl.d2, xp, b, wp, S2D_TAPMASK, S2D_KDMASK, inner, pl.inner, st)) != CFUN_OK) return rc;
+  {
+    const long long tot = (long long)d->Cout * d->Cin * 27;
+    w_s2d3_gather_kernel<<<grid_for(tot), 256, 0, st>>>(wp, out, d->Cout, d->Cin);
+    CFUN_LAUNCH_CHECK();
+  }
   if (dbias) return simt_bias_grad(b, (long long)d->N * d->Dout * d->Hout * d->Wout, d->Cout, dbias, st);
   return CFUN_OK;
 }

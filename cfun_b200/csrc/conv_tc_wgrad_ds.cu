@@ -48,6 +48,9 @@ struct DsParams {
   int ci0;                    // first input channel of the slice (dW addressing); X groups start at ci0 / 8
   int Npad;                   // MMA N
   int T9, ng9;                // (kh,kw) taps per CTA, number of tap groups
+  int ntap;                   // selected (kh,kw) taps (9 for a dense 3^3 kernel)
+  int tap_list[9];            // their indices kh*3+kw; the space-to-depth weight gradient needs only {0,1,3,4}
+  int kd_mask;                // bit kd set = this kd plane of dW is wanted
   int tilesH, tilesW;
   int nsplit, stages;
   int tmem_cols;
@@ -69,7 +72,7 @@ conv_tc_wgrad_ds_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int parts = p.nsplit == 3 ? 2 : 1;
   const int t9_0 = blockIdx.y * p.T9;
-  const int nt9 = min(p.T9, 9 - t9_0);
+  const int nt9 = min(p.T9, p.ntap - t9_0);
   const int g0 = blockIdx.z * p.Gt;                      // first dY channel group of this M tile
   const long long u_beg = (long long)blockIdx.x * p.units_per_cta;
   const long long u_end = min(p.units_total, u_beg + p.units_per_cta);
@@ -128,7 +131,7 @@ conv_tc_wgrad_ds_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid
       const uint32_t first = it == 0 ? 0u : 1u;
 #pragma unroll 1
       for (int t = 0; t < nt9; ++t) {
-        const int t9 = t9_0 + t;
+        const int t9 = p.tap_list[t9_0 + t];
         const int kh = t9 / 3, kw = t9 - kh * 3;
         const uint32_t dcol = tmem_base + (uint32_t)(t * p.Npad);
         const uint32_t toff = (uint32_t)(kh * DS_WH + kw);            // 16-byte rows: halo line kh, voxel kw
@@ -161,13 +164,13 @@ conv_tc_wgrad_ds_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid
     const int rg = row >> 3;
     const int g = rg / 3, s = rg - g * 3;
     const int co = (g0 + g) * 8 + (row & 7);
-    const bool row_ok = g < p.Gt && co < p.Cout;
     const int kd = 2 - s;
+    const bool row_ok = g < p.Gt && co < p.Cout && ((p.kd_mask >> kd) & 1);
     mbar_wait(tmem_full_bar, 0, 430);
     tc_fence_after();
     if (niter > 0) {
       for (int t = 0; t < nt9; ++t) {
-        const int tap = kd * 9 + t9_0 + t;
+        const int tap = kd * 9 + p.tap_list[t9_0 + t];
         for (int j = 0; j < p.Npad; j += 16) {
           uint32_t r[16];
           tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * p.Npad + j), r);
@@ -198,7 +201,7 @@ struct DsPlan {
   size_t act_y, act_x, off_yh, off_yl, off_xh, off_xl, total, smem;
 };
 
-static bool make_ds_plan(const cfun_conv3d_desc* d, DsPlan& pl) {
+static bool make_ds_plan(const cfun_conv3d_desc* d, DsPlan& pl, int ntap = 9) {
   if (!d || d->sD != 1 || d->sH != 1 || d->sW != 1) return false;
   if (d->kD != 3 || d->kH != 3 || d->kW != 3 || d->pD != 1 || d->pH != 1 || d->pW != 1) return false;
   if (d->Hin < 8 || d->Win < 8) return false;
@@ -209,9 +212,9 @@ static bool make_ds_plan(const cfun_conv3d_desc* d, DsPlan& pl) {
   pl.Gx = (int)align_up((size_t)cdiv(pl.Gx_total, pl.slices), 2);
   pl.Npad = pl.Gx * 8;
   if (pl.Npad > 128 || pl.slices > 8) return false;
-  pl.T9 = std::min(9, 512 / pl.Npad);
-  pl.ng9 = (int)cdiv(9, pl.T9);
-  pl.T9 = (int)cdiv(9, pl.ng9);
+  pl.T9 = std::min(ntap, 512 / pl.Npad);
+  pl.ng9 = (int)cdiv(ntap, pl.T9);
+  pl.T9 = (int)cdiv(ntap, pl.ng9);
   int cols = 32;
   while (cols < pl.T9 * pl.Npad) cols <<= 1;
   if (cols > 512) return false;
@@ -277,7 +280,7 @@ static int encode_gp_map_ds(CUtensorMap* m, void* base, int W, int H, long long 
 // gy_pack: channel groups the dY pack was written with (>= Gy_total; the fused backward shares the data gradient's pack,
 // whose group count is rounded up to a multiple of 2 -- the extra group is zeros)
 int ds_launch(const cfun_conv3d_desc* d, const DsPlan& pl, __nv_bfloat16* yh, __nv_bfloat16* yl, __nv_bfloat16* xh,
-              __nv_bfloat16* xl, float* dw, bool split, int gy_pack, cudaStream_t st) {
+              __nv_bfloat16* xl, float* dw, bool split, int gy_pack, cudaStream_t st, int tap_mask = 0x1FF, int kd_mask = 7) {
   CUtensorMap myh, myl, mxh, mxl;
   int rc;
   const long long planes = (long long)d->N * (d->Din + 2);
@@ -289,6 +292,9 @@ int ds_launch(const cfun_conv3d_desc* d, const DsPlan& pl, __nv_bfloat16* yh, __
   DsParams p;
   p.N = d->N; p.D = d->Din; p.H = d->Hin; p.W = d->Win; p.Cout = d->Cout; p.Cin = d->Cin;
   p.Gt = pl.Gt; p.Gx = pl.Gx; p.Npad = pl.Npad; p.T9 = pl.T9; p.ng9 = pl.ng9;
+  p.ntap = 0;
+  for (int t = 0; t < 9; ++t) { p.tap_list[t] = 0; if ((tap_mask >> t) & 1) p.tap_list[p.ntap++] = t; }
+  p.kd_mask = kd_mask;
   p.tilesH = (int)cdiv(d->Hin, DS_HT); p.tilesW = (int)cdiv(d->Win, DS_WT);
   p.nsplit = split ? 3 : 1;
   p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
@@ -345,6 +351,35 @@ int ds_bwd_weight_packed(const cfun_conv3d_desc* d, __nv_bfloat16* yh, __nv_bflo
   CFUN_CHECK_ARG(yh && yl && xh && xl && dw && gy_pack >= pl.Gy_total);
   CFUN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * d->Cin * 27, st));
   return ds_launch(d, pl, yh, yl, xh, xl, dw, true, gy_pack, st);
+}
+
+// Sub-kernel weight gradient: only the (kh,kw) taps of tap_mask and the kd planes of kd_mask are computed and written
+// (dw is zero elsewhere).  conv_s2d.cu uses it with {kh,kw in {0,1}} x {kd in {0,1}}: the 2x2x2 space-to-depth kernel is
+// the corresponding corner of a 3x3x3 / pad-1 kernel.
+bool ds_masked_supported(const cfun_conv3d_desc* d, int tap_mask) {
+  DsPlan pl;
+  return make_ds_plan(d, pl, __builtin_popcount(tap_mask & 0x1FF)) && d->Cin >= 16 && (d->Cin & 3) == 0 && d->Cout >= 8 && (d->Cout & 3) == 0;
+}
+size_t ds_masked_workspace(const cfun_conv3d_desc* d, int tap_mask) {
+  DsPlan pl;
+  return make_ds_plan(d, pl, __builtin_popcount(tap_mask & 0x1FF)) ? pl.total : 0;
+}
+int ds_conv_bwd_weight_masked(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, int tap_mask, int kd_mask,
+                              void* ws, size_t ws_bytes, cudaStream_t st) {
+  DsPlan pl;
+  CFUN_CHECK_ARG(make_ds_plan(d, pl, __builtin_popcount(tap_mask & 0x1FF)));
+  CFUN_CHECK_ARG(x && dy && dw && ws && get_tensor_map_encoder());
+  const size_t base = align_up((size_t)ws, 1024);
+  if (ws_bytes < pl.total || base + pl.total - 2048 > (size_t)ws + ws_bytes) { set_error("conv3d d-stacked wgrad (masked): workspace too small"); return CFUN_ERR_WORKSPACE; }
+  __nv_bfloat16* yh = reinterpret_cast<__nv_bfloat16*>(base + pl.off_yh);
+  __nv_bfloat16* yl = reinterpret_cast<__nv_bfloat16*>(base + pl.off_yl);
+  __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(base + pl.off_xh);
+  __nv_bfloat16* xl = reinterpret_cast<__nv_bfloat16*>(base + pl.off_xl);
+  int rc;
+  if ((rc = launch_pack_act_gp(dy, yh, yl, d->N, d->Dout, d->Hout, d->Wout, d->Cout, pl.Gy_total, st)) != CFUN_OK) return rc;
+  if ((rc = launch_pack_act_gp(x, xh, xl, d->N, d->Din, d->Hin, d->Win, d->Cin, pl.Gx_total, st)) != CFUN_OK) return rc;
+  CFUN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * d->Cin * 27, st));
+  return ds_launch(d, pl, yh, yl, xh, xl, dw, true, pl.Gy_total, st, tap_mask, kd_mask);
 }
 
 int tc_debug_read_ds(int* out8) {
