@@ -36,6 +36,10 @@ CONV_CASES = [
     (1, 1, 12, 12, 12, 20, 3, 1, 1, False),                     # U-Net first conv (Cin = 1)
     (1, 48, 8, 8, 8, 80, 3, 1, 1, True),                        # >64 output channels
     (3, 24, 5, 7, 6, 36, 3, 1, 1, True),                        # odd everything
+    (1, 1, 12, 20, 70, 24, (5, 7, 7), 2, (2, 3, 3), True),      # LiTS stem (LiTS_2017/backbone.py:124): conv_c1.cu <24;5,7,7;2>
+    (2, 1, 9, 10, 37, 32, 3, 1, 1, False),                      # LiTS U-Net first conv (base 32): conv_c1.cu <32;3,3,3;1>
+    (1, 1, 21, 9, 66, 16, (3, 7, 7), 2, (1, 3, 3), True),       # heart stem, ragged tiles in every direction
+    (4, 1, 6, 7, 34, 20, 3, 1, 1, False),                       # heart U-Net first conv, ragged
 ]
 
 
@@ -414,6 +418,39 @@ def test_conv3d_tcgen05_strided_tiny_and_stacked_wgrad(ops, case):
         assert sup[2], "stride-1 3^3 weight gradients run on tensor cores"
     if sup[2]:
         assert rel_err(wc.grad.cpu().numpy(), wr.grad.numpy()) < TOL
+
+
+@pytest.mark.parametrize("case", [(2, 24, 12, 16, 16, 40, True), (1, 40, 12, 24, 16, 20, False), (1, 160, 5, 16, 16, 80, True),
+                                  (1, 128, 8, 16, 16, 256, True)])
+def test_conv3d_fused_backward_keeps_forward_pack(ops, case):
+    """AUTO picks the fused path (cfun_conv3d_fwd_keep_pack + cfun_conv3d_bwd_fused) for these shapes: same results as
+    the three separate calls and as fp32, including the no-input-gradient case (first layer of a network)."""
+    import ctypes as C
+    from cfun_b200._lib import lib
+    N, Cin, D, H, W, Cout, need_dx = case
+    g = torch.Generator().manual_seed(sum(case[:6]))
+    x = torch.randn(N, Cin, D, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) * (1.0 / (Cin * 27) ** 0.5)
+    b = torch.randn(Cout, generator=g)
+    xr, wr, br = x.clone().requires_grad_(need_dx), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.conv3d(xr, wr, br, padding=1)
+    dy = torch.randn(yr.shape, generator=g)
+    yr.backward(dy)
+    d = ops._conv_desc(x.shape, w.shape, 1, 1)
+    assert lib.cfun_conv3d_pack_bytes(C.byref(d)) > 0, "the fused path must take this shape"
+    xc, wc, bc = x.cuda().requires_grad_(need_dx), w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    yc = ops.conv3d(xc, wc, bc, 1, 1)
+    assert yc.grad_fn is not None and yc.grad_fn.fused
+    yc.backward(dy.cuda())
+    torch.cuda.synchronize()
+    assert ops.tc_debug_status() is None
+    assert rel_err(yc.detach().cpu().numpy(), yr.detach().numpy()) < TOL
+    assert rel_err(wc.grad.cpu().numpy(), wr.grad.numpy()) < TOL
+    assert rel_err(bc.grad.cpu().numpy(), br.grad.numpy()) < TOL
+    if need_dx:
+        assert rel_err(xc.grad.cpu().numpy(), xr.grad.numpy()) < TOL
+    else:
+        assert xc.grad is None
 
 
 def test_conv3d_tcgen05_single_pass_is_fast_mode_only(ops):
