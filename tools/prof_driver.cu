@@ -22,6 +22,11 @@ int main(int argc, char** argv) {
   else if (!strcmp(which, "l3")) { N = 4; Ci = 80; S = 48; Co = 80; }
   else if (!strcmp(which, "thin")) { N = 4; Ci = 20; S = 96; Co = 20; }
   else if (!strcmp(which, "s2")) { N = 4; Ci = 20; S = 96; Co = 40; st = 2; }
+  // small shapes for compute-sanitizer runs (same kernels, seconds instead of minutes)
+  else if (!strcmp(which, "small")) { N = 2; Ci = 24; S = 24; Co = 40; }
+  else if (!strcmp(which, "smallhx")) { N = 1; Ci = 96; S = 16; Co = 160; }
+  else if (!strcmp(which, "smalls2")) { N = 1; Ci = 20; S = 32; Co = 40; st = 2; }
+  else if (!strcmp(which, "smallwide")) { N = 1; Ci = 176; S = 16; Co = 48; }
   d.N = N; d.Cin = Ci; d.Din = d.Hin = d.Win = S; d.Cout = Co;
   d.kD = d.kH = d.kW = 3; d.sD = d.sH = d.sW = st; d.pD = d.pH = d.pW = 1;
   d.Dout = d.Hout = d.Wout = (S + 2 - 3) / st + 1;
