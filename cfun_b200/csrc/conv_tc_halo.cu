@@ -54,6 +54,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+int launch_pack_act_gp(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int C, int G, cudaStream_t st);
+
 struct HlParams {
   int N, D, H, W, Cout;       // output extents == input extents (pad 1, stride 1)
   int CPC;                    // K chunks of 16 channels
@@ -307,8 +309,77 @@ __global__ void __launch_bounds__(256) pack_w_halo_kernel(const float* __restric
   }
 }
 
-// host-side launcher so that other translation units (conv_tc_wgrad_halo.cu) can reuse the group-planar pack
+// Same pack through a shared-memory transpose: a block reads TV consecutive voxels x C channels with coalesced float4 loads
+// (the voxel-major reads of pack_act_gp_kernel touch 32-byte pieces 4 C bytes apart) and writes, per channel group, TV
+// consecutive 16-byte rows.  Row pitch G*8 + 4 floats keeps the 16-byte shared-memory reads of a quarter warp on distinct
+// banks.  Blocks [ntile_blocks, gridDim.x) zero the d = -1 / D padding planes.
+__global__ void __launch_bounds__(256) pack_act_gp_tiled_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                                                __nv_bfloat16* __restrict__ lo, int N, int D, int H, int W, int C, int G,
+                                                                int TV, long long ntile_blocks) {
+  extern __shared__ __align__(16) float tile[];
+  const long long HW = (long long)H * W;
+  const long long DHW = (long long)D * HW;
+  const long long vox = (long long)N * DHW;                  // real voxels
+  const long long vox_p = (long long)N * (D + 2) * HW;       // padded voxels per group
+  const int Cs = G * 8 + 4;
+  if ((long long)blockIdx.x >= ntile_blocks) {               // zero planes: (g, n, first/last, hw) rows of 16 bytes
+    const long long total = (long long)G * N * 2 * HW;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (long long i = ((long long)blockIdx.x - ntile_blocks) * blockDim.x + threadIdx.x; i < total;
+         i += (long long)(gridDim.x - ntile_blocks) * blockDim.x) {
+      const long long hw = i % HW;
+      long long r = i / HW;
+      const int which = (int)(r % 2); r /= 2;
+      const int n = (int)(r % N);
+      const int g = (int)(r / N);
+      const long long pos = ((long long)n * (D + 2) + (which ? D + 1 : 0)) * HW + hw;
+      reinterpret_cast<uint4*>(hi)[(long long)g * vox_p + pos] = z;
+      if (lo) reinterpret_cast<uint4*>(lo)[(long long)g * vox_p + pos] = z;
+    }
+    return;
+  }
+  const long long v0 = (long long)blockIdx.x * TV;
+  const int nv = (int)min((long long)TV, vox - v0);
+  const int c4n = C >> 2;
+  for (int i = threadIdx.x; i < nv * c4n; i += blockDim.x) {
+    const int v = i / c4n, c4 = i - v * c4n;
+    const float4 f = __ldg(reinterpret_cast<const float4*>(x + (v0 + v) * (long long)C) + c4);
+    *reinterpret_cast<float4*>(tile + v * Cs + 4 * c4) = f;
+  }
+  const int padc = G * 8 - C;                                // zero the channels beyond C (multiple of 4)
+  for (int i = threadIdx.x; i < nv * padc; i += blockDim.x) tile[(i / padc) * Cs + C + (i % padc)] = 0.f;
+  __syncthreads();
+  for (int i = threadIdx.x; i < nv * G; i += blockDim.x) {
+    const int g = i / nv, v = i - g * nv;
+    const float4 a = *reinterpret_cast<const float4*>(tile + v * Cs + 8 * g);
+    const float4 b = *reinterpret_cast<const float4*>(tile + v * Cs + 8 * g + 4);
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    __align__(16) __nv_bfloat16 h[8];
+    __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split_bf16(f[j], h[j], l[j]);
+    const long long gv = v0 + v;
+    const long long n = gv / DHW, rem = gv - n * DHW;
+    const long long pos = (n * (D + 2) + 1) * HW + rem;
+    reinterpret_cast<uint4*>(hi)[(long long)g * vox_p + pos] = *reinterpret_cast<const uint4*>(h);
+    if (lo) reinterpret_cast<uint4*>(lo)[(long long)g * vox_p + pos] = *reinterpret_cast<const uint4*>(l);
+  }
+}
+
+// host-side launcher (also used by conv_tc_hx.cu, conv_tc_wgrad_ds.cu, conv_fused.cu)
 int launch_pack_act_gp(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int C, int G, cudaStream_t st) {
+  const char* e = getenv("CFUN_PACK_TILED");          // "0": the one-thread-per-row kernel (A/B measurements)
+  const int Cs = G * 8 + 4;
+  int TV = std::min(128, (12288 / Cs) / 32 * 32);
+  if ((C & 3) == 0 && TV >= 32 && !(e && e[0] == '0')) {
+    const long long vox = (long long)N * D * H * W;
+    const long long ntile = cdiv(vox, TV);
+    const long long zrows = (long long)G * N * 2 * H * W;
+    const long long nz = std::max<long long>(1, std::min<long long>(cdiv(zrows, 256), 2LL * num_sms()));
+    pack_act_gp_tiled_kernel<<<(unsigned)(ntile + nz), 256, (size_t)TV * Cs * sizeof(float), st>>>(x, hi, lo, N, D, H, W, C, G, TV, ntile);
+    CFUN_LAUNCH_CHECK();
+    return CFUN_OK;
+  }
   long long total = (long long)G * N * (D + 2) * H * W;
   pack_act_gp_kernel<<<(unsigned)std::min<long long>(cdiv(total, 256), 32LL * num_sms()), 256, 0, st>>>(x, hi, lo, N, D, H, W, C, G);
   CFUN_LAUNCH_CHECK();
@@ -389,9 +460,8 @@ int hl_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const floa
   __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(base + pl.off_w);
   {
     if (!(ext_hi && ext_ready)) {
-      long long total = (long long)pl.G * pl.N * (pl.D + 2) * pl.H * pl.W;
-      pack_act_gp_kernel<<<(unsigned)std::min<long long>(cdiv(total, 256), 32LL * num_sms()), 256, 0, st>>>(src, ah, split ? al : nullptr, pl.N, pl.D, pl.H, pl.W, pl.Cs, pl.G);
-      CFUN_LAUNCH_CHECK();
+      int prc = launch_pack_act_gp(src, ah, split ? al : nullptr, pl.N, pl.D, pl.H, pl.W, pl.Cs, pl.G, st);
+      if (prc != CFUN_OK) return prc;
     }
     long long wt = (long long)pl.CPC * 3 * parts * 9 * 2 * pl.Npad * 8;
     pack_w_halo_kernel<<<(unsigned)std::min<long long>(cdiv(wt, 256), 4LL * num_sms()), 256, 0, st>>>(w, wp, d->Cout, d->Cin, pl.Npad, pl.CPC, parts, pass == CFUN_PASS_BWD_DATA ? 1 : 0);
