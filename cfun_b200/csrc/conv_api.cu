@@ -27,6 +27,12 @@ bool c1_supported(const cfun_conv3d_desc* d, int pass);
 int c1_conv_fwd(const cfun_conv3d_desc* d, const float* x, const float* w, const float* bias, float* y, int epi, cudaStream_t st);
 int c1_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, float* dbias, cudaStream_t st);
 
+// conv_pw.cu: streaming kernels for 1x1x1 convs with <= 8 output channels (segmentation / RPN heads); part of SIMT
+bool pw_supported(const cfun_conv3d_desc* d, int pass);
+int pw_conv_fwd(const cfun_conv3d_desc* d, const float* x, const float* w, const float* bias, float* y, int epi, cudaStream_t st);
+int pw_conv_bwd_data(const cfun_conv3d_desc* d, const float* dy, const float* w, float* dx, cudaStream_t st);
+int pw_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, float* dbias, cudaStream_t st);
+
 static int resolve(const cfun_conv3d_desc* d, int pass, int algo) {
   if (algo == CFUN_CONV_ALGO_AUTO) {
     const char* e = getenv("CFUN_CONV_ALGO");  // "simt" pins the CUDA-core path (debug / A-B measurements)
@@ -61,6 +67,7 @@ extern "C" int cfun_conv3d_fwd(const cfun_conv3d_desc* d, const float* x, const 
   CFUN_CHECK_ARG(d != nullptr);
   int a = resolve(d, CFUN_PASS_FWD, algo);
   if (a == CFUN_CONV_ALGO_SIMT && c1_supported(d, CFUN_PASS_FWD)) return c1_conv_fwd(d, x, w, bias, y, epi_flags, as_stream(stream));
+  if (a == CFUN_CONV_ALGO_SIMT && pw_supported(d, CFUN_PASS_FWD)) return pw_conv_fwd(d, x, w, bias, y, epi_flags, as_stream(stream));
   if (a == CFUN_CONV_ALGO_SIMT) return simt_conv_fwd(d, x, w, bias, y, epi_flags, ws, ws_bytes, as_stream(stream));
   CFUN_CHECK_ARG(tc_supported(d, CFUN_PASS_FWD));
   return tc_conv_fwd(d, x, w, bias, y, epi_flags, a == CFUN_CONV_ALGO_TC1 ? 1 : 3, ws, ws_bytes, as_stream(stream));
@@ -70,6 +77,7 @@ extern "C" int cfun_conv3d_bwd_data(const cfun_conv3d_desc* d, const float* dy, 
                                     size_t ws_bytes, void* stream) {
   CFUN_CHECK_ARG(d != nullptr);
   int a = resolve(d, CFUN_PASS_BWD_DATA, algo);
+  if (a == CFUN_CONV_ALGO_SIMT && pw_supported(d, CFUN_PASS_BWD_DATA)) return pw_conv_bwd_data(d, dy, w, dx, as_stream(stream));
   if (a == CFUN_CONV_ALGO_SIMT) return simt_conv_bwd_data(d, dy, w, dx, ws, ws_bytes, as_stream(stream));
   CFUN_CHECK_ARG(tc_supported(d, CFUN_PASS_BWD_DATA));
   return tc_conv_bwd_data(d, dy, w, dx, a == CFUN_CONV_ALGO_TC1 ? 1 : 3, ws, ws_bytes, as_stream(stream));
@@ -80,6 +88,7 @@ extern "C" int cfun_conv3d_bwd_weight(const cfun_conv3d_desc* d, const float* x,
   CFUN_CHECK_ARG(d != nullptr);
   int a = resolve(d, CFUN_PASS_BWD_WEIGHT, algo);
   if (a == CFUN_CONV_ALGO_SIMT && c1_supported(d, CFUN_PASS_BWD_WEIGHT)) return c1_conv_bwd_weight(d, x, dy, dw, dbias, as_stream(stream));
+  if (a == CFUN_CONV_ALGO_SIMT && pw_supported(d, CFUN_PASS_BWD_WEIGHT)) return pw_conv_bwd_weight(d, x, dy, dw, dbias, as_stream(stream));
   if (a == CFUN_CONV_ALGO_SIMT) return simt_conv_bwd_weight(d, x, dy, dw, dbias, ws, ws_bytes, as_stream(stream));
   CFUN_CHECK_ARG(tc_supported(d, CFUN_PASS_BWD_WEIGHT));
   return tc_conv_bwd_weight(d, x, dy, dw, dbias, a == CFUN_CONV_ALGO_TC1 ? 1 : 3, ws, ws_bytes, as_stream(stream));

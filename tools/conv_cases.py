@@ -30,6 +30,8 @@ HX = [(1, 16, 16, 16, 3, 1, 1), (2, 24, 20, 40, 3, 1, 1), (1, 80, 16, 80, 3, 1, 
 C1 = [(1, 1, 256, 16, (3, 7, 7), 2, (1, 3, 3)), (4, 1, 96, 20, 3, 1, 1), (1, 1, 40, 16, (3, 7, 7), 2, (1, 3, 3)), (2, 1, 21, 20, 3, 1, 1)]
 WIDE = [(4, 160, 24, 160, 3, 1, 1), (4, 160, 24, 80, 3, 1, 1), (4, 320, 12, 320, 3, 1, 1), (4, 320, 12, 160, 3, 1, 1), (1, 128, 32, 256, 3, 1, 1),
         (1, 176, 9, 24, 3, 1, 1), (1, 128, 32, 128, 3, 1, 1), (1, 96, 16, 48, 3, 1, 1)]
+PW = [(4, 40, 96, 8, 1, 1, 0), (4, 80, 48, 8, 1, 1, 0), (4, 160, 24, 8, 1, 1, 0), (1, 256, 32, 2, 1, 1, 0), (1, 256, 32, 6, 1, 1, 0),
+      (2, 12, 9, 5, 1, 1, 0)]
 STRIDED = [(4, 20, 96, 40, 3, 2, 1), (4, 40, 48, 80, 3, 2, 1), (4, 80, 24, 160, 3, 2, 1), (4, 160, 12, 320, 3, 2, 1)]
 
 
@@ -52,7 +54,7 @@ def med(fn, flush, iters=5):
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "unet"
     passes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["fwd", "dgrad", "wgrad"]
-    cases = {"unet": UNET, "small": SMALL, "all": SMALL + UNET, "strided": STRIDED, "wide": WIDE, "c1": C1, "hx": HX, "tiny": TINY}[which]
+    cases = {"unet": UNET, "small": SMALL, "all": SMALL + UNET, "strided": STRIDED, "pw": PW, "wide": WIDE, "c1": C1, "hx": HX, "tiny": TINY}[which]
     dev = torch.device("cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for (N, Ci, S, Co, k, st, pd) in cases:
