@@ -22,7 +22,8 @@ size_t tc_workspace(const cfun_conv3d_desc* d, int pass);
 int hl_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
                int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st);
 int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
-               int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st);
+               int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st,
+               int tapmask);
 int ds_bwd_weight_packed(const cfun_conv3d_desc* d, __nv_bfloat16* yh, __nv_bfloat16* yl, int gy_pack, __nv_bfloat16* xh,
                          __nv_bfloat16* xl, float* dw, cudaStream_t st);
 int launch_pack_act_gp(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int C, int G,
@@ -45,7 +46,7 @@ static size_t act_bytes(const cfun_conv3d_desc* d, int pass) {
 static int run_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
                     void* ws, size_t ws_bytes, __nv_bfloat16* hi, __nv_bfloat16* lo, bool ready, cudaStream_t st) {
   if (hl_supported(d, pass)) return hl_conv_ex(d, pass, src, w, bias, dst, epi, 3, ws, ws_bytes, hi, lo, ready, st);
-  return hx_conv_ex(d, pass, src, w, bias, dst, epi, 3, ws, ws_bytes, hi, lo, ready, st);
+  return hx_conv_ex(d, pass, src, w, bias, dst, epi, 3, ws, ws_bytes, hi, lo, ready, st, 0x7FFFFFF);
 }
 }  // namespace cfun
 

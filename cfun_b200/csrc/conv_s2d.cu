@@ -12,6 +12,8 @@
 // The permutations X <-> X' are pure fp32 copies (NDHWC rows of Cin floats move as a block); when 8 Cin exceeds the
 // weight-gradient kernel's 256-channel limit X' is written as P parity-group tensors of 8 Cin / P channels.
 #include "common.cuh"
+#include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace cfun {
 
@@ -28,6 +30,12 @@ bool ds_masked_supported(const cfun_conv3d_desc* d, int tap_mask);          // c
 size_t ds_masked_workspace(const cfun_conv3d_desc* d, int tap_mask);
 int ds_conv_bwd_weight_masked(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, int tap_mask, int kd_mask,
                               void* ws, size_t ws_bytes, cudaStream_t st);
+bool hx_supported(const cfun_conv3d_desc* d, int pass);                      // conv_tc_hx.cu
+size_t hx_workspace(const cfun_conv3d_desc* d, int pass);
+int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
+               int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st,
+               int tapmask);
+constexpr int S2D_MASK27 = 0x361B;    // taps (kd,kh,kw) in {0,1}^3 of the embedding 3x3x3 kernel: bits {0,1,3,4,9,10,12,13}
 constexpr int S2D_TAPMASK = 0x1B;     // (kh,kw) in {0,1}^2 -> kh*3+kw in {0,1,3,4}
 constexpr int S2D_KDMASK = 0x3;       // kd in {0,1}
 
@@ -82,6 +90,32 @@ __global__ void __launch_bounds__(256) w_s2d_kernel(float* __restrict__ w, float
   }
 }
 
+// W (Cout, Cin, 27) -> W3 (Cout, 8 Cin, 27): the 2x2x2 space-to-depth kernel as the {0,1}^3 corner of a 3x3x3 / pad-1 kernel
+// (W3[co][(q,ci)][k'] = W[co][ci][k] with per axis (k',q) -> k: (0,1)->0, (1,0)->1, (1,1)->2; zero elsewhere)
+__global__ void __launch_bounds__(256) w_s2d3_embed_kernel(const float* __restrict__ w, float* __restrict__ w3, int Cout, int Cin) {
+  const long long total = (long long)Cout * 8 * Cin * 27;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t3 = (int)(i % 27);
+    long long r = i / 27;
+    const int ci = (int)(r % Cin); r /= Cin;
+    const int q = (int)(r % 8);
+    const int co = (int)(r / 8);
+    const int kp[3] = {t3 / 9, (t3 / 3) % 3, t3 % 3};
+    bool live = true;
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int qa = (q >> (2 - a)) & 1;
+      int ka = 0;
+      if (kp[a] == 0) { live = live && qa == 1; ka = 0; }
+      else if (kp[a] == 1) ka = qa ? 2 : 1;
+      else live = false;
+      k = k * 3 + ka;
+    }
+    w3[i] = live ? w[((long long)co * Cin + ci) * 27 + k] : 0.f;
+  }
+}
+
 // dW3 (Cout, 8 Cin, 27) of the embedding 3^3 kernel (only the taps with kd,kh,kw in {0,1} are filled) -> dW (Cout, Cin, 27)
 __global__ void __launch_bounds__(256) w_s2d3_gather_kernel(const float* __restrict__ w3, float* __restrict__ w, int Cout, int Cin) {
   const long long total = (long long)Cout * Cin * 27;
@@ -103,8 +137,9 @@ __global__ void __launch_bounds__(256) w_s2d3_gather_kernel(const float* __restr
 }
 
 struct S2dPlan {
-  cfun_conv3d_desc d2;       // the stride-1 2x2x2 problem (Cin' = 8 Cin / P per tensor for the weight gradient)
+  cfun_conv3d_desc d2;       // the stride-1 problem on X' (8 Cin channels): 2x2x2, or its 3x3x3 embedding when `embed`
   int P;
+  bool embed;                // forward / data gradient through the tap-masked halo kernel (conv_tc_hx.cu) on the 3^3 embedding
   size_t act, wgt, inner, total;
 };
 
@@ -131,6 +166,21 @@ static bool make_s2d_plan(const cfun_conv3d_desc* d, int pass, S2dPlan& pl) {
     pl.inner = ds_masked_workspace(&e, S2D_TAPMASK);
     pl.total = pl.act + pl.wgt + pl.inner + 2048;
     return pl.inner > 0;
+  }
+  // forward / data gradient: the halo kernel on the 3^3 embedding with a tap mask (the activation halo is loaded once
+  // per K chunk instead of once per tap: 20->40 @ 96^3 forward 0.98 -> see DESIGN.md); else the per-tap kernel on 2^3
+  pl.embed = false;
+  {
+    const char* x = getenv("CFUN_TC_S2D");
+    e.kD = e.kH = e.kW = 3;
+    // (only up to 8 Cin = 320 channels: beyond, 80->160 @ 24^3 measures 0.22 vs 0.16 ms on the per-tap kernel)
+    if (!(x && x[0] == 'p') && 8 * d->Cin <= 320 && hx_supported(&e, pass)) {
+      pl.embed = true;
+      pl.wgt = align_up((size_t)d->Cout * 8 * d->Cin * 27 * 4, 1024);
+      pl.inner = hx_workspace(&e, pass);
+      pl.total = pl.act + pl.wgt + pl.inner + 2048;
+      return pl.inner > 0;
+    }
   }
   e.kD = e.kH = e.kW = 2;
   if (!tc_capable(&e, pass)) return false;
@@ -167,6 +217,20 @@ int s2d_conv(const cfun_conv3d_desc* d, int pass, const float* a, const float* b
   const long long xtotal = (long long)d->N * d->Din * d->Hin * d->Win * (d->Cin >> 2);
   const long long wtotal = (long long)d->Cout * 8 * d->Cin * 8;
   int rc;
+  if (pl.embed && pass != CFUN_PASS_BWD_WEIGHT) {
+    const long long w3total = (long long)d->Cout * 8 * d->Cin * 27;
+    w_s2d3_embed_kernel<<<grid_for(w3total), 256, 0, st>>>(b, wp, d->Cout, d->Cin);
+    CFUN_LAUNCH_CHECK();
+    if (pass == CFUN_PASS_FWD) {
+      s2d_kernel<false><<<grid_for(xtotal), 256, 0, st>>>(const_cast<float*>(a), xp, d->N, d->Din, d->Hin, d->Win, d->Cin, 1);
+      CFUN_LAUNCH_CHECK();
+      return hx_conv_ex(&pl.d2, CFUN_PASS_FWD, xp, wp, bias, out, epi, nsplit, inner, pl.inner, nullptr, nullptr, false, st, S2D_MASK27);
+    }
+    if ((rc = hx_conv_ex(&pl.d2, CFUN_PASS_BWD_DATA, a, wp, nullptr, xp, 0, nsplit, inner, pl.inner, nullptr, nullptr, false, st, S2D_MASK27)) != CFUN_OK) return rc;
+    s2d_kernel<true><<<grid_for(xtotal), 256, 0, st>>>(out, xp, d->N, d->Din, d->Hin, d->Win, d->Cin, 1);
+    CFUN_LAUNCH_CHECK();
+    return CFUN_OK;
+  }
   if (pass == CFUN_PASS_FWD) {                     // a = x, b = w
     s2d_kernel<false><<<grid_for(xtotal), 256, 0, st>>>(const_cast<float*>(a), xp, d->N, d->Din, d->Hin, d->Win, d->Cin, 1);
     CFUN_LAUNCH_CHECK();

@@ -84,13 +84,17 @@ struct HxParams {
   int nsplit, tmem_cols, epi;
   int TPS, bstages, b_stage_bytes;   // taps per weight stage (9 or 3), ring depth, stage bytes
   int cluster;                // CTAs per cluster (1, 2, 4)
+  int tapmask;                // bit t (0..26, kernel's own tap order) set = tap t is live (MASKED instantiations only)
   int debug;                  // bring-up (CFUN_HX_DEBUG): 1 = every CTA loads whole stages itself (no multicast loads)
   const float* bias;
   float* y;
   const uint8_t* wpack;       // [ntile][chunk][kd][tap9][kgroup2][part][Npad][8] bf16 (hi rows, then lo rows)
 };
 
-template <int TPS>   // taps per weight stage: 9 (one kd plane) or 3 (one (kd, kh) row) -- compile-time so the issue loop is straight-line
+// TPS: taps per weight stage, 9 (one kd plane) or 3 (one (kd, kh) row) -- compile-time so the issue loop is straight-line.
+// MASKED: only the taps of p.tapmask are multiplied and weight stages without a live tap are neither loaded nor waited for
+// (conv_s2d.cu: a 2x2x2 kernel embedded as one corner of the 3x3x3 stencil).
+template <int TPS, bool MASKED>
 __global__ void __launch_bounds__(HX_THREADS, 1)
 conv_tc_hx_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_l, const HxParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -168,6 +172,7 @@ conv_tc_hx_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
         for (int it = 0; it < p.iters; ++it) {
           const uint8_t* src = p.wpack + (size_t)nt * p.CPC * spc * (size_t)p.b_stage_bytes + (size_t)rank * slice;
           for (int q = 0; q < p.CPC * spc; ++q, src += p.b_stage_bytes) {
+            if (MASKED && !((p.tapmask >> ((q % spc) * TPS)) & ((1 << TPS) - 1))) continue;
             mbar_wait(&b_empty[st], ph ^ 1u, 520);
             mbar_arrive_expect_tx(&b_full[st], (uint32_t)p.b_stage_bytes);
             uint8_t* dst = b_ring + (size_t)st * p.b_stage_bytes + (size_t)rank * slice;
@@ -205,6 +210,7 @@ conv_tc_hx_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
           const uint32_t a_hi0 = desc_addr(a_base + (uint32_t)(slot * a_slot_bytes)) | a_lbo;
           const uint32_t a_lo0 = a_hi0 + (uint32_t)((2 * HX_PLANE) >> 4);
           for (int s = 0; s < spc; ++s) {
+            if (MASKED && !((p.tapmask >> (s * TPS)) & ((1 << TPS) - 1))) continue;
             mbar_wait(&b_full[st], bph, 550);
             tc_fence_after();
             const uint32_t b0 = desc_addr(b_base + (uint32_t)(st * p.b_stage_bytes)) | b_lbo;
@@ -212,7 +218,18 @@ conv_tc_hx_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
             const uint32_t a_s = (uint32_t)((tap0 / 9) * HX_HH * HX_WH + ((tap0 % 9) / 3) * HX_WH);   // halo row of (kd, kh0)
 #pragma unroll
             for (int t = 0; t < TPS; ++t) {
-              {
+              if (MASKED) {
+                if ((p.tapmask >> (tap0 + t)) & 1) {
+                  const uint32_t aoff = a_s + (uint32_t)((t / 3) * HX_WH + (t % 3));
+                  const uint64_t a_hi = desc_join(a_hiword, a_hi0 + aoff);
+                  const uint64_t b_all = desc_join(b_hiword, b0 + (uint32_t)t * b_tap);
+                  if (leader) {
+                    umma_bf16(dcol, a_hi, b_all, idesc_2n, acc);
+                    if (parts == 2) umma_bf16_acc(dcol, desc_join(a_hiword, a_lo0 + aoff), b_all, idesc_n);
+                  }
+                  acc = 1;
+                }
+              } else {
                 const uint32_t aoff = a_s + (uint32_t)((t / 3) * HX_WH + (t % 3));
                 const uint64_t a_hi = desc_join(a_hiword, a_hi0 + aoff);
                 const uint64_t b_all = desc_join(b_hiword, b0 + (uint32_t)t * b_tap);
@@ -223,7 +240,7 @@ conv_tc_hx_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
                 }
               }
             }
-            acc = 1;
+            if (!MASKED) acc = 1;
             if (leader) {
               if (p.cluster > 1) hx_commit_mc(&b_empty[st], (p.debug & 2) ? self_mask : cmask);    // this CTA is done with its copy: tell every producer
               else umma_commit(&b_empty[st]);
@@ -425,7 +442,7 @@ static void pick_cluster(size_t smem, long long ntiles, size_t w_pass_bytes, int
       at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       int nclusters = 0;
-      if (cudaOccupancyMaxActiveClusters(&nclusters, conv_tc_hx_kernel<9>, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (cudaOccupancyMaxActiveClusters(&nclusters, conv_tc_hx_kernel<9, false>, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
       const int g = std::min(nclusters * cl, num_sms() / cl * cl);
       if (g * 10 >= num_sms() * 9 || forced) { cached_cluster = cl; cached_grid = g; break; }
     }
@@ -437,7 +454,8 @@ static void pick_cluster(size_t smem, long long ntiles, size_t w_pass_bytes, int
 }
 
 int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
-               int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st);
+               int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st,
+               int tapmask = 0x7FFFFFF);
 int hx_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
             int nsplit, void* ws, size_t ws_bytes, cudaStream_t st) {
   return hx_conv_ex(d, pass, src, w, bias, dst, epi, nsplit, ws, ws_bytes, nullptr, nullptr, false, st);
@@ -447,8 +465,10 @@ size_t hx_pack_bytes(const cfun_conv3d_desc* d, int pass) {
   return make_hx_plan(d, pass, pl) ? pl.act_bytes : 0;
 }
 // ext_hi / ext_lo: see hl_conv_ex (conv_tc_halo.cu)
+// tapmask: live taps of w (bit kd*9+kh*3+kw); masked taps are assumed to hold zero weights and are skipped
 int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
-               int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st) {
+               int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st,
+               int tapmask) {
   HxPlan pl;
   CFUN_CHECK_ARG(make_hx_plan(d, pass, pl));
   CFUN_CHECK_ARG((src || ext_ready) && w && dst && ws && get_tensor_map_encoder());
@@ -469,8 +489,10 @@ int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const floa
   }
   static bool attr_set = false;
   if (!attr_set) {     // before the occupancy query of pick_cluster
-    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_hx_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_hx_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_hx_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_hx_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_hx_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_hx_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   CUtensorMap mh, ml;
@@ -511,8 +533,17 @@ int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const floa
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  if (pl.TPS == 9) CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<9>, mh, ml, p));
-  else CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<3>, mh, ml, p));
+  const bool masked = (tapmask & 0x7FFFFFF) != 0x7FFFFFF;
+  p.tapmask = 0;
+  for (int t = 0; t < 27; ++t)      // the data gradient runs on mirrored taps (pack_w_hx_kernel mode 1)
+    if ((tapmask >> t) & 1) p.tapmask |= 1 << (pass == CFUN_PASS_BWD_DATA ? 26 - t : t);
+  if (pl.TPS == 9) {
+    if (masked) CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<9, true>, mh, ml, p));
+    else CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<9, false>, mh, ml, p));
+  } else {
+    if (masked) CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<3, true>, mh, ml, p));
+    else CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<3, false>, mh, ml, p));
+  }
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;
 }
