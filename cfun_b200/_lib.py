@@ -54,6 +54,8 @@ SIGNATURES = {
     "cfun_affine_act_fwd": (_i, [_p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p]),
     "cfun_affine_act_bwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p]),
     "cfun_instnorm_bwd_apply": (_i, [_p, _p, _p, _p, _p, _i, _ll, _i, _p]),
+    "cfun_cat2_channels": (_i, [_p, _i, _p, _i, _p, _ll, _p]),
+    "cfun_split2_channels": (_i, [_p, _i, _i, _p, _p, _ll, _p]),
     "cfun_maxpool2_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "cfun_maxpool2_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "cfun_tc_debug_status": (_i, [C.POINTER(C.c_int)]),

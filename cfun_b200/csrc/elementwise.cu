@@ -461,6 +461,39 @@ extern "C" int cfun_instnorm_bwd_apply(const float* x, const float* a, const flo
   return CFUN_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// channel concatenation of two NDHWC tensors (torch.cat(dim=1) of the U-Net skip connections, mask_branch.py:189,197,
+// 204,211) and its backward (split): float4 rows, one pass, instead of torch's strided copy kernels
+// ---------------------------------------------------------------------------------------------------------
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) cat2_kernel(float* __restrict__ a, float* __restrict__ b, float* __restrict__ o, long long M,
+                                                   int C1q, int C2q) {
+  const int Cq = C1q + C2q;
+  const long long total = M * Cq;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i / Cq;
+    const int c = (int)(i - v * Cq);
+    float4* src = c < C1q ? reinterpret_cast<float4*>(a) + v * C1q + c : reinterpret_cast<float4*>(b) + v * C2q + (c - C1q);
+    float4* cat = reinterpret_cast<float4*>(o) + i;
+    if (SPLIT) *src = *cat;
+    else *cat = *src;
+  }
+}
+
+extern "C" int cfun_cat2_channels(const float* a, int C1, const float* b, int C2, float* out, long long M, void* stream) {
+  CFUN_CHECK_ARG(a && b && out && M > 0 && C1 > 0 && C2 > 0 && C1 % 4 == 0 && C2 % 4 == 0);
+  cat2_kernel<false><<<pick_blocks(M * ((C1 + C2) / 4)), 256, 0, as_stream(stream)>>>(const_cast<float*>(a), const_cast<float*>(b), out, M, C1 / 4, C2 / 4);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
+extern "C" int cfun_split2_channels(const float* cat, int C1, int C2, float* a, float* b, long long M, void* stream) {
+  CFUN_CHECK_ARG(a && b && cat && M > 0 && C1 > 0 && C2 > 0 && C1 % 4 == 0 && C2 % 4 == 0);
+  cat2_kernel<true><<<pick_blocks(M * ((C1 + C2) / 4)), 256, 0, as_stream(stream)>>>(a, b, const_cast<float*>(cat), M, C1 / 4, C2 / 4);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
 extern "C" int cfun_maxpool2_fwd(const float* x, float* y, int N, int D, int H, int W, int C, void* stream) {
   CFUN_CHECK_ARG(x && y && N > 0 && C > 0 && D > 0 && H > 0 && W > 0 && D % 2 == 0 && H % 2 == 0 && W % 2 == 0);
   cudaStream_t st = as_stream(stream);

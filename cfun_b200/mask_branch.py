@@ -101,21 +101,21 @@ class Modified3DUNet(nn.Module):
 
         out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l0, out)
         out = IN(self.conv3d_l0(out))
-        out = torch.cat([out, ctx[4]], dim=1)
+        out = ops.cat_channels(out, ctx[4])
         out = IN(self.conv_norm_lrelu_l1[0](out))
         out = self.conv3d_l1(out)
         out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l1, out)
-        out = torch.cat([out, ctx[3]], dim=1)
+        out = ops.cat_channels(out, ctx[3])
         out = IN(self.conv_norm_lrelu_l2[0](out))
         ds2 = out
         out = self.conv3d_l2(out)
         out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l2, out)
-        out = torch.cat([out, ctx[2]], dim=1)
+        out = ops.cat_channels(out, ctx[2])
         out = IN(self.conv_norm_lrelu_l3[0](out))
         ds3 = out
         out = self.conv3d_l3(out)
         out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l3, out)
-        out = torch.cat([out, context_1], dim=1)
+        out = ops.cat_channels(out, context_1)
         out = IN(self.conv_norm_lrelu_l4[0](out))
         out_pred = self.conv3d_l4(out)
         # deep supervision (mask_branch.py:209-215)

@@ -124,6 +124,9 @@ int cfun_affine_act_bwd(const float* x, const float* a, const float* b, int a_ns
  * as a = m*rstd', b = -m*mean*rstd'). */
 int cfun_instnorm_bwd_apply(const float* x, const float* a, const float* b, const double* stat_acc, float* dx, int N,
                             long long S, int C, void* stream);
+/* torch.cat([a, b], dim=1) of two NDHWC tensors with M = N*D*H*W rows (mask_branch.py:189,197,204,211) and its backward */
+int cfun_cat2_channels(const float* a, int C1, const float* b, int C2, float* out, long long M, void* stream);
+int cfun_split2_channels(const float* cat, int C1, int C2, float* a, float* b, long long M, void* stream);
 int cfun_maxpool2_fwd(const float* x, float* y, int N, int D, int H, int W, int C, void* stream);
 int cfun_maxpool2_bwd(const float* x, const float* y, const float* dy, float* dx, int N, int D, int H, int W, int C,
                       void* stream);

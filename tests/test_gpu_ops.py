@@ -123,6 +123,21 @@ def test_instnorm_lrelu(ops, C, up, use_drop):
     assert rel_err(xc.grad.cpu().numpy(), xr.grad.numpy()) < 2 * TOL
 
 
+def test_cat_channels_fwd_bwd(ops):
+    """ops.cat_channels == torch.cat(dim=1) on channels-last tensors, and its backward splits the gradient"""
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(2, 20, 5, 6, 7, generator=g)
+    b = torch.randn(2, 40, 5, 6, 7, generator=g)
+    ac, bc = ops.to_cl(a.cuda()).requires_grad_(True), ops.to_cl(b.cuda()).requires_grad_(True)
+    out = ops.cat_channels(ac, bc)
+    assert ops.is_cl(out) and torch.equal(out.cpu(), torch.cat([a, b], 1))
+    w = torch.randn(out.shape, generator=g)
+    (out * w.cuda()).sum().backward()
+    assert torch.equal(ac.grad.cpu(), w[:, :20]) and torch.equal(bc.grad.cpu(), w[:, 20:])
+    odd = ops.cat_channels(ac[:, :3], bc)          # channel counts that are not multiples of 4 fall back to torch.cat
+    assert torch.equal(odd.detach().cpu(), torch.cat([a[:, :3], b], 1))
+
+
 def test_affine_act_residual_and_pool(ops):
     g = torch.Generator().manual_seed(5)
     x, r = torch.randn(2, 16, 4, 6, 8, generator=g), torch.randn(2, 16, 4, 6, 8, generator=g)
