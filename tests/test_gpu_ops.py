@@ -213,6 +213,44 @@ def test_nms_bit_exact_random(ops, n, thr, mx):
     assert np.array_equal(U.non_max_suppression(b, sc, thr, mx), O.non_max_suppression(b, sc, thr, mx))
 
 
+def _config5_boxes(n=10000):
+    """BASELINE.json config 5 / SURVEY.md 8d: 10 000 random 3-D proposals over a 256^3 map, default_rng(0)"""
+    rng = np.random.default_rng(0)
+    c = rng.uniform(0, 256, size=(n, 3)); s = rng.uniform(16, 128, size=(n, 3))
+    b = np.clip(np.concatenate([c - s / 2, c + s / 2], 1), 0, 256).astype(np.float32)
+    sc = rng.uniform(0, 1, size=n).astype(np.float32)
+    return b, sc
+
+
+@pytest.mark.parametrize("thr,mx", [(0.7, 500), (0.7, 10000), (0.3, 10000)])
+def test_nms_bit_exact_config5_10k(ops, thr, mx):
+    """full-size micro-benchmark configuration: the kept indices equal the numpy restatement, in order"""
+    from cfun_b200 import utils as U
+    b, sc = _config5_boxes()
+    got = U.non_max_suppression(b, sc, thr, mx)
+    want = O.non_max_suppression(b, sc, thr, mx)
+    assert got.dtype == np.int32 and np.array_equal(got, want), (len(got), len(want))
+    # size-independent properties: kept boxes are mutually below the threshold, in descending score order
+    assert np.all(np.diff(sc[got]) <= 0)
+    k = got[:200]
+    for i, a in enumerate(k[:-1]):
+        assert np.all(O.compute_iou(b[a], b[k[i + 1:]], None, None) <= thr)
+
+
+def test_roi_crop_resize_config5_10k(ops):
+    """10 000 boxes over a [1,256,256,256] map (the mask-branch case, model.py:1413), pool 12^3: every 25th box against the
+    CPU restatement; all-zero rows exactly where the oracle leaves zeros"""
+    b, _ = _config5_boxes()
+    boxes = torch.from_numpy(b / 256.0)
+    g = torch.Generator().manual_seed(11)
+    fmap = torch.randn(1, 256, 256, 256, generator=g)
+    out = ops.roi_crop_resize(cuda(fmap)[None], None, cuda(boxes), None, (12, 12, 12), True)
+    assert tuple(out.shape) == (10000, 1, 12, 12, 12)
+    sel = torch.arange(0, 10000, 25)
+    ref = O.roi_align(fmap, (12, 12, 12), boxes[sel])
+    assert rel_err(out[sel.cuda()].cpu().numpy(), ref.numpy()) < 1e-5
+
+
 def test_decode_clip_and_proposals(ops):
     from cfun_b200 import model as M
     g = load_golden("proposal")
