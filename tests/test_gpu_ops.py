@@ -232,9 +232,10 @@ def test_nms_bit_exact_config5_10k(ops, thr, mx):
     assert got.dtype == np.int32 and np.array_equal(got, want), (len(got), len(want))
     # size-independent properties: kept boxes are mutually below the threshold, in descending score order
     assert np.all(np.diff(sc[got]) <= 0)
+    vol = ((b[:, 3] - b[:, 0]) * (b[:, 4] - b[:, 1])) * (b[:, 5] - b[:, 2])
     k = got[:200]
     for i, a in enumerate(k[:-1]):
-        assert np.all(O.compute_iou(b[a], b[k[i + 1:]], None, None) <= thr)
+        assert np.all(O.compute_iou(b[a], b[k[i + 1:]], vol[a], vol[k[i + 1:]]) <= np.float32(thr))
 
 
 def test_roi_crop_resize_config5_10k(ops):
