@@ -1,7 +1,7 @@
 """BASELINE.json config 5 micro-benchmark: 3-D NMS and RoI crop-resize on 10 000 random proposals over a
 256^3 map, one GPU.  CUDA-event medians of 5 runs; the numpy / torch-CPU restatement timed beside them."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import numpy as np
 import torch

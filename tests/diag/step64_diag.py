@@ -1,12 +1,12 @@
 """Which parameter gradients of the golden 64^3 train step sit furthest from the float64 value (GPU box only).
 
-  python tools/step64_diag.py [beginning|finetune]
+  python tests/diag/step64_diag.py [beginning|finetune]
 Prints, for the CUDA path under the current environment (CFUN_* switches), the relative deviation of every gradient norm
 from the float64 norm (tests/golden/step64_fp64.npz) next to the reference's own fp32 deviation.
 """
 import os
 import sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -54,7 +54,7 @@ def test_layers_match_reference_golden(stage):
     grads = {k: p.grad for k, p in unet.named_parameters()}
     # Deep U-Net weight gradients pass through ~20 InstanceNorm backward passes, which amplify per-conv rounding ~100x.
     # The tensor-core convs carry 16 mantissa bits per operand (split-bf16, ~5e-6 per conv), so
-    # these gradients sit 4e-4 .. 1.2e-2 from the float64 value: tools/layer_diff.py shows the tensor-core forward differs
+    # these gradients sit 4e-4 .. 1.2e-2 from the float64 value: tests/diag/layer_diff.py shows the tensor-core forward differs
     # from the CUDA-core forward by 6e-6 .. 1e-5 at every layer input (as designed), and tools/layer_precision.sh shows that
     # this forward perturbation alone moves conv_norm_lrelu_l4.0.weight.grad by 1.15e-2 -- the weight gradient of a conv that
     # feeds an InstanceNorm is orthogonal to the weight itself (the norm removes scale), i.e. a sum with ~1000x cancellation.
@@ -101,7 +101,7 @@ def test_whole_train_step_64_matches_reference_golden(stage):
     # Per-tensor gradient norms against the FLOAT64 value of the same step (oracle/gen_fp64_yardstick.py).  The U-Net
     # weight gradients are ~1000x-cancelling sums behind InstanceNorm: the reference's own fp32 arithmetic sits up to
     # 1.1e-3 from float64 on them, the CUDA path (split-bf16 tensor-core convs, 16 mantissa bits per operand, every
-    # activation within 1e-5 of fp32) up to 2.9e-3 (conv3d_c1_2, tools/step64_diag.py); everything outside the U-Net
+    # activation within 1e-5 of fp32) up to 2.9e-3 (conv3d_c1_2, tests/diag/step64_diag.py); everything outside the U-Net
     # agrees to 1e-5.  Bound: 5e-3 per tensor here, 1e-3 on the total gradient norm below.
     n64 = load_golden("step64_fp64")[stage + "/grad_norms64"]
     dev64 = np.abs(norms[big] / n64[big] - 1)
