@@ -164,3 +164,65 @@ def test_two_rank_gloo_gradient_allreduce(tmp_path):
         out, _ = p.communicate(timeout=240)
         assert p.returncode == 0, out
         assert "ok" in out
+
+
+def test_nifti_round_trip_and_reference_surface(tmp_path):
+    """cfun_b200.nifti: the slice of nibabel the reference driver uses (heart_main.py:211,300-303,349-352)"""
+    import gzip
+    import struct
+    from cfun_b200 import nifti
+    rng = np.random.default_rng(0)
+    aff = np.array([[0.4, 0, 0, -100.0], [0, 0.5, 0, -90.0], [0, 0, 0.8, 30.0], [0, 0, 0, 1.0]])
+    for dt, ext in ((np.int16, ".nii.gz"), (np.int32, ".nii"), (np.float32, ".nii.gz"), (np.uint8, ".nii")):
+        vol = (rng.normal(0, 300, size=(7, 9, 5))).astype(dt)
+        p = str(tmp_path / ("v" + ext))
+        nifti.save(nifti.Nifti1Image(vol, aff), p)
+        img = nifti.load(p)
+        got = img.get_data().copy()
+        assert got.dtype == vol.dtype and got.shape == (7, 9, 5) and np.array_equal(got, vol)
+        assert np.allclose(img.affine, aff) and np.allclose(img.header.get_zooms(), (0.4, 0.5, 0.8))
+        assert img.get_fdata().dtype == np.float64
+    # a big-endian file with scl_slope / scl_inter and a qform-only affine, written by hand
+    vol = np.arange(24, dtype=">i2").reshape((2, 3, 4), order="F")
+    hdr = bytearray(348)
+    struct.pack_into(">i", hdr, 0, 348)
+    struct.pack_into(">8h", hdr, 40, 3, 2, 3, 4, 1, 1, 1, 1)
+    struct.pack_into(">2h", hdr, 70, 4, 16)
+    struct.pack_into(">8f", hdr, 76, 1.0, 2.0, 3.0, 4.0, 1, 1, 1, 1)
+    struct.pack_into(">3f", hdr, 108, 352.0, 0.5, 10.0)
+    struct.pack_into(">2h", hdr, 252, 1, 0)
+    struct.pack_into(">6f", hdr, 256, 0.0, 0.0, 0.0, 5.0, 6.0, 7.0)
+    hdr[344:348] = b"n+1\0"
+    p = str(tmp_path / "be.nii.gz")
+    with gzip.open(p, "wb") as f:
+        f.write(bytes(hdr) + b"\0" * 4 + vol.tobytes(order="F"))
+    img = nifti.load(p)
+    assert np.allclose(img.get_data(), np.arange(24).reshape((2, 3, 4), order="F") * 0.5 + 10.0)
+    assert np.allclose(img.affine, np.array([[2.0, 0, 0, 5], [0, 3.0, 0, 6], [0, 0, 4.0, 7], [0, 0, 0, 1]]))
+    with pytest.raises(ValueError):
+        (tmp_path / "junk.nii").write_bytes(b"x" * 400)
+        nifti.load(str(tmp_path / "junk.nii"))
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/heart_main.py"), reason="reference tree not present")
+def test_reference_driver_imports_against_the_shims():
+    """heart_main.py, unmodified, resolves `config`, `model`, `utils` (and nibabel) to this repository: its Config /
+    Dataset subclasses build on our base classes and its derived shapes match the reference's"""
+    import importlib.util
+    from cfun_b200 import nifti
+    nifti.install_as_nibabel()
+    saved = sys.dont_write_bytecode
+    sys.dont_write_bytecode = True
+    try:
+        spec = importlib.util.spec_from_file_location("heart_main_ref", "/root/reference/heart_main.py")
+        m = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(m)
+    finally:
+        sys.dont_write_bytecode = saved
+    assert m.HeartConfig.__mro__[1].__module__ == "cfun_b200.config"
+    assert m.HeartDataset.__mro__[1].__module__ == "cfun_b200.utils"
+    cfg = m.HeartConfig("beginning")
+    assert list(cfg.IMAGE_SHAPE) == [320, 320, 192, 1] and tuple(cfg.MASK_SHAPE) == (96, 96, 96) and cfg.NUM_CLASSES == 8
+    assert tuple(m.HeartConfig("finetune").MASK_SHAPE) == (192, 192, 192)
+    ds = m.HeartDataset()
+    assert hasattr(ds, "add_class") and hasattr(ds, "prepare") and callable(m.train) and callable(m.test)
