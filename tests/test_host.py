@@ -226,3 +226,60 @@ def test_reference_driver_imports_against_the_shims():
     assert tuple(m.HeartConfig("finetune").MASK_SHAPE) == (192, 192, 192)
     ds = m.HeartDataset()
     assert hasattr(ds, "add_class") and hasattr(ds, "prepare") and callable(m.train) and callable(m.test)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/heart_main.py"), reason="reference tree not present")
+def test_reference_dataset_feeds_our_data_layer(tmp_path):
+    """The reference's own HeartDataset (heart_main.py:181-261, unmodified) reading synthetic NIfTI volumes through the
+    nibabel stand-in, fed to this repository's data layer (model.Dataset -> load_image_gt): the host side of
+    `heart_main.py train` up to the H2D copy."""
+    import importlib.util
+    import json
+    import types
+    from cfun_b200 import nifti, model as M, utils as U
+    nifti.install_as_nibabel()
+    saved = sys.dont_write_bytecode
+    sys.dont_write_bytecode = True
+    try:
+        spec = importlib.util.spec_from_file_location("heart_main_ref2", "/root/reference/heart_main.py")
+        hm = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(hm)
+    finally:
+        sys.dont_write_bytecode = saved
+    rng = np.random.default_rng(3)
+    entries = []
+    for i in range(14):                       # load_heart() keeps entries [13:] for 'train' and [:13] for 'val'
+        if i in (0, 13):
+            vol = np.clip(np.round(rng.normal(0, 300, size=(40, 40, 24))), -1024, 3071).astype(np.int16)
+            lab = np.zeros((40, 40, 24), dtype=np.int16)
+            lab[10:30, 12:32, 6:18] = rng.integers(1, 8, size=(20, 20, 12))
+            nifti.save(nifti.Nifti1Image(vol, np.diag([0.5, 0.5, 0.8, 1.0])), str(tmp_path / ("img%d.nii.gz" % i)))
+            nifti.save(nifti.Nifti1Image(lab, np.diag([0.5, 0.5, 0.8, 1.0])), str(tmp_path / ("lab%d.nii.gz" % i)))
+        j = 0 if i < 13 else 13
+        entries.append({"image": str(tmp_path / ("img%d.nii.gz" % j)), "label": str(tmp_path / ("lab%d.nii.gz" % j))})
+    (tmp_path / "dataset.json").write_text(json.dumps({"train_and_test": entries}))
+    hm.args = types.SimpleNamespace(data=str(tmp_path) + "/")
+
+    class SmallConfig(hm.HeartConfig):
+        IMAGE_MIN_DIM = 64
+        IMAGE_MAX_DIM = 64
+        RPN_ANCHOR_SCALES = (16, 32)
+
+    cfg = SmallConfig("beginning")
+    ds = hm.HeartDataset()
+    ds.load_heart("train")
+    ds.prepare()
+    assert ds.num_classes == 8 and len(ds.image_ids) == 1
+    item = M.Dataset(ds, cfg)[0]
+    image, meta, mask = item
+    assert image.shape == (64, 64, 64, 1) and mask.shape == (64, 64, 64)
+    assert set(np.unique(mask)) <= set(range(8)) and mask.max() > 0
+    anchors = U.generate_pyramid_anchors(cfg.RPN_ANCHOR_SCALES, cfg.RPN_ANCHOR_RATIOS, M.compute_backbone_shapes(cfg, cfg.IMAGE_SHAPE),
+                                         cfg.BACKBONE_STRIDES, cfg.RPN_ANCHOR_STRIDE)
+    np.random.seed(0)
+    images, rpn_match, rpn_bbox, class_ids, boxes, masks = M.load_image_gt(image, mask, 0, ds, cfg, anchors)
+    assert images.shape == (1, 64, 64, 64) and images.dtype == np.float32 and abs(float(images.mean())) < 1e-3
+    assert rpn_match.shape == (anchors.shape[0], 1) and (rpn_match == 1).sum() > 0
+    assert class_ids.tolist() == list(range(1, 8)) and boxes.shape == (7, 6) and masks.shape == (8, 64, 64, 64)
+    z1, y1, x1, z2, y2, x2 = boxes[0]
+    assert 0 <= z1 < z2 <= 64 and 0 <= y1 < y2 <= 64 and 0 <= x1 < x2 <= 64
