@@ -366,6 +366,14 @@ __global__ void __launch_bounds__(256) pack_act_gp_tiled_kernel(const float* __r
   }
 }
 
+// host-side launcher of the weight pack (used by conv_tc_hc.cu)
+int launch_pack_w_halo(const float* w, __nv_bfloat16* out, int Cout, int Cin, int Npad, int CPC, int parts, int mode, cudaStream_t st) {
+  const long long wt = (long long)CPC * 3 * parts * 9 * 2 * Npad * 8;
+  pack_w_halo_kernel<<<(unsigned)std::min<long long>(cdiv(wt, 256), 4LL * num_sms()), 256, 0, st>>>(w, out, Cout, Cin, Npad, CPC, parts, mode);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
 // host-side launcher (also used by conv_tc_hx.cu, conv_tc_wgrad_ds.cu, conv_fused.cu)
 int launch_pack_act_gp(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int C, int G, cudaStream_t st) {
   const char* e = getenv("CFUN_PACK_TILED");          // "0": the one-thread-per-row kernel (A/B measurements)

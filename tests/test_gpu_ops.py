@@ -507,6 +507,14 @@ def test_conv3d_fused_backward_keeps_forward_pack(ops, case):
         assert xc.grad is None
 
 
+@pytest.mark.skipif(__import__("os").environ.get("CFUN_TC_COL") != "1",
+                    reason="conv_tc_hc.cu (column-pass halo kernel) is experimental and opt-in: CFUN_TC_COL=1")
+@pytest.mark.parametrize("case", HALO_CASES + [(2, 40, 13, 32, 16, 40, 3, 1, False, False), (1, 24, 4, 16, 8, 16, 3, 1, True, False)])
+def test_conv3d_tcgen05_column_pass(ops, case):
+    """the column-pass kernel against fp32 (forward + data gradient), incl. a depth that is not a multiple of the column"""
+    test_conv3d_tcgen05_fwd_dgrad(ops, case)
+
+
 def test_conv3d_tcgen05_single_pass_is_fast_mode_only(ops):
     g = torch.Generator().manual_seed(9)
     x = torch.randn(1, 64, 12, 12, 12, generator=g)
