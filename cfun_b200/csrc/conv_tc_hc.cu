@@ -1,6 +1,8 @@
-// EXPERIMENTAL (opt-in: CFUN_TC_COL=1) -- written at the end of round 1 without GPU time left to validate it; it compiles,
-// it is never selected by default, and tests/test_gpu_ops.py::test_conv3d_tcgen05_column_pass is skipped unless the switch
-// is set.  Validate with `CFUN_TC_COL=1 python tools/conv_cases.py unet fwd,dgrad` before enabling it.
+// EXPERIMENTAL (opt-in: CFUN_TC_COL=1), kept as a measured negative result.  Validated on B200 with the torch-free driver
+// (`tools/prof_driver.bin unet 1 cmpcol`, profiles/r01_column_pass_ab.txt): forward and data gradient are BIT-IDENTICAL to
+// conv_tc_halo.cu (same MMA order per tile), no pipeline time-outs -- but 40->40 @ 4x96^3 takes 1.47 ms against 1.33 ms.
+// So the remaining gap of the halo kernel is not the shared-memory write traffic this variant removes; the default dispatch
+// never selects it, and tests/test_gpu_ops.py::test_conv3d_tcgen05_column_pass runs only with the switch set.
 //
 // tcgen05 3x3x3 / stride 1 / pad 1 convolution for thin layers, "column pass" variant of conv_tc_halo.cu.
 //
