@@ -70,6 +70,12 @@ struct HlParams {
   const uint8_t* wpack;       // [chunk][kd][tap9][kgroup2][part][Npad][8] bf16 (hi rows, then lo rows)
 };
 
+// LEAN (opt-in, CFUN_TC_LEAN=1, split mode only; not yet validated): the ncu source page of this kernel
+// (profiles/r01_ncu_unet_halo_fwd_dgrad_ds_wgrad.json capture) shows the MMA warp never waits on a barrier, yet issues one MMA
+// per ~74 cycles against the ~50 the pipe needs: each tap pays a BSSY/BSYNC pair for its own `if (leader)` region plus a
+// re-load of p.nsplit (LDCU + UISETP).  LEAN hoists the leader branch around the whole 9-tap stage (commit included) and
+// makes the hi/lo split a compile-time fact.
+template <bool LEAN>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_l, const HlParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -167,6 +173,22 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
             tc_fence_after();
             const uint32_t b0 = desc_addr(b_base + (uint32_t)(st * b_stage_bytes)) | b_lbo;
             const uint32_t a_kd = (uint32_t)(kd * HL_HH * HL_WH);
+            if (LEAN) {
+              if (leader) {                         // one divergent region per weight stage: 18 MMAs + the commit
+#pragma unroll
+                for (int t9 = 0; t9 < 9; ++t9) {
+                  const uint32_t aoff = a_kd + (uint32_t)((t9 / 3) * HL_WH + (t9 % 3));
+                  const uint64_t b_all = desc_join(b_hiword, b0 + (uint32_t)t9 * b_tap);
+                  if (t9 == 0) umma_bf16(dcol, desc_join(a_hiword, a_hi0 + aoff), b_all, idesc_2n, acc);
+                  else umma_bf16_acc(dcol, desc_join(a_hiword, a_hi0 + aoff), b_all, idesc_2n);
+                  umma_bf16_acc(dcol, desc_join(a_hiword, a_lo0 + aoff), b_all, idesc_n);
+                }
+                umma_commit(&b_empty[st]);
+              }
+              acc = 1;
+              __syncwarp();
+              continue;
+            }
 #pragma unroll
             for (int t9 = 0; t9 < 9; ++t9) {
               const uint32_t aoff = a_kd + (uint32_t)((t9 / 3) * HL_WH + (t9 % 3));     // halo row of tap (kd, kh, kw)
@@ -498,11 +520,14 @@ int hl_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const floa
   p.wpack = reinterpret_cast<const uint8_t*>(wp);
   static bool attr_set = false;
   if (!attr_set) {
-    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const unsigned grid = (unsigned)std::min<long long>(p.ntiles, num_sms());
-  conv_tc_halo_kernel<<<grid, HL_THREADS, pl.smem, st>>>(mh, ml, p);
+  const char* lean = getenv("CFUN_TC_LEAN");
+  if (split && lean && lean[0] == '1') conv_tc_halo_kernel<true><<<grid, HL_THREADS, pl.smem, st>>>(mh, ml, p);
+  else conv_tc_halo_kernel<false><<<grid, HL_THREADS, pl.smem, st>>>(mh, ml, p);
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;
 }

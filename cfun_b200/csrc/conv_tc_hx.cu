@@ -94,7 +94,9 @@ struct HxParams {
 // TPS: taps per weight stage, 9 (one kd plane) or 3 (one (kd, kh) row) -- compile-time so the issue loop is straight-line.
 // MASKED: only the taps of p.tapmask are multiplied and weight stages without a live tap are neither loaded nor waited for
 // (conv_s2d.cu: a 2x2x2 kernel embedded as one corner of the 3x3x3 stencil).
-template <int TPS, bool MASKED>
+// LEAN (opt-in, CFUN_TC_LEAN=1, split mode, un-masked; not yet validated): one leader region per weight stage instead of one
+// per tap (see the note at conv_tc_halo_kernel).
+template <int TPS, bool MASKED, bool LEAN>
 __global__ void __launch_bounds__(HX_THREADS, 1)
 conv_tc_hx_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_l, const HxParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -216,6 +218,24 @@ conv_tc_hx_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
             const uint32_t b0 = desc_addr(b_base + (uint32_t)(st * p.b_stage_bytes)) | b_lbo;
             const int tap0 = s * TPS;                             // first tap (0..26) of this stage
             const uint32_t a_s = (uint32_t)((tap0 / 9) * HX_HH * HX_WH + ((tap0 % 9) / 3) * HX_WH);   // halo row of (kd, kh0)
+            if (LEAN) {
+              if (leader) {
+#pragma unroll
+                for (int t = 0; t < TPS; ++t) {
+                  const uint32_t aoff = a_s + (uint32_t)((t / 3) * HX_WH + (t % 3));
+                  const uint64_t b_all = desc_join(b_hiword, b0 + (uint32_t)t * b_tap);
+                  if (t == 0) umma_bf16(dcol, desc_join(a_hiword, a_hi0 + aoff), b_all, idesc_2n, acc);
+                  else umma_bf16_acc(dcol, desc_join(a_hiword, a_hi0 + aoff), b_all, idesc_2n);
+                  umma_bf16_acc(dcol, desc_join(a_hiword, a_lo0 + aoff), b_all, idesc_n);
+                }
+                if (p.cluster > 1) hx_commit_mc(&b_empty[st], cmask);
+                else umma_commit(&b_empty[st]);
+              }
+              acc = 1;
+              __syncwarp();
+              if (++st == p.bstages) { st = 0; bph ^= 1u; }
+              continue;
+            }
 #pragma unroll
             for (int t = 0; t < TPS; ++t) {
               if (MASKED) {
@@ -442,7 +462,7 @@ static void pick_cluster(size_t smem, long long ntiles, size_t w_pass_bytes, int
       at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
       int nclusters = 0;
-      if (cudaOccupancyMaxActiveClusters(&nclusters, conv_tc_hx_kernel<9, false>, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (cudaOccupancyMaxActiveClusters(&nclusters, conv_tc_hx_kernel<9, false, false>, &cfg) != cudaSuccess) { cudaGetLastError(); continue; }
       const int g = std::min(nclusters * cl, num_sms() / cl * cl);
       if (g * 10 >= num_sms() * 9 || forced) { cached_cluster = cl; cached_grid = g; break; }
     }
@@ -489,10 +509,12 @@ int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const floa
   }
   static bool attr_set = false;
   if (!attr_set) {     // before the occupancy query of pick_cluster
-    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_hx_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_hx_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_hx_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_hx_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_hx_kernel<9, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_hx_kernel<3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_hx_kernel<9, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_hx_kernel<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_hx_kernel<9, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_hx_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   CUtensorMap mh, ml;
@@ -537,12 +559,16 @@ int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const floa
   p.tapmask = 0;
   for (int t = 0; t < 27; ++t)      // the data gradient runs on mirrored taps (pack_w_hx_kernel mode 1)
     if ((tapmask >> t) & 1) p.tapmask |= 1 << (pass == CFUN_PASS_BWD_DATA ? 26 - t : t);
+  const char* le = getenv("CFUN_TC_LEAN");
+  const bool lean = split && !masked && !p.debug && le && le[0] == '1';
   if (pl.TPS == 9) {
-    if (masked) CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<9, true>, mh, ml, p));
-    else CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<9, false>, mh, ml, p));
+    if (masked) CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<9, true, false>, mh, ml, p));
+    else if (lean) CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<9, false, true>, mh, ml, p));
+    else CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<9, false, false>, mh, ml, p));
   } else {
-    if (masked) CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<3, true>, mh, ml, p));
-    else CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<3, false>, mh, ml, p));
+    if (masked) CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<3, true, false>, mh, ml, p));
+    else if (lean) CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<3, false, true>, mh, ml, p));
+    else CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<3, false, false>, mh, ml, p));
   }
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;

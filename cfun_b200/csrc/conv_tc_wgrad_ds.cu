@@ -59,6 +59,9 @@ struct DsParams {
   float* dw;
 };
 
+// LEAN (opt-in, CFUN_TC_LEAN=1, split mode; not yet validated): one leader region per unit instead of one per K step
+// (see the note at conv_tc_halo_kernel)
+template <bool LEAN>
 __global__ void __launch_bounds__(DS_THREADS, 1)
 conv_tc_wgrad_ds_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid_constant__ CUtensorMap map_yl,
                         const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, const DsParams p) {
@@ -129,6 +132,29 @@ conv_tc_wgrad_ds_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid
       const uint32_t x_hi = desc_addr(sb + (uint32_t)(parts * p.y_bytes)) | b_lbo;
       const uint32_t x_lo = desc_addr(sb + (uint32_t)(parts * p.y_bytes + p.x_bytes)) | b_lbo;
       const uint32_t first = it == 0 ? 0u : 1u;
+      if (LEAN) {
+        if (leader) {
+#pragma unroll 1
+          for (int t = 0; t < nt9; ++t) {
+            const int t9 = p.tap_list[t9_0 + t];
+            const int kh = t9 / 3, kw = t9 - kh * 3;
+            const uint32_t dcol = tmem_base + (uint32_t)(t * p.Npad);
+            const uint32_t toff = (uint32_t)(kh * DS_WH + kw);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint64_t a_hi = desc_join(a_hiword, y_hi + (uint32_t)(j * 2 * DS_WT));
+              const uint64_t b_hi = desc_join(b_hiword, x_hi + (uint32_t)(j * 2 * DS_WH) + toff);
+              if (j == 0) umma_bf16(dcol, a_hi, b_hi, idesc, first);
+              else umma_bf16_acc(dcol, a_hi, b_hi, idesc);
+              umma_bf16_acc(dcol, desc_join(a_hiword, y_lo + (uint32_t)(j * 2 * DS_WT)), b_hi, idesc);
+              umma_bf16_acc(dcol, a_hi, desc_join(b_hiword, x_lo + (uint32_t)(j * 2 * DS_WH) + toff), idesc);
+            }
+          }
+          umma_commit(&empty_bar[slot]);
+        }
+        __syncwarp();
+        continue;
+      }
 #pragma unroll 1
       for (int t = 0; t < nt9; ++t) {
         const int t9 = p.tap_list[t9_0 + t];
@@ -308,13 +334,17 @@ int ds_launch(const cfun_conv3d_desc* d, const DsPlan& pl, __nv_bfloat16* yh, __
   p.dw = dw;
   static bool attr_set = false;
   if (!attr_set) {
-    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_ds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_ds_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_ds_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   dim3 grid((unsigned)ctas, (unsigned)pl.ng9, (unsigned)pl.mtiles);
+  const char* le = getenv("CFUN_TC_LEAN");
+  const bool lean = split && le && le[0] == '1';
   for (int sl = 0; sl < pl.slices; ++sl) {     // groups beyond Gx_total in the last slice are TMA zero fill
     p.ci0 = sl * pl.Gx * 8;
-    conv_tc_wgrad_ds_kernel<<<grid, DS_THREADS, pl.smem, st>>>(myh, myl, mxh, mxl, p);
+    if (lean) conv_tc_wgrad_ds_kernel<true><<<grid, DS_THREADS, pl.smem, st>>>(myh, myl, mxh, mxl, p);
+    else conv_tc_wgrad_ds_kernel<false><<<grid, DS_THREADS, pl.smem, st>>>(myh, myl, mxh, mxl, p);
     CFUN_LAUNCH_CHECK();
   }
   return CFUN_OK;

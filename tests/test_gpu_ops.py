@@ -515,6 +515,15 @@ def test_conv3d_tcgen05_column_pass(ops, case):
     test_conv3d_tcgen05_fwd_dgrad(ops, case)
 
 
+@pytest.mark.skipif(__import__("os").environ.get("CFUN_TC_LEAN") != "1",
+                    reason="lean-issue kernel variants are opt-in until validated on hardware: run the suite with CFUN_TC_LEAN=1")
+@pytest.mark.parametrize("case", HALO_CASES + TC_CASES[:3])
+def test_conv3d_tcgen05_lean_issue_variants(ops, case):
+    """CFUN_TC_LEAN=1 selects conv_tc_halo_kernel<true> / conv_tc_hx_kernel<..., true> / conv_tc_wgrad_ds_kernel<true>:
+    same results as fp32 (and, being the same MMAs in the same order, as the default variants)"""
+    test_conv3d_tcgen05_fwd_dgrad(ops, case)
+
+
 def test_conv3d_tcgen05_single_pass_is_fast_mode_only(ops):
     g = torch.Generator().manual_seed(9)
     x = torch.randn(1, 64, 12, 12, 12, generator=g)
