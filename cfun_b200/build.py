@@ -10,7 +10,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libcfun_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-         "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+         "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("CFUN_NVCC_FLAGS", "").split()
 
 
 def sources():
@@ -21,6 +21,7 @@ def _digest():
     h = hashlib.sha256()
     files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
     files.append(os.path.join(os.path.dirname(HERE), "include", "cfun_b200.h"))
+    h.update(" ".join(FLAGS).encode())
     for f in files:
         h.update(f.encode())
         with open(f, "rb") as fh:

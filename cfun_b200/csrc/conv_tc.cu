@@ -357,17 +357,11 @@ size_t hx_workspace(const cfun_conv3d_desc* d, int pass);
 int hx_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
             int nsplit, void* ws, size_t ws_bytes, cudaStream_t st);
 int tc_debug_read_hx(int* out8);
-bool hc_supported(const cfun_conv3d_desc* d, int pass);     // conv_tc_hc.cu: column-pass variant, EXPERIMENTAL (CFUN_TC_COL=1)
-size_t hc_workspace(const cfun_conv3d_desc* d, int pass);
-int hc_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
-            int nsplit, void* ws, size_t ws_bytes, cudaStream_t st);
-int tc_debug_read_hc(int* out8);
 bool hl_supported(const cfun_conv3d_desc* d, int pass);
 size_t hl_workspace(const cfun_conv3d_desc* d, int pass);
 int hl_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
             int nsplit, void* ws, size_t ws_bytes, cudaStream_t st);
 int tc_debug_read_halo(int* out8);
-int tc_debug_read_hw(int* out8);
 int tc_debug_read_ds(int* out8);
 
 bool wg_capable(const cfun_conv3d_desc* d);   // conv_tc_wgrad.cu
@@ -418,7 +412,6 @@ bool tc_preferred(const cfun_conv3d_desc* d, int pass) {
 size_t tc_workspace(const cfun_conv3d_desc* d, int pass) {
   if (d && d->sD == 2) return s2d_workspace(d, pass);
   if (pass == CFUN_PASS_BWD_WEIGHT) return tc_wgrad_workspace(d);
-  if (hc_supported(d, pass)) return std::max(hc_workspace(d, pass), hl_supported(d, pass) ? hl_workspace(d, pass) : hx_workspace(d, pass));
   if (hl_supported(d, pass)) return hl_workspace(d, pass);
   if (hx_supported(d, pass)) return hx_workspace(d, pass);
   TcPlan pl;
@@ -516,7 +509,6 @@ int tc_conv_fwd(const cfun_conv3d_desc* d, const float* x, const float* w, const
                 void* ws, size_t ws_bytes, cudaStream_t st) {
   CFUN_CHECK_ARG(!(epi & CFUN_EPI_BIAS) || bias);
   if (d->sD == 2) return s2d_conv(d, CFUN_PASS_FWD, x, w, bias, y, nullptr, epi, nsplit, ws, ws_bytes, st);
-  if (hc_supported(d, CFUN_PASS_FWD)) return hc_conv(d, CFUN_PASS_FWD, x, w, bias, y, epi, nsplit, ws, ws_bytes, st);
   // thin layers (Cin <= 64): conv_tc_halo.cu, measured 7-10 % faster there; everything else 3^3: conv_tc_hx.cu
   if (hl_supported(d, CFUN_PASS_FWD)) return hl_conv(d, CFUN_PASS_FWD, x, w, bias, y, epi, nsplit, ws, ws_bytes, st);
   if (hx_supported(d, CFUN_PASS_FWD)) return hx_conv(d, CFUN_PASS_FWD, x, w, bias, y, epi, nsplit, ws, ws_bytes, st);
@@ -526,7 +518,6 @@ int tc_conv_fwd(const cfun_conv3d_desc* d, const float* x, const float* w, const
 int tc_conv_bwd_data(const cfun_conv3d_desc* d, const float* dy, const float* w, float* dx, int nsplit, void* ws,
                      size_t ws_bytes, cudaStream_t st) {
   if (d->sD == 2) return s2d_conv(d, CFUN_PASS_BWD_DATA, dy, w, nullptr, dx, nullptr, 0, nsplit, ws, ws_bytes, st);
-  if (hc_supported(d, CFUN_PASS_BWD_DATA)) return hc_conv(d, CFUN_PASS_BWD_DATA, dy, w, nullptr, dx, 0, nsplit, ws, ws_bytes, st);
   if (hl_supported(d, CFUN_PASS_BWD_DATA)) return hl_conv(d, CFUN_PASS_BWD_DATA, dy, w, nullptr, dx, 0, nsplit, ws, ws_bytes, st);
   if (hx_supported(d, CFUN_PASS_BWD_DATA)) return hx_conv(d, CFUN_PASS_BWD_DATA, dy, w, nullptr, dx, 0, nsplit, ws, ws_bytes, st);
   return run_tc(d, CFUN_PASS_BWD_DATA, dy, w, nullptr, dx, 0, nsplit, ws, ws_bytes, st);
@@ -566,17 +557,12 @@ extern "C" int cfun_tc_debug_status(int* out8_host) {
   if (rc != CFUN_OK) return rc;
   rc = tc_debug_read_halo(c);
   if (rc != CFUN_OK) return rc;
-  int e[8];
-  rc = tc_debug_read_hw(e);
-  if (rc != CFUN_OK) return rc;
-  int f[8], g[8], h[8];
+  int f[8], g[8];
   rc = tc_debug_read_ds(f);
   if (rc != CFUN_OK) return rc;
   rc = tc_debug_read_hx(g);
   if (rc != CFUN_OK) return rc;
-  rc = tc_debug_read_hc(h);
-  if (rc != CFUN_OK) return rc;
   for (int i = 0; i < 8; ++i)
-    out8_host[i] = a[0] ? a[i] : (b[0] ? b[i] : (c[0] ? c[i] : (e[0] ? e[i] : (f[0] ? f[i] : (g[0] ? g[i] : h[i])))));
+    out8_host[i] = a[0] ? a[i] : (b[0] ? b[i] : (c[0] ? c[i] : (f[0] ? f[i] : g[i])));
   return CFUN_OK;
 }

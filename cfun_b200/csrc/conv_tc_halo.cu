@@ -7,37 +7,40 @@
 //   * activations are packed "group-planar": [Kp/8 groups][N*(D+2)][H][W][8 ch] split-bf16 (zero planes at d = -1, D), so a
 //     TMA box (80 elements = 10 voxels x 8 ch, 18 rows, 3 planes) lands as one plane of 16-byte rows per 8-channel group;
 //   * with the un-swizzled ("interleave") K-major canonical layout ((8,n),2):((1,SBO),LBO) a 128-row operand is 16 groups of 8
-//     consecutive 16-byte rows; rows = w (contiguous), groups = h lines (SBO = 10*16 B), the second 8-channel half of a K=16
-//     step is the next plane (LBO = plane size), and tap (kd,kh,kw) is just start address + ((kd*18 + kh)*10 + kw)*16;
+//     consecutive 16-byte rows; rows = w (contiguous), groups = h lines (SBO = 10*16 B), and tap (kd,kh,kw) of channel group g
+//     is just start address = plane(g) + ((kd*18 + kh)*10 + kw)*16;
 //   * every inner TMA coordinate is a multiple of 8 elements (16 B), the alignment rule the weight-gradient kernel ran into.
-// Weights stream through a 3-stage ring as contiguous 16-B-row planes (one stage = one K-chunk x one kd plane of 9 taps).
-// Persistent CTAs, TMEM accumulator double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1; the halo ring
-// is per K-chunk, so chunk c of tile i+1 loads while chunks c+1.. of tile i are still being consumed.
-// Split-bf16 x3 arithmetic as in conv_tc.cu, issued as TWO MMAs per (tap, K-chunk): the weight tile holds the hi rows and
-// the lo rows back to back, so  A_hi x [B_hi ; B_lo]  is one N = 2*Npad instruction (hi*hi and hi*lo land in adjacent
-// accumulator column ranges, summed in the epilogue) and  A_lo x B_hi  a second N = Npad instruction.  The kernel is
-// shared-memory-bandwidth bound on the 4 KB A operand (ncu: tensor pipe 27 % active, SM throughput 74 %), and this reads A
-// twice instead of three times.  The data gradient is the same kernel with flipped / transposed weights.
+//
+// Round 2 (what the measurements said): these kernels are bound by SHARED-MEMORY BANDWIDTH -- every tcgen05.mma re-reads
+// its 4 KB A tile and N x 32 B of B from shared memory at 128 B/clk and the TMA fills share that port; the round-1 kernel ran
+// at 1.1 x that model, and the issue-rate fix ("LEAN") was worth 0-4 %.  So this version removes bytes, not instructions:
+//   * EXACT K.  The contraction index is (channel group, tap), 27 G entries of 8 channels; one K = 16 MMA step takes ANY two
+//     entries, because the second half of a K-major operand sits at an arbitrary LBO from the first.  Entries are paired in
+//     group-major order ((g,t),(g,t+1)), the pair straddling two groups has LBO = 2 planes - tap offset.  Cin = 20 (3
+//     groups) needs 41 steps instead of 54 (K padded to 32), Cin = 40 (5 groups) 68 instead of 81 (K padded to 48).
+//   * Only the G real channel groups are loaded (3 instead of 4 planes at 20 channels, 5 instead of 6 at 40), each with its own
+//     full/empty barrier pair, so group g of the next tile streams in while groups g+1.. of this tile are being multiplied.
+//   * RESIDENT WEIGHTS where they fit beside the halo (20->20, 40->20 dgrad: 84..126 KB): loaded once per CTA instead of
+//     once per 128-voxel tile (110 KB per tile before); otherwise streamed through a ring of step-granular stages.
+// Split-bf16 x3 arithmetic as in conv_tc.cu, issued as TWO MMAs per step: the weight tile holds the hi rows and the lo rows
+// back to back, so  A_hi x [B_hi ; B_lo]  is one N = 2*Npad instruction (hi*hi and hi*lo land in adjacent accumulator
+// column ranges, summed in the epilogue) and  A_lo x B_hi  a second N = Npad instruction.
+// Persistent CTAs, TMEM accumulator double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+// The data gradient is the same kernel with flipped / transposed weights.
 #include "tc_ptx.cuh"
 #include <cstdlib>
 
 namespace cfun {
 
-constexpr int HL_THREADS = 192;
+constexpr int HL_THREADS = 224;                      // warp 0: halo producer, 1: MMA issuer, 2..5: epilogue, 6: weight producer
 constexpr int HL_HT = 16, HL_WT = 8;                 // output slab 1 x 16 x 8
 constexpr int HL_HH = HL_HT + 2, HL_WH = HL_WT + 2;  // halo 3 x 18 x 10
 constexpr int HL_PLANE_DATA = 3 * HL_HH * HL_WH * 16;   // 8640 B: one 8-channel group, one part
 constexpr int HL_PLANE = (HL_PLANE_DATA + 127) / 128 * 128;   // 8704: plane pitch (TMA smem destinations are 128 B aligned)
-constexpr int HL_MAX_CPC = 4;                        // Kp <= 64
-constexpr int HL_BSTAGES = 3;
+constexpr int HL_MAX_G = 8;                          // Cin <= 64
+constexpr int HL_MAX_STEPS = 27 * HL_MAX_G / 2;      // 108
+constexpr int HL_MAX_BSTAGES = 8;
 
-__device__ __forceinline__ uint64_t make_desc_interleave(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell); layout type 0 = no swizzle
-  return d;
-}
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
@@ -56,51 +59,64 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 int launch_pack_act_gp(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int C, int G, cudaStream_t st);
 
+// ---- compile-time step table (G = real channel groups) -------------------------------------------------------------------
+// entry e = (group g = e / 27, tap t = e % 27) lives at plane 2g (hi; lo = the next plane) + halo row of the tap; all in 16-byte units
+__host__ __device__ constexpr uint32_t hl_entry_off16(int e) {
+  return (uint32_t)(((2 * (e / 27)) * HL_PLANE + ((((e % 27) / 9) * HL_HH + ((e % 27) % 9) / 3) * HL_WH + (e % 27) % 3) * 16) >> 4);
+}
+// A-descriptor low word of step s relative to the halo slot: start address >> 4 | LBO >> 4 << 16.  With an odd entry count the
+// last step pairs the previous tap (multiplied by zero weights, see pack_w_halo_kernel) with the last real entry, so that both
+// K halves read initialised shared memory.
+__host__ __device__ constexpr uint32_t hl_a_word(int G, int s) {
+  return 2 * s + 1 < 27 * G ? (hl_entry_off16(2 * s) | ((hl_entry_off16(2 * s + 1) - hl_entry_off16(2 * s)) << 16))
+                            : ((hl_entry_off16(2 * s) - 1u) | (1u << 16));
+}
+// segment g = the steps whose first entry lies in group g: [seg_begin(g), seg_begin(g + 1)); 14, 13, 14, ... steps.  For even g
+// (and g + 1 < G) the last step of the segment straddles into group g + 1.  Weight stages are half segments: 7 + (7 | 6) steps.
+__host__ __device__ constexpr int hl_seg_begin(int g) { return (27 * g + 1) / 2; }
+constexpr int HL_HALF = 7;
+
 struct HlParams {
   int N, D, H, W, Cout;       // output extents == input extents (pad 1, stride 1)
-  int CPC;                    // K chunks of 16 channels
   int Npad;                   // MMA N
   int tilesH, tilesW;
   long long ntiles;
   int nsplit;
   int tmem_cols;
   int epi;
+  int resident;               // 1: the whole weight pack is loaded once per CTA; 0: ring of bstages stages of HL_HALF steps
+  int bstages;
   const float* bias;
   float* y;
-  const uint8_t* wpack;       // [chunk][kd][tap9][kgroup2][part][Npad][8] bf16 (hi rows, then lo rows)
+  const uint8_t* wpack;       // [step][khalf2][part][Npad][8] bf16 (hi rows, then lo rows)
 };
 
-// LEAN (opt-in, CFUN_TC_LEAN=1, split mode only; not yet validated): the ncu source page of this kernel
-// (profiles/r01_ncu_unet_halo_fwd_dgrad_ds_wgrad.json capture) shows the MMA warp never waits on a barrier, yet issues one MMA
-// per ~74 cycles against the ~50 the pipe needs: each tap pays a BSSY/BSYNC pair for its own `if (leader)` region plus a
-// re-load of p.nsplit (LDCU + UISETP).  LEAN hoists the leader branch around the whole 9-tap stage (commit included) and
-// makes the hi/lo split a compile-time fact.
-template <bool LEAN>
+template <int G, bool SPLIT>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_l, const HlParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_raw);       // [HL_MAX_CPC]
-  uint64_t* a_empty = a_full + HL_MAX_CPC;
-  uint64_t* b_full = a_empty + HL_MAX_CPC;                        // [HL_BSTAGES]
-  uint64_t* b_empty = b_full + HL_BSTAGES;
-  uint64_t* t_full = b_empty + HL_BSTAGES;                        // [2]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_raw);       // [HL_MAX_G]
+  uint64_t* a_empty = a_full + HL_MAX_G;
+  uint64_t* b_full = a_empty + HL_MAX_G;                          // [HL_MAX_BSTAGES]
+  uint64_t* b_empty = b_full + HL_MAX_BSTAGES;
+  uint64_t* t_full = b_empty + HL_MAX_BSTAGES;                    // [2]
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
   uint8_t* base = smem_raw + 1024 + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
+  constexpr int NSTEPS = (27 * G + 1) / 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int parts = p.nsplit == 3 ? 2 : 1;
-  const int a_slot_bytes = parts * 2 * HL_PLANE;                  // one K chunk: 2 channel groups x parts
-  const int nrows = parts * p.Npad;                               // weight rows per K-group: hi rows then lo rows
-  const int b_stage_bytes = 9 * 2 * nrows * 16;
-  uint8_t* a_ring = base;
-  uint8_t* b_ring = base + (size_t)p.CPC * a_slot_bytes;
+  constexpr int parts = SPLIT ? 2 : 1;
+  const int nrows = parts * p.Npad;                               // weight rows per K half: hi rows then lo rows
+  const int step_bytes = 2 * nrows * 16;
+  uint8_t* a_slot = base;                                         // planes [g][part]
+  uint8_t* b_ring = base + (size_t)G * 2 * HL_PLANE;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_h);
     if (parts == 2) prefetch_tmap(&map_l);
-    for (int i = 0; i < p.CPC; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < HL_BSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < G; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < HL_MAX_BSTAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
     fence_barrier_init();
   }
@@ -111,9 +127,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== producer: halo (TMA tensor) + weights (bulk) =====================
+    // ===================== halo producer: one TMA box per (group, part), one barrier pair per group =====================
     if (lane == 0) {
-      uint32_t bcount = 0;
       int local = 0;
       for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++local) {
         long long t = tile;
@@ -124,91 +139,99 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
         const int c_w = (wb * HL_WT - 1) * 8;          // inner coordinate in elements (multiple of 8 -> 16 B aligned)
         const int c_h = hb * HL_HT - 1;
         const int c_nd = n * (p.D + 2) + d;            // padded plane index of d-1
-        for (int c = 0; c < p.CPC; ++c) {
-          mbar_wait(&a_empty[c], (uint32_t)((local & 1) ^ 1), 210);
-          mbar_arrive_expect_tx(&a_full[c], (uint32_t)(parts * 2 * HL_PLANE_DATA));
-          uint8_t* slot = a_ring + (size_t)c * a_slot_bytes;
-          for (int g = 0; g < 2; ++g) {
-            tma_load_4d(&map_h, &a_full[c], slot + g * HL_PLANE, c_w, c_h, c_nd, 2 * c + g);
-            if (parts == 2) tma_load_4d(&map_l, &a_full[c], slot + (2 + g) * HL_PLANE, c_w, c_h, c_nd, 2 * c + g);
-          }
-          for (int kd = 0; kd < 3; ++kd, ++bcount) {
-            const int st = (int)(bcount % HL_BSTAGES);
-            mbar_wait(&b_empty[st], (uint32_t)(((bcount / HL_BSTAGES) & 1) ^ 1), 220);
-            mbar_arrive_expect_tx(&b_full[st], (uint32_t)b_stage_bytes);
-            const uint8_t* src = p.wpack + ((size_t)(c * 3 + kd)) * (size_t)b_stage_bytes;
-            bulk_load(b_ring + (size_t)st * b_stage_bytes, src, (uint32_t)b_stage_bytes, &b_full[st]);
+        for (int g = 0; g < G; ++g) {
+          mbar_wait(&a_empty[g], (uint32_t)((local & 1) ^ 1), 210);
+          mbar_arrive_expect_tx(&a_full[g], (uint32_t)(parts * HL_PLANE_DATA));
+          tma_load_4d(&map_h, &a_full[g], a_slot + (size_t)(2 * g) * HL_PLANE, c_w, c_h, c_nd, g);
+          if (parts == 2) tma_load_4d(&map_l, &a_full[g], a_slot + (size_t)(2 * g + 1) * HL_PLANE, c_w, c_h, c_nd, g);
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      if (p.resident) {
+        const uint32_t total = (uint32_t)(NSTEPS * step_bytes);
+        mbar_arrive_expect_tx(&b_full[0], total);
+        for (uint32_t off = 0; off < total; off += 32768u)
+          bulk_load(b_ring + off, p.wpack + off, min(32768u, total - off), &b_full[0]);
+      } else {
+        int st = 0;
+        uint32_t ph = 0;
+        for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+          for (int q = 0; q < 2 * G; ++q) {              // stage q = half q & 1 of segment q >> 1
+            const int g = q >> 1;
+            const int s0 = hl_seg_begin(g) + (q & 1) * HL_HALF;
+            const int s1 = (q & 1) ? hl_seg_begin(g + 1) : s0 + HL_HALF;
+            const uint32_t bytes = (uint32_t)((min(s1, NSTEPS) - s0) * step_bytes);
+            mbar_wait(&b_empty[st], ph ^ 1u, 220);
+            mbar_arrive_expect_tx(&b_full[st], bytes);
+            bulk_load(b_ring + (size_t)st * HL_HALF * step_bytes, p.wpack + (size_t)s0 * step_bytes, bytes, &b_full[st]);
+            if (++st == p.bstages) { st = 0; ph ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform loop, elected lane issues: tc_ptx.cuh "issue-rate note") ==========
-    {
-      const uint32_t leader = elect_one();
-      const uint32_t idesc_n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t idesc_2n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nrows >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t a_base = smem_u32(a_ring), b_base = smem_u32(b_ring);
-      // descriptor = constant high word (SBO, version) | low word (start address >> 4, LBO >> 4 in bits 16..29)
-      const uint32_t a_hiword = (uint32_t)(make_desc_interleave(0, HL_PLANE, HL_WH * 16) >> 32);
-      const uint32_t b_hiword = (uint32_t)(make_desc_interleave(0, (uint32_t)(nrows * 16), 128) >> 32);
-      const uint32_t a_lbo = (uint32_t)(HL_PLANE >> 4) << 16, b_lbo = (uint32_t)nrows << 16;
-      const uint32_t b_tap = (uint32_t)(2 * nrows);                 // 16-byte rows per tap in a weight stage
-      uint32_t bcount = 0;
-      int local = 0;
-      for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++local) {
-        const int buf = local & 1;
-        mbar_wait(&t_empty[buf], (uint32_t)(((local >> 1) & 1) ^ 1), 230);
-        tc_fence_after();
-        const uint32_t dcol = tmem_base + (uint32_t)(buf * nrows);
-        uint32_t acc = 0;
-        for (int c = 0; c < p.CPC; ++c) {
-          mbar_wait(&a_full[c], (uint32_t)(local & 1), 240);
-          tc_fence_after();
-          const uint32_t a_hi0 = desc_addr(a_base + (uint32_t)(c * a_slot_bytes)) | a_lbo;
-          const uint32_t a_lo0 = a_hi0 + (uint32_t)((2 * HL_PLANE) >> 4);
-          for (int kd = 0; kd < 3; ++kd, ++bcount) {
-            const int st = (int)(bcount % HL_BSTAGES);
-            mbar_wait(&b_full[st], (uint32_t)((bcount / HL_BSTAGES) & 1), 250);
-            tc_fence_after();
-            const uint32_t b0 = desc_addr(b_base + (uint32_t)(st * b_stage_bytes)) | b_lbo;
-            const uint32_t a_kd = (uint32_t)(kd * HL_HH * HL_WH);
-            if (LEAN) {
-              if (leader) {                         // one divergent region per weight stage: 18 MMAs + the commit
+    // ===================== MMA issuer: warp-uniform control, one straight-line leader region per weight stage ==========
+    // A single warp retires a dependent instruction every ~4 cycles and the queue in front of the tensor pipe holds ~6 MMAs
+    // (tools/umma_queue.cu), so the instruction count between MMAs IS the issue rate: the step table is compile-time
+    // (template G) and every loop-carried quantity is a function of the uniform induction variable `it`, which keeps the
+    // descriptors in uniform registers (no R2UR).
+    const uint32_t leader = elect_one();
+    const uint32_t idesc_n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc_2n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nrows >> 3) << 17) | ((128u >> 4) << 24);
+    // descriptor = constant high word (SBO, version) | low word (start address >> 4, LBO >> 4 in bits 16..29)
+    constexpr uint32_t a_hiword = (uint32_t)((HL_WH * 16) >> 4) | (1u << 14);
+    constexpr uint32_t b_hiword = (uint32_t)(128 >> 4) | (1u << 14);
+    const uint32_t a_base = desc_addr(smem_u32(a_slot));
+    const uint32_t b_base = desc_addr(smem_u32(b_ring)) | ((uint32_t)nrows << 16);
+    const uint32_t stepw = (uint32_t)(step_bytes >> 4);
+    const uint32_t stagew = stepw * HL_HALF;
+    constexpr uint32_t lo_off = (uint32_t)(HL_PLANE >> 4);          // lo plane of a group follows its hi plane
+    const uint32_t ring_n = (uint32_t)p.bstages;
+    const uint32_t ring_inv = 0xFFFFFFFFu / ring_n + 1u;            // cnt / ring_n == umulhi(cnt, ring_inv) for cnt < 2^32 / ring_n
+    const int iters = (int)((p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+    if (p.resident) { mbar_wait(&b_full[0], 0, 245); tc_fence_after(); }
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t buf = (uint32_t)it & 1u;
+      mbar_wait(&t_empty[buf], (((uint32_t)it >> 1) & 1u) ^ 1u, 230);
+      const uint32_t dcol = tmem_base + buf * (uint32_t)nrows;
 #pragma unroll
-                for (int t9 = 0; t9 < 9; ++t9) {
-                  const uint32_t aoff = a_kd + (uint32_t)((t9 / 3) * HL_WH + (t9 % 3));
-                  const uint64_t b_all = desc_join(b_hiword, b0 + (uint32_t)t9 * b_tap);
-                  if (t9 == 0) umma_bf16(dcol, desc_join(a_hiword, a_hi0 + aoff), b_all, idesc_2n, acc);
-                  else umma_bf16_acc(dcol, desc_join(a_hiword, a_hi0 + aoff), b_all, idesc_2n);
-                  umma_bf16_acc(dcol, desc_join(a_hiword, a_lo0 + aoff), b_all, idesc_n);
-                }
-                umma_commit(&b_empty[st]);
-              }
-              acc = 1;
-              __syncwarp();
-              continue;
-            }
+      for (int g = 0; g < G; ++g) {
+        mbar_wait(&a_full[g], buf, 240);
+        if ((g & 1) == 0 && g + 1 < G) mbar_wait(&a_full[g + 1], buf, 241);     // the last step of an even segment straddles
 #pragma unroll
-            for (int t9 = 0; t9 < 9; ++t9) {
-              const uint32_t aoff = a_kd + (uint32_t)((t9 / 3) * HL_WH + (t9 % 3));     // halo row of tap (kd, kh, kw)
-              const uint64_t a_hi = desc_join(a_hiword, a_hi0 + aoff);
-              const uint64_t b_all = desc_join(b_hiword, b0 + (uint32_t)t9 * b_tap);
-              if (leader) {
-                if (t9 == 0) umma_bf16(dcol, a_hi, b_all, idesc_2n, acc);   // [hi*hi | hi*lo] into columns [0,N) and [N,2N)
-                else umma_bf16_acc(dcol, a_hi, b_all, idesc_2n);
-                if (parts == 2) umma_bf16_acc(dcol, desc_join(a_hiword, a_lo0 + aoff), b_all, idesc_n);   // lo*hi: first Npad rows only
-              }
-            }
-            acc = 1;
-            if (leader) umma_commit(&b_empty[st]);
-            __syncwarp();
+        for (int h = 0; h < 2; ++h) {
+          const int s0 = hl_seg_begin(g) + h * HL_HALF;
+          const int s1 = h ? hl_seg_begin(g + 1) : s0 + HL_HALF;
+          const uint32_t cnt = (uint32_t)it * (2 * G) + (uint32_t)(2 * g + h);   // weight stage counter
+          const uint32_t lap = __umulhi(cnt, ring_inv);
+          const uint32_t st = cnt - lap * ring_n;
+          uint32_t bw;
+          if (p.resident) bw = b_base + (uint32_t)s0 * stepw;
+          else {
+            mbar_wait(&b_full[st], lap & 1u, 250);
+            bw = b_base + st * stagew;
           }
-          if (leader) umma_commit(&a_empty[c]);
+          tc_fence_after();
+          if (leader) {
+#pragma unroll
+            for (int s = s0; s < s1; ++s) {
+              if (s < NSTEPS) {
+                const uint64_t b_all = desc_join(b_hiword, bw + (uint32_t)(s - s0) * stepw);
+                const uint32_t aw = a_base + hl_a_word(G, s);         // low 14 bits: address, bits 16..29: LBO (no carry between them)
+                if (s == 0) umma_bf16(dcol, desc_join(a_hiword, aw), b_all, idesc_2n, 0u);     // [hi*hi | hi*lo]
+                else umma_bf16_acc(dcol, desc_join(a_hiword, aw), b_all, idesc_2n);
+                if (parts == 2) umma_bf16_acc(dcol, desc_join(a_hiword, aw + lo_off), b_all, idesc_n);   // lo*hi: first Npad rows only
+              }
+            }
+            if (!p.resident) umma_commit(&b_empty[st]);
+            if (h == 1) umma_commit(&a_empty[g]);
+            if (h == 1 && g == G - 1) umma_commit(&t_full[buf]);
+          }
           __syncwarp();
         }
-        if (leader) umma_commit(&t_full[buf]);
-        __syncwarp();
       }
     }
   } else {
@@ -304,27 +327,28 @@ __global__ void __launch_bounds__(256) pack_act_gp_kernel(const float* __restric
   }
 }
 
-// w (Cout, Cin, 27) fp32 -> [chunk][kd][tap9][kgroup2][part][Npad][8] bf16.  mode 1 = data gradient (rows = ci, k = co,
+// w (Cout, Cin, 27) fp32 -> [step][khalf2][part][Npad][8] bf16: K half `khalf` of step s is entry e = 2 s + khalf of the
+// (channel group, tap) list, i.e. channels 8 (e / 27) .. + 7 at tap e % 27.  mode 1 = data gradient (rows = ci, k = co,
 // taps mirrored).
 __global__ void __launch_bounds__(256) pack_w_halo_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout,
-                                                          int Cin, int Npad, int CPC, int parts, int mode) {
-  const long long total = (long long)CPC * 3 * parts * 9 * 2 * Npad * 8;
+                                                          int Cin, int Npad, int G, int nsteps, int parts, int mode) {
+  const long long total = (long long)nsteps * 2 * parts * Npad * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long r = i;
-    const int e = (int)(r % 8); r /= 8;
+    const int e8 = (int)(r % 8); r /= 8;
     const int row = (int)(r % Npad); r /= Npad;
     const int part = (int)(r % parts); r /= parts;
-    const int kg = (int)(r % 2); r /= 2;
-    const int t9 = (int)(r % 9); r /= 9;
-    const int kd = (int)(r % 3); r /= 3;
-    const int c = (int)r;
-    const int k = c * 16 + kg * 8 + e;
-    int tap = kd * 9 + t9;
+    const int kh = (int)(r % 2); r /= 2;
+    int ent = 2 * (int)r + kh;
+    if ((G & 1) && (int)r == nsteps - 1) ent = kh ? 27 * G - 1 : 27 * G;      // odd entry count: (zero weights, last entry), see hl_a_word
+    const int g = ent / 27;
+    const int k = g * 8 + e8;
+    int tap = ent - g * 27;
     int co, ci;
     if (mode == 0) { co = row; ci = k; }
     else { co = k; ci = row; tap = 26 - tap; }
     float v = 0.f;
-    if (co < Cout && ci < Cin) v = w[((long long)co * Cin + ci) * 27 + tap];
+    if (g < G && co < Cout && ci < Cin) v = w[((long long)co * Cin + ci) * 27 + tap];
     __nv_bfloat16 h, l;
     split_bf16(v, h, l);
     out[i] = part == 0 ? h : l;
@@ -388,10 +412,10 @@ __global__ void __launch_bounds__(256) pack_act_gp_tiled_kernel(const float* __r
   }
 }
 
-// host-side launcher of the weight pack (used by conv_tc_hc.cu)
-int launch_pack_w_halo(const float* w, __nv_bfloat16* out, int Cout, int Cin, int Npad, int CPC, int parts, int mode, cudaStream_t st) {
-  const long long wt = (long long)CPC * 3 * parts * 9 * 2 * Npad * 8;
-  pack_w_halo_kernel<<<(unsigned)std::min<long long>(cdiv(wt, 256), 4LL * num_sms()), 256, 0, st>>>(w, out, Cout, Cin, Npad, CPC, parts, mode);
+static int launch_pack_w_halo(const float* w, __nv_bfloat16* out, int Cout, int Cin, int Npad, int G, int nsteps, int parts, int mode,
+                              cudaStream_t st) {
+  const long long wt = (long long)nsteps * 2 * parts * Npad * 8;
+  pack_w_halo_kernel<<<(unsigned)std::min<long long>(cdiv(wt, 256), 4LL * num_sms()), 256, 0, st>>>(w, out, Cout, Cin, Npad, G, nsteps, parts, mode);
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;
 }
@@ -417,7 +441,7 @@ int launch_pack_act_gp(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int
 }
 
 struct HlPlan {
-  int Cs, Ct, N, D, H, W, Kp, G, CPC, Npad, tmem_cols;
+  int Cs, Ct, N, D, H, W, Kp, Gp, G, nsteps, Npad, tmem_cols, resident, sps, bstages;
   size_t off_ah, off_al, off_w, total, act_bytes, w_bytes, smem;
 };
 
@@ -431,20 +455,31 @@ static bool make_hl_plan(const cfun_conv3d_desc* d, int pass, HlPlan& pl) {
   if (pl.H < 8 || pl.W < 8) return false;
   if ((long long)pl.W * 8 > 0x7fffffffLL) return false;
   pl.Kp = (int)align_up((size_t)pl.Cs, 16);
-  pl.G = pl.Kp / 8;
-  pl.CPC = pl.Kp / 16;
-  if (pl.CPC > HL_MAX_CPC) return false;
+  pl.Gp = pl.Kp / 8;                                       // groups in the pack (16-channel granularity, shared with hx / wgrad)
+  pl.G = (int)cdiv(pl.Cs, 8);                              // groups that hold real channels: the only ones loaded and multiplied
+  if (pl.G > HL_MAX_G) return false;
+  pl.nsteps = (27 * pl.G + 1) / 2;
   pl.Npad = (int)align_up((size_t)pl.Ct, 16);
   if (pl.Npad > 128) return false;                         // [hi | lo] accumulator pairs, double buffered: 4 * Npad <= 512
   int cols = 32;
   while (cols < 4 * pl.Npad) cols <<= 1;
   pl.tmem_cols = cols;
-  const size_t a_bytes = (size_t)pl.CPC * 2 * 2 * HL_PLANE;
-  const size_t b_bytes = (size_t)HL_BSTAGES * 2 * 9 * 2 * pl.Npad * 16;
-  pl.smem = 2048 + a_bytes + b_bytes;
-  if (pl.smem > 225 * 1024) return false;
-  pl.act_bytes = align_up((size_t)pl.G * pl.N * (pl.D + 2) * pl.H * pl.W * 16, 1024);
-  pl.w_bytes = align_up((size_t)pl.CPC * 3 * 2 * 9 * 2 * pl.Npad * 16, 1024);
+  const size_t a_bytes = (size_t)pl.G * 2 * HL_PLANE;
+  const size_t step_bytes = (size_t)2 * 2 * pl.Npad * 16;
+  const size_t budget = 227 * 1024 - 2048 - a_bytes;
+  pl.w_bytes = align_up((size_t)pl.nsteps * step_bytes, 1024);
+  const char* e = getenv("CFUN_HL_RESIDENT");              // "0": always stream the weights (A/B measurements)
+  if (pl.w_bytes <= budget && !(e && e[0] == '0')) {
+    pl.resident = 1; pl.sps = pl.nsteps; pl.bstages = 1;
+    pl.smem = 2048 + a_bytes + pl.w_bytes;
+  } else {
+    pl.resident = 0;
+    pl.sps = HL_HALF;
+    pl.bstages = (int)std::min<size_t>(HL_MAX_BSTAGES, budget / (pl.sps * step_bytes));
+    if (pl.bstages < 2) return false;
+    pl.smem = 2048 + a_bytes + (size_t)pl.bstages * pl.sps * step_bytes;
+  }
+  pl.act_bytes = align_up((size_t)pl.Gp * pl.N * (pl.D + 2) * pl.H * pl.W * 16, 1024);
   pl.off_ah = 0; pl.off_al = pl.act_bytes; pl.off_w = 2 * pl.act_bytes;
   pl.total = 2 * pl.act_bytes + pl.w_bytes + 2048;
   return true;
@@ -490,17 +525,16 @@ int hl_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const floa
   __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(base + pl.off_w);
   {
     if (!(ext_hi && ext_ready)) {
-      int prc = launch_pack_act_gp(src, ah, split ? al : nullptr, pl.N, pl.D, pl.H, pl.W, pl.Cs, pl.G, st);
+      int prc = launch_pack_act_gp(src, ah, split ? al : nullptr, pl.N, pl.D, pl.H, pl.W, pl.Cs, pl.Gp, st);
       if (prc != CFUN_OK) return prc;
     }
-    long long wt = (long long)pl.CPC * 3 * parts * 9 * 2 * pl.Npad * 8;
-    pack_w_halo_kernel<<<(unsigned)std::min<long long>(cdiv(wt, 256), 4LL * num_sms()), 256, 0, st>>>(w, wp, d->Cout, d->Cin, pl.Npad, pl.CPC, parts, pass == CFUN_PASS_BWD_DATA ? 1 : 0);
-    CFUN_LAUNCH_CHECK();
+    int prc = launch_pack_w_halo(w, wp, d->Cout, d->Cin, pl.Npad, pl.G, pl.nsteps, parts, pass == CFUN_PASS_BWD_DATA ? 1 : 0, st);
+    if (prc != CFUN_OK) return prc;
   }
   CUtensorMap mh, ml;
   for (int part = 0; part < 2; ++part) {
     void* b = part == 0 ? (void*)ah : (void*)(split ? al : ah);
-    cuuint64_t dims[4] = {(cuuint64_t)pl.W * 8, (cuuint64_t)pl.H, (cuuint64_t)pl.N * (pl.D + 2), (cuuint64_t)pl.G};
+    cuuint64_t dims[4] = {(cuuint64_t)pl.W * 8, (cuuint64_t)pl.H, (cuuint64_t)pl.N * (pl.D + 2), (cuuint64_t)pl.Gp};
     cuuint64_t strides[3] = {(cuuint64_t)pl.W * 16, (cuuint64_t)pl.H * pl.W * 16, (cuuint64_t)pl.N * (pl.D + 2) * pl.H * pl.W * 16};
     cuuint32_t box[4] = {HL_WH * 8, HL_HH, 3, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
@@ -511,23 +545,32 @@ int hl_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const floa
   }
   HlParams p;
   p.N = pl.N; p.D = pl.D; p.H = pl.H; p.W = pl.W; p.Cout = pl.Ct;
-  p.CPC = pl.CPC; p.Npad = pl.Npad;
+  p.Npad = pl.Npad;
   p.tilesH = (int)cdiv(pl.H, HL_HT); p.tilesW = (int)cdiv(pl.W, HL_WT);
   p.ntiles = (long long)pl.N * pl.D * p.tilesH * p.tilesW;
   p.nsplit = split ? 3 : 1;
   p.tmem_cols = pl.tmem_cols;
   p.epi = epi; p.bias = bias; p.y = dst;
+  p.resident = pl.resident; p.bstages = pl.bstages;
   p.wpack = reinterpret_cast<const uint8_t*>(wp);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   const unsigned grid = (unsigned)std::min<long long>(p.ntiles, num_sms());
-  const char* lean = getenv("CFUN_TC_LEAN");
-  if (split && lean && lean[0] == '1') conv_tc_halo_kernel<true><<<grid, HL_THREADS, pl.smem, st>>>(mh, ml, p);
-  else conv_tc_halo_kernel<false><<<grid, HL_THREADS, pl.smem, st>>>(mh, ml, p);
+#define CFUN_HL_LAUNCH(GG)                                                                                                   \
+  case GG: {                                                                                                                 \
+    static bool attr_set = false;                                                                                            \
+    if (!attr_set) {                                                                                                         \
+      CFUN_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<GG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));     \
+      CFUN_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<GG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));    \
+      attr_set = true;                                                                                                       \
+    }                                                                                                                        \
+    if (split) conv_tc_halo_kernel<GG, true><<<grid, HL_THREADS, pl.smem, st>>>(mh, ml, p);                                  \
+    else conv_tc_halo_kernel<GG, false><<<grid, HL_THREADS, pl.smem, st>>>(mh, ml, p);                                       \
+    break;                                                                                                                   \
+  }
+  switch (pl.G) {
+    CFUN_HL_LAUNCH(2) CFUN_HL_LAUNCH(3) CFUN_HL_LAUNCH(4) CFUN_HL_LAUNCH(5) CFUN_HL_LAUNCH(6) CFUN_HL_LAUNCH(7) CFUN_HL_LAUNCH(8)
+    default: set_error("conv3d halo: unsupported channel group count %d", pl.G); return CFUN_ERR_INVALID;
+  }
+#undef CFUN_HL_LAUNCH
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;
 }

@@ -94,8 +94,9 @@ struct HxParams {
 // TPS: taps per weight stage, 9 (one kd plane) or 3 (one (kd, kh) row) -- compile-time so the issue loop is straight-line.
 // MASKED: only the taps of p.tapmask are multiplied and weight stages without a live tap are neither loaded nor waited for
 // (conv_s2d.cu: a 2x2x2 kernel embedded as one corner of the 3x3x3 stencil).
-// LEAN (opt-in, CFUN_TC_LEAN=1, split mode, un-masked; not yet validated): one leader region per weight stage instead of one
-// per tap (see the note at conv_tc_halo_kernel).
+// LEAN (split mode, un-masked: the default there): one leader region per weight stage instead of one per tap -- straight-line
+// MMA issue, 3.5 instead of 9.5 SASS instructions per MMA.  Bit-identical to the per-tap form; worth 0-4 % on B200, because
+// the kernel is bound by operand fetch from shared memory, not by issue (profiles/r02_lean_validation.txt).
 template <int TPS, bool MASKED, bool LEAN>
 __global__ void __launch_bounds__(HX_THREADS, 1)
 conv_tc_hx_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_l, const HxParams p) {
@@ -559,8 +560,7 @@ int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const floa
   p.tapmask = 0;
   for (int t = 0; t < 27; ++t)      // the data gradient runs on mirrored taps (pack_w_hx_kernel mode 1)
     if ((tapmask >> t) & 1) p.tapmask |= 1 << (pass == CFUN_PASS_BWD_DATA ? 26 - t : t);
-  const char* le = getenv("CFUN_TC_LEAN");
-  const bool lean = split && !masked && !p.debug && le && le[0] == '1';
+  const bool lean = split && !masked && !p.debug;   // validated bit-identical on B200 (profiles/r02_lean_validation.txt)
   if (pl.TPS == 9) {
     if (masked) CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<9, true, false>, mh, ml, p));
     else if (lean) CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<9, false, true>, mh, ml, p));

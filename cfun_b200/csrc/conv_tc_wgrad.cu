@@ -295,10 +295,6 @@ bool ds_supported(const cfun_conv3d_desc* d);     // conv_tc_wgrad_ds.cu (d-stac
 size_t ds_workspace(const cfun_conv3d_desc* d);
 int ds_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, float* dbias, int nsplit,
                        void* ws, size_t ws_bytes, cudaStream_t st);
-bool hw_supported(const cfun_conv3d_desc* d);
-size_t hw_workspace(const cfun_conv3d_desc* d);
-int hw_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, float* dbias, int nsplit,
-                       void* ws, size_t ws_bytes, cudaStream_t st);
 
 int s2d_conv(const cfun_conv3d_desc* d, int pass, const float* a, const float* b, const float* bias, float* out, float* dbias,
              int epi, int nsplit, void* ws, size_t ws_bytes, cudaStream_t st);   // conv_s2d.cu
@@ -311,7 +307,7 @@ bool wg_capable(const cfun_conv3d_desc* d) {
 }
 
 bool tc_wgrad_supported(const cfun_conv3d_desc* d) {
-  if (ds_supported(d) || hw_supported(d)) return true;
+  if (ds_supported(d)) return true;
   WgPlan pl;
   if (!make_wg_plan(d, pl)) return false;
   if (d->kD * d->kH * d->kW < 27) return false;
@@ -321,7 +317,6 @@ bool tc_wgrad_supported(const cfun_conv3d_desc* d) {
 
 size_t tc_wgrad_workspace(const cfun_conv3d_desc* d) {
   if (ds_supported(d)) return ds_workspace(d);
-  if (hw_supported(d)) return hw_workspace(d);
   WgPlan pl;
   if (!make_wg_plan(d, pl)) return 0;
   return pl.total;
@@ -347,7 +342,6 @@ int tc_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* d
                        void* ws, size_t ws_bytes, cudaStream_t st) {
   if (d->sD == 2) return s2d_conv(d, CFUN_PASS_BWD_WEIGHT, x, dy, nullptr, dw, dbias, 0, nsplit, ws, ws_bytes, st);
   if (ds_supported(d)) return ds_conv_bwd_weight(d, x, dy, dw, dbias, nsplit, ws, ws_bytes, st);
-  if (hw_supported(d)) return hw_conv_bwd_weight(d, x, dy, dw, dbias, nsplit, ws, ws_bytes, st);
   WgPlan pl;
   CFUN_CHECK_ARG(make_wg_plan(d, pl));
   CFUN_CHECK_ARG(x && dy && dw && ws && get_tensor_map_encoder());

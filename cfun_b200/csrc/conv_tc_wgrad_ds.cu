@@ -1,15 +1,21 @@
-// tcgen05 weight gradient of a 3x3x3 / stride 1 / pad 1 convolution, "d-stacked" variant for thin-channel layers.
+// tcgen05 weight gradient of a 3x3x3 / stride 1 / pad 1 convolution: kd stacked along M, kw stacked along N.
 //
 //   dW[kd][kh][kw][co][ci] = sum_{n,d,h,w} dY[n,d,h,w,co] * X[n, d+kd-1, h+kh-1, w+kw-1, ci]
 //
-// conv_tc_wgrad_halo.cu feeds M = 128 accumulator rows with Cout channels only (20..40 of 128 rows useful in the top
-// levels of the U-Net, where 2/3 of the weight-gradient time goes) and splits kd over CTAs.  Here the work unit is one
-// 18 x 10 halo plane p of X, and the A operand stacks the THREE dY planes that meet it (d = p-1, p, p+1 <-> kd = 2, 1, 0)
-// along M: with the group-planar pack [C/8][N*(D+2)][H][W][8ch] one TMA box {8 w, 16 h, 3 planes, Gy groups} lands in
-// shared memory as 3*Gy planes of 2 KB at a uniform pitch, which is exactly the MN-major un-swizzled canonical layout
-// with SBO = 2 KB: accumulator row = (channel group, d-shift, channel) -> up to 5 groups x 3 shifts x 8 = 120 of 128 rows.
-// The (kh,kw) taps stay free views of the X halo plane (descriptor start address), each tap owns Npad fp32 TMEM columns.
-// Per unit: 9 taps x 8 K-steps x 3 split-bf16 MMAs instead of 27 x 8 x 3, two TMA instructions per operand part.
+// Both operands come from the group-planar split-bf16 pack [C/8][N*(D+2)][H][W][8ch] (zero planes at d = -1, D) that the
+// forward / data-gradient kernels use, and both are MN-major un-swizzled UMMA operands (16-byte rows = one voxel of one
+// 8-channel group; 8 consecutive rows = 8 voxels of a line = one K atom; LBO = line pitch, SBO = plane pitch).
+// The work unit is one HT x 8 tile of one X plane p:
+//   * A (M = 128 accumulator rows): the THREE dY planes d = p-1, p, p+1 (kd = 2, 1, 0) of up to 5 channel groups, one TMA
+//     box {8 w, HT h, 3 planes, Gt groups}: row = (channel group, kd, channel) -> 120 of 128 rows used at 40 channels.
+//   * B (N = KW * 8 Gx columns): KW copies of the X tile, shifted by kw - 1 voxels along w (a TMA inner coordinate may be
+//     any multiple of 16 bytes = one voxel), each copy Gx planes of (HT + 2) x 8 voxels: column = (kw, channel group,
+//     channel).  The kh taps stay free views (start address + kh lines), each kh owns N fp32 TMEM columns.
+// Why: these kernels are bound by shared-memory bandwidth, not by the tensor pipe -- every tcgen05.mma re-reads its 4 KB A
+// tile and its N x 32 B B tile from shared memory at 128 B/clk, and the TMA fills share that port (measured: the previous
+// kernel, 9 (kh,kw) taps x N = Cin <= 48, ran at 1.10 x that model: 11.9 k cycles per 128 voxels of a 40->40 layer).
+// Stacking kw along N needs 3 x fewer MMAs for the same products: (3 x 8 x 3) x (4 KB + 4 KB) instead of (9 x 8 x 3) x
+// (4 KB + 1.5 KB) per 128 voxels, at the price of writing the X tile three times.
 // Voxels are split across CTAs (split-K) and flushed once with fp32 atomics into dW (zero-initialised by the caller side).
 #include "tc_ptx.cuh"
 #include <cstdlib>
@@ -17,10 +23,10 @@
 namespace cfun {
 
 constexpr int DS_THREADS = 192;
-constexpr int DS_HT = 16, DS_WT = 8, DS_HH = 18, DS_WH = 10;
-constexpr int DS_YP = DS_HT * DS_WT * 16;        // 2048 B: one dY plane of one channel group
-constexpr int DS_XP = DS_HH * DS_WH * 16;        // 2880 B: one X halo plane of one channel group (box-packed pitch)
-constexpr int DS_MAX_GT = 5;                     // channel groups per M tile: 5 x 3 shifts = 15 of 16 row groups
+constexpr int DS_WT = 8;                         // tile width (voxels) = one K atom
+constexpr int DS_LINE = DS_WT * 16;              // 128 B: one line of one channel group
+constexpr int DS_MAX_GT = 5;                     // dY channel groups per M tile: 5 x 3 kd = 15 of 16 row groups
+constexpr int DS_MAX_STAGES = 6;
 
 int launch_pack_act_gp(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int C, int G,
                        cudaStream_t st);   // conv_tc_halo.cu
@@ -43,25 +49,23 @@ __device__ __forceinline__ void tma_load_4d_ds(const CUtensorMap* map, uint64_t*
 
 struct DsParams {
   int N, D, H, W, Cout, Cin;
+  int HT;                     // tile height (8 or 16 lines): K = HT * 8 voxels per unit, HT / 2 MMA K-steps
   int Gt;                     // dY channel groups per M tile (<= 5)
-  int Gx;                     // X channel groups of this launch's Cin slice (Npad / 8)
-  int ci0;                    // first input channel of the slice (dW addressing); X groups start at ci0 / 8
-  int Npad;                   // MMA N
-  int T9, ng9;                // (kh,kw) taps per CTA, number of tap groups
-  int ntap;                   // selected (kh,kw) taps (9 for a dense 3^3 kernel)
-  int tap_list[9];            // their indices kh*3+kw; the space-to-depth weight gradient needs only {0,1,3,4}
+  int Gx;                     // X channel groups of this launch's Cin slice
+  int slices;                 // Cin slices of Gx groups = gridDim.y (slice s: input channels from s * 8 Gx)
+  int nkw, nkh;               // stacked kw copies / kh views
+  int kw_list[3], kh_list[3];
   int kd_mask;                // bit kd set = this kd plane of dW is wanted
+  int Ntot;                   // MMA N: 8 * Gx * nkw rounded up to 16 (the padding columns read whatever follows, never stored)
   int tilesH, tilesW;
   int nsplit, stages;
   int tmem_cols;
+  int yp, xp;                 // plane pitches: HT * 128 (dY), (HT + 2) * 128 (X)
   int y_bytes, x_bytes, stage_bytes;
   long long units_total, units_per_cta;
   float* dw;
 };
 
-// LEAN (opt-in, CFUN_TC_LEAN=1, split mode; not yet validated): one leader region per unit instead of one per K step
-// (see the note at conv_tc_halo_kernel)
-template <bool LEAN>
 __global__ void __launch_bounds__(DS_THREADS, 1)
 conv_tc_wgrad_ds_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid_constant__ CUtensorMap map_yl,
                         const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, const DsParams p) {
@@ -74,9 +78,8 @@ conv_tc_wgrad_ds_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int parts = p.nsplit == 3 ? 2 : 1;
-  const int t9_0 = blockIdx.y * p.T9;
-  const int nt9 = min(p.T9, p.ntap - t9_0);
   const int g0 = blockIdx.z * p.Gt;                      // first dY channel group of this M tile
+  const int ci0 = blockIdx.y * p.Gx * 8;                 // first input channel of this N slice
   const long long u_beg = (long long)blockIdx.x * p.units_per_cta;
   const long long u_end = min(p.units_total, u_beg + p.units_per_cta);
   const int niter = (int)max(0LL, u_end - u_beg);
@@ -109,82 +112,60 @@ conv_tc_wgrad_ds_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid
         const int plane0 = n * (p.D + 2) + pl;           // padded index of dY plane pl-1 (and of X plane pl, minus one)
         for (int part = 0; part < parts; ++part) {
           tma_load_4d_ds(part == 0 ? &map_yh : &map_yl, &full_bar[slot], sb + (size_t)part * p.y_bytes, wb * DS_WT * 8,
-                         hb * DS_HT, plane0, g0);
-          tma_load_4d_ds(part == 0 ? &map_xh : &map_xl, &full_bar[slot], sb + (size_t)parts * p.y_bytes + (size_t)part * p.x_bytes,
-                         (wb * DS_WT - 1) * 8, hb * DS_HT - 1, plane0 + 1, p.ci0 >> 3);
+                         hb * p.HT, plane0, g0);
+          uint8_t* xb = sb + (size_t)parts * p.y_bytes + (size_t)part * p.x_bytes;
+          for (int k = 0; k < p.nkw; ++k)
+            tma_load_4d_ds(part == 0 ? &map_xh : &map_xl, &full_bar[slot], xb + (size_t)k * p.Gx * p.xp,
+                           (wb * DS_WT - 1 + p.kw_list[k]) * 8, hb * p.HT - 1, plane0 + 1, ci0 >> 3);
         }
       }
     }
   } else if (warp == 1) {
-    // warp-uniform issue loop (tc_ptx.cuh "issue-rate note"): descriptors = constant high word + 16-byte offsets
+    // descriptors = constant high word + 16-byte offsets in the low word; one leader region per unit
     const uint32_t leader = elect_one();
-    // both operands MN-major (bits 15, 16), bf16 x bf16 -> fp32, M = 128, N = Npad
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t a_hiword = (uint32_t)(make_desc_mn_ds(0, DS_WT * 16, DS_YP) >> 32);
-    const uint32_t b_hiword = (uint32_t)(make_desc_mn_ds(0, DS_WH * 16, DS_XP) >> 32);
-    const uint32_t a_lbo = (uint32_t)((DS_WT * 16) >> 4) << 16, b_lbo = (uint32_t)((DS_WH * 16) >> 4) << 16;
+    // both operands MN-major (bits 15, 16), bf16 x bf16 -> fp32, M = 128, N = Ntot
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Ntot >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t a_hiword = (uint32_t)(make_desc_mn_ds(0, DS_LINE, (uint32_t)p.yp) >> 32);
+    const uint32_t b_hiword = (uint32_t)(make_desc_mn_ds(0, DS_LINE, (uint32_t)p.xp) >> 32);
+    const uint32_t lbo = (uint32_t)(DS_LINE >> 4) << 16;
+    const int ksteps = p.HT >> 1;
     for (int it = 0; it < niter; ++it) {
       const int slot = it % p.stages;
       mbar_wait(&full_bar[slot], (uint32_t)((it / p.stages) & 1), 420);
       tc_fence_after();
-      const uint32_t sb = smem_u32(ring + (size_t)slot * p.stage_bytes);
-      const uint32_t y_hi = desc_addr(sb) | a_lbo, y_lo = desc_addr(sb + (uint32_t)p.y_bytes) | a_lbo;
-      const uint32_t x_hi = desc_addr(sb + (uint32_t)(parts * p.y_bytes)) | b_lbo;
-      const uint32_t x_lo = desc_addr(sb + (uint32_t)(parts * p.y_bytes + p.x_bytes)) | b_lbo;
-      const uint32_t first = it == 0 ? 0u : 1u;
-      if (LEAN) {
-        if (leader) {
+      if (leader) {
+        const uint32_t sb = smem_u32(ring + (size_t)slot * p.stage_bytes);
+        const uint32_t y_hi = desc_addr(sb) | lbo, y_lo = desc_addr(sb + (uint32_t)p.y_bytes) | lbo;
+        const uint32_t x_hi = desc_addr(sb + (uint32_t)(parts * p.y_bytes)) | lbo;
+        const uint32_t x_lo = desc_addr(sb + (uint32_t)(parts * p.y_bytes + p.x_bytes)) | lbo;
+        const uint32_t first = it == 0 ? 0u : 1u;
 #pragma unroll 1
-          for (int t = 0; t < nt9; ++t) {
-            const int t9 = p.tap_list[t9_0 + t];
-            const int kh = t9 / 3, kw = t9 - kh * 3;
-            const uint32_t dcol = tmem_base + (uint32_t)(t * p.Npad);
-            const uint32_t toff = (uint32_t)(kh * DS_WH + kw);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint64_t a_hi = desc_join(a_hiword, y_hi + (uint32_t)(j * 2 * DS_WT));
-              const uint64_t b_hi = desc_join(b_hiword, x_hi + (uint32_t)(j * 2 * DS_WH) + toff);
-              if (j == 0) umma_bf16(dcol, a_hi, b_hi, idesc, first);
-              else umma_bf16_acc(dcol, a_hi, b_hi, idesc);
-              umma_bf16_acc(dcol, desc_join(a_hiword, y_lo + (uint32_t)(j * 2 * DS_WT)), b_hi, idesc);
-              umma_bf16_acc(dcol, a_hi, desc_join(b_hiword, x_lo + (uint32_t)(j * 2 * DS_WH) + toff), idesc);
-            }
-          }
-          umma_commit(&empty_bar[slot]);
-        }
-        __syncwarp();
-        continue;
-      }
-#pragma unroll 1
-      for (int t = 0; t < nt9; ++t) {
-        const int t9 = p.tap_list[t9_0 + t];
-        const int kh = t9 / 3, kw = t9 - kh * 3;
-        const uint32_t dcol = tmem_base + (uint32_t)(t * p.Npad);
-        const uint32_t toff = (uint32_t)(kh * DS_WH + kw);            // 16-byte rows: halo line kh, voxel kw
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          // K step j = lines 2j, 2j+1 of every dY plane (2 x 8 rows of 16 B) and the same lines, shifted, of the halo plane
-          const uint64_t a_hi = desc_join(a_hiword, y_hi + (uint32_t)(j * 2 * DS_WT));
-          const uint64_t b_hi = desc_join(b_hiword, x_hi + (uint32_t)(j * 2 * DS_WH) + toff);
-          if (leader) {
+        for (int t = 0; t < p.nkh; ++t) {
+          const uint32_t dcol = tmem_base + (uint32_t)(t * p.Ntot);
+          const uint32_t toff = (uint32_t)(p.kh_list[t] * (DS_LINE >> 4));          // 16-byte rows: line kh of the X tile
+#pragma unroll 2
+          for (int j = 0; j < ksteps; ++j) {
+            // K step j = lines 2j, 2j+1 of every dY plane and lines 2j+kh, 2j+kh+1 of every X plane (2 x 8 voxels)
+            const uint32_t ko = (uint32_t)(j * 2 * (DS_LINE >> 4));
+            const uint64_t a_hi = desc_join(a_hiword, y_hi + ko);
+            const uint64_t b_hi = desc_join(b_hiword, x_hi + ko + toff);
             if (j == 0) umma_bf16(dcol, a_hi, b_hi, idesc, first);
             else umma_bf16_acc(dcol, a_hi, b_hi, idesc);
             if (parts == 2) {
-              const uint64_t a_lo = desc_join(a_hiword, y_lo + (uint32_t)(j * 2 * DS_WT));
-              const uint64_t b_lo = desc_join(b_hiword, x_lo + (uint32_t)(j * 2 * DS_WH) + toff);
-              umma_bf16_acc(dcol, a_lo, b_hi, idesc);
-              umma_bf16_acc(dcol, a_hi, b_lo, idesc);
+              umma_bf16_acc(dcol, desc_join(a_hiword, y_lo + ko), b_hi, idesc);
+              umma_bf16_acc(dcol, a_hi, desc_join(b_hiword, x_lo + ko + toff), idesc);
             }
           }
         }
+        umma_commit(&empty_bar[slot]);
       }
-      if (leader) umma_commit(&empty_bar[slot]);
       __syncwarp();
     }
     if (leader) umma_commit(tmem_full_bar);
     __syncwarp();
   } else {
     // accumulator row = (channel group g, d-shift s, channel): row group rg = 3 g + s, s <-> dY plane p-1+s <-> kd = 2 - s
+    // accumulator column (within the kh block) = (kw copy, channel group, channel)
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const int rg = row >> 3;
@@ -192,20 +173,25 @@ conv_tc_wgrad_ds_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid
     const int co = (g0 + g) * 8 + (row & 7);
     const int kd = 2 - s;
     const bool row_ok = g < p.Gt && co < p.Cout && ((p.kd_mask >> kd) & 1);
+    const int ncopy = p.Gx * 8;
     mbar_wait(tmem_full_bar, 0, 430);
     tc_fence_after();
     if (niter > 0) {
-      for (int t = 0; t < nt9; ++t) {
-        const int tap = kd * 9 + p.tap_list[t9_0 + t];
-        for (int j = 0; j < p.Npad; j += 16) {
+      for (int t = 0; t < p.nkh; ++t) {
+        for (int j = 0; j < p.nkw * ncopy; j += 16) {
           uint32_t r[16];
-          tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * p.Npad + j), r);
+          tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(t * p.Ntot + j), r);
           tmem_ld_wait();
           if (row_ok) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const int ci = p.ci0 + j + i;
-              if (ci < p.Cin) atomicAdd(p.dw + ((long long)co * p.Cin + ci) * 27 + tap, __uint_as_float(r[i]));
+              const int col = j + i;
+              const int k = col / ncopy;
+              const int ci = ci0 + (col - k * ncopy);
+              if (k < p.nkw && ci < p.Cin) {
+                const int tap = kd * 9 + p.kh_list[t] * 3 + p.kw_list[k];
+                atomicAdd(p.dw + ((long long)co * p.Cin + ci) * 27 + tap, __uint_as_float(r[i]));
+              }
             }
           }
         }
@@ -221,53 +207,55 @@ conv_tc_wgrad_ds_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid
 }
 
 struct DsPlan {
-  int Gy_total, Gt, Gx, Npad, T9, ng9, mtiles, stages, tmem_cols;
-  int Gx_total, slices;        // input channels are processed in `slices` launches of Gx groups (MMA N = 8 Gx <= 128)
-  int y_bytes, x_bytes, stage_bytes;
+  int Gy_total, Gt, Gx, mtiles, stages, tmem_cols, HT, Ntot, nkw, nkh;
+  int Gx_total, slices;        // input channels are processed in `slices` launches of Gx groups
+  int yp, xp, y_bytes, x_bytes, stage_bytes;
   size_t act_y, act_x, off_yh, off_yl, off_xh, off_xl, total, smem;
 };
 
-static bool make_ds_plan(const cfun_conv3d_desc* d, DsPlan& pl, int ntap = 9) {
+static bool make_ds_plan(const cfun_conv3d_desc* d, DsPlan& pl, int nkh = 3, int nkw = 3) {
   if (!d || d->sD != 1 || d->sH != 1 || d->sW != 1) return false;
   if (d->kD != 3 || d->kH != 3 || d->kW != 3 || d->pD != 1 || d->pH != 1 || d->pW != 1) return false;
   if (d->Hin < 8 || d->Win < 8) return false;
+  if (nkh < 1 || nkh > 3 || nkw < 1 || nkw > 3) return false;
+  pl.nkh = nkh; pl.nkw = nkw;
   pl.Gy_total = (int)cdiv(d->Cout, 8);
-  pl.Gx_total = (int)align_up((size_t)d->Cin, 16) / 8;
-  // wide inputs: slices of <= 80 channels (10 groups) keep two pipeline stages of X planes + 3 dY planes in shared memory
-  pl.slices = pl.Gx_total <= 10 ? 1 : (int)cdiv(pl.Gx_total, 10);
-  pl.Gx = (int)align_up((size_t)cdiv(pl.Gx_total, pl.slices), 2);
-  pl.Npad = pl.Gx * 8;
-  if (pl.Npad > 128 || pl.slices > 8) return false;
-  pl.T9 = std::min(ntap, 512 / pl.Npad);
-  pl.ng9 = (int)cdiv(ntap, pl.T9);
-  pl.T9 = (int)cdiv(ntap, pl.ng9);
+  pl.Gx_total = (int)align_up((size_t)d->Cin, 16) / 8;    // groups in the X pack (shared with the forward: 16-channel chunks)
+  const int gx_real = (int)cdiv(d->Cin, 8);
+  // nkh accumulator blocks of N = 8 * nkw * Gx (rounded up to 16) columns must fit the 512 TMEM columns, N <= 256
+  int gx_max = 0;
+  for (int g = 1; g <= 32; ++g) {
+    const int n = (int)align_up((size_t)8 * nkw * g, 16);
+    if (n <= 256 && nkh * n <= 512) gx_max = g;
+  }
+  if (gx_max == 0) return false;
+  pl.slices = (int)cdiv(gx_real, gx_max);
+  if (pl.slices > 16) return false;
+  pl.Gx = (int)cdiv(gx_real, pl.slices);
+  pl.Ntot = (int)align_up((size_t)8 * nkw * pl.Gx, 16);
   int cols = 32;
-  while (cols < pl.T9 * pl.Npad) cols <<= 1;
-  if (cols > 512) return false;
+  while (cols < nkh * pl.Ntot) cols <<= 1;
   pl.tmem_cols = cols;
-  pl.x_bytes = pl.Gx * DS_XP;
-  // M = 128 always reads 16 row groups (32 KB) from the dY tile base; what lies behind the real 3*Gt planes only feeds
-  // accumulator rows that are never read back, but it must be inside the allocation: slack after the ring
+  pl.mtiles = (int)cdiv(pl.Gy_total, DS_MAX_GT);
+  pl.Gt = (int)cdiv(pl.Gy_total, pl.mtiles);              // balanced M tiles (10 groups -> 2 x 5, 6 -> 2 x 3)
+  // tile height: 16 lines when at least 3 pipeline stages fit, else 8
   const size_t budget = 227 * 1024 - 2048;
-  pl.Gt = 0;
-  for (int gt = std::min(pl.Gy_total, DS_MAX_GT); gt >= 1; --gt) {
-    const size_t yb = (size_t)gt * 3 * DS_YP;
-    const size_t stage = align_up(2 * (yb + (size_t)pl.x_bytes), 1024);
-    const size_t slack = 32 * 1024;
-    if (2 * stage + slack <= budget) {
-      pl.Gt = gt;
-      pl.y_bytes = (int)yb;
-      pl.stage_bytes = (int)stage;
-      pl.stages = (int)std::min<size_t>(4, (budget - slack) / stage);
-      pl.smem = 2048 + pl.stages * stage + slack;
+  pl.HT = 0;
+  for (int ht = (d->Hin >= 16 ? 16 : 8); ht >= 8; ht -= 8) {
+    const int yp = ht * DS_LINE, xp = (ht + 2) * DS_LINE;
+    const size_t yb = (size_t)pl.Gt * 3 * yp, xb = (size_t)nkw * pl.Gx * xp;
+    const size_t stage = align_up(2 * (yb + xb), 1024);
+    // M = 128 always reads 16 dY planes and N = Ntot may read one X plane more than was loaded: keep that inside the allocation
+    const size_t slack = (size_t)16 * yp + xp;
+    const int st = (int)std::min<size_t>(DS_MAX_STAGES, (budget - slack) / stage);
+    if (st >= 3 || (ht == 8 && st >= 2)) {
+      pl.HT = ht; pl.yp = yp; pl.xp = xp; pl.y_bytes = (int)yb; pl.x_bytes = (int)xb; pl.stage_bytes = (int)stage;
+      pl.stages = st;
+      pl.smem = 2048 + (size_t)st * stage + slack;
       break;
     }
   }
-  if (pl.Gt == 0) return false;
-  pl.mtiles = (int)cdiv(pl.Gy_total, pl.Gt);
-  // balance the M tiles (e.g. 10 groups -> 2 x 5, 6 groups -> 2 x 3)
-  pl.Gt = (int)cdiv(pl.Gy_total, pl.mtiles);
-  pl.y_bytes = pl.Gt * 3 * DS_YP;
+  if (pl.HT == 0) return false;
   pl.act_y = align_up((size_t)pl.Gy_total * d->N * (d->Dout + 2) * d->Hout * d->Wout * 16, 1024);
   pl.act_x = align_up((size_t)pl.Gx_total * d->N * (d->Din + 2) * d->Hin * d->Win * 16, 1024);
   pl.off_yh = 0; pl.off_yl = pl.act_y; pl.off_xh = 2 * pl.act_y; pl.off_xl = 2 * pl.act_y + pl.act_x;
@@ -275,14 +263,14 @@ static bool make_ds_plan(const cfun_conv3d_desc* d, DsPlan& pl, int ntap = 9) {
   return true;
 }
 
+static bool ds_shape_ok(const cfun_conv3d_desc* d) { return d->Cin >= 16 && (d->Cin & 3) == 0 && d->Cout >= 8 && (d->Cout & 3) == 0; }
+
 bool ds_supported(const cfun_conv3d_desc* d) {
-  const char* e = getenv("CFUN_TC_WGDS");        // "0" falls back to the kd-split halo kernel (A/B measurements)
+  const char* e = getenv("CFUN_TC_WGDS");        // "0" falls back to the channel-major kernel (A/B measurements)
   if (e && e[0] == '0') return false;
-  const char* h = getenv("CFUN_TC_HALO");
-  if (h && h[0] == '0') return false;
   DsPlan pl;
   if (!make_ds_plan(d, pl)) return false;
-  return d->Cin >= 16 && (d->Cin & 3) == 0 && d->Cout >= 8 && (d->Cout & 3) == 0;
+  return ds_shape_ok(d);
 }
 size_t ds_workspace(const cfun_conv3d_desc* d) {
   DsPlan pl;
@@ -302,7 +290,18 @@ static int encode_gp_map_ds(CUtensorMap* m, void* base, int W, int H, long long 
   return CFUN_OK;
 }
 
-// yh/yl/xh/xl: group-planar split-bf16 packs (pack_act_gp) of dY (Gy_total groups) and X (Gx groups)
+// tap_mask (bits kh*3+kw) must be a product set {kh} x {kw}
+static bool split_tap_mask(int tap_mask, int* kh_list, int& nkh, int* kw_list, int& nkw) {
+  int khm = 0, kwm = 0;
+  for (int t = 0; t < 9; ++t) if ((tap_mask >> t) & 1) { khm |= 1 << (t / 3); kwm |= 1 << (t % 3); }
+  nkh = nkw = 0;
+  for (int i = 0; i < 3; ++i) { kh_list[i] = kw_list[i] = 0; }
+  for (int i = 0; i < 3; ++i) { if ((khm >> i) & 1) kh_list[nkh++] = i; if ((kwm >> i) & 1) kw_list[nkw++] = i; }
+  for (int a = 0; a < nkh; ++a) for (int b = 0; b < nkw; ++b) if (!((tap_mask >> (kh_list[a] * 3 + kw_list[b])) & 1)) return false;
+  return nkh > 0 && nkw > 0;
+}
+
+// yh/yl/xh/xl: group-planar split-bf16 packs (pack_act_gp) of dY (gy_pack groups) and X (Gx_total groups)
 // gy_pack: channel groups the dY pack was written with (>= Gy_total; the fused backward shares the data gradient's pack,
 // whose group count is rounded up to a multiple of 2 -- the extra group is zeros)
 int ds_launch(const cfun_conv3d_desc* d, const DsPlan& pl, __nv_bfloat16* yh, __nv_bfloat16* yl, __nv_bfloat16* xh,
@@ -310,43 +309,39 @@ int ds_launch(const cfun_conv3d_desc* d, const DsPlan& pl, __nv_bfloat16* yh, __
   CUtensorMap myh, myl, mxh, mxl;
   int rc;
   const long long planes = (long long)d->N * (d->Din + 2);
-  if ((rc = encode_gp_map_ds(&myh, yh, d->Wout, d->Hout, planes, gy_pack, DS_WT * 8, DS_HT, 3, pl.Gt)) != CFUN_OK) return rc;
-  if ((rc = encode_gp_map_ds(&myl, split ? yl : yh, d->Wout, d->Hout, planes, gy_pack, DS_WT * 8, DS_HT, 3, pl.Gt)) != CFUN_OK) return rc;
-  if ((rc = encode_gp_map_ds(&mxh, xh, d->Win, d->Hin, planes, pl.Gx_total, DS_WH * 8, DS_HH, 1, pl.Gx)) != CFUN_OK) return rc;
-  if ((rc = encode_gp_map_ds(&mxl, split ? xl : xh, d->Win, d->Hin, planes, pl.Gx_total, DS_WH * 8, DS_HH, 1, pl.Gx)) != CFUN_OK) return rc;
+  if ((rc = encode_gp_map_ds(&myh, yh, d->Wout, d->Hout, planes, gy_pack, DS_WT * 8, pl.HT, 3, pl.Gt)) != CFUN_OK) return rc;
+  if ((rc = encode_gp_map_ds(&myl, split ? yl : yh, d->Wout, d->Hout, planes, gy_pack, DS_WT * 8, pl.HT, 3, pl.Gt)) != CFUN_OK) return rc;
+  if ((rc = encode_gp_map_ds(&mxh, xh, d->Win, d->Hin, planes, pl.Gx_total, DS_WT * 8, pl.HT + 2, 1, pl.Gx)) != CFUN_OK) return rc;
+  if ((rc = encode_gp_map_ds(&mxl, split ? xl : xh, d->Win, d->Hin, planes, pl.Gx_total, DS_WT * 8, pl.HT + 2, 1, pl.Gx)) != CFUN_OK) return rc;
 
   DsParams p;
   p.N = d->N; p.D = d->Din; p.H = d->Hin; p.W = d->Win; p.Cout = d->Cout; p.Cin = d->Cin;
-  p.Gt = pl.Gt; p.Gx = pl.Gx; p.Npad = pl.Npad; p.T9 = pl.T9; p.ng9 = pl.ng9;
-  p.ntap = 0;
-  for (int t = 0; t < 9; ++t) { p.tap_list[t] = 0; if ((tap_mask >> t) & 1) p.tap_list[p.ntap++] = t; }
+  p.HT = pl.HT; p.Gt = pl.Gt; p.Gx = pl.Gx; p.Ntot = pl.Ntot;
+  CFUN_CHECK_ARG(split_tap_mask(tap_mask, p.kh_list, p.nkh, p.kw_list, p.nkw));
+  CFUN_CHECK_ARG(p.nkh == pl.nkh && p.nkw == pl.nkw);
   p.kd_mask = kd_mask;
-  p.tilesH = (int)cdiv(d->Hin, DS_HT); p.tilesW = (int)cdiv(d->Win, DS_WT);
+  p.tilesH = (int)cdiv(d->Hin, pl.HT); p.tilesW = (int)cdiv(d->Win, DS_WT);
   p.nsplit = split ? 3 : 1;
   p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
+  p.yp = pl.yp; p.xp = pl.xp;
   p.y_bytes = pl.y_bytes; p.x_bytes = pl.x_bytes; p.stage_bytes = pl.stage_bytes;
   p.units_total = (long long)d->N * d->Din * p.tilesH * p.tilesW;
-  const int ygroups = pl.ng9 * pl.mtiles;
-  long long ctas = std::max<long long>(1, num_sms() / ygroups);
+  p.slices = pl.slices;
+  // split-K over CTAs: every (M tile, Cin slice) pair owns its own dW block, so the more of those there are the fewer
+  // voxel splits (and atomic flushes of the same block) are needed to fill the SMs
+  long long ctas = std::max<long long>(1, num_sms() / (pl.mtiles * pl.slices));
   ctas = std::min<long long>(ctas, cdiv(p.units_total, 4));
   p.units_per_cta = cdiv(p.units_total, ctas);
   ctas = cdiv(p.units_total, p.units_per_cta);
   p.dw = dw;
   static bool attr_set = false;
   if (!attr_set) {
-    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_ds_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_ds_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CFUN_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_ds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  dim3 grid((unsigned)ctas, (unsigned)pl.ng9, (unsigned)pl.mtiles);
-  const char* le = getenv("CFUN_TC_LEAN");
-  const bool lean = split && le && le[0] == '1';
-  for (int sl = 0; sl < pl.slices; ++sl) {     // groups beyond Gx_total in the last slice are TMA zero fill
-    p.ci0 = sl * pl.Gx * 8;
-    if (lean) conv_tc_wgrad_ds_kernel<true><<<grid, DS_THREADS, pl.smem, st>>>(myh, myl, mxh, mxl, p);
-    else conv_tc_wgrad_ds_kernel<false><<<grid, DS_THREADS, pl.smem, st>>>(myh, myl, mxh, mxl, p);
-    CFUN_LAUNCH_CHECK();
-  }
+  dim3 grid((unsigned)ctas, (unsigned)pl.slices, (unsigned)pl.mtiles);   // groups beyond Gx_total in the last slice are TMA zero fill
+  conv_tc_wgrad_ds_kernel<<<grid, DS_THREADS, pl.smem, st>>>(myh, myl, mxh, mxl, p);
+  CFUN_LAUNCH_CHECK();
   return CFUN_OK;
 }
 
@@ -383,21 +378,26 @@ int ds_bwd_weight_packed(const cfun_conv3d_desc* d, __nv_bfloat16* yh, __nv_bflo
   return ds_launch(d, pl, yh, yl, xh, xl, dw, true, gy_pack, st);
 }
 
-// Sub-kernel weight gradient: only the (kh,kw) taps of tap_mask and the kd planes of kd_mask are computed and written
-// (dw is zero elsewhere).  conv_s2d.cu uses it with {kh,kw in {0,1}} x {kd in {0,1}}: the 2x2x2 space-to-depth kernel is
-// the corresponding corner of a 3x3x3 / pad-1 kernel.
+// Sub-kernel weight gradient: only the (kh,kw) taps of tap_mask (a product set) and the kd planes of kd_mask are computed
+// and written (dw is zero elsewhere).  conv_s2d.cu uses it with {kh,kw in {0,1}} x {kd in {0,1}}: the 2x2x2 space-to-depth
+// kernel is the corresponding corner of a 3x3x3 / pad-1 kernel.
+static bool make_masked_plan(const cfun_conv3d_desc* d, int tap_mask, DsPlan& pl) {
+  int khl[3], kwl[3], nkh, nkw;
+  if (!split_tap_mask(tap_mask & 0x1FF, khl, nkh, kwl, nkw)) return false;
+  return make_ds_plan(d, pl, nkh, nkw);
+}
 bool ds_masked_supported(const cfun_conv3d_desc* d, int tap_mask) {
   DsPlan pl;
-  return make_ds_plan(d, pl, __builtin_popcount(tap_mask & 0x1FF)) && d->Cin >= 16 && (d->Cin & 3) == 0 && d->Cout >= 8 && (d->Cout & 3) == 0;
+  return make_masked_plan(d, tap_mask, pl) && ds_shape_ok(d);
 }
 size_t ds_masked_workspace(const cfun_conv3d_desc* d, int tap_mask) {
   DsPlan pl;
-  return make_ds_plan(d, pl, __builtin_popcount(tap_mask & 0x1FF)) ? pl.total : 0;
+  return make_masked_plan(d, tap_mask, pl) ? pl.total : 0;
 }
 int ds_conv_bwd_weight_masked(const cfun_conv3d_desc* d, const float* x, const float* dy, float* dw, int tap_mask, int kd_mask,
                               void* ws, size_t ws_bytes, cudaStream_t st) {
   DsPlan pl;
-  CFUN_CHECK_ARG(make_ds_plan(d, pl, __builtin_popcount(tap_mask & 0x1FF)));
+  CFUN_CHECK_ARG(make_masked_plan(d, tap_mask, pl));
   CFUN_CHECK_ARG(x && dy && dw && ws && get_tensor_map_encoder());
   const size_t base = align_up((size_t)ws, 1024);
   if (ws_bytes < pl.total || base + pl.total - 2048 > (size_t)ws + ws_bytes) { set_error("conv3d d-stacked wgrad (masked): workspace too small"); return CFUN_ERR_WORKSPACE; }
@@ -409,7 +409,7 @@ int ds_conv_bwd_weight_masked(const cfun_conv3d_desc* d, const float* x, const f
   if ((rc = launch_pack_act_gp(dy, yh, yl, d->N, d->Dout, d->Hout, d->Wout, d->Cout, pl.Gy_total, st)) != CFUN_OK) return rc;
   if ((rc = launch_pack_act_gp(x, xh, xl, d->N, d->Din, d->Hin, d->Win, d->Cin, pl.Gx_total, st)) != CFUN_OK) return rc;
   CFUN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * d->Cin * 27, st));
-  return ds_launch(d, pl, yh, yl, xh, xl, dw, true, pl.Gy_total, st, tap_mask, kd_mask);
+  return ds_launch(d, pl, yh, yl, xh, xl, dw, true, pl.Gy_total, st, tap_mask & 0x1FF, kd_mask);
 }
 
 int tc_debug_read_ds(int* out8) {

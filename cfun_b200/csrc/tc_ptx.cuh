@@ -33,17 +33,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline bug must surface as a reported error, never as a hung GPU.  On time-out the first offender
-// records (site, block, thread, parity) in g_tc_debug and every later wait falls through immediately, so the kernel
-// drains and terminates; the host reads the record with cfun_tc_debug_status().
+// Bounded wait: a pipeline bug must surface as a reported error, never as a hung GPU and never as silently wrong
+// results.  On time-out the first offender records (site, block, thread, parity) in g_tc_debug and TRAPS: the launch
+// fails, the CUDA context reports the error at the next synchronising call and every later library call returns
+// CFUN_ERR_CUDA.  Bring-up builds (CFUN_NVCC_FLAGS=-DCFUN_TC_NOTRAP) fall through instead, so that the kernel drains and
+// the host can read the record with cfun_tc_debug_status().
 static __device__ int g_tc_debug[8];   // one copy per translation unit (no -rdc); each TU exports a reader
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int site = 0) {
+  // The spin itself must be tight: the latency from a barrier's completion to the waiter's next instruction is on the critical
+  // path of every producer/consumer hand-off (a system-scope flag load per failed try cost ~1 us of wake-up latency and ~15 %
+  // of the conv kernels' time).  The debug flag is polled once per 256 failed tries.
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+    if ((spin & 255u) != 255u) continue;
     if (spin > (1u << 22) || *((volatile int*)&g_tc_debug[0]) != 0) {
       if (atomicCAS(&g_tc_debug[0], 0, site + 1) == 0) {
         g_tc_debug[1] = (int)blockIdx.x; g_tc_debug[2] = (int)blockIdx.y; g_tc_debug[3] = (int)threadIdx.x;
         g_tc_debug[4] = (int)parity; g_tc_debug[5] = (int)spin;
       }
+#ifndef CFUN_TC_NOTRAP
+      __trap();
+#endif
       return;
     }
   }

@@ -441,6 +441,10 @@ NEW_TC_CASES = [
     (2, 24, 5, 18, 10, 40, 3, 1, 1, "d-stacked wgrad (conv_tc_wgrad_ds.cu): 3 + 5 channel groups, ragged slabs"),
     (1, 80, 6, 16, 16, 80, 3, 1, 1, "d-stacked wgrad: two M tiles of 5 groups, two tap groups"),
     (2, 16, 2, 8, 8, 16, 3, 1, 1, "d-stacked wgrad: two channel groups, D smaller than the 3-plane stack"),
+    (1, 20, 3, 24, 24, 20, 3, 1, 1, "kw-stacked wgrad: 3 groups x 3 kw = 72 columns padded to N = 80, 8-line tiles"),
+    (1, 16, 3, 40, 16, 16, 3, 1, 1, "kw-stacked wgrad: 16-line tiles (3 stages fit), ragged H (40 = 2.5 tiles)"),
+    (1, 128, 3, 16, 16, 48, 3, 1, 1, "kw-stacked wgrad: Cin 128 = 3 channel slices (6, 6, 4 groups: the last one zero-filled)"),
+    (1, 40, 4, 11, 13, 40, 3, 1, 1, "kw-stacked wgrad: W, H not multiples of 8 (TMA zero fill on both sides of every copy)"),
 ]
 
 
@@ -505,23 +509,6 @@ def test_conv3d_fused_backward_keeps_forward_pack(ops, case):
         assert rel_err(xc.grad.cpu().numpy(), xr.grad.numpy()) < TOL
     else:
         assert xc.grad is None
-
-
-@pytest.mark.skipif(__import__("os").environ.get("CFUN_TC_COL") != "1",
-                    reason="conv_tc_hc.cu (column-pass halo kernel) is experimental and opt-in: CFUN_TC_COL=1")
-@pytest.mark.parametrize("case", HALO_CASES + [(2, 40, 13, 32, 16, 40, 3, 1, False, False), (1, 24, 4, 16, 8, 16, 3, 1, True, False)])
-def test_conv3d_tcgen05_column_pass(ops, case):
-    """the column-pass kernel against fp32 (forward + data gradient), incl. a depth that is not a multiple of the column"""
-    test_conv3d_tcgen05_fwd_dgrad(ops, case)
-
-
-@pytest.mark.skipif(__import__("os").environ.get("CFUN_TC_LEAN") != "1",
-                    reason="lean-issue kernel variants are opt-in until validated on hardware: run the suite with CFUN_TC_LEAN=1")
-@pytest.mark.parametrize("case", HALO_CASES + TC_CASES[:3])
-def test_conv3d_tcgen05_lean_issue_variants(ops, case):
-    """CFUN_TC_LEAN=1 selects conv_tc_halo_kernel<true> / conv_tc_hx_kernel<..., true> / conv_tc_wgrad_ds_kernel<true>:
-    same results as fp32 (and, being the same MMAs in the same order, as the default variants)"""
-    test_conv3d_tcgen05_fwd_dgrad(ops, case)
 
 
 def test_conv3d_tcgen05_single_pass_is_fast_mode_only(ops):

@@ -48,46 +48,6 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&ws, wsb + 4096));
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  if (argc > 3 && !strcmp(argv[3], "cmpcol")) {
-    // A/B of the experimental column-pass kernel (CFUN_TC_COL=1) against the default path on the same inputs:
-    // forward and data gradient, max |difference| relative to max |default|, and both timings
-    std::vector<float> r0(ny > nx ? ny : nx), r1(ny > nx ? ny : nx);
-    CK(cudaMemcpy(y, hy.data(), ny * 4, cudaMemcpyHostToDevice));     // dY for the data gradient lives in y2
-    float* y2;
-    CK(cudaMalloc(&y2, ny * 4));
-    CK(cudaMemcpy(y2, hy.data(), ny * 4, cudaMemcpyHostToDevice));
-    for (int pass = 0; pass < 2; ++pass) {
-      float ms[2] = {0, 0};
-      for (int col = 0; col < 2; ++col) {
-        if (col) setenv("CFUN_TC_COL", "1", 1); else unsetenv("CFUN_TC_COL");
-        size_t need = cfun_conv3d_workspace_size(&d, pass, CFUN_CONV_ALGO_AUTO);
-        if (need > wsb + 4096) { printf("workspace too small for col=%d\n", col); return 1; }
-        for (int r = 0; r < 3; ++r) {
-          cudaEventRecord(e0);
-          int rc = pass == 0 ? cfun_conv3d_fwd(&d, x, w, nullptr, y, 0, CFUN_CONV_ALGO_AUTO, ws, wsb + 4096, nullptr)
-                             : cfun_conv3d_bwd_data(&d, y2, w, dx, CFUN_CONV_ALGO_AUTO, ws, wsb + 4096, nullptr);
-          cudaEventRecord(e1);
-          CK(cudaDeviceSynchronize());
-          if (rc) { printf("col=%d pass %d rc %d (%s)\n", col, pass, rc, cfun_last_error()); return 1; }
-          cudaEventElapsedTime(&ms[col], e0, e1);
-        }
-        int dbg[8];
-        cfun_tc_debug_status(dbg);
-        if (dbg[0]) printf("col=%d pass %d: pipeline wait timed out at site %d\n", col, pass, dbg[0] - 1);
-        CK(cudaMemcpy((col ? r1 : r0).data(), pass == 0 ? y : dx, (pass == 0 ? ny : nx) * 4, cudaMemcpyDeviceToHost));
-      }
-      double mx = 0, df = 0;
-      const size_t cnt = pass == 0 ? ny : nx;
-      for (size_t i = 0; i < cnt; ++i) {
-        double a = r0[i], b = r1[i];
-        if (fabs(a) > mx) mx = fabs(a);
-        if (!(fabs(a - b) <= df)) df = fabs(a - b);
-      }
-      printf("CMPCOL %s %s: default %.3f ms, column-pass %.3f ms, max|diff| / max|default| = %.3e\n", which, pass == 0 ? "fwd" : "dgrad",
-             ms[0], ms[1], df / (mx > 0 ? mx : 1));
-    }
-    return 0;
-  }
   const char* names[3] = {"fwd", "dgrad", "wgrad"};
   for (int r = 0; r < reps; ++r) {
     for (int pass = 0; pass < 3; ++pass) {

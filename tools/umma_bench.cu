@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cstring>
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -17,6 +18,10 @@ struct Cfg {
   int nmma;
   int reps;
   int nissue;    // issuing warps (each its own accumulator columns and commit barrier)
+  uint32_t idesc2;   // alternation experiment (round 2): instruction descriptor of the "other" MMA shape, 0 = off
+  int block;         // consecutive MMAs per shape (1 = hi, lo, hi, lo, ...; 8 = 8 x hi then 8 x lo)
+  uint32_t a2_off;   // A start offset of the second shape
+  int commit_every;  // commit experiment: a tcgen05.commit (to a barrier nobody waits on) after every commit_every-th group of 16 MMAs, 0 = off
 };
 
 __device__ __forceinline__ uint64_t mk_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
@@ -28,15 +33,18 @@ __device__ __forceinline__ uint64_t mk_desc(uint32_t saddr, uint32_t lbo, uint32
   return d;
 }
 
-__global__ void __launch_bounds__(128, 1) bench_kernel(Cfg c, long long* out) {
+template <int BLOCK>
+__global__ void __launch_bounds__(128, 1) bench_kernel_t(Cfg c, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[4];
+  __shared__ uint64_t dummy_bar;
   __shared__ long long tmax[4];
   __shared__ uint32_t tslot;
   for (int i = threadIdx.x; i < 200 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[i])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&dummy_bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -64,17 +72,21 @@ __global__ void __launch_bounds__(128, 1) bench_kernel(Cfg c, long long* out) {
       const uint32_t as = c.a_step >> 4, bs = c.b_step >> 4;
       long long t0 = clock64();
 #pragma unroll 1
-      for (int i = 0; i < c.nmma; i += 8) {
+      for (int i = 0; i < c.nmma; i += 16) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)u * as);
-          const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)u * bs);
+        for (int u = 0; u < 16; ++u) {
+          const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)(u & 7) * as);
+          const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)(u & 7) * bs);
+          const bool second = BLOCK > 0 && ((u / (BLOCK > 0 ? BLOCK : 1)) & 1);
+          const uint64_t da2 = da + (uint64_t)(c.a2_off >> 4);
           if (leader)
             asm volatile(
                 "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem),
-                "l"(da), "l"(db), "r"(c.idesc));
+                "l"(second ? da2 : da), "l"(db), "r"(second ? c.idesc2 : c.idesc));
         }
+        if (c.commit_every && leader && ((i >> 4) % c.commit_every) == c.commit_every - 1)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&dummy_bar)) : "memory");
       }
       if (leader) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
       uint32_t ok = 0;
@@ -99,15 +111,28 @@ __global__ void __launch_bounds__(128, 1) bench_kernel(Cfg c, long long* out) {
   }
 }
 
+static void launch_bench(const Cfg& c, long long* out) {
+  switch (c.idesc2 ? c.block : 0) {
+    case 1: bench_kernel_t<1><<<148, 128, 200 * 1024>>>(c, out); break;
+    case 2: bench_kernel_t<2><<<148, 128, 200 * 1024>>>(c, out); break;
+    case 4: bench_kernel_t<4><<<148, 128, 200 * 1024>>>(c, out); break;
+    case 8: bench_kernel_t<8><<<148, 128, 200 * 1024>>>(c, out); break;
+    default: bench_kernel_t<0><<<148, 128, 200 * 1024>>>(c, out); break;
+  }
+}
 static uint32_t idesc(int N, bool a_mn, bool b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) | ((uint32_t)(N >> 3) << 17) |
          ((128u >> 4) << 24);
 }
 
-int main() {
+int main(int argc, char** argv) {
   long long* out;
   cudaMalloc(&out, 148 * sizeof(long long));
-  cudaFuncSetAttribute(bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench_kernel_t<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench_kernel_t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench_kernel_t<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench_kernel_t<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(bench_kernel_t<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   struct Row { const char* name; bool a_mn, b_mn; uint32_t a_lbo, a_sbo, a_layout, b_lbo, b_sbo, b_layout, a_step, b_step, a_off, b_off; };
   const uint32_t B0 = 100 * 1024;
   Row rows[] = {
@@ -126,7 +151,61 @@ int main() {
       {"MN-major noswz A sbo128 lbo2048 (dense), B kmaj dense", true, false, 2048, 128, 0, 2048, 128, 0, 0, 0, 0, B0},
       {"K-major dense A, MN-major B sbo2880 lbo160", false, true, 2048, 128, 0, 160, 2880, 0, 0, 320, 0, B0},
       {"K-major dense A, MN-major B sbo128 lbo2048 dense", false, true, 2048, 128, 0, 2048, 128, 0, 0, 0, 0, B0},
+      // round 2: exact-K pairing in conv_tc_halo.cu puts the second K half at an arbitrary (small) LBO
+      {"K-major noswz sbo160 lbo16 (tap kw+1), B dense", false, false, 16, 160, 0, 2048, 128, 0, 16, 0, 0, B0},
+      {"K-major noswz sbo160 lbo128, B dense", false, false, 128, 160, 0, 2048, 128, 0, 16, 0, 0, B0},
+      {"K-major noswz sbo160 lbo2528 (kd wrap), B dense", false, false, 2528, 160, 0, 2048, 128, 0, 16, 0, 0, B0},
+      {"K-major noswz sbo160 lbo11296 (group straddle), B dense", false, false, 11296, 160, 0, 2048, 128, 0, 16, 0, 0, B0},
+      {"K-major noswz sbo160 lbo8704, B dense, A stepping 32 B", false, false, 8704, 160, 0, 2048, 128, 0, 32, 0, 0, B0},
   };
+  if (argc > 1 && !strcmp(argv[1], "alt")) {
+    // does switching the MMA shape (N = 2 Npad for A_hi x [B_hi;B_lo], N = Npad for A_lo x B_hi) between consecutive
+    // instructions cost anything?  cycles per PAIR of MMAs for block sizes 1, 2, 4, 8 and for two same-shape MMAs
+    printf("alternation: cycles per (N1, N2) pair, halo-A layout; block = consecutive MMAs of one shape\n");
+    const int pairs[][2] = {{96, 48}, {64, 32}, {96, 96}, {48, 48}, {64, 64}, {32, 32}, {256, 128}};
+    for (auto& pr : pairs) {
+      printf("N1=%3d N2=%3d :", pr[0], pr[1]);
+      for (int block : {1, 2, 4, 8}) {
+        Cfg c;
+        c.idesc = idesc(pr[0], false, false); c.idesc2 = idesc(pr[1], false, false);
+        c.a_off = 0; c.b_off = B0; c.a_lbo = 8704; c.a_sbo = 160; c.a_layout = 0; c.b_lbo = 2048; c.b_sbo = 128; c.b_layout = 0;
+        c.a_step = 16; c.b_step = 0; c.nmma = 512; c.reps = 4; c.nissue = 1; c.block = block; c.a2_off = 17408; c.commit_every = 0;
+        launch_bench(c, out);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf(" ERR(%s)", cudaGetErrorString(e)); break; }
+        long long h[148];
+        cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+        long long mx = 0;
+        for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+        printf("  block %d: %6.1f", block, 2.0 * (double)mx / c.nmma);
+      }
+      printf("\n");
+    }
+    return 0;
+  }
+  if (argc > 1 && !strcmp(argv[1], "commit")) {
+    printf("commit cadence: cycles per (N1, N2) pair with a tcgen05.commit after every k x 16 MMAs (k = 0: none)\n");
+    const int pairs[][2] = {{96, 48}, {64, 32}, {128, 128}};
+    for (auto& pr : pairs) {
+      printf("N1=%3d N2=%3d :", pr[0], pr[1]);
+      for (int k : {0, 4, 2, 1}) {
+        Cfg c;
+        c.idesc = idesc(pr[0], false, false); c.idesc2 = idesc(pr[1], false, false);
+        c.a_off = 0; c.b_off = B0; c.a_lbo = 8704; c.a_sbo = 160; c.a_layout = 0; c.b_lbo = 2048; c.b_sbo = 128; c.b_layout = 0;
+        c.a_step = 16; c.b_step = 0; c.nmma = 512; c.reps = 4; c.nissue = 1; c.block = 1; c.a2_off = 17408; c.commit_every = k;
+        launch_bench(c, out);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf(" ERR(%s)", cudaGetErrorString(e)); break; }
+        long long h[148];
+        cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+        long long mx = 0;
+        for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+        printf("  every %2d MMAs: %6.1f", k * 16, 2.0 * (double)mx / c.nmma);
+      }
+      printf("\n");
+    }
+    return 0;
+  }
   const int Ns[] = {32, 48, 64, 96, 128};
   printf("%-62s", "layout \\ N: cycles per MMA (M=128,K=16)");
   for (int N : Ns) printf(" %6d", N);
@@ -134,7 +213,7 @@ int main() {
   int ri = 0;
   for (const Row& r : rows) for (int nissue = 1; nissue <= 4; ++nissue) {
     if (nissue == 1) ++ri;
-    if (ri != 1 && ri != 8) continue;
+    if (nissue != 1 || (ri != 1 && ri != 4 && ri < 15)) continue;
     printf("%-50s issuers=%d ", r.name, nissue);
     for (int N : Ns) {
       Cfg c;
@@ -143,8 +222,8 @@ int main() {
       c.a_lbo = r.a_lbo; c.a_sbo = r.a_sbo; c.a_layout = r.a_layout;
       c.b_lbo = r.b_lbo; c.b_sbo = r.b_sbo; c.b_layout = r.b_layout;
       c.a_step = r.a_step; c.b_step = r.b_step;
-      c.nmma = 512; c.reps = 4; c.nissue = nissue;
-      bench_kernel<<<148, 128, 200 * 1024>>>(c, out);
+      c.nmma = 512; c.reps = 4; c.nissue = nissue; c.idesc2 = 0; c.block = 1; c.a2_off = 0; c.commit_every = 0;
+      launch_bench(c, out);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf(" ERR(%s)", cudaGetErrorString(e)); break; }
       long long h[148];
