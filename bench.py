@@ -3,10 +3,15 @@
 
   python bench.py --gpus N --steps K --warmup W          (N>1: launched by torch.distributed.run, one rank per GPU)
   python bench.py --impl reference ...                   (the reference's own CPU path: the oracle port, host cores)
+  python bench.py --impl reference-cuda ...              (same layers through stock torch / cuDNN on the same GPU: the
+                                                          library kernel-to-beat of SURVEY.md 8d)
+  python bench.py --stage finetune                       (192^3 masks, 5^3 conv, Sobel edge loss; own FLOP figure)
+  python bench.py --workload config5                     (BASELINE config 5: NMS + RoI crop-resize micro-benchmark)
+  python bench.py --workload lits                        (BASELINE config 3: LiTS widths, 256x320x320 input)
 
 A "step" is one pass of the hot path over one synthetic 256^3 int16 CT volume (SURVEY.md 8d recipe, HeartConfig at
-256^3, 8 classes, stage 'beginning'): mold -> P3D/FPN -> RPN -> proposals (sort/decode/NMS) -> detection targets ->
-RoI crops -> classifier head + U-Net mask head -> six losses -> backward -> global-norm clip + SGD(momentum).
+256^3, 8 classes): mold -> P3D/FPN -> RPN -> proposals (sort/decode/NMS) -> detection targets -> RoI crops ->
+classifier head + U-Net mask head -> six losses -> backward -> global-norm clip + SGD(momentum) -- in BOTH arms.
 `value` is timed with the step's raw inputs already in HBM; `e2e` times the public call
 MaskRCNN.train_step_from_host with pinned host buffers (H2D + D2H of the losses inside the timed region).
 Weak scaling: every rank processes its own volume each step; the only collective is one NCCL all-reduce of the
@@ -23,8 +28,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FWD_GFLOP_PER_VOLUME = 1314.6        # SURVEY.md 8d / BASELINE.md: H256, 4 positive / 12 RoIs, 'beginning'
-STEP_TFLOP_PER_VOLUME = 3.94
+METRIC = "ct_volumes_per_sec_fwd_bwd"
+PERM_SEED = 4321          # host torch.randperm draws of detection_target_layer (both arms)
+DROP_SEED = 7             # Dropout3d channel masks, generated on the host and injected (both arms)
 
 
 def parse():
@@ -32,11 +38,14 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
+    ap.add_argument("--workload", default="config2", choices=["config2", "config5", "lits"])
     ap.add_argument("--image-dim", type=int, default=256)
-    ap.add_argument("--stage", default="beginning")
+    ap.add_argument("--stage", default="beginning", choices=["beginning", "finetune"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--profile-calls", default=None, help="write a per-library-call timing table of one eager step here")
+    ap.add_argument("--kernel-table", default=None, help="write a per-kernel CUPTI table of one eager step here")
     ap.add_argument("--conv-algo", default="auto", choices=["auto", "simt", "tc", "tc1"])
     ap.add_argument("--no-graphs", action="store_true", help="run the heads eagerly instead of as CUDA graphs")
     return ap.parse_args()
@@ -51,33 +60,23 @@ def measured_peaks():
     return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
 
 
-def bench_weights(shapes, seed):
-    """MaskRCNN.initialize_weights recipe (reference model.py:1306-1319: xavier_uniform conv weights, zero conv bias,
-    N(0, 0.01) linear weights, BN at identity) with a per-tensor generator keyed by (seed, name), so the GPU arm and the
-    CPU reference arm can build bit-identical weights from a seed alone."""
-    import math
-    import zlib
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the committed `ncu --set full` capture
+    summary profiles/r02_ncu_conv_kernels.json (never a number taken in this run); None if that capture has no such row."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_conv_kernels.json")
+    try:
+        for row in json.load(open(p))["launches"]:
+            if row.get("key") == key:
+                return float(row["dram_bytes_read"]) + float(row["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
+def drop_masks(n=4):
     import torch
-    sd = {}
-    for k, shp in shapes.items():
-        shp = tuple(shp)
-        g = torch.Generator().manual_seed((seed * 7919 + zlib.crc32(k.encode())) % (2 ** 31 - 1))
-        if k.endswith("num_batches_tracked"):
-            sd[k] = torch.zeros(shp, dtype=torch.long)
-        elif k.endswith("running_var") or (k.endswith(".weight") and len(shp) == 1):
-            sd[k] = torch.ones(shp)
-        elif k.endswith("running_mean") or k.endswith(".bias"):
-            sd[k] = torch.zeros(shp)
-        elif len(shp) == 5:
-            rf = shp[2] * shp[3] * shp[4]
-            bound = math.sqrt(6.0 / (shp[1] * rf + shp[0] * rf))
-            sd[k] = (torch.rand(shp, generator=g) * 2 - 1) * bound
-        else:
-            sd[k] = torch.randn(shp, generator=g) * 0.01
-    return sd
-
-
-WEIGHT_SEED = 2     # chosen (see DESIGN.md) so that the synthetic volume yields 4 positive / 12 sampled RoIs
+    g = torch.Generator().manual_seed(DROP_SEED)
+    return [(torch.rand(n, c, 1, 1, 1, generator=g) > 0.6).float() / 0.4 for c in (20, 40, 80, 160, 320)]
 
 
 class ClockSampler(threading.Thread):
@@ -143,65 +142,77 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on the host cores
+# reference arm / cpu baseline: the oracle port on the host cores.  Imports nothing that loads libcfun_b200.so.
 # ---------------------------------------------------------------------------------------------------------
-def cpu_step_runner(image_dim, stage, weight_seed=WEIGHT_SEED):
-    """Returns (fn, cores): fn() runs ONE full train step (forward, 6 losses, backward, clip) of the CPU oracle on a
-    synthetic volume with the same recipe as the GPU arm."""
+def cpu_step_runner(image_dim, stage, weight_seed=None, volume_seed=None):
+    """Returns (step, cores, state): step() runs ONE full train step (restore weights, forward, 6 losses, backward, clip,
+    SGD with momentum / weight decay) of the CPU oracle on the synthetic volume of the shared recipe
+    (cfun_b200.workload: pure numpy, no native library)."""
     import numpy as np
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cfun_oracle as O
     from shapes import maskrcnn_shapes
     from cfun_b200 import config as Cf
-    from cfun_b200.synth import synth_volume, gt_box_from_label, place_label_cube, label_from_cube
-    import cfun_b200.model as M                      # host-side target builder only (numpy)
+    from cfun_b200 import workload as Wk
+    weight_seed = Wk.WEIGHT_SEED if weight_seed is None else weight_seed
+    volume_seed = Wk.VOLUME_SEED if volume_seed is None else volume_seed
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    mask_pool = 96 if image_dim >= 128 else 32
-    scales = (64, 128) if image_dim >= 256 else ((32, 64) if image_dim >= 128 else (16, 32))
-    cube = 70 * image_dim // 256
+    mask_pool, scales, cube = Wk.shape_params(image_dim)
     cfg = O.Cfg(image_dim=image_dim, stage=stage, mask_pool=mask_pool, anchor_scales=scales)
     pcfg = Cf.heart_config(image_dim, stage, mask_pool=mask_pool, anchor_scales=scales)
-    sd = bench_weights(maskrcnn_shapes(), weight_seed)
+    sd = Wk.bench_weights(maskrcnn_shapes(), weight_seed)
     trainable = [k for k, v in sd.items() if v.dtype == torch.float32 and "running" not in k and ".bn" not in k
                  and ".C1.1." not in k and "downsample.1" not in k]
     anchors = cfg.anchors().numpy()
-    vol, _ = synth_volume(image_dim, 1000, cube)
+    vol, _ = Wk.synth_volume(image_dim, volume_seed, cube)
     image = torch.from_numpy(np.ascontiguousarray(O.mold_image(vol.astype(np.float32)[..., None]).transpose((3, 2, 0, 1))[None])).float()
-    # label placement from this arm's own proposals (see cfun_b200.synth.place_label_cube)
+    # label placement from this arm's own proposals (see cfun_b200.workload.place_label_cube)
     with torch.no_grad():
         p2, p3 = O.fpn_forward(sd, image)
         lv = [O.rpn_forward(sd, p) for p in (p2, p3)]
         rois, _, _ = O.proposal_layer(torch.cat([l[1] for l in lv], 1)[0], torch.cat([l[2] for l in lv], 1)[0],
                                       cfg.anchors(), cfg.POST_NMS_ROIS_TRAINING, cfg.RPN_NMS_THRESHOLD, cfg.PRE_NMS_LIMIT,
                                       cfg.IMAGE_SHAPE, cfg.RPN_BBOX_STD_DEV)
-    placed = place_label_cube(rois.numpy(), image_dim)
+    placed = Wk.place_label_cube(rois.numpy(), image_dim)
     if placed is None:
         raise RuntimeError("no label placement gives 4 positive RoIs for weight seed %d" % weight_seed)
-    lab = label_from_cube(image_dim, placed[0], placed[1], 1000)
-    boxes = gt_box_from_label(lab, 8)
-    np.random.seed(1000)
-    rpn_match, rpn_bbox = M.build_rpn_targets(anchors, boxes[:1].astype(np.float32), pcfg)
+    lab = Wk.label_from_cube(image_dim, placed[0], placed[1], volume_seed)
+    boxes = Wk.gt_box_from_label(lab, 8)
+    np.random.seed(volume_seed % (2 ** 31))
+    rpn_match, rpn_bbox = Wk.build_rpn_targets(anchors, boxes[:1].astype(np.float32), pcfg)
     labt = lab.transpose((2, 0, 1))
     gt_masks = torch.from_numpy(np.stack([(labt == c) for c in range(8)]).astype(np.float32))
     args = (image, torch.from_numpy(rpn_match.astype(np.int32)), torch.from_numpy(rpn_bbox).float(), torch.arange(1, 8).int(),
             torch.from_numpy(boxes.astype(np.float32)), gt_masks)
-    state = {"pos": None}
+    leaves = {k: sd[k].detach().clone().requires_grad_(True) for k in trainable}
+    snap = {k: v.detach().clone() for k, v in leaves.items()}
+    decay = [leaves[k] for k in trainable if "bn" not in k]
+    nodecay = [leaves[k] for k in trainable if "bn" in k]
+    groups = [{"params": decay, "weight_decay": pcfg.WEIGHT_DECAY}]
+    if nodecay:
+        groups.append({"params": nodecay, "weight_decay": 0.0})
+    opt = torch.optim.SGD(groups, lr=pcfg.LEARNING_RATE, momentum=pcfg.LEARNING_MOMENTUM)
+    sd2 = dict(sd)
+    sd2.update(leaves)
+    state = {"pos": None, "rois": None, "losses": None, "grad_norm": None}
 
     def step():
-        g = torch.Generator().manual_seed(7)
-        torch.manual_seed(77)
-        leaves = {k: sd[k].detach().clone().requires_grad_(True) for k in trainable}
-        sd2 = dict(sd)
-        sd2.update(leaves)
-        # Dropout3d draws for up to 4 positives; the oracle slices them to the actual positive count
-        drop = [(torch.rand(4, c, 1, 1, 1, generator=g) > 0.6).float() / 0.4 for c in (20, 40, 80, 160, 320)]
-        out = O.train_forward(sd2, cfg, *args, drop=drop)
+        with torch.no_grad():                 # every step is "the first step from the same checkpoint", as in the GPU arm
+            for k, v in leaves.items():
+                v.copy_(snap[k])
+        opt.state.clear()
+        opt.zero_grad(set_to_none=True)
+        torch.manual_seed(PERM_SEED)
+        out = O.train_forward(sd2, cfg, *args, drop=drop_masks(4))
         out["loss"].sum().backward()
-        torch.nn.utils.clip_grad_norm_(list(leaves.values()), 5.0)
+        norm = torch.nn.utils.clip_grad_norm_(list(leaves.values()), 5.0)
+        opt.step()
         state["pos"] = int((out["target_class_ids"] > 0).sum())
         state["rois"] = int(out["target_class_ids"].shape[0])
+        state["losses"] = [float(out["loss"].sum())] + [float(l.sum()) for l in out["losses"]]
+        state["grad_norm"] = float(norm)
         return out
 
     return step, cores, state
@@ -211,38 +222,115 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from cfun_b200 import workload as Wk
     step, cores, state = cpu_step_runner(args.image_dim, args.stage)
+    budget = 240.0                                    # bound the whole run to a few minutes of host time
     t0 = time.time()
-    warm = min(args.warmup, 1)
+    step()
+    t_first = time.time() - t0
+    warm = max(0, min(args.warmup, int(0.25 * budget / max(t_first, 1e-3))) - 1)
     for _ in range(warm):
         step()
-    t_first = time.time() - t0 if warm else None
-    budget = 240.0
-    k = args.steps
-    if t_first:
-        k = max(1, min(args.steps, int(budget / max(t_first, 1e-3))))
+    k = max(1, min(args.steps, int(0.75 * budget / max(t_first, 1e-3))))
     t0 = time.time()
     for _ in range(k):
         step()
     dt = time.time() - t0
     v = k / dt
-    sample = "%d full %d^3 volume train step(s) (fwd+6 losses+bwd+clip) of the oracle port, torch-CPU fp32, %d threads; %d of %d requested steps timed to bound the run" % (
-        k, args.image_dim, cores, k, args.steps)
-    line = {"impl": "reference", "metric": "ct_volumes_per_sec_fwd_bwd", "value": v, "unit": "volumes/s", "n_gpus": args.gpus,
-            "steps": k, "warmup": warm, "ms_per_step": 1000.0 * dt / k, "higher_is_better": True, "scaling": "weak",
+    sample = ("%d full %d^3 volume train step(s) (fwd + 6 losses + bwd + clip + SGD) of the oracle port, torch-CPU fp32, %d threads; "
+              "%d warm-up step(s); %d of %d requested steps timed to bound the run" % (k, args.image_dim, cores, warm + 1, k, args.steps))
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "volumes/s", "n_gpus": args.gpus,
+            "steps": k, "warmup": warm + 1, "ms_per_step": 1000.0 * dt / k, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "MM-WHS-shape %d^3 synthetic CT, 8-class heart, full train step, stage %s" % (args.image_dim, args.stage),
-                       "positives": state.get("pos"), "rois": state.get("rois")},
+            "config": {"workload": Wk.workload_name(args.image_dim, args.stage), "positives": state["pos"], "rois": state["rois"],
+                       "weight_seed": Wk.WEIGHT_SEED, "volume_seed": Wk.VOLUME_SEED, "losses_last_step": state["losses"],
+                       "grad_norm_last_step": state["grad_norm"]},
             "cpu_baseline": {"value": v, "unit": "volumes/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------------------
+# library comparator on the same GPU: the oracle port's torch layers through cuDNN (SURVEY.md 8d "kernel to beat")
+# ---------------------------------------------------------------------------------------------------------
+def library_baseline(dim, stage, dev, steps=2):
+    """The conv layers of one train step (P3D/FPN/RPN on the dim^3 volume, classifier head on 12 RoI crops, U-Net on
+    4 x 96^3 crops + mask CE; forward + backward) as stock torch ops on the GPU: NCDHW, cudnn.benchmark on, TF32 off and
+    on.  No proposal / NMS / target logic and no optimizer step, so it UNDER-counts the library's step."""
+    import torch
+    import torch.nn.functional as F
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cfun_oracle as O
+    from shapes import maskrcnn_shapes
+    from cfun_b200 import workload as Wk
+    mask_pool, _, _ = Wk.shape_params(dim)
+    sd = {k: v.to(dev) for k, v in Wk.bench_weights(maskrcnn_shapes(), Wk.WEIGHT_SEED).items()}
+    leaves = [v.requires_grad_(True) for k, v in sd.items() if v.dtype == torch.float32 and v.dim() == 5]
+    g = torch.Generator().manual_seed(3)
+    image = torch.randn(1, 1, dim, dim, dim, generator=g).to(dev)
+    pooled = torch.randn(12, 128, 12, 12, 12, generator=g).to(dev)
+    crops = torch.randn(4, 1, mask_pool, mask_pool, mask_pool, generator=g).to(dev)
+    side = mask_pool * (2 if stage == "finetune" else 1)
+    tgt = torch.randint(0, 8, (4, side, side, side), generator=g).to(dev)
+    drop = [d.to(dev) for d in drop_masks(4)]
+    res = {}
+    old = (torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for tf32 in (False, True):
+            torch.backends.cudnn.benchmark = True
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+
+            def one():
+                for v in leaves:
+                    v.grad = None
+                p2, p3 = O.fpn_forward(sd, image)
+                lv = [O.rpn_forward(sd, p) for p in (p2, p3)]
+                c_logits, _, c_bbox = O.classifier_forward(sd, pooled)
+                m_logits = O.unet_forward(sd, crops, stage, drop)
+                loss = sum(l[0].mean() + l[2].mean() for l in lv) + c_logits.mean() + c_bbox.mean() + F.cross_entropy(m_logits, tgt)
+                loss.backward()
+            one(); one()
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(steps):
+                one()
+            e.record()
+            torch.cuda.synchronize()
+            res["tf32_on" if tf32 else "tf32_off"] = s.elapsed_time(e) / steps
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return {"ms_per_step_fp32": res["tf32_off"], "ms_per_step_tf32": res["tf32_on"],
+            "value_fp32": 1000.0 / res["tf32_off"], "value_tf32": 1000.0 / res["tf32_on"], "unit": "volumes/s",
+            "covers": "conv layers of one step only (P3D/FPN/RPN at %d^3, classifier head on 12 RoIs, U-Net on 4x%d^3, mask CE; "
+                      "fwd+bwd) through torch %s / cuDNN %s, NCDHW, cudnn.benchmark=True; no proposal/NMS/target logic, no "
+                      "optimizer step" % (dim, mask_pool, torch.__version__, torch.backends.cudnn.version())}
+
+
+def run_reference_cuda(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    from cfun_b200 import workload as Wk
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    lb = library_baseline(args.image_dim, args.stage, dev, steps=max(1, args.steps))
+    line = {"impl": "reference-cuda", "metric": METRIC, "value": lb["value_fp32"], "unit": "volumes/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": 2, "ms_per_step": lb["ms_per_step_fp32"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": Wk.workload_name(args.image_dim, args.stage) + " -- LAYERS ONLY, see covers"}, "gpu_library_baseline": lb}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------
-def time_kernel(fn, iters=5, flush=None):
+def time_kernel(fn, iters=5, flush=None, kernel_only=False):
+    """median CUDA-event time of fn() on the current stream; kernel_only: the library's own bracket around the main kernel
+    of the LAST library call fn() makes (cfun_kernel_timing)"""
     import torch
+    from cfun_b200 import ops
     fn()
     torch.cuda.synchronize()
     ts = []
@@ -254,17 +342,136 @@ def time_kernel(fn, iters=5, flush=None):
         fn()
         e.record()
         torch.cuda.synchronize()
-        ts.append(s.elapsed_time(e))
+        ts.append(ops.last_kernel_ms() if kernel_only else s.elapsed_time(e))
     ts.sort()
     return ts[len(ts) // 2]
+
+
+def build_gpu_case(dim, stage, dev, rank=0, conv_algo="auto"):
+    """Model with the shared weights + one synthetic volume whose label placement gives 4 positives / 12 RoIs (off the
+    clock).  Used by bench.py and by tests/test_gpu_model.py::test_train_step_256_matches_cpu_oracle."""
+    import torch
+    from cfun_b200 import model as M, config as Cf, ops
+    from cfun_b200 import workload as Wk
+    from cfun_b200.synth import StepInputs
+    ops.set_conv_algo({"auto": ops.ALGO_AUTO, "simt": ops.ALGO_SIMT, "tc": ops.ALGO_TC, "tc1": ops.ALGO_TC1}[conv_algo])
+    mask_pool, scales, cube = Wk.shape_params(dim)
+    cfg = Cf.heart_config(dim, stage, mask_pool=mask_pool, anchor_scales=scales)
+    net = M.MaskRCNN(cfg, "/tmp/_cfun_bench")
+    net.load_state_dict(Wk.bench_weights({k: tuple(v.shape) for k, v in net.state_dict().items()}, Wk.WEIGHT_SEED), strict=True)
+    net = net.to(dev)
+    anchors_np = net.anchors.cpu().numpy()
+    for attempt in range(32):       # a volume whose untrained proposals admit a 4-positive label placement
+        vol_seed = Wk.VOLUME_SEED + rank * 10007 + attempt
+        vol, _ = Wk.synth_volume(dim, vol_seed, cube)
+        with torch.no_grad():
+            img = ops.mold_volume_i16(torch.from_numpy(vol).to(dev))
+            rois = net.rpn_proposals(img, "training")[5][0]
+        placed = Wk.place_label_cube(rois.cpu().numpy(), dim)
+        del img, rois
+        if placed is not None:
+            lab = Wk.label_from_cube(dim, placed[0], placed[1], vol_seed)
+            return net, cfg, StepInputs(cfg, anchors_np, dim, vol_seed, cube, vol=vol, lab=lab), vol_seed
+    raise RuntimeError("no synthetic volume admits a 4-positive label placement (rank %d)" % rank)
+
+
+def kernel_rooflines(dev, peaks, stage):
+    """Live rooflines of the dominant kernels: CUDA events around the main kernel itself (cfun_kernel_timing), L2 flushed
+    between iterations.  tensor: algorithmic FLOPs / measured bf16 burst peak; hbm: algorithmic bytes / measured copy peak."""
+    import torch
+    from cfun_b200 import ops
+    from cfun_b200.layers import Conv3d
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > L2 (126 MB)
+    out = {}
+    ops.kernel_timing(True)
+    try:
+        def conv_case(N, Ci, S, Co, name, module, key_prefix):
+            conv = Conv3d(Ci, Co, 3, padding=1, bias=False).to(dev)
+            x = ops.to_cl(torch.randn(N, Ci, S, S, S, device=dev)).requires_grad_(True)
+            fl = 2.0 * N * S ** 3 * Ci * Co * 27
+            y = conv(x)
+            dy = ops.to_cl(torch.randn_like(y))
+            rows = {}
+            with torch.no_grad():
+                t_all = time_kernel(lambda: conv(x), flush=flush)
+                rows["fwd"] = (time_kernel(lambda: conv(x), flush=flush, kernel_only=True), t_all)
+
+            def bwd():
+                x.grad = None
+                conv.weight.grad = None
+                conv(x).backward(dy)
+            # fused backward: dY pack -> data-gradient kernel -> weight-gradient kernel (the last one is what the bracket holds)
+            rows["wgrad"] = (time_kernel(bwd, flush=flush, kernel_only=True), None)
+            res = {}
+            for ps, (t, t_call) in rows.items():
+                ach = fl / (t * 1e-3) / 1e12
+                res[ps] = {"kernel": "%s %s 3x3x3 %d->%d @ %dx%d^3 (%s), main kernel only" % (
+                               {"fwd": "conv3d forward", "wgrad": "conv3d weight gradient"}[ps], module, Ci, Co, N, S, name),
+                           "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                           "frac": ach / peaks["bf16_tflops"], "ms": t, "algorithmic_flop": fl,
+                           "traffic": ncu_traffic("%s_%s" % (key_prefix, ps)),
+                           "traffic_unit": "bytes per launch (dram read + write, profiles/r02_ncu_conv_kernels.json)",
+                           "peak_source": peaks["source"] + " bf16 burst"}
+                if t_call is not None:
+                    res[ps]["ms_with_operand_packs"] = t_call
+            del x, y, dy, conv
+            return res
+        u = conv_case(4, 40, 96, 40, "mask_branch conv_norm_lrelu_l4.0", "conv_tc_halo_kernel / conv_tc_wgrad_ds_kernel", "unet40")
+        h = conv_case(1, 128, 32, 256, "RPN.conv_shared, north-star headline conv", "conv_tc_hx_kernel / conv_tc_wgrad_ds_kernel", "rpn")
+        note = ("parity mode issues 3 bf16 MMAs per product (split-bf16, DESIGN.md 4): frac is capped at 1/3; the ncu "
+                "tensor-pipe-active figures are in profiles/r02_ncu_conv_kernels.json")
+        out["roofline"] = dict(u["wgrad"], note=note + "; this is the kernel with the largest share of the step "
+                               "(profiles/r02_step_kernel_table.txt)")
+        out["roofline_fwd"] = dict(u["fwd"], note=note)
+        out["headline_conv"] = {"fwd": h["fwd"], "wgrad": h["wgrad"]}
+    finally:
+        ops.kernel_timing(False)
+    # dominant element-wise pass: backward of InstanceNorm + LeakyReLU over a 40-channel 4 x 96^3 tensor (reads x and dy, writes dx)
+    x = ops.to_cl(torch.randn(4, 40, 96, 96, 96, device=dev)).requires_grad_(True)
+    y = ops.instnorm_lrelu(x)
+    dy = ops.to_cl(torch.randn_like(y))
+
+    def in_bwd():
+        x.grad = None
+        ops.instnorm_lrelu(x).backward(dy)
+    with torch.no_grad():
+        t_f = time_kernel(lambda: ops.instnorm_lrelu(x), flush=flush)
+    t_fb = time_kernel(in_bwd, flush=flush)
+    nb = x.numel() * 4.0
+    # forward: stats pass reads x, apply pass reads x and writes y (3 tensor passes); backward: pass 1 reads x, dy and writes a partial
+    # dx, pass 2 reads x and the partial and writes dx (5 tensor passes, 3 algorithmic: read x, read dy, write dx)
+    gbs = 3 * nb / ((t_fb - t_f) * 1e-3) / 1e9
+    out["roofline_hbm"] = {"kernel": "InstanceNorm+LeakyReLU backward (affine_act_bwd + in_bwd_apply) over 40 ch x 4 x 96^3, whole op",
+                           "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                           "ms": t_fb - t_f, "algorithmic_bytes": 3 * nb, "traffic": None, "peak_source": peaks["source"] + " copy"}
+    del x, y, dy
+    if stage == "finetune":
+        P, M = 4, 192
+        pred = ops.to_cl(torch.softmax(torch.randn(P, 8, M, M, M, device=dev), 1)).requires_grad_(True)
+        tgt = torch.randint(0, 8, (P, M, M, M), device=dev)
+        with torch.no_grad():
+            t_f = time_kernel(lambda: ops.sobel_edge_loss(pred, tgt), flush=flush)
+
+        def fb():
+            pred.grad = None
+            ops.sobel_edge_loss(pred, tgt).backward()
+        t_fb = time_kernel(fb, flush=flush)
+        alg = 2.0 * P * 7 * M ** 3 * 4                  # SURVEY 8d: predicted and target planes of the 7 foreground classes, read once
+        out["roofline_sobel"] = {"kernel": "3-D Sobel edge loss forward (sobel_pass1/2) at 4 x 7 x 192^3", "bound": "hbm",
+                                 "achieved": alg / (t_f * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                 "frac": alg / (t_f * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": t_f, "ms_fwd_bwd": t_fb,
+                                 "algorithmic_bytes": alg, "traffic": None, "peak_source": peaks["source"] + " copy"}
+        del pred, tgt
+    del flush
+    return out
 
 
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from cfun_b200 import model as M, config as Cf, ops
-    from cfun_b200.synth import StepInputs
+    from cfun_b200 import ops
+    from cfun_b200 import workload as Wk
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -285,40 +492,14 @@ def run_ours(args):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    algo = {"auto": ops.ALGO_AUTO, "simt": ops.ALGO_SIMT, "tc": ops.ALGO_TC, "tc1": ops.ALGO_TC1}[args.conv_algo]
-    ops.set_conv_algo(algo)
 
     dim = args.image_dim
-    mask_pool = 96 if dim >= 128 else 32
-    scales = (64, 128) if dim >= 256 else ((32, 64) if dim >= 128 else (16, 32))
-    cube = 70 * dim // 256
-    cfg = Cf.heart_config(dim, args.stage, mask_pool=mask_pool, anchor_scales=scales)
-
-    # weights: the reference's own initialisation (MaskRCNN.initialize_weights, bit-identical RNG consumption) from a
-    # per-tensor seeded recipe shared with the CPU arm; label cube placed where the untrained detector's proposals
-    # cluster so that the sampled RoI set is the 4 positives / 12 RoIs the FLOP figure is quoted for
-    from cfun_b200.synth import synth_volume, place_label_cube, label_from_cube
-    net = M.MaskRCNN(cfg, "/tmp/_cfun_bench")
-    net.load_state_dict(bench_weights({k: tuple(v.shape) for k, v in net.state_dict().items()}, WEIGHT_SEED), strict=True)
-    net = net.to(dev)
-    anchors_np = net.anchors.cpu().numpy()
-    pool = []
-    vol_seed = None
-    for attempt in range(32):       # a volume whose untrained proposals admit a 4-positive label placement (off the clock)
-        vol_seed = 1000 + rank * 10007 + attempt
-        vol, _ = synth_volume(dim, vol_seed, cube)
-        with torch.no_grad():
-            img = ops.mold_volume_i16(torch.from_numpy(vol).to(dev))
-            rois = net.rpn_proposals(img, "training")[5][0]
-        placed = place_label_cube(rois.cpu().numpy(), dim)
-        del img, rois
-        if placed is not None:
-            lab = label_from_cube(dim, placed[0], placed[1], vol_seed)
-            pool.append(StepInputs(cfg, anchors_np, dim, vol_seed, cube, vol=vol, lab=lab))
-            break
-    if not pool:
-        raise RuntimeError("no synthetic volume admits a 4-positive label placement (rank %d)" % rank)
-    weight_seed = WEIGHT_SEED
+    # weights: the reference's own initialisation (MaskRCNN.initialize_weights) from a per-tensor seeded recipe shared with
+    # the CPU arm; label cube placed where the untrained detector's proposals cluster so that the sampled RoI set is the
+    # 4 positives / 12 RoIs the FLOP figure is quoted for
+    net, cfg, inputs, vol_seed = build_gpu_case(dim, args.stage, dev, rank, args.conv_algo)
+    pool = [inputs]
+    net.mask.modified_u_net.injected_drop = [d.to(dev) for d in drop_masks(4)]   # same host-generated Dropout3d masks as the CPU arm
     opt = net.make_optimizer(cfg.LEARNING_RATE)
     if world > 1:   # identical replicas: broadcast rank 0's parameters once
         dist.broadcast(opt.flat_param, src=0)
@@ -332,7 +513,7 @@ def run_ours(args):
     def run_step(fn, *a):
         opt.flat_param.copy_(snap_p)
         opt.flat_mom.copy_(snap_m)
-        torch.manual_seed(4321 + rank)       # same host randperm draws -> same sampled RoIs
+        torch.manual_seed(PERM_SEED)       # same host randperm draws -> same sampled RoIs (and the same as the CPU arm)
         return fn(opt, *a)
     dev_inputs = [[t.to(dev) for t in p.tensors()] for p in pool]
     torch.cuda.synchronize()
@@ -381,7 +562,7 @@ def run_ours(args):
     s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s2.record()
     for i in range(args.steps):
-        out = run_step(net.train_step_from_host, pool[i % len(pool)])
+        run_step(net.train_step_from_host, pool[i % len(pool)])
     e2.record()
     barrier()
     t2 = torch.tensor([s2.elapsed_time(e2)], device=dev)
@@ -395,16 +576,36 @@ def run_ours(args):
         run_step(net.train_step_device, *dev_inputs[0])
         rows = ops.profile_stop()
         agg = {}
-        for name, tag, t in rows:
+        for name, tag, tt in rows:
             a = agg.setdefault((name, tag), [0, 0.0])
             a[0] += 1
-            a[1] += t
-        tot = sum(t for _, _, t in rows)
+            a[1] += tt
+        tot = sum(tt for _, _, tt in rows)
         with open(args.profile_calls, "w") as f:
             f.write("# library calls of one eager train step, CUDA-event time per call (includes inter-call gaps on the stream)\n")
             f.write("# total %.2f ms over %d calls\n" % (tot, len(rows)))
-            for (name, tag), (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-                f.write("%8.3f ms %5.1f%% x%-4d %s %s\n" % (t, 100 * t / tot, n, name, tag))
+            for (name, tag), (n, tt) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                f.write("%8.3f ms %5.1f%% x%-4d %s %s\n" % (tt, 100 * tt / tot, n, name, tag))
+    if args.kernel_table and rank == 0:    # off the clock: one eager step under CUPTI (torch.profiler), device time per kernel
+        from torch.profiler import profile, ProfilerActivity
+        net.enable_graphs(False)
+        run_step(net.train_step_device, *dev_inputs[0])
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            run_step(net.train_step_device, *dev_inputs[0])
+            torch.cuda.synchronize()
+        agg = {}
+        for ev in prof.events():
+            if ev.device_type is not None and str(ev.device_type).endswith("CUDA"):
+                a = agg.setdefault(ev.name, [0, 0.0])
+                a[0] += 1
+                a[1] += ev.device_time_total / 1000.0 if hasattr(ev, "device_time_total") else ev.cuda_time_total / 1000.0
+        tot = sum(v[1] for v in agg.values())
+        with open(args.kernel_table, "w") as f:
+            f.write("# one eager %d^3 train step, stage %s (%d positive / %d RoIs), device time per kernel from CUPTI (torch.profiler)\n" % (dim, args.stage, pos, rois))
+            f.write("# total kernel time %.2f ms over %d launches\n" % (tot, sum(v[0] for v in agg.values())))
+            for name, (n, tt) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+                f.write("%9.3f ms %5.1f%% %5d  %s\n" % (tt, 100 * tt / tot, n, name[:140]))
 
     if rank != 0:
         if world > 1:
@@ -414,67 +615,54 @@ def run_ours(args):
     value = world * args.steps / (ms / 1000.0)
     e2e_value = world * args.steps / (ms_e2e / 1000.0)
     peaks = measured_peaks()
-
-    # ---- roofline of the dominant kernel, measured live with CUDA events on our stream ------------------------
-    from cfun_b200.layers import Conv3d
-    roof = kern = None
-    if dim >= 256:
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > L2 (126 MB)
-        conv = Conv3d(40, 40, 3, padding=1, bias=False).to(dev)
-        x = ops.to_cl(torch.randn(4, 40, 96, 96, 96, device=dev))
-        with torch.no_grad():
-            t_dom = time_kernel(lambda: conv(x), flush=flush)
-        fl = 2.0 * 4 * 96 ** 3 * 40 * 40 * 27
-        ach = fl / (t_dom * 1e-3) / 1e12
-        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of conv_tc_halo_kernel for this launch, from the committed
-        # ncu --set full capture profiles/r01_ncu_unet_halo_fwd_dgrad_ds_wgrad.json (694.1 MB read: the two split-bf16
-        # activation packs once; 532.6 MB written: the fp32 output once) -- equal to the algorithmic bytes, no re-reads
-        roof = {"kernel": "conv3d fwd 3x3x3 40->40 @ 4x96^3 (mask_branch conv_norm_lrelu_l4.0, largest FLOP share of the step; "
-                          "pack_act_gp + pack_w_halo + conv_tc_halo_kernel)",
-                "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": ach / peaks["bf16_tflops"], "traffic": 1226.7e6, "traffic_unit": "bytes per launch (ncu dram read + write)",
-                "peak_source": peaks["source"] + " bf16 burst",
-                "ms": t_dom, "algorithmic_flop": fl,
-                "note": "parity mode issues 3 bf16 MMAs per product (split-bf16, DESIGN.md 4): frac is capped at 1/3; ncu "
-                        "tensor-pipe active 57 % for this kernel, 80 % for the 128->256 headline conv"}
-        conv2 = Conv3d(128, 256, 3, padding=1).to(dev)
-        x2 = ops.to_cl(torch.randn(1, 128, 32, 32, 32, device=dev))
-        with torch.no_grad():
-            t_h = time_kernel(lambda: conv2(x2), flush=flush)
-        fl2 = 2.0 * 32 ** 3 * 128 * 256 * 27
-        kern = {"kernel": "conv3d fwd 3x3x3 128->256 @ 32^3 (RPN.conv_shared, north-star headline conv)", "ms": t_h,
-                "achieved_tflops": fl2 / (t_h * 1e-3) / 1e12, "frac_of_bf16_peak": fl2 / (t_h * 1e-3) / 1e12 / peaks["bf16_tflops"]}
-        del flush, x, x2
+    step_tflop = Wk.STEP_TFLOP[args.stage]
+    roofs = kernel_rooflines(dev, peaks, args.stage) if dim >= 256 else {}
 
     cpu = None
+    loss_check = None
     if world == 1 and not args.no_cpu_baseline:
         try:
             step, cores, st = cpu_step_runner(dim, args.stage)
+            step()                                   # warm-up (thread pool, oneDNN primitive caches)
             t0 = time.time()
             step()
             dt = time.time() - t0
             cpu = {"value": 1.0 / dt, "unit": "volumes/s", "cores": cores, "kind": "port",
-                   "sample": "1 full %d^3 volume train step (fwd+6 losses+bwd+clip) of the CPU oracle port, torch-CPU fp32, cold "
-                             "(no warm-up), %d positives / %d RoIs" % (dim, st.get("pos"), st.get("rois"))}
+                   "sample": "1 full %d^3 volume train step (fwd + 6 losses + bwd + clip + SGD) of the CPU oracle port, torch-CPU fp32, "
+                             "after 1 warm-up step, %d positives / %d RoIs" % (dim, st["pos"], st["rois"]),
+                   "losses": st["losses"]}
+            if (st["pos"], st["rois"]) == (pos, rois):
+                d = [abs(a - b) / max(abs(b), 1e-6) for a, b in zip(losses, st["losses"]) if abs(b) > 0]
+                loss_check = {"max_rel_diff_vs_cpu_oracle": max(d), "compared": "total + six losses of the same step, same inputs / weights / draws"}
         except Exception as ex:   # never let the baseline leg break the measurement
             cpu = {"value": None, "unit": "volumes/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
+    lib = None
+    if world == 1 and not args.no_library_baseline and dim >= 128:
+        try:
+            lib = library_baseline(dim, args.stage, dev)
+        except Exception as ex:
+            lib = {"failed": repr(ex)}
 
     h2d = pool[0].nbytes()
     line = {
-        "metric": "ct_volumes_per_sec_fwd_bwd", "value": value, "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": value, "unit": "volumes/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "MM-WHS-shape %d^3 synthetic int16 CT, 8-class heart, full train step (fwd+bwd+clip+SGD), stage %s, 1 volume/GPU/step" % (dim, args.stage),
-                   "parallelism": "dp%d" % world, "positives": pos, "rois": rois, "roi_counts_per_timed_step": roi_counts, "weight_seed": weight_seed, "volume_seed": vol_seed,
-                   "conv_algo": args.conv_algo, "cuda_graphs": (not args.no_graphs), "l2": "per-step working set (~10 GB of activations) exceeds the 126 MB L2; no explicit flush",
+        "config": {"workload": Wk.workload_name(dim, args.stage), "parallelism": "dp%d" % world, "positives": pos, "rois": rois,
+                   "roi_counts_per_timed_step": roi_counts, "weight_seed": Wk.WEIGHT_SEED, "volume_seed": vol_seed,
+                   "conv_algo": args.conv_algo, "cuda_graphs": (not args.no_graphs),
+                   "l2": "per-step working set (~10 GB of activations) exceeds the 126 MB L2; no explicit flush",
                    "losses_last_step": losses},
-        "step_tflop": STEP_TFLOP_PER_VOLUME, "achieved_step_tflops": value * STEP_TFLOP_PER_VOLUME / max(world, 1),
-        "step_frac_of_bf16_sustained": value * STEP_TFLOP_PER_VOLUME / max(world, 1) / peaks["bf16_tflops_sustained"],
+        "step_tflop": step_tflop, "achieved_step_tflops": value * step_tflop / max(world, 1),
+        "step_frac_of_bf16_sustained": value * step_tflop / max(world, 1) / peaks["bf16_tflops_sustained"],
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": "volumes/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 7 * 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "roofline": roof, "headline_conv": kern, "cpu_baseline": cpu,
+        "roofline": roofs.get("roofline"), "roofline_fwd": roofs.get("roofline_fwd"), "roofline_hbm": roofs.get("roofline_hbm"),
+        "headline_conv": roofs.get("headline_conv"), "cpu_baseline": cpu, "loss_check": loss_check, "gpu_library_baseline": lib,
     }
+    if "roofline_sobel" in roofs:
+        line["roofline_sobel"] = roofs["roofline_sobel"]
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -482,7 +670,15 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.workload == "config5":
+        from cfun_b200.microbench import run_config5
+        run_config5(a, measured_peaks())
+    elif a.workload == "lits":
+        from cfun_b200.lits_bench import run_lits
+        run_lits(a, measured_peaks())
+    elif a.impl == "reference":
         run_reference(a)
+    elif a.impl == "reference-cuda":
+        run_reference_cuda(a)
     else:
         run_ours(a)

@@ -21,9 +21,11 @@ def _load():
     from . import build as _build
     try:
         _build.build()
-    except Exception:
-        if not os.path.exists(LIB_PATH):
-            raise
+    except Exception as ex:
+        # a stale binary must never be loaded silently: fall back to the existing .so only if it was built from exactly
+        # these sources (e.g. a GPU box without nvcc running a snapshot whose library travelled with it)
+        if not (os.path.exists(LIB_PATH) and _build.is_current()):
+            raise RuntimeError("libcfun_b200.so is missing or older than cfun_b200/csrc and the rebuild failed: %r" % (ex,))
     return C.CDLL(LIB_PATH)
 
 
@@ -37,6 +39,8 @@ SIGNATURES = {
     "cfun_version": (_i, []),
     "cfun_launch_count": (C.c_ulonglong, []),
     "cfun_device_is_sm100": (_i, []),
+    "cfun_kernel_timing": (_i, [_i]),
+    "cfun_last_kernel_ms": (_i, [C.POINTER(C.c_float)]),
     "cfun_conv3d_workspace_size": (_sz, [_D, _i, _i]),
     "cfun_conv3d_pick_algo": (_i, [_D, _i]),
     "cfun_conv3d_supported": (_i, [_D, _i, _i]),

@@ -29,6 +29,12 @@ def _digest():
     return h.hexdigest()
 
 
+def is_current():
+    """the in-tree library exists and its stamp matches the digest of the current sources + flags"""
+    stamp = os.path.join(LIBDIR, "build.sha256")
+    return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == _digest()
+
+
 def build(force=False, verbose=False):
     """Idempotent and safe under concurrent callers (one rank per GPU imports the package at the same time): an
     exclusive file lock serialises the build, objects go to a private directory and the library is renamed into place."""

@@ -22,7 +22,35 @@ int num_sms() {
   }
   return cached[dev];
 }
+static bool g_timing = false;
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+static bool g_timed = false;
+void timing_begin(cudaStream_t st) {
+  if (g_timing) cudaEventRecord(g_ev0, st);
+}
+void timing_end(cudaStream_t st) {
+  if (g_timing) { cudaEventRecord(g_ev1, st); g_timed = true; }
+}
 }  // namespace cfun
+
+extern "C" int cfun_kernel_timing(int on) {
+  using namespace cfun;
+  if (on && !g_ev0) {
+    CFUN_CUDA(cudaEventCreate(&g_ev0));
+    CFUN_CUDA(cudaEventCreate(&g_ev1));
+  }
+  g_timing = on != 0;
+  g_timed = false;
+  return CFUN_OK;
+}
+extern "C" int cfun_last_kernel_ms(float* ms) {
+  using namespace cfun;
+  CFUN_CHECK_ARG(ms != nullptr);
+  if (!g_timed) { set_error("cfun_last_kernel_ms: no timed kernel launch since cfun_kernel_timing(1)"); return CFUN_ERR_INVALID; }
+  CFUN_CUDA(cudaEventSynchronize(g_ev1));
+  CFUN_CUDA(cudaEventElapsedTime(ms, g_ev0, g_ev1));
+  return CFUN_OK;
+}
 
 extern "C" const char* cfun_last_error(void) { return cfun::g_err; }
 extern "C" int cfun_version(void) { return 100; }

@@ -45,6 +45,12 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 
 int num_sms();
 
+// Measurement hook (cfun_kernel_timing / cfun_last_kernel_ms): when switched on, the tensor-core conv launchers bracket their
+// MAIN kernel (not the operand packs) with CUDA events on the launching stream, so that bench.py can report the roofline of
+// the kernel itself, live, without a profiler.  Off by default; costs nothing then.
+void timing_begin(cudaStream_t st);
+void timing_end(cudaStream_t st);
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -562,8 +562,10 @@ int hl_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const floa
       CFUN_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<GG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));    \
       attr_set = true;                                                                                                       \
     }                                                                                                                        \
+    timing_begin(st);                                                                                                        \
     if (split) conv_tc_halo_kernel<GG, true><<<grid, HL_THREADS, pl.smem, st>>>(mh, ml, p);                                  \
     else conv_tc_halo_kernel<GG, false><<<grid, HL_THREADS, pl.smem, st>>>(mh, ml, p);                                       \
+    timing_end(st);                                                                                                          \
     break;                                                                                                                   \
   }
   switch (pl.G) {

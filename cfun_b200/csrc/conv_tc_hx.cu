@@ -561,6 +561,7 @@ int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const floa
   for (int t = 0; t < 27; ++t)      // the data gradient runs on mirrored taps (pack_w_hx_kernel mode 1)
     if ((tapmask >> t) & 1) p.tapmask |= 1 << (pass == CFUN_PASS_BWD_DATA ? 26 - t : t);
   const bool lean = split && !masked && !p.debug;   // validated bit-identical on B200 (profiles/r02_lean_validation.txt)
+  timing_begin(st);
   if (pl.TPS == 9) {
     if (masked) CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<9, true, false>, mh, ml, p));
     else if (lean) CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<9, false, true>, mh, ml, p));
@@ -570,6 +571,7 @@ int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const floa
     else if (lean) CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<3, false, true>, mh, ml, p));
     else CFUN_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_hx_kernel<3, false, false>, mh, ml, p));
   }
+  timing_end(st);
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;
 }

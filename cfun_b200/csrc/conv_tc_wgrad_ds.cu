@@ -340,7 +340,9 @@ int ds_launch(const cfun_conv3d_desc* d, const DsPlan& pl, __nv_bfloat16* yh, __
     attr_set = true;
   }
   dim3 grid((unsigned)ctas, (unsigned)pl.slices, (unsigned)pl.mtiles);   // groups beyond Gx_total in the last slice are TMA zero fill
+  timing_begin(st);
   conv_tc_wgrad_ds_kernel<<<grid, DS_THREADS, pl.smem, st>>>(myh, myl, mxh, mxl, p);
+  timing_end(st);
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;
 }

@@ -86,9 +86,9 @@ __global__ void __launch_bounds__(256) fc_bwd_data_kernel(int M, int Nout, long 
   }
 }
 
-// dw[n,k] = sum_m dy[m,n] x[m,k]   (M <= 16)
+// dw[n,k] (+)= sum_m dy[m,n] x[m,k]   (M <= 16 rows per launch; accumulate = 1 adds to what an earlier row chunk wrote)
 __global__ void __launch_bounds__(256) fc_bwd_weight_kernel(int M, int Nout, long long K, const float* __restrict__ dy,
-                                                            const float* __restrict__ x, float* __restrict__ dw) {
+                                                            const float* __restrict__ x, float* __restrict__ dw, int accumulate) {
   extern __shared__ float dys[];  // [Nout][16]
   for (int e = threadIdx.x; e < Nout * 16; e += blockDim.x) {
     int n = e / 16, m = e % 16;
@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(256) fc_bwd_weight_kernel(int M, int Nout, lon
         s = fmaf(d.x, xv[4 * q], s); s = fmaf(d.y, xv[4 * q + 1], s);
         s = fmaf(d.z, xv[4 * q + 2], s); s = fmaf(d.w, xv[4 * q + 3], s);
       }
-      dw[(long long)n * K + k] = s;
+      float* o = dw + (long long)n * K + k;
+      *o = accumulate ? *o + s : s;
     }
   }
 }
@@ -129,27 +130,37 @@ extern "C" int cfun_fc_fwd(int M, int Nout, long long K, const float* x, const f
                            void* stream) {
   CFUN_CHECK_ARG(M >= 0 && Nout > 0 && K > 0);
   if (M == 0) return CFUN_OK;
-  CFUN_CHECK_ARG(x && w && y && M <= 128);
+  CFUN_CHECK_ARG(x && w && y);
   cudaStream_t st = as_stream(stream);
   fc_init_kernel<<<(unsigned)cdiv((long long)M * Nout, 256), 256, 0, st>>>(y, bias, M, Nout);
   CFUN_LAUNCH_CHECK();
   long long slabs = std::min<long long>(cdiv(K, 32), 6LL * num_sms());
   int kslab = (int)align_up((size_t)cdiv(K, slabs), 32);
   dim3 grid((unsigned)cdiv(K, kslab), (unsigned)cdiv(Nout, 128));
-  if (M <= 16) fc_fwd_kernel<1><<<grid, 256, 0, st>>>(M, Nout, K, x, w, y, kslab);
-  else if (M <= 32) fc_fwd_kernel<2><<<grid, 256, 0, st>>>(M, Nout, K, x, w, y, kslab);
-  else if (M <= 64) fc_fwd_kernel<4><<<grid, 256, 0, st>>>(M, Nout, K, x, w, y, kslab);
-  else fc_fwd_kernel<8><<<grid, 256, 0, st>>>(M, Nout, K, x, w, y, kslab);
-  CFUN_LAUNCH_CHECK();
+  // any number of rows (the reference has no limit: TRAIN_ROIS_PER_IMAGE is 200 in the base Config, POST_NMS_ROIS_INFERENCE
+  // 1000): chunks of <= 128 rows, each one pass over the weights
+  for (int m0 = 0; m0 < M; m0 += 128) {
+    const int Mc = std::min(128, M - m0);
+    const float* xc = x + (long long)m0 * K;
+    float* yc = y + (long long)m0 * Nout;
+    if (Mc <= 16) fc_fwd_kernel<1><<<grid, 256, 0, st>>>(Mc, Nout, K, xc, w, yc, kslab);
+    else if (Mc <= 32) fc_fwd_kernel<2><<<grid, 256, 0, st>>>(Mc, Nout, K, xc, w, yc, kslab);
+    else if (Mc <= 64) fc_fwd_kernel<4><<<grid, 256, 0, st>>>(Mc, Nout, K, xc, w, yc, kslab);
+    else fc_fwd_kernel<8><<<grid, 256, 0, st>>>(Mc, Nout, K, xc, w, yc, kslab);
+    CFUN_LAUNCH_CHECK();
+  }
   return CFUN_OK;
 }
 
 extern "C" int cfun_fc_bwd_data(int M, int Nout, long long K, const float* dy, const float* w, float* dx, void* stream) {
   CFUN_CHECK_ARG(M >= 0 && Nout > 0 && K > 0);
   if (M == 0) return CFUN_OK;
-  CFUN_CHECK_ARG(dy && w && dx && M <= 16 && Nout <= 512);
-  fc_bwd_data_kernel<<<(unsigned)std::min<long long>(cdiv(K, 256), 8LL * num_sms()), 256, Nout * 16 * sizeof(float), as_stream(stream)>>>(M, Nout, K, dy, w, dx);
-  CFUN_LAUNCH_CHECK();
+  CFUN_CHECK_ARG(dy && w && dx && Nout <= 512);
+  for (int m0 = 0; m0 < M; m0 += 16) {      // row chunks of 16 (the kernel's register tile); rows are independent
+    fc_bwd_data_kernel<<<(unsigned)std::min<long long>(cdiv(K, 256), 8LL * num_sms()), 256, Nout * 16 * sizeof(float), as_stream(stream)>>>(
+        std::min(16, M - m0), Nout, K, dy + (long long)m0 * Nout, w, dx + (long long)m0 * K);
+    CFUN_LAUNCH_CHECK();
+  }
   return CFUN_OK;
 }
 
@@ -162,9 +173,12 @@ extern "C" int cfun_fc_bwd_weight(int M, int Nout, long long K, const float* dy,
     if (dbias) CFUN_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * Nout, st));
     return CFUN_OK;
   }
-  CFUN_CHECK_ARG(dy && x && M <= 16 && Nout <= 512);
-  fc_bwd_weight_kernel<<<(unsigned)std::min<long long>(cdiv(K, 256), 8LL * num_sms()), 256, Nout * 16 * sizeof(float), st>>>(M, Nout, K, dy, x, dw);
-  CFUN_LAUNCH_CHECK();
+  CFUN_CHECK_ARG(dy && x && Nout <= 512);
+  for (int m0 = 0; m0 < M; m0 += 16) {      // row chunks of 16, accumulated into dw
+    fc_bwd_weight_kernel<<<(unsigned)std::min<long long>(cdiv(K, 256), 8LL * num_sms()), 256, Nout * 16 * sizeof(float), st>>>(
+        std::min(16, M - m0), Nout, K, dy + (long long)m0 * Nout, x + (long long)m0 * K, dw, m0 > 0 ? 1 : 0);
+    CFUN_LAUNCH_CHECK();
+  }
   if (dbias) {
     fc_dbias_kernel<<<(unsigned)cdiv(Nout, 128), 128, 0, st>>>(M, Nout, dy, dbias);
     CFUN_LAUNCH_CHECK();

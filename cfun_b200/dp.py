@@ -56,6 +56,12 @@ class FlatSGD(object):
         ops.sumsq_into(self.flat_grad, self.sumsq)
         return self.sumsq
 
+    def clip_(self):
+        """clip_grad_norm_(params, clip_norm) on the accumulated flat gradient, in place, without a host sync (the
+        non-stepping iterations of gradient accumulation, reference model.py:1641)"""
+        norm = torch.sqrt(self.grad_norm()).float()
+        self.flat_grad.mul_(torch.clamp(self.clip_norm / (norm + 1e-6), max=1.0))
+
     def step(self):
         self.allreduce_grads()
         self.grad_norm()

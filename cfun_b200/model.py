@@ -398,39 +398,7 @@ def compute_losses(rpn_match, rpn_bbox, rpn_class_logits, rpn_pred_bbox, target_
 # ---------------------------------------------------------------------------------------------------------
 #  Host-side data preparation (off the hot path; kept so train_model / detect can run)
 # ---------------------------------------------------------------------------------------------------------
-def build_rpn_targets(anchors, gt_boxes, config):
-    """anchor/GT matching and delta targets (reference model.py:1090-1181), vectorised numpy."""
-    n_t = config.RPN_TRAIN_ANCHORS_PER_IMAGE
-    rpn_match = np.zeros([anchors.shape[0]], dtype=np.int32)
-    rpn_bbox = np.zeros((n_t, 6))
-    va = np.prod(anchors[:, 3:] - anchors[:, :3], axis=1)
-    overlaps = np.zeros((anchors.shape[0], gt_boxes.shape[0]))
-    for j, g in enumerate(gt_boxes):
-        lo = np.maximum(anchors[:, :3], g[:3])
-        hi = np.minimum(anchors[:, 3:], g[3:])
-        inter = np.prod(np.maximum(hi - lo, 0)[:, ::-1], axis=1)
-        overlaps[:, j] = inter / (np.prod(g[3:] - g[:3]) + va - inter + 1e-6)
-    amax = np.argmax(overlaps, axis=1)
-    vmax = overlaps[np.arange(overlaps.shape[0]), amax]
-    rpn_match[vmax < 0.3] = -1
-    rpn_match[np.argmax(overlaps, axis=0)] = 1
-    rpn_match[vmax >= 0.7] = 1
-    ids = np.where(rpn_match == 1)[0]
-    extra = len(ids) - n_t // 2
-    if extra > 0:
-        rpn_match[np.random.choice(ids, extra, replace=False)] = 0
-    ids = np.where(rpn_match == -1)[0]
-    extra = len(ids) - (n_t - np.sum(rpn_match == 1))
-    if extra > 0:
-        rpn_match[np.random.choice(ids, extra, replace=False)] = 0
-    ids = np.where(rpn_match == 1)[0]
-    a = anchors[ids]
-    g = gt_boxes[amax[ids]]
-    asz, gsz = a[:, 3:] - a[:, :3], g[:, 3:] - g[:, :3]
-    actr, gctr = a[:, :3] + 0.5 * asz, g[:, :3] + 0.5 * gsz
-    tgt = np.concatenate([(gctr - actr) / asz, np.log(gsz / asz)], axis=1) / np.asarray(config.RPN_BBOX_STD_DEV)
-    rpn_bbox[:len(ids)] = tgt[:n_t]
-    return rpn_match, rpn_bbox
+from .workload import build_rpn_targets      # host-side numpy restatement (reference model.py:1090-1181), shared with bench.py
 
 
 def mold_image(images):
@@ -547,10 +515,15 @@ class MaskRCNN(nn.Module):
         self.build(config=config, test_flag=test_flag)
         self.initialize_weights()
         self._graphed_tails = None
+        self._graph_ws_gen = 0
         self.graph_kernel_counts = {}
         self.graph_replays = {}
 
     def build(self, config, test_flag=False):
+        if getattr(config, "TRAIN_BN", False):
+            # the reference itself never trains BatchNorm on this path (model.py:1297-1304 freezes it, :1401-1406 forces eval);
+            # FrozenBatchNorm3d has no statistics update and no scale/shift gradient, so refuse instead of silently ignoring
+            raise NotImplementedError("config.TRAIN_BN = True is not supported: BatchNorm runs frozen (reference model.py:1297-1304)")
         h, w, d = config.IMAGE_SHAPE[:3]
         if h / 16 != int(h / 16) or w / 16 != int(w / 16) or d / 16 != int(d / 16):
             raise Exception("Image size must be dividable by 16. Use 256, 320, 512, ... etc.")
@@ -688,6 +661,11 @@ class MaskRCNN(nn.Module):
             drops = unet._drop_masks(P, dev)
             if drops[0] is None:
                 drops = [torch.ones((P, unet.base_n_filter * m), device=dev) for m in (1, 2, 4, 8, 16)]
+            if self._graphed_tails and ops.workspace_generation() != self._graph_ws_gen:
+                # the shared conv workspace was reallocated after these graphs were captured (a larger RoI split or image):
+                # they hold the freed buffer's address in kernel arguments and tensor maps -- drop them, re-capture lazily
+                self._graphed_tails = {}
+                self.graph_kernel_counts = {}
             tail = self._graphed_tails.get((P, R), self._tail) if self._graphed_tails is not None else self._tail
             if self._graphed_tails is not None and (P, R) not in self._graphed_tails:
                 tail = self._capture_tail(P, R, p2, p3, images, rois, p_rois, target_class_ids, target_deltas, target_mask, drops)
@@ -712,6 +690,7 @@ class MaskRCNN(nn.Module):
         split, captured lazily on first use.  Call after the optimizer has re-homed the parameters (FlatSGD) and after one
         eager step (so that the conv workspace has reached its final size)."""
         self._graphed_tails = {} if on else None
+        self._graph_ws_gen = ops.workspace_generation()
         self.graph_kernel_counts = {}
         self.graph_replays = {}
 
@@ -729,7 +708,10 @@ class MaskRCNN(nn.Module):
         graphed = torch.cuda.make_graphed_callables(fresh, args, num_warmup_iters=1, allow_unused_input=True)
         # kernels per replay (forward + backward): launches during capture = (1 warm-up + 1 capture) iterations
         self.graph_kernel_counts[(P, R)] = (launch_count() - n0) // 2
+        if self._graphed_tails and ops.workspace_generation() != self._graph_ws_gen:
+            self._graphed_tails = {}          # the warm-up of this capture grew the workspace: older graphs are stale
         self._graphed_tails[(P, R)] = graphed
+        self._graph_ws_gen = ops.workspace_generation()
         return graphed
 
     def train_step_device(self, optimizer, vol_i16, label_hwd, rpn_match, rpn_bbox, gt_boxes, gt_class_ids):
@@ -850,11 +832,14 @@ class MaskRCNN(nn.Module):
             batch_count += 1
             images, metas, rpn_match, rpn_bbox, gt_class_ids, gt_boxes, gt_masks = self._batch_to_device(inputs, angle, dataset)
             loss, losses = self.forward_backward(images, metas, rpn_match, rpn_bbox, gt_class_ids, gt_boxes, gt_masks)
-            # reference clips after every backward and steps every BATCH_SIZE volumes (model.py:1641-1645)
+            # reference: clip_grad_norm_ on the ACCUMULATED gradient after every backward, optimizer step every BATCH_SIZE
+            # volumes (model.py:1641-1645).  The clip of the stepping iteration is fused into FlatSGD.step().
             if (batch_count % self.config.BATCH_SIZE) == 0:
                 optimizer.step()
                 optimizer.zero_grad()
                 batch_count = 0
+            else:
+                optimizer.clip_()
             vals = torch.stack([loss.detach().reshape(())] + [l.detach().reshape(()) for l in losses]).cpu().numpy()
             sums += vals / steps
             if step == steps - 1:

@@ -32,6 +32,17 @@ def tc_debug_status():
     return None if vals[0] == 0 else tuple(vals[:6])
 
 
+def kernel_timing(on):
+    """bracket the main kernel of every tensor-core conv call with CUDA events (bench.py rooflines)"""
+    check(lib.cfun_kernel_timing(1 if on else 0), "cfun_kernel_timing")
+
+
+def last_kernel_ms():
+    ms = C.c_float(0)
+    check(lib.cfun_last_kernel_ms(C.byref(ms)), "cfun_last_kernel_ms")
+    return float(ms.value)
+
+
 def launch_count():
     """CUDA kernels launched by libcfun_b200.so so far in this process"""
     return int(lib.cfun_launch_count())
@@ -74,16 +85,23 @@ def zeros_cl(N, Cc, D, H, W, device, dtype=torch.float32):
 
 
 _ws = {}
+_ws_gen = {"n": 0}
 
 
 def workspace(nbytes, device):
-    """Stream-ordered scratch reused by consecutive calls on the same device (grown geometrically)."""
+    """Stream-ordered scratch reused by consecutive calls on the same device (grown geometrically).  Every reallocation
+    bumps workspace_generation(): anything that baked the old address in (captured CUDA graphs) must be rebuilt."""
     key = (device.index if device.index is not None else torch.cuda.current_device())
     buf = _ws.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes * 1.25) + 4096, 1 << 20), dtype=torch.uint8, device=device)
         _ws[key] = buf
+        _ws_gen["n"] += 1
     return buf
+
+
+def workspace_generation():
+    return _ws_gen["n"]
 
 
 _prof = {"on": False, "rows": []}

@@ -35,6 +35,12 @@ int cfun_version(void);
 unsigned long long cfun_launch_count(void);
 /* 1 when the current device is compute capability 10.x (tcgen05 / TMA paths usable). */
 int cfun_device_is_sm100(void);
+/* Measurement hook (no reference counterpart: the reference times with time.time(), model.py:1354,1560).  After
+ * cfun_kernel_timing(1) every tensor-core conv entry point brackets its MAIN kernel (not the operand packs) with CUDA
+ * events on the caller's stream; cfun_last_kernel_ms waits for the most recent one and returns its duration.  bench.py
+ * uses it for the live roofline of the dominant kernels.  cfun_kernel_timing(0) switches it off (the default). */
+int cfun_kernel_timing(int on);
+int cfun_last_kernel_ms(float* ms);
 
 /* ------------------------------------------------------------------------------------------
  * conv3d  -- replaces every nn.Conv3d on the path: backbone.py:14-55,124 ; model.py:131-134,

@@ -169,3 +169,63 @@ def test_cuda_graph_heads_match_eager():
                   "mask.modified_u_net.conv3d_c1_1.weight", "fpn.P2_conv2.weight"):
             assert rel_err(gr[k].cpu().numpy(), g_eager[k].cpu().numpy()) < 1e-4, k
     assert net.graph_replays[(1, 3)] >= 2 and net.graph_kernel_counts[(1, 3)] > 100
+
+
+def test_train_step_256_matches_cpu_oracle():
+    """Parity AT THE BENCHMARKED CONFIGURATION (BASELINE config 2: 256^3 volume, 4 positive / 12 RoIs, 96^3 mask crops):
+    the six losses and the total gradient norm of one GPU train step against the CPU oracle port on the same synthetic
+    volume, weights, RoI permutations and Dropout3d masks -- the very step bench.py times in both arms."""
+    import bench
+    dev = torch.device("cuda")
+    net, cfg, inputs, vol_seed = bench.build_gpu_case(256, "beginning", dev)
+    net.mask.modified_u_net.injected_drop = [d.to(dev) for d in bench.drop_masks(4)]
+    opt = net.make_optimizer(cfg.LEARNING_RATE)
+    opt.zero_grad()
+    vol, label, rpn_match, rpn_bbox, gt_boxes, gt_class_ids = [t.to(dev) for t in inputs.tensors()]
+    from cfun_b200 import ops
+    image = ops.mold_volume_i16(vol)
+    torch.manual_seed(bench.PERM_SEED)
+    loss, losses = net.forward_backward(image, None, rpn_match.view(1, -1, 1), rpn_bbox.unsqueeze(0), gt_class_ids.unsqueeze(0),
+                                        gt_boxes.unsqueeze(0), label.permute(2, 0, 1).to(torch.int32).contiguous())
+    got = np.array([float(loss.sum())] + [float(l.sum()) for l in losses])
+    gnorm = float(torch.sqrt(opt.grad_norm()).item())
+    assert net.last_roi_counts == (4, 12), net.last_roi_counts
+    step, cores, st = bench.cpu_step_runner(256, "beginning", volume_seed=vol_seed)
+    step()
+    assert (st["pos"], st["rois"]) == (4, 12)
+    want = np.array(st["losses"])
+    assert np.allclose(got, want, rtol=5e-4, atol=1e-6), (got, want)
+    assert abs(gnorm - st["grad_norm"]) < 1e-3 * st["grad_norm"], (gnorm, st["grad_norm"])
+
+
+def test_graphs_are_dropped_when_the_conv_workspace_is_reallocated():
+    """captured head graphs bake the shared workspace's address in (kernel arguments, tensor maps): when a later call
+    grows the workspace the graphs must be re-captured, not replayed into the freed block"""
+    from cfun_b200 import config as Cf, ops
+    g = load_golden("step64_beginning")
+    cfg = Cf.heart_config(64, "beginning", mask_pool=32, anchor_scales=(16, 32))
+    net, sd = build(cfg, int(g["seed_weights"]))
+    inp = golden_step_inputs(g)
+    net.mask.modified_u_net.injected_drop = inp["drop"]
+    dev = torch.device("cuda")
+    args = (inp["image"].to(dev), None, inp["rpn_match"].to(dev)[None, :, None], inp["rpn_bbox"].to(dev)[None],
+            torch.arange(1, 8).int().to(dev)[None], inp["gt_boxes"].to(dev)[None], inp["gt_masks"].to(dev)[None])
+
+    def run():
+        net.zero_grad(set_to_none=True)
+        torch.manual_seed(int(g["seed_perm"]))
+        loss, losses = net.forward_backward(*args)
+        torch.cuda.synchronize()
+        return np.array([float(l) for l in losses])
+    ref = run()
+    net.enable_graphs()
+    run(); run()
+    assert len(net._graphed_tails) == 1
+    gen = ops.workspace_generation()
+    big = ops.workspace(ops._ws[dev.index if dev.index is not None else torch.cuda.current_device()].numel() * 2, dev)   # forces a reallocation
+    assert ops.workspace_generation() == gen + 1
+    junk = torch.full((big.numel() // 8,), float("nan"), device=dev)      # likely lands in the freed block
+    got = run()                                                          # must re-capture, not replay the stale graph
+    assert np.allclose(got, ref, rtol=1e-5, atol=1e-7), (got, ref)
+    assert net._graph_ws_gen == ops.workspace_generation()
+    del junk

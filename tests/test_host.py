@@ -283,3 +283,25 @@ def test_reference_dataset_feeds_our_data_layer(tmp_path):
     assert class_ids.tolist() == list(range(1, 8)) and boxes.shape == (7, 6) and masks.shape == (8, 64, 64, 64)
     z1, y1, x1, z2, y2, x2 = boxes[0]
     assert 0 <= z1 < z2 <= 64 and 0 <= y1 < y2 <= 64 and 0 <= x1 < x2 <= 64
+
+
+def test_train_bn_is_refused_not_ignored():
+    """BatchNorm runs frozen on this path (reference model.py:1297-1304,1401-1406); TRAIN_BN = True has no implementation
+    and must raise instead of silently training nothing."""
+    from cfun_b200 import config as Cf
+    src = open(os.path.join(ROOT, "cfun_b200", "model.py")).read()
+    assert 'raise NotImplementedError("config.TRAIN_BN = True is not supported' in src
+    cfg = Cf.heart_config(64, "beginning", mask_pool=32, anchor_scales=(16, 32), TRAIN_BN=True)
+    assert cfg.TRAIN_BN is True
+
+
+def test_reference_arm_does_not_load_the_native_library():
+    """`bench.py --impl reference` must not map libcfun_b200.so into its process: its inputs and weights come
+    from cfun_b200.workload / cfun_b200.config, which import neither ops nor model."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.argv=['bench.py']; import bench; import cfun_b200.workload, cfun_b200.config; "
+            "maps = open('/proc/self/maps').read(); assert 'libcfun_b200' not in maps, 'native library mapped'; "
+            "assert 'cfun_b200.model' not in sys.modules and 'cfun_b200.ops' not in sys.modules; print('clean')") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "clean" in out.stdout, out.stderr[-2000:]
