@@ -1,4 +1,4 @@
-"""BASELINE.json config 5 through bench.py (`--workload config5`): 3-D NMS and RoI crop-resize on 10 000 random proposals
+"""Part of bench.py (kept outside the product package: its CPU legs execute oracle/).  BASELINE.json config 5 through bench.py (`--workload config5`): 3-D NMS and RoI crop-resize on 10 000 random proposals
 over a 256^3 map, one GPU (SURVEY.md 8d recipe: centres U(0,256)^3, sides U(16,128)^3, clipped, scores U(0,1),
 default_rng(0)).  CUDA-event medians with the L2 flushed between iterations; the CPU restatement (`--impl reference`, and
 the cpu_baseline leg of the GPU arm) is the oracle's numpy NMS (reference utils.py:122-157) and crop + trilinear resize
@@ -10,7 +10,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.abspath(__file__))
 NMS_SETTINGS = ((0.7, 500), (0.7, 10000), (0.3, 10000))
 
 
@@ -70,7 +70,7 @@ def run_config5(args, peaks):
         print(json.dumps(line))
         return
     import torch
-    from . import ops, utils as U
+    from cfun_b200 import ops, utils as U
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

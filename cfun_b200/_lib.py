@@ -83,6 +83,8 @@ SIGNATURES = {
     "cfun_sumsq": (_i, [_p, _ll, _p, _p]),
     "cfun_sgd_clip_step": (_i, [_p, _p, _p, _p, _ll, _p, _f, _f, _f, _f, _i, _p]),
     "cfun_mold_volume_i16": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "cfun_resize_linear3d": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p]),
+    "cfun_unmold_mask_argmax": (_i, [_p, _i, _i, _i, _i, _ll, _ll, C.POINTER(C.c_int), _i, _i, _i, _p, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -726,6 +726,18 @@ class MaskRCNN(nn.Module):
         optimizer.step()
         return torch.stack([loss.detach().reshape(())] + [l.detach().reshape(()) for l in losses])
 
+    def train_step_from_volume(self, optimizer, vol_i16, label_hwd, keys_pos=None, keys_neg=None):
+        """train_step_device with the per-step targets generated ON THE DEVICE: GT box of the label
+        volume (load_image_gt, reference model.py:1058-1076) and RPN match / delta targets (build_rpn_targets,
+        model.py:1090-1181).  Inputs: the raw int16 scan [H,W,D] and its class-id label [H,W,D], both on the device."""
+        from . import targets
+        cfg = self.config
+        label_dhw = label_hwd.permute(2, 0, 1).to(torch.int32).contiguous()
+        gt_boxes = targets.gt_box_from_label(label_dhw, cfg.NUM_CLASSES)
+        rpn_match, rpn_bbox = targets.build_rpn_targets(self.anchors, gt_boxes[:1], cfg, keys_pos, keys_neg)
+        gt_class_ids = torch.arange(1, cfg.NUM_CLASSES, dtype=torch.int32, device=vol_i16.device)
+        return self.train_step_device(optimizer, vol_i16, label_hwd, rpn_match, rpn_bbox, gt_boxes, gt_class_ids)
+
     def train_step_from_host(self, optimizer, step_inputs):
         """The end-to-end call: pinned host buffers of one volume -> H2D -> train_step_device -> D2H of the 7 losses."""
         dev = self.anchors.device
@@ -735,14 +747,14 @@ class MaskRCNN(nn.Module):
 
     # -- inference ------------------------------------------------------------------------------------------
     def detect(self, images):
-        """reference model.py:1341-1389"""
+        """reference model.py:1341-1389.  images: list of [H,W,D,C] arrays (the raw scans).  The resize + normalisation
+        before the network and the mask resize + paste + argmax after it run on the device; what
+        crosses PCIe is the raw scan in, the detections [n,8] and one uint8 class-id volume out."""
         start_time = time.time()
-        molded_images, image_metas, windows = self.mold_inputs(images)
-        molded = torch.from_numpy(molded_images).float().cuda()
+        molded, image_metas, windows = self.mold_inputs_device(images)
         with torch.no_grad():
             detections, mrcnn_mask = self.predict([molded, image_metas], mode='inference')
         detections = detections.detach().cpu().numpy()
-        mrcnn_mask = mrcnn_mask.permute(0, 1, 3, 4, 5, 2).detach().cpu().numpy()
         print("detect done, using time", time.time() - start_time)
         results = []
         for i, image in enumerate(images):
@@ -751,35 +763,71 @@ class MaskRCNN(nn.Module):
             results.append({"rois": rois, "class_ids": class_ids, "scores": scores, "mask": mask})
         return results
 
-    def mold_inputs(self, images):
-        molded_images, image_metas, windows = [], [], []
+    def mold_inputs_device(self, images):
+        """mold_inputs (reference model.py:1774-1810) with the arithmetic on the device: order-1 resize to
+        [IMAGE_MAX_DIM, IMAGE_MAX_DIM, IMAGE_MIN_DIM] ('self' mode), cast back to the scan dtype, (x - mean) / std,
+        [H,W,D,C] -> [C,D,H,W].  Returns (molded device tensor [N,1,D,H,W], image_metas, windows)."""
         c = self.config
+        dev = self.anchors.device
+        molded, metas, windows = [], [], []
         for image in images:
-            molded, window, scale, padding, crop = utils.resize_image(image, min_dim=c.IMAGE_MIN_DIM, max_dim=c.IMAGE_MAX_DIM,
-                                                                      min_scale=c.IMAGE_MIN_SCALE, mode=c.IMAGE_RESIZE_MODE)
-            molded = mold_image(molded).transpose((3, 2, 0, 1))
-            molded_images.append(molded)
+            if image.shape[3] != 1:
+                raise RuntimeError("single-channel scans only (IMAGE_CHANNEL_COUNT = 1 in every CFUN config)")
+            h, w, d = image.shape[:3]
+            if c.IMAGE_RESIZE_MODE == "none":
+                tgt, window = (h, w, d), (0, 0, 0, d, h, w)
+            elif c.IMAGE_RESIZE_MODE == "self":
+                tgt, window = (c.IMAGE_MAX_DIM, c.IMAGE_MAX_DIM, c.IMAGE_MIN_DIM), (0, 0, 0, c.IMAGE_MIN_DIM, c.IMAGE_MAX_DIM, c.IMAGE_MAX_DIM)
+            else:
+                raise NotImplementedError("IMAGE_RESIZE_MODE %r is not used by the CFUN configs" % c.IMAGE_RESIZE_MODE)
+            vol = np.ascontiguousarray(image[..., 0])
+            if vol.dtype == np.int16:
+                v = torch.from_numpy(vol).to(dev)
+                if tuple(tgt) != (h, w, d):
+                    v = ops.resize_linear3d(v, tgt)
+                m = ops.mold_volume_i16(v)                                      # [1,1,D,H,W]
+            else:
+                v = torch.from_numpy(vol.astype(np.float32)).to(dev)
+                if tuple(tgt) != (h, w, d):
+                    v = ops.resize_linear3d(v, tgt)
+                if np.issubdtype(vol.dtype, np.integer):
+                    v = torch.trunc(v)                                          # .astype(image_dtype) of the reference
+                v = (v - v.mean()) / v.std(unbiased=False)
+                m = v.permute(2, 0, 1)[None, None].contiguous()
+            molded.append(m)
             windows.append(window)
-            image_metas.append(compose_image_meta(0, image.shape, window, np.zeros([c.NUM_CLASSES], dtype=np.int32)))
-        return np.stack(molded_images), np.stack(image_metas), np.stack(windows)
+            metas.append(compose_image_meta(0, image.shape, window, np.zeros([c.NUM_CLASSES], dtype=np.int32)))
+        return torch.cat(molded, 0), np.stack(metas), np.stack(windows)
+
+    def mold_inputs(self, images):
+        """reference signature (numpy out): the device computation of mold_inputs_device, copied back"""
+        molded, metas, windows = self.mold_inputs_device(images)
+        return molded.cpu().numpy(), metas, windows
 
     def unmold_detections(self, detections, mrcnn_mask, image_shape, window):
-        """reference model.py:1812-1864"""
+        """reference model.py:1812-1864.  detections [n,8] numpy; mrcnn_mask the class probabilities of every detection,
+        either the device tensor predict() returned ([n,ncls,d,h,w]) or the reference's numpy layout [n,d,h,w,ncls];
+        image_shape [C,D,H,W] of the original scan.  The box arithmetic is a handful of integers (host); the mask resize +
+        paste + argmax is one device kernel (ops.unmold_mask_argmax)."""
         zero_ix = np.where(detections[:, 6] == 0)[0]
         N = zero_ix[0] if zero_ix.shape[0] > 0 else detections.shape[0]
         boxes = detections[:N, :6].astype(np.int32)
         scores = detections[:N, 7]
-        masks = mrcnn_mask[np.arange(N)]
+        keep = np.arange(N)
         sc = np.array([image_shape[1] / (window[3] - window[0]), image_shape[2] / (window[4] - window[1]),
                        image_shape[3] / (window[5] - window[2])] * 2)
         sh = np.array(list(window[:3]) * 2)
         boxes = np.multiply(boxes - sh, sc).astype(np.int32)
         bad = np.where((boxes[:, 3] - boxes[:, 0]) * (boxes[:, 4] - boxes[:, 1]) * (boxes[:, 5] - boxes[:, 2]) <= 0)[0]
         if bad.shape[0] > 0:
-            boxes, scores, masks = np.delete(boxes, bad, 0), np.delete(scores, bad, 0), np.delete(masks, bad, 0)
-        full_mask = np.argmax(utils.unmold_mask(masks[0], boxes[0], image_shape), axis=3)
+            boxes, scores, keep = np.delete(boxes, bad, 0), np.delete(scores, bad, 0), np.delete(keep, bad, 0)
+        if torch.is_tensor(mrcnn_mask):
+            m0 = mrcnn_mask[int(keep[0])]                                        # [ncls,d,h,w]
+        else:
+            m0 = torch.from_numpy(np.ascontiguousarray(mrcnn_mask[int(keep[0])])).to(self.anchors.device).permute(3, 0, 1, 2)
+        full_mask = ops.unmold_mask_argmax(m0, boxes[0], image_shape[1:4]).cpu().numpy().astype(np.int64)
         boxes[:, [0, 1, 2, 3, 4, 5]] = boxes[:, [1, 2, 0, 4, 5, 3]]
-        return boxes, np.arange(1, 8), scores, full_mask.transpose((1, 2, 0))
+        return boxes, np.arange(1, 8), scores, full_mask
 
     # -- training loop ------------------------------------------------------------------------------------------
     def make_optimizer(self, learning_rate):

@@ -626,6 +626,36 @@ def sgd_clip_step(p, g, mom, wd_mask, sumsq, max_norm, lr, momentum, weight_deca
          float(lr), float(momentum), float(weight_decay), 0, _stream())
 
 
+def resize_linear3d(vol_hwd, out_shape):
+    """order-1 resize of a raw scan [H,W,D] (int16 or float32, on device) to out_shape, reference utils.resize_image
+    'self' mode semantics (utils.py:389-393); same dtype out"""
+    _require_cuda(vol_hwd)
+    assert vol_hwd.dim() == 3 and vol_hwd.dtype in (torch.int16, torch.float32)
+    vol_hwd = vol_hwd.contiguous()
+    H, W, D = vol_hwd.shape
+    H2, W2, D2 = [int(v) for v in out_shape]
+    out = torch.empty((H2, W2, D2), dtype=vol_hwd.dtype, device=vol_hwd.device)
+    _run("cfun_resize_linear3d", _ptr(vol_hwd), H, W, D, _ptr(out), H2, W2, D2, 0 if vol_hwd.dtype == torch.int16 else 1, _stream())
+    return out
+
+
+def unmold_mask_argmax(mask_cdhw, box6, image_dhw):
+    """class-probability crop of one detection [ncls,d,h,w] (device, any dense layout) -> uint8 class-id volume [H,W,D]:
+    utils.unmold_mask + argmax (reference utils.py:443-460, model.py:1851-1853) fused"""
+    _require_cuda(mask_cdhw)
+    m = mask_cdhw.float()
+    ncls, md, mh, mw = m.shape
+    vs = m.stride(3)
+    if not (m.stride(2) == mw * vs and m.stride(1) == mh * mw * vs):
+        m = m.contiguous()
+        vs = 1
+    D, H, W = [int(v) for v in image_dhw]
+    out = torch.empty((H, W, D), dtype=torch.uint8, device=m.device)
+    box = (C.c_int * 6)(*[int(v) for v in box6])
+    _run("cfun_unmold_mask_argmax", _ptr(m), ncls, md, mh, mw, m.stride(0), vs, box, D, H, W, _ptr(out), _stream())
+    return out
+
+
 def mold_volume_i16(vol_hwd):
     """int16 [H,W,D] CT volume on device -> molded fp32 [1,1,D,H,W] (model.mold_image + the HWD->DHW transpose)."""
     _require_cuda(vol_hwd)

@@ -214,6 +214,24 @@ int cfun_sgd_clip_step(float* p, const float* g, float* mom, const unsigned char
  * vol is [H,W,D] int16 as stored; out is [1,1,D,H,W] (== NDHWC for C=1).  acc: 2 zeroed doubles. */
 int cfun_mold_volume_i16(const short* vol_hwd, int H, int W, int D, double* acc, float* out_dhw, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Inference pre / post-processing on the device.
+ *
+ * cfun_resize_linear3d: utils.resize_image(mode='self') (reference utils.py:389-393, called from MaskRCNN.mold_inputs,
+ * model.py:1774-1810): order-1 resize of a raw scan src[H][W][D] to dst[H2][W2][D2], skimage >= 0.19 / scipy.ndimage.zoom
+ * (order 1, 'grid-constant', grid_mode=True) semantics in float64, cast back to the scan dtype by C truncation.
+ * dtype 0 = int16, 1 = float32 (same type in and out).
+ *
+ * cfun_unmold_mask_argmax: utils.unmold_mask + np.argmax of MaskRCNN.unmold_detections (reference utils.py:443-460,
+ * model.py:1851-1853) fused: trilinear (align_corners=False) resize of one detection's class-probability crop
+ * (ncls x md x mh x mw, element (c,z,y,x) at mask[c*class_stride + ((z*mh+y)*mw+x)*voxel_stride]) to the box
+ * box6_host = (z1,y1,x1,z2,y2,x2) (host ints, pixels of the original scan), zeros elsewhere, argmax over classes;
+ * out[H][W][D] uint8 class ids (the [H,W,D] order unmold_detections returns).
+ * ------------------------------------------------------------------------------------------ */
+int cfun_resize_linear3d(const void* src, int H, int W, int D, void* dst, int H2, int W2, int D2, int dtype, void* stream);
+int cfun_unmold_mask_argmax(const float* mask, int ncls, int md, int mh, int mw, long long class_stride, long long voxel_stride,
+                            const int* box6_host, int D, int H, int W, unsigned char* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

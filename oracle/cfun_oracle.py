@@ -703,3 +703,60 @@ def train_step_grads(sd, cfg, trainable, *args, **kw):
     coef = min(1.0, 5.0 / (norm + 1e-6))
     grads = {k: g * coef for k, g in grads.items()}
     return out, grads, norm
+
+
+# --------------------------------------------------------------------------------------
+#  Inference pre / post-processing (model.py:1774-1864, utils.py:342-393, 443-460)
+# --------------------------------------------------------------------------------------
+def zoom_linear(vol, out_shape):
+    """utils.resize(order=1, mode='constant') as skimage >= 0.19 evaluates it: scipy.ndimage.zoom(order=1,
+    mode='grid-constant', cval=0, grid_mode=True) -- source coordinate (o + 0.5) * in / out - 0.5, linear blend of the two
+    neighbours with everything outside the volume equal to 0, float64.  vol [H,W,D] -> out_shape (separable restatement)."""
+    v = np.asarray(vol, dtype=np.float64)
+    for ax, n_out in enumerate(out_shape):
+        n_in = v.shape[ax]
+        cc = (np.arange(n_out) + 0.5) * (n_in / float(n_out)) - 0.5
+        i0 = np.floor(cc).astype(np.int64)
+        t = cc - i0
+        pad = np.concatenate([np.zeros_like(np.take(v, [0], axis=ax)), v, np.zeros_like(np.take(v, [0], axis=ax))], axis=ax)
+        a = np.take(pad, np.clip(i0 + 1, 0, n_in + 1), axis=ax)
+        b = np.take(pad, np.clip(i0 + 2, 0, n_in + 1), axis=ax)
+        shp = [1] * v.ndim
+        shp[ax] = n_out
+        v = a * (1.0 - t).reshape(shp) + b * t.reshape(shp)
+    return v
+
+
+def mold_inputs(image_hwdc, min_dim, max_dim):
+    """MaskRCNN.mold_inputs for IMAGE_RESIZE_MODE 'self' (model.py:1774-1810, utils.py:389-393): order-1 resize to
+    [max, max, min], cast back to the image dtype (C truncation), (x - mean) / std, [H,W,D,C] -> [C,D,H,W]."""
+    img = np.asarray(image_hwdc)
+    r = zoom_linear(img[..., 0], (max_dim, max_dim, min_dim)).astype(img.dtype)[..., None]
+    molded = mold_image(r).transpose((3, 2, 0, 1))
+    window = (0, 0, 0, min_dim, max_dim, max_dim)
+    return molded.astype(np.float32), window
+
+
+def unmold_detections(detections, mask0_cdhw, image_shape_cdhw, window):
+    """model.py:1812-1864 + utils.unmold_mask:443-460.  detections [n,8] (z1,y1,x1,z2,y2,x2,class,score), mask0 the class
+    probabilities [ncls,d,h,w] of detection 0.  Returns (boxes [n,6] in (y1,x1,z1,y2,x2,z2), scores, full_mask [H,W,D])."""
+    zero_ix = np.where(detections[:, 6] == 0)[0]
+    N = zero_ix[0] if zero_ix.shape[0] > 0 else detections.shape[0]
+    boxes = detections[:N, :6].astype(np.int32)
+    scores = detections[:N, 7]
+    sc = np.array([image_shape_cdhw[1] / (window[3] - window[0]), image_shape_cdhw[2] / (window[4] - window[1]),
+                   image_shape_cdhw[3] / (window[5] - window[2])] * 2)
+    sh = np.array(list(window[:3]) * 2)
+    boxes = np.multiply(boxes - sh, sc).astype(np.int32)
+    bad = np.where((boxes[:, 3] - boxes[:, 0]) * (boxes[:, 4] - boxes[:, 1]) * (boxes[:, 5] - boxes[:, 2]) <= 0)[0]
+    if bad.shape[0] > 0:
+        boxes, scores = np.delete(boxes, bad, 0), np.delete(scores, bad, 0)
+        assert 0 not in bad, "restatement covers the case the goldens exercise: detection 0 survives"
+    z1, y1, x1, z2, y2, x2 = [int(v) for v in boxes[0]]
+    m = torch.from_numpy(np.ascontiguousarray(mask0_cdhw)).float().unsqueeze(0)
+    m = F.interpolate(m, size=(z2 - z1, y2 - y1, x2 - x1), mode='trilinear', align_corners=False)[0].numpy()
+    full = np.zeros((m.shape[0], image_shape_cdhw[1], image_shape_cdhw[2], image_shape_cdhw[3]), dtype=np.float32)
+    full[:, z1:z2, y1:y2, x1:x2] = m
+    full_mask = np.argmax(full, axis=0)
+    boxes = boxes[:, [1, 2, 0, 4, 5, 3]]
+    return boxes, scores, full_mask.transpose((1, 2, 0))

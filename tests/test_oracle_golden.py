@@ -205,3 +205,18 @@ def test_c_restatement_of_nms_agrees_with_numpy_oracle_and_goldens():
     b = np.clip(np.concatenate([c - s / 2, c + s / 2], 1), 0, 256).astype(np.float32)
     sc = rng.uniform(0, 1, size=4000).astype(np.float32)
     assert np.array_equal(c_nms(b, sc, 0.7, 500), O.non_max_suppression(b, sc, 0.7, 500))
+
+
+def test_inference_pre_post_processing_matches_reference_golden():
+    """mold_inputs ('self' resize + normalise) and unmold_detections (box rescale, trilinear unmold_mask, argmax) of the
+    oracle against MaskRCNN.detect() of the unmodified reference (oracle/gen_golden_inference.py, BASELINE config 1)."""
+    import scipy.ndimage as ndi
+    g = load_golden("inference64")
+    vol = g["vol"]
+    z = ndi.zoom(vol.astype(np.float64), [64 / 80, 64 / 72, 64 / 48], order=1, mode="grid-constant", cval=0, grid_mode=True)
+    assert np.array_equal(O.zoom_linear(vol, (64, 64, 64)), z)            # the restatement IS scipy's arithmetic, bit for bit
+    molded, window = O.mold_inputs(vol[..., None], 64, 64)
+    assert rel_err(molded, g["molded"]) < 1e-6 and tuple(window) == tuple(g["window"])
+    boxes, scores, full = O.unmold_detections(g["detections"], g["mask0"], (1, 48, 80, 72), g["window"])
+    assert np.array_equal(boxes, g["rois"]) and np.array_equal(scores, g["scores"])
+    assert np.array_equal(full.astype(np.uint8), g["full_mask"])
