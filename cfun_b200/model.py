@@ -166,7 +166,8 @@ def detection_target_layer(proposals, gt_class_ids, gt_boxes, gt_masks, config):
 
     positive_count = 0
     if pos_all.numel() > 0:
-        want = int(config.TRAIN_ROIS_PER_IMAGE * config.ROI_POSITIVE_RATIO)
+        want = config.TRAIN_ROIS_PER_IMAGE * config.ROI_POSITIVE_RATIO
+        want = int(round(want)) if getattr(config, "ROI_COUNT_ROUND", False) else int(want)      # LiTS_2017/model.py:448 rounds
         perm = torch.randperm(pos_all.numel())[:want].to(dev)
         positive_indices = pos_all[perm]
         positive_count = positive_indices.numel()
@@ -177,13 +178,14 @@ def detection_target_layer(proposals, gt_class_ids, gt_boxes, gt_masks, config):
         deltas = ops.box_refinement(positive_rois, roi_gt_boxes, config.BBOX_STD_DEV)
         label = _label_volume(gt_masks)
         dense = bool(getattr(config, "DENSE_MASK_TARGETS", False))
-        onehot, index = ops.mask_target_crop(label, positive_rois, 8 if gt_masks.dim() == 3 else gt_masks.shape[0],
+        onehot, index = ops.mask_target_crop(label, positive_rois, getattr(config, "NUM_CLASSES", 8) if gt_masks.dim() == 3 else gt_masks.shape[0],
                                              config.MASK_SHAPE, onehot=dense, index=not dense)
         masks = onehot if dense else index
 
     negative_count = 0
     if neg_all.numel() > 0 and positive_count > 0:
-        want = int((1.0 / config.ROI_POSITIVE_RATIO) * positive_count - positive_count)
+        want = (1.0 / config.ROI_POSITIVE_RATIO) * positive_count - positive_count
+        want = int(round(want)) if getattr(config, "ROI_COUNT_ROUND", False) else int(want)
         perm = torch.randperm(neg_all.numel())[:want].to(dev)
         negative_indices = neg_all[perm]
         negative_count = negative_indices.numel()
@@ -370,18 +372,31 @@ def compute_mrcnn_mask_loss(target_masks, target_class_ids, pred_masks, class_we
     return F.cross_entropy(pred_masks[pos], y_true, weight=class_weight)
 
 
-def compute_mrcnn_mask_edge_loss(target_masks, target_class_ids, pred_masks):
-    """3-D Sobel edge-agreement loss (reference :938-981) as one fused stencil kernel (forward) + two (backward)."""
+def compute_mrcnn_mask_edge_loss(target_masks, target_class_ids, pred_masks, mode="magnitude"):
+    """3-D Sobel edge-agreement loss (reference :938-981; mode "raw" = LiTS_2017/model.py:943-981) as one fused stencil
+    kernel (forward) + two (backward)."""
     if target_class_ids.shape[0] == 0:
         return _zero_loss(target_class_ids)
     pos = torch.nonzero(target_class_ids > 0)[:, 0]
     P = pos.shape[0]
     tgt = _mask_index(target_masks, torch.arange(P, device=pos.device))     # reference takes target_masks[:P]
-    return ops.sobel_edge_loss(pred_masks[pos], tgt)
+    return ops.sobel_edge_loss(pred_masks[pos], tgt, ops.SOBEL_RAW if mode == "raw" else ops.SOBEL_MAGNITUDE)
 
 
 def compute_losses(rpn_match, rpn_bbox, rpn_class_logits, rpn_pred_bbox, target_class_ids, mrcnn_class_logits,
-                   target_deltas, mrcnn_bbox, target_mask, mrcnn_mask, mrcnn_mask_logits, stage):
+                   target_deltas, mrcnn_bbox, target_mask, mrcnn_mask, mrcnn_mask_logits, stage, config=None):
+    if config is not None and getattr(config, "STAGED_LOSSES", False):
+        # LiTS_2017/model.py:985-1001: detector losses in 'beginning', mask losses (weighted CE + raw-Sobel edge) afterwards
+        zero = _zero_loss(rpn_class_logits)
+        binary_ids = (target_class_ids > 0).long()
+        if stage == 'beginning':
+            return [compute_rpn_class_loss(rpn_match, rpn_class_logits), compute_rpn_bbox_loss(rpn_bbox, rpn_match, rpn_pred_bbox),
+                    compute_mrcnn_class_loss(binary_ids, mrcnn_class_logits),
+                    compute_mrcnn_bbox_loss(target_deltas, binary_ids, mrcnn_bbox), zero, zero]
+        w = getattr(config, "MASK_CLASS_WEIGHT", None)
+        cw = None if w is None else torch.tensor(w, dtype=torch.float32, device=mrcnn_mask_logits.device)
+        return [zero, zero, zero, zero, compute_mrcnn_mask_loss(target_mask, target_class_ids, mrcnn_mask_logits, cw),
+                compute_mrcnn_mask_edge_loss(target_mask, target_class_ids, mrcnn_mask, config.EDGE_LOSS_MODE)]
     rpn_class_loss = compute_rpn_class_loss(rpn_match, rpn_class_logits)
     rpn_bbox_loss = compute_rpn_bbox_loss(rpn_bbox, rpn_match, rpn_pred_bbox)
     binary_ids = (target_class_ids > 0).long()
@@ -469,30 +484,46 @@ class HeadsTail(nn.Module):
     only difference is that the positive rows are addressed as [:P] instead of through torch.nonzero, which lets
     torch.cuda.make_graphed_callables capture forward and backward (about 1500 of the step's kernel launches)."""
 
-    def __init__(self, classifier, mask, stage):
+    def __init__(self, classifier, mask, stage, config=None):
         super().__init__()
         self.classifier = classifier
         self.mask = mask
         self.stage = stage
+        self.staged = bool(getattr(config, "STAGED_LOSSES", False))
+        self.edge_mode = ops.SOBEL_RAW if getattr(config, "EDGE_LOSS_MODE", "magnitude") == "raw" else ops.SOBEL_MAGNITUDE
+        w = getattr(config, "MASK_CLASS_WEIGHT", None)
+        self.class_weight = None if w is None else [float(v) for v in w]
+        self.class_weight_t = None          # device tensor, created eagerly (never inside a CUDA-graph capture): ensure_device()
+
+    def ensure_device(self, dev):
+        if self.class_weight is not None and (self.class_weight_t is None or self.class_weight_t.device != dev):
+            self.class_weight_t = torch.tensor(self.class_weight, dtype=torch.float32, device=dev)
+        return self
 
     def forward(self, p2, p3, image, rois, p_rois, class_ids, deltas, mask_index, d0, d1, d2, d3, d4):
         P = p_rois.shape[0]
         unet = self.mask.modified_u_net
         saved = unet.injected_drop
         unet.injected_drop = [d0, d1, d2, d3, d4] if unet.training and unet.use_dropout else None
+        zero = torch.zeros((), device=p2.device)
+        run_cls = not (self.staged and self.stage != 'beginning')       # LiTS: the heads of the stage that is not trained are skipped
+        run_mask = not (self.staged and self.stage == 'beginning')
         try:
-            c_logits, _, c_bbox = self.classifier([p2, p3], rois)
-            m_logits, m_probs = self.mask([image, image], p_rois)
+            if run_cls:
+                c_logits, _, c_bbox = self.classifier([p2, p3], rois)
+            if run_mask:
+                m_logits, m_probs = self.mask([image, image], p_rois)
         finally:
             unet.injected_drop = saved
-        binary = (class_ids > 0).long()
-        l_cls = F.cross_entropy(c_logits, binary)
-        l_box = F.smooth_l1_loss(c_bbox[:P, 1, :], deltas[:P])
-        l_mask = F.cross_entropy(m_logits, mask_index)
-        if self.stage == 'finetune':
-            l_edge = ops.sobel_edge_loss(m_probs, mask_index).reshape(())
-        else:
-            l_edge = torch.zeros((), device=p2.device)
+        l_cls = l_box = l_mask = l_edge = zero
+        if run_cls:
+            binary = (class_ids > 0).long()
+            l_cls = F.cross_entropy(c_logits, binary)
+            l_box = F.smooth_l1_loss(c_bbox[:P, 1, :], deltas[:P])
+        if run_mask:
+            l_mask = F.cross_entropy(m_logits, mask_index, weight=self.class_weight_t)
+            if self.stage == 'finetune' or (self.staged and self.stage != 'beginning'):
+                l_edge = ops.sobel_edge_loss(m_probs, mask_index, self.edge_mode).reshape(())
         return torch.stack([l_cls, l_box, l_mask, l_edge])
 
 
@@ -541,7 +572,12 @@ class MaskRCNN(nn.Module):
         self.mask = Mask(1, config.MASK_POOL_SIZE, config.NUM_CLASSES, config.UNET_MASK_BRANCH_CHANNEL, config.STAGE,
                          test_flag)
         # not registered as a sub-module (would duplicate state_dict keys): shares classifier / mask by reference
-        object.__setattr__(self, "_tail", HeadsTail(self.classifier, self.mask, config.STAGE))
+        self.mask.modified_u_net.use_dropout = bool(getattr(config, "UNET_DROPOUT", True))
+        object.__setattr__(self, "_tail", HeadsTail(self.classifier, self.mask, config.STAGE, config))
+        if getattr(config, "STAGED_LOSSES", False) and config.STAGE != 'beginning':
+            for m in (self.fpn, self.rpn):          # LiTS_2017/model.py:1309-1311: the detector is frozen after 'beginning'
+                for p in m.parameters():
+                    p.requires_grad = False
         if not config.TRAIN_BN:
             for m in self.modules():
                 if isinstance(m, nn.BatchNorm3d):
@@ -644,16 +680,21 @@ class MaskRCNN(nn.Module):
         self.train()
         cfg = self.config
         dev = images.device
-        p2, p3, rpn_class_logits, rpn_class, rpn_pred_bbox, rpn_rois = self.rpn_proposals(images, 'training')
+        frozen = bool(getattr(cfg, "STAGED_LOSSES", False)) and cfg.STAGE != 'beginning'    # LiTS: detector frozen, mask losses only
+        with torch.set_grad_enabled(not frozen):
+            p2, p3, rpn_class_logits, rpn_class, rpn_pred_bbox, rpn_rois = self.rpn_proposals(images, 'training')
         h, w, d = cfg.IMAGE_SHAPE[:3]
         scale = _f32([d, h, w, d, h, w], dev)
         p_rois, rois, target_class_ids, target_deltas, target_mask = \
             detection_target_layer(rpn_rois, gt_class_ids, gt_boxes / scale, gt_masks, cfg)
         P, R = int(p_rois.shape[0]), int(rois.shape[0])
         self.last_roi_counts = (P, R)
-        rpn_class_loss = compute_rpn_class_loss(rpn_match, rpn_class_logits)
-        rpn_bbox_loss = compute_rpn_bbox_loss(rpn_bbox, rpn_match, rpn_pred_bbox)
         zero = _zero_loss(rpn_class_logits)
+        if frozen:
+            rpn_class_loss = rpn_bbox_loss = zero
+        else:
+            rpn_class_loss = compute_rpn_class_loss(rpn_match, rpn_class_logits)
+            rpn_bbox_loss = compute_rpn_bbox_loss(rpn_bbox, rpn_match, rpn_pred_bbox)
         if P > 0:
             if target_mask.dim() == 5:
                 target_mask = torch.argmax(target_mask.long(), dim=1)
@@ -666,6 +707,7 @@ class MaskRCNN(nn.Module):
                 # they hold the freed buffer's address in kernel arguments and tensor maps -- drop them, re-capture lazily
                 self._graphed_tails = {}
                 self.graph_kernel_counts = {}
+            self._tail.ensure_device(dev)
             tail = self._graphed_tails.get((P, R), self._tail) if self._graphed_tails is not None else self._tail
             if self._graphed_tails is not None and (P, R) not in self._graphed_tails:
                 tail = self._capture_tail(P, R, p2, p3, images, rois, p_rois, target_class_ids, target_deltas, target_mask, drops)
@@ -681,7 +723,8 @@ class MaskRCNN(nn.Module):
             head_losses = [zero, zero, zero, zero]
         losses = [rpn_class_loss, rpn_bbox_loss] + head_losses
         loss = self.weighted_loss(losses)
-        loss.sum().backward()
+        if loss.requires_grad:
+            loss.sum().backward()
         return loss, losses
 
     # -- CUDA graphs for the heads ----------------------------------------------------------------------------
@@ -703,7 +746,7 @@ class MaskRCNN(nn.Module):
         n0 = launch_count()
         # make_graphed_callables patches an nn.Module's forward in place: capture a fresh HeadsTail per RoI split (it only
         # references the shared classifier / mask modules) so that self._tail stays the eager path
-        fresh = HeadsTail(self.classifier, self.mask, self.config.STAGE)
+        fresh = HeadsTail(self.classifier, self.mask, self.config.STAGE, self.config).ensure_device(p2.device)
         fresh.train(self.training)
         graphed = torch.cuda.make_graphed_callables(fresh, args, num_warmup_iters=1, allow_unused_input=True)
         # kernels per replay (forward + backward): launches during capture = (1 warm-up + 1 capture) iterations

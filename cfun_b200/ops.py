@@ -584,34 +584,40 @@ def mask_target_crop(label_dhw, rois, ncls, mask_shape, onehot=True, index=True)
 # --------------------------------------------------------------------------------------------------------
 class SobelEdgeLossFn(Function):
     @staticmethod
-    def forward(ctx, pred, tgt_index):
+    def forward(ctx, pred, tgt_index, mode):
         _require_cuda(pred, tgt_index)
         pred = to_cl(pred)
-        P, ncls, M = pred.shape[0], pred.shape[1], pred.shape[2]
-        assert pred.shape[3] == M and pred.shape[4] == M, "cubic mask crops only (config MASK_SHAPE)"
+        P, ncls, Md, Mh, Mw = pred.shape
         tgt_index = tgt_index.contiguous()
-        assert tgt_index.dtype == torch.int64 and tuple(tgt_index.shape) == (P, M, M, M)
+        assert tgt_index.dtype == torch.int64 and tuple(tgt_index.shape) == (P, Md, Mh, Mw)
         loss = torch.empty(1, device=pred.device)
         ws = workspace(4096, pred.device)
-        _run("cfun_sobel_edge_loss_fwd", _ptr(pred), _ptr(tgt_index), P, M, ncls, _ptr(loss), _ptr(ws), ws.numel(), _stream())
+        _run("cfun_sobel_edge_loss_fwd", _ptr(pred), _ptr(tgt_index), P, Md, Mh, Mw, ncls, mode, _ptr(loss), _ptr(ws), ws.numel(),
+             _stream())
         ctx.save_for_backward(pred, tgt_index)
+        ctx.mode = mode
         return loss
 
     @staticmethod
     def backward(ctx, dloss):
         pred, tgt_index = ctx.saved_tensors
-        P, ncls, M = pred.shape[0], pred.shape[1], pred.shape[2]
+        P, ncls, Md, Mh, Mw = pred.shape
         g = dloss.reshape(1).contiguous().float()
-        dpred = empty_cl(P, ncls, M, M, M, pred.device)
-        nb = lib.cfun_sobel_edge_workspace_size(P, M, ncls)
+        dpred = empty_cl(P, ncls, Md, Mh, Mw, pred.device)
+        nb = lib.cfun_sobel_edge_workspace_size(P, Md, Mh, Mw, ncls, ctx.mode)
         ws = workspace(nb, pred.device)
-        _run("cfun_sobel_edge_loss_bwd", _ptr(pred), _ptr(tgt_index), P, M, ncls, _ptr(g), _ptr(dpred), _ptr(ws), ws.numel(),
-             _stream())
-        return dpred, None
+        _run("cfun_sobel_edge_loss_bwd", _ptr(pred), _ptr(tgt_index), P, Md, Mh, Mw, ncls, ctx.mode, _ptr(g), _ptr(dpred), _ptr(ws),
+             ws.numel(), _stream())
+        return dpred, None, None
 
 
-def sobel_edge_loss(pred_probs, tgt_index):
-    return SobelEdgeLossFn.apply(pred_probs, tgt_index)
+SOBEL_MAGNITUDE, SOBEL_RAW = 0, 1
+
+
+def sobel_edge_loss(pred_probs, tgt_index, mode=SOBEL_MAGNITUDE):
+    """pred_probs [P,ncls,d,h,w], tgt_index int64 [P,d,h,w].  mode SOBEL_MAGNITUDE: reference model.py:938-981 (heart);
+    SOBEL_RAW: LiTS_2017/model.py:943-981."""
+    return SobelEdgeLossFn.apply(pred_probs, tgt_index, mode)
 
 
 # --------------------------------------------------------------------------------------------------------

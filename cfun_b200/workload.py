@@ -122,7 +122,9 @@ def _iou_many(boxes, cands):
 
 
 def _final_gt_box(center, side, dim):
-    """label cube (start, L) and the GT box load_image_gt derives from it (+5 % margin, floor / ceil, clipped)"""
+    """label cube (start, L) and the GT box load_image_gt derives from it (+5 % margin, floor / ceil, clipped).
+    dim: scalar (cubic volume) or (D, H, W)"""
+    dim = np.broadcast_to(np.asarray(dim), (3,))
     L = int(round(side / 1.1))
     start = np.clip(np.round(center - L / 2.0).astype(int), 0, dim - L)
     lo = np.floor(np.maximum(0, start - 0.05 * L))
@@ -136,7 +138,8 @@ def place_label_cube(rois_norm, dim, want=4, sides=(72, 80, 88, 96, 104), margin
     places the synthetic label cube where the untrained detector's proposals cluster: the cube whose GT box (as
     load_image_gt derives it, reference model.py:1058-1075) has the most proposals with IoU >= 0.5 (at least `want`, none
     within `margin` of the threshold).  Returns (start_zyx, side, n_positive_candidates) or None."""
-    boxes = np.asarray(rois_norm, dtype=np.float64) * dim
+    d3 = np.broadcast_to(np.asarray(dim, dtype=np.float64), (3,))
+    boxes = np.asarray(rois_norm, dtype=np.float64) * np.concatenate([d3, d3])
     ctr = 0.5 * (boxes[:, :3] + boxes[:, 3:])
     cents = [ctr]
     d2 = ((ctr[:, None, :] - ctr[None, :, :]) ** 2).sum(-1)
@@ -163,10 +166,12 @@ def place_label_cube(rois_norm, dim, want=4, sides=(72, 80, 88, 96, 104), margin
     return best[1], best[2], best[3]
 
 
-def label_from_cube(dim, start_zyx, side, seed):
-    """uint8 label volume [H,W,D] with a cube of uniformly random classes 1..7 at (z,y,x) = start"""
+def label_from_cube(dim, start_zyx, side, seed, num_classes=8):
+    """uint8 label volume [H,W,D] with a cube of uniformly random classes 1..num_classes-1 at (z,y,x) = start.
+    dim: scalar (cubic volume) or (D, H, W)"""
     rng = np.random.default_rng(seed)
-    lab = np.zeros((dim, dim, dim), dtype=np.uint8)      # [H,W,D]
+    D, H, W = [int(v) for v in np.broadcast_to(np.asarray(dim), (3,))]
+    lab = np.zeros((H, W, D), dtype=np.uint8)      # [H,W,D]
     z, y, x = [int(v) for v in start_zyx]
-    lab[y:y + side, x:x + side, z:z + side] = rng.integers(1, 8, size=(side, side, side), dtype=np.uint8)
+    lab[y:y + side, x:x + side, z:z + side] = rng.integers(1, num_classes, size=(side, side, side), dtype=np.uint8)
     return lab

@@ -195,11 +195,14 @@ int cfun_mask_target_crop(const int* label, int D, int H, int W, const float* ro
  *   (tgt==j+1)); classes 1..7 (the reference's literal range(7)); loss = sum_ij mse(mag_p, mag_t) / P.
  *   magnitude = sqrt(g0^2 + g1^2 + g0^2) -- response 0 twice, response 2 unused (model.py:969-972).
  * ------------------------------------------------------------------------------------------ */
-size_t cfun_sobel_edge_workspace_size(int P, int M, int ncls);
-int cfun_sobel_edge_loss_fwd(const float* pred, const long long* tgt_index, int P, int M, int ncls, float* loss,
-                             void* ws, size_t ws_bytes, void* stream);
-/* dpred += grad_scale[0] * dloss/dpred  (dpred zero-initialised by caller) */
-int cfun_sobel_edge_loss_bwd(const float* pred, const long long* tgt_index, int P, int M, int ncls,
+/* The crop is Md x Mh x Mw (cubic for the heart configs, (32,80,80) / (64,160,160) for LiTS); classes 1..ncls-1 contribute.
+ * mode 0: heart, MSE between the magnitudes sqrt(g0^2+g1^2+g0^2) (model.py:969-975); mode 1: LiTS, MSE between the raw three
+ * Sobel responses (LiTS_2017/model.py:967-975). */
+size_t cfun_sobel_edge_workspace_size(int P, int Md, int Mh, int Mw, int ncls, int mode);
+int cfun_sobel_edge_loss_fwd(const float* pred, const long long* tgt_index, int P, int Md, int Mh, int Mw, int ncls, int mode,
+                             float* loss, void* ws, size_t ws_bytes, void* stream);
+/* dpred = grad_scale[0] * dloss/dpred (every element written) */
+int cfun_sobel_edge_loss_bwd(const float* pred, const long long* tgt_index, int P, int Md, int Mh, int Mw, int ncls, int mode,
                              const float* grad_scale, float* dpred, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------

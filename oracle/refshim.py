@@ -41,13 +41,26 @@ def _skimage_resize(image, output_shape, order=1, mode="constant", cval=0, clip=
 
 
 _loaded = {}
+_loaded_by_root = {}
 
 
-def load():
-    """Returns dict of reference modules: model, utils, backbone, mask_branch, config."""
+def load(subdir=None):
+    """Returns dict of reference modules: model, utils, backbone, mask_branch, config.  subdir="LiTS_2017" loads the liver
+    variant (same module names, its own directory) instead of the heart tree."""
+    if subdir:
+        return _load_from(os.path.join(REF_ROOT, subdir), "cfunref_%s_" % subdir.lower())
     if _loaded:
         return _loaded
-    if not available():
+    _loaded.update(_load_from(REF_ROOT, "cfunref_"))
+    return _loaded
+
+
+def _load_from(ref_root, tag):
+    if ref_root in _loaded_by_root:
+        return _loaded_by_root[ref_root]
+    _loaded = {}
+    REF_ROOT = ref_root
+    if not os.path.isfile(os.path.join(REF_ROOT, "model.py")):
         raise RuntimeError("reference tree not present at %s" % REF_ROOT)
     import torch
     import torch.nn as nn
@@ -73,9 +86,10 @@ def load():
         for k in ("model", "utils", "backbone", "mask_branch", "config"):
             m = sys.modules.pop(k, None)
             if m is not None:
-                sys.modules["cfunref_" + k] = m
+                sys.modules[tag + k] = m
         sys.modules.update(saved)
     _loaded.update(mods)
+    _loaded_by_root[ref_root] = _loaded
     return _loaded
 
 

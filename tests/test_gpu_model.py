@@ -334,3 +334,67 @@ def test_device_rpn_targets_match_reference(case):
     assert (m2 == 1).sum() == min((pre == 1).sum(), cfg.RPN_TRAIN_ANCHORS_PER_IMAGE // 2)
     assert (m2 != 0).sum() == min((pre != 0).sum(), cfg.RPN_TRAIN_ANCHORS_PER_IMAGE)
     assert np.all((m2 != 0) <= (pre != 0)) and np.all(m2[m2 != 0] == pre[m2 != 0])
+
+
+def test_lits_variant_matches_lits_reference_golden():
+    """BASELINE config 3 / SURVEY.md 8f rank 4: the LiTS_2017 copy of the model as configuration switches of the same
+    modules -- P3D35 (4 + 5 bottlenecks) with the 5x7x7 stem and 24 / 48 planes, FPN 160, RPN 160->320, base-32 U-Net without
+    Dropout3d on a non-cubic crop (incl. the literal 128->256 3^3 stride-2 conv, conv3d_c4), weighted mask CE [1,1,100] and
+    the raw-Sobel edge loss -- against goldens from the UNMODIFIED LiTS_2017 reference (oracle/gen_golden_lits.py)."""
+    from cfun_b200 import config as Cf, model as M, ops
+    g = load_golden("lits_layers")
+    cfg = Cf.lits_config("together", 32, 48, (32, 48, 32), RPN_ANCHOR_SCALES=(16, 32))
+    net = M.MaskRCNN(cfg, "/tmp/_cfun_test")
+    ours = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert sorted(ours) == list(g["state_keys"]), "checkpoint ABI of the LiTS model (332 entries)"
+    net.load_state_dict(det_state(ours, seed=300), strict=True)
+    net = net.cuda()
+    for p in net.parameters():
+        if p.dtype == torch.float32 and p.dim() == 5:
+            p.requires_grad = True                       # the golden takes detector gradients too
+    net.train()
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    p2, p3 = net.fpn(x)
+    assert rel_err(p2.detach().cpu().numpy(), g["p2"]) < TOL and rel_err(p3.detach().cpu().numpy(), g["p3"]) < TOL
+    logits, probs, bbox = net.rpn(p2)
+    assert rel_err(logits.detach().cpu().numpy(), g["rpn_logits"]) < TOL
+    assert rel_err(probs.detach().cpu().numpy(), g["rpn_probs"]) < TOL
+    assert rel_err(bbox.detach().cpu().numpy(), g["rpn_bbox"]) < TOL
+    (p2.square().sum() + p3.sum()).backward()
+    assert rel_err(net.fpn.C1[0].weight.grad.cpu().numpy(), g["g_stem"]) < TOL
+    assert rel_err(net.fpn.P2_conv2.weight.grad.flatten()[::11].cpu().numpy(), g["g_P2_conv2"]) < TOL
+    assert rel_err(net.fpn.C3[4].conv2.weight.grad.cpu().numpy(), g["g_C3_4_conv2"]) < TOL
+    assert rel_err(x.grad.cpu().numpy(), g["gx"]) < TOL
+    unet = net.mask.modified_u_net
+    assert unet.use_dropout is False and unet.base_n_filter == 32
+    net.zero_grad()
+    y = unet(torch.from_numpy(g["crops"]).cuda())
+    assert tuple(y.shape) == tuple(g["unet_shape"])
+    # (32,48,32) crops leave 2 x 3 x 2 voxels per InstanceNorm at the bottom level: same conditioning (and bound) as the
+    # 32^3 inference golden above; measured 1.2e-4
+    assert rel_err(y.detach().flatten()[::7].cpu().numpy(), g["unet_out"]) < 3e-4
+    w = torch.cos(torch.arange(y.numel(), dtype=torch.float32) * 0.37).view(y.shape).cuda()
+    (y * w).sum().backward()
+    # U-Net weight gradients behind ~20 InstanceNorm backward passes: same conditioning argument (and bound) as the heart test
+    assert rel_err(unet.conv3d_c1_1.weight.grad.cpu().numpy(), g["g_unet_c1_1"]) < 3e-2
+    assert rel_err(unet.conv_norm_lrelu_l4[0].weight.grad.flatten()[::5].cpu().numpy(), g["g_unet_l4"]) < 3e-2
+    assert rel_err(unet.conv3d_c4.weight.grad.flatten()[::13].cpu().numpy(), g["g_unet_c4"]) < 3e-2
+    # losses
+    l = load_golden("lits_losses")
+    lab = torch.from_numpy(l["target_label"]).cuda()
+    tcls = torch.from_numpy(l["target_class_ids"]).cuda()
+    mlog = torch.from_numpy(l["mask_logits"]).cuda().requires_grad_(True)
+    cw = torch.tensor(cfg.MASK_CLASS_WEIGHT, device="cuda")
+    l_mask = M.compute_mrcnn_mask_loss(lab, tcls, mlog, cw)
+    assert abs(float(l_mask) - float(l["mask_loss"])) < 1e-5 * abs(float(l["mask_loss"]))
+    (gm,) = torch.autograd.grad(l_mask, mlog)
+    assert rel_err(gm.cpu().numpy(), l["g_mask"]) < 1e-5
+    mprob = torch.softmax(mlog.detach(), 1).requires_grad_(True)
+    l_edge = M.compute_mrcnn_mask_edge_loss(lab, tcls, mprob, "raw")
+    assert abs(float(l_edge) - float(l["edge_loss"].sum())) < 1e-4 * abs(float(l["edge_loss"].sum()))
+    (ge,) = torch.autograd.grad(l_edge.sum(), mprob)
+    assert rel_err(ge.cpu().numpy(), l["g_edge"]) < 1e-4
+    # staged training (LiTS_2017/model.py:985-1001, 1309-1311): outside 'beginning' the detector is frozen
+    frozen = [k for k, p in M.MaskRCNN(cfg, "/tmp/_cfun_test").named_parameters() if not p.requires_grad]
+    assert any(k.startswith("fpn.") for k in frozen) and any(k.startswith("rpn.") for k in frozen)
+    assert not any(k.startswith("mask.") for k in frozen)
