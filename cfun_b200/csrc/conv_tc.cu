@@ -391,7 +391,7 @@ bool tc_supported(const cfun_conv3d_desc* d, int pass) {
     if (e && e[0] == '0') return false;
     return tc_wgrad_supported(d);
   }
-  if (hx_supported(d, pass)) return true;
+  if (hl_supported(d, pass) || hx_supported(d, pass)) return true;
   TcPlan pl;
   if (!make_plan(d, pass, pl)) return false;
   const int taps = pl.kD * pl.kH * pl.kW;

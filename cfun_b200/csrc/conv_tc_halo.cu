@@ -34,11 +34,12 @@ namespace cfun {
 
 constexpr int HL_THREADS = 224;                      // warp 0: halo producer, 1: MMA issuer, 2..5: epilogue, 6: weight producer
 constexpr int HL_HT = 16, HL_WT = 8;                 // output slab 1 x 16 x 8
-constexpr int HL_HH = HL_HT + 2, HL_WH = HL_WT + 2;  // halo 3 x 18 x 10
-constexpr int HL_PLANE_DATA = 3 * HL_HH * HL_WH * 16;   // 8640 B: one 8-channel group, one part
-constexpr int HL_PLANE = (HL_PLANE_DATA + 127) / 128 * 128;   // 8704: plane pitch (TMA smem destinations are 128 B aligned)
+// kernel size KS = 3 (halo 3 x 18 x 10) or 5 (5 x 20 x 12: out_upscale_conv, mask_branch.py:87-88, at 192^3 in stage finetune)
+__host__ __device__ constexpr int hl_hh(int KS) { return HL_HT + KS - 1; }
+__host__ __device__ constexpr int hl_wh(int KS) { return HL_WT + KS - 1; }
+__host__ __device__ constexpr int hl_plane_data(int KS) { return KS * hl_hh(KS) * hl_wh(KS) * 16; }      // one 8-channel group, one part
+__host__ __device__ constexpr int hl_plane(int KS) { return (hl_plane_data(KS) + 127) / 128 * 128; }     // plane pitch (128 B aligned)
 constexpr int HL_MAX_G = 8;                          // Cin <= 64
-constexpr int HL_MAX_STEPS = 27 * HL_MAX_G / 2;      // 108
 constexpr int HL_MAX_BSTAGES = 8;
 
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -61,19 +62,23 @@ int launch_pack_act_gp(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int
 
 // ---- compile-time step table (G = real channel groups) -------------------------------------------------------------------
 // entry e = (group g = e / 27, tap t = e % 27) lives at plane 2g (hi; lo = the next plane) + halo row of the tap; all in 16-byte units
-__host__ __device__ constexpr uint32_t hl_entry_off16(int e) {
-  return (uint32_t)(((2 * (e / 27)) * HL_PLANE + ((((e % 27) / 9) * HL_HH + ((e % 27) % 9) / 3) * HL_WH + (e % 27) % 3) * 16) >> 4);
+__host__ __device__ constexpr uint32_t hl_entry_off16(int KS, int e) {
+  return (uint32_t)(((2 * (e / (KS * KS * KS))) * hl_plane(KS) +
+                     ((((e % (KS * KS * KS)) / (KS * KS)) * hl_hh(KS) + ((e % (KS * KS * KS)) % (KS * KS)) / KS) * hl_wh(KS) +
+                      (e % (KS * KS * KS)) % KS) * 16) >> 4);
 }
 // A-descriptor low word of step s relative to the halo slot: start address >> 4 | LBO >> 4 << 16.  With an odd entry count the
 // last step pairs the previous tap (multiplied by zero weights, see pack_w_halo_kernel) with the last real entry, so that both
 // K halves read initialised shared memory.
-__host__ __device__ constexpr uint32_t hl_a_word(int G, int s) {
-  return 2 * s + 1 < 27 * G ? (hl_entry_off16(2 * s) | ((hl_entry_off16(2 * s + 1) - hl_entry_off16(2 * s)) << 16))
-                            : ((hl_entry_off16(2 * s) - 1u) | (1u << 16));
+__host__ __device__ constexpr uint32_t hl_a_word(int KS, int G, int s) {
+  return 2 * s + 1 < KS * KS * KS * G
+             ? (hl_entry_off16(KS, 2 * s) | ((hl_entry_off16(KS, 2 * s + 1) - hl_entry_off16(KS, 2 * s)) << 16))
+             : ((hl_entry_off16(KS, 2 * s) - 1u) | (1u << 16));
 }
-// segment g = the steps whose first entry lies in group g: [seg_begin(g), seg_begin(g + 1)); 14, 13, 14, ... steps.  For even g
-// (and g + 1 < G) the last step of the segment straddles into group g + 1.  Weight stages are half segments: 7 + (7 | 6) steps.
-__host__ __device__ constexpr int hl_seg_begin(int g) { return (27 * g + 1) / 2; }
+// segment g = the steps whose first entry lies in group g: [seg_begin(g), seg_begin(g + 1)); 14, 13, 14, ... steps for T = 27
+// taps (63, 62, ... for T = 125).  For even g (and g + 1 < G) the last step of the segment straddles into group g + 1.
+// Weight stages are pieces of <= HL_HALF = 7 steps of a segment.
+__host__ __device__ constexpr int hl_seg_begin(int T, int g) { return (T * g + 1) / 2; }
 constexpr int HL_HALF = 7;
 
 struct HlParams {
@@ -91,7 +96,7 @@ struct HlParams {
   const uint8_t* wpack;       // [step][khalf2][part][Npad][8] bf16 (hi rows, then lo rows)
 };
 
-template <int G, bool SPLIT>
+template <int G, bool SPLIT, int KS>
 __global__ void __launch_bounds__(HL_THREADS, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_l, const HlParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -104,7 +109,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
   uint8_t* base = smem_raw + 1024 + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
-  constexpr int NSTEPS = (27 * G + 1) / 2;
+  constexpr int T = KS * KS * KS, PAD = KS / 2;
+  constexpr int NSTEPS = (T * G + 1) / 2;
+  constexpr int HL_PLANE = hl_plane(KS), HL_PLANE_DATA = hl_plane_data(KS), HL_WH = hl_wh(KS);
+  constexpr int NH = (hl_seg_begin(T, 1) + HL_HALF - 1) / HL_HALF;        // stages per segment (the longest segment is the first)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int parts = SPLIT ? 2 : 1;
   const int nrows = parts * p.Npad;                               // weight rows per K half: hi rows then lo rows
@@ -136,9 +144,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
         const int hb = (int)(t % p.tilesH); t /= p.tilesH;
         const int d = (int)(t % p.D);
         const int n = (int)(t / p.D);
-        const int c_w = (wb * HL_WT - 1) * 8;          // inner coordinate in elements (multiple of 8 -> 16 B aligned)
-        const int c_h = hb * HL_HT - 1;
-        const int c_nd = n * (p.D + 2) + d;            // padded plane index of d-1
+        const int c_w = (wb * HL_WT - PAD) * 8;        // inner coordinate in elements (multiple of 8 -> 16 B aligned)
+        const int c_h = hb * HL_HT - PAD;
+        const int c_nd = n * (p.D + 2 * PAD) + d;      // padded plane index of d - PAD
         for (int g = 0; g < G; ++g) {
           mbar_wait(&a_empty[g], (uint32_t)((local & 1) ^ 1), 210);
           mbar_arrive_expect_tx(&a_full[g], (uint32_t)(parts * HL_PLANE_DATA));
@@ -159,11 +167,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
         int st = 0;
         uint32_t ph = 0;
         for (long long tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-          for (int q = 0; q < 2 * G; ++q) {              // stage q = half q & 1 of segment q >> 1
-            const int g = q >> 1;
-            const int s0 = hl_seg_begin(g) + (q & 1) * HL_HALF;
-            const int s1 = (q & 1) ? hl_seg_begin(g + 1) : s0 + HL_HALF;
-            const uint32_t bytes = (uint32_t)((min(s1, NSTEPS) - s0) * step_bytes);
+          for (int q = 0; q < NH * G; ++q) {             // stage q = piece q % NH of segment q / NH
+            const int g = q / NH;
+            const int s0 = hl_seg_begin(T, g) + (q % NH) * HL_HALF;
+            const int s1 = min(min(s0 + HL_HALF, hl_seg_begin(T, g + 1)), NSTEPS);
+            if (s0 >= s1) continue;
+            const uint32_t bytes = (uint32_t)((s1 - s0) * step_bytes);
             mbar_wait(&b_empty[st], ph ^ 1u, 220);
             mbar_arrive_expect_tx(&b_full[st], bytes);
             bulk_load(b_ring + (size_t)st * HL_HALF * step_bytes, p.wpack + (size_t)s0 * step_bytes, bytes, &b_full[st]);
@@ -182,7 +191,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
     const uint32_t idesc_n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t idesc_2n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nrows >> 3) << 17) | ((128u >> 4) << 24);
     // descriptor = constant high word (SBO, version) | low word (start address >> 4, LBO >> 4 in bits 16..29)
-    constexpr uint32_t a_hiword = (uint32_t)((HL_WH * 16) >> 4) | (1u << 14);
+    constexpr uint32_t a_hiword = (uint32_t)((HL_WH * 16) >> 4) | (1u << 14);          // SBO = one halo line
     constexpr uint32_t b_hiword = (uint32_t)(128 >> 4) | (1u << 14);
     const uint32_t a_base = desc_addr(smem_u32(a_slot));
     const uint32_t b_base = desc_addr(smem_u32(b_ring)) | ((uint32_t)nrows << 16);
@@ -202,10 +211,22 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
         mbar_wait(&a_full[g], buf, 240);
         if ((g & 1) == 0 && g + 1 < G) mbar_wait(&a_full[g + 1], buf, 241);     // the last step of an even segment straddles
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int s0 = hl_seg_begin(g) + h * HL_HALF;
-          const int s1 = h ? hl_seg_begin(g + 1) : s0 + HL_HALF;
-          const uint32_t cnt = (uint32_t)it * (2 * G) + (uint32_t)(2 * g + h);   // weight stage counter
+        for (int h = 0; h < NH; ++h) {
+          const int s0 = hl_seg_begin(T, g) + h * HL_HALF;
+          const int seg_end = hl_seg_begin(T, g + 1) < NSTEPS ? hl_seg_begin(T, g + 1) : NSTEPS;
+          const int s1 = s0 + HL_HALF < seg_end ? s0 + HL_HALF : seg_end;
+          if (s0 >= s1) continue;
+          const bool last_piece = s1 == seg_end;
+          // weight stage counter: stages of a tile are numbered in issue order (the producer skips the same empty pieces)
+          int before = 0;
+#pragma unroll
+          for (int gg = 0; gg < G; ++gg) {
+            const int sb = hl_seg_begin(T, gg), se = hl_seg_begin(T, gg + 1) < NSTEPS ? hl_seg_begin(T, gg + 1) : NSTEPS;
+            const int pieces = (se - sb + HL_HALF - 1) / HL_HALF;
+            if (gg < g) before += pieces;
+          }
+          constexpr int STAGES_PER_TILE = []() { int n = 0; for (int gg = 0; gg < G; ++gg) { const int sb = hl_seg_begin(T, gg); const int se = hl_seg_begin(T, gg + 1) < NSTEPS ? hl_seg_begin(T, gg + 1) : NSTEPS; n += (se - sb + HL_HALF - 1) / HL_HALF; } return n; }();
+          const uint32_t cnt = (uint32_t)it * STAGES_PER_TILE + (uint32_t)(before + h);
           const uint32_t lap = __umulhi(cnt, ring_inv);
           const uint32_t st = cnt - lap * ring_n;
           uint32_t bw;
@@ -220,15 +241,15 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
             for (int s = s0; s < s1; ++s) {
               if (s < NSTEPS) {
                 const uint64_t b_all = desc_join(b_hiword, bw + (uint32_t)(s - s0) * stepw);
-                const uint32_t aw = a_base + hl_a_word(G, s);         // low 14 bits: address, bits 16..29: LBO (no carry between them)
+                const uint32_t aw = a_base + hl_a_word(KS, G, s);     // low 14 bits: address, bits 16..29: LBO (no carry between them)
                 if (s == 0) umma_bf16(dcol, desc_join(a_hiword, aw), b_all, idesc_2n, 0u);     // [hi*hi | hi*lo]
                 else umma_bf16_acc(dcol, desc_join(a_hiword, aw), b_all, idesc_2n);
                 if (parts == 2) umma_bf16_acc(dcol, desc_join(a_hiword, aw + lo_off), b_all, idesc_n);   // lo*hi: first Npad rows only
               }
             }
             if (!p.resident) umma_commit(&b_empty[st]);
-            if (h == 1) umma_commit(&a_empty[g]);
-            if (h == 1 && g == G - 1) umma_commit(&t_full[buf]);
+            if (last_piece) umma_commit(&a_empty[g]);
+            if (last_piece && g == G - 1) umma_commit(&t_full[buf]);
           }
           __syncwarp();
         }
@@ -293,23 +314,23 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
 
 // x fp32 NDHWC [N,D,H,W,C] -> group-planar split bf16 [Kp/8][N*(D+2)][H][W][8]; d-planes 0 and D+1 of every sample are zero
 __global__ void __launch_bounds__(256) pack_act_gp_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
-                                                          __nv_bfloat16* __restrict__ lo, int N, int D, int H, int W, int C, int G) {
+                                                          __nv_bfloat16* __restrict__ lo, int N, int D, int H, int W, int C, int G, int P) {
   const long long HW = (long long)H * W;
-  const long long vox_p = (long long)N * (D + 2) * HW;      // padded voxel count per group
+  const long long vox_p = (long long)N * (D + 2 * P) * HW;  // padded voxel count per group (P zero planes on each side)
   const long long total = vox_p * G;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long pv = i % vox_p;
     const int g = (int)(i / vox_p);
     const long long plane = pv / HW;                        // n*(D+2) + d'
-    const int dp = (int)(plane % (D + 2));
-    const int n = (int)(plane / (D + 2));
+    const int dp = (int)(plane % (D + 2 * P));
+    const int n = (int)(plane / (D + 2 * P));
     __align__(16) __nv_bfloat16 h[8];
     __align__(16) __nv_bfloat16 l[8];
-    if (dp == 0 || dp == D + 1) {
+    if (dp < P || dp >= D + P) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) { h[j] = __float2bfloat16_rn(0.f); l[j] = h[j]; }
     } else {
-      const long long src = (((long long)n * D + (dp - 1)) * HW + (pv % HW)) * C + g * 8;
+      const long long src = (((long long)n * D + (dp - P)) * HW + (pv % HW)) * C + g * 8;
       float v[8];
       if (g * 8 + 8 <= C && (C & 3) == 0) {
         float4 a = __ldg(reinterpret_cast<const float4*>(x + src));
@@ -331,7 +352,7 @@ __global__ void __launch_bounds__(256) pack_act_gp_kernel(const float* __restric
 // (channel group, tap) list, i.e. channels 8 (e / 27) .. + 7 at tap e % 27.  mode 1 = data gradient (rows = ci, k = co,
 // taps mirrored).
 __global__ void __launch_bounds__(256) pack_w_halo_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout,
-                                                          int Cin, int Npad, int G, int nsteps, int parts, int mode) {
+                                                          int Cin, int Npad, int G, int nsteps, int parts, int mode, int T) {
   const long long total = (long long)nsteps * 2 * parts * Npad * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     long long r = i;
@@ -340,15 +361,15 @@ __global__ void __launch_bounds__(256) pack_w_halo_kernel(const float* __restric
     const int part = (int)(r % parts); r /= parts;
     const int kh = (int)(r % 2); r /= 2;
     int ent = 2 * (int)r + kh;
-    if ((G & 1) && (int)r == nsteps - 1) ent = kh ? 27 * G - 1 : 27 * G;      // odd entry count: (zero weights, last entry), see hl_a_word
-    const int g = ent / 27;
+    if (((T * G) & 1) && (int)r == nsteps - 1) ent = kh ? T * G - 1 : T * G;      // odd entry count: (zero weights, last entry), see hl_a_word
+    const int g = ent / T;
     const int k = g * 8 + e8;
-    int tap = ent - g * 27;
+    int tap = ent - g * T;
     int co, ci;
     if (mode == 0) { co = row; ci = k; }
-    else { co = k; ci = row; tap = 26 - tap; }
+    else { co = k; ci = row; tap = T - 1 - tap; }
     float v = 0.f;
-    if (g < G && co < Cout && ci < Cin) v = w[((long long)co * Cin + ci) * 27 + tap];
+    if (g < G && co < Cout && ci < Cin) v = w[((long long)co * Cin + ci) * T + tap];
     __nv_bfloat16 h, l;
     split_bf16(v, h, l);
     out[i] = part == 0 ? h : l;
@@ -361,24 +382,24 @@ __global__ void __launch_bounds__(256) pack_w_halo_kernel(const float* __restric
 // banks.  Blocks [ntile_blocks, gridDim.x) zero the d = -1 / D padding planes.
 __global__ void __launch_bounds__(256) pack_act_gp_tiled_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                                                                 __nv_bfloat16* __restrict__ lo, int N, int D, int H, int W, int C, int G,
-                                                                int TV, long long ntile_blocks) {
+                                                                int TV, long long ntile_blocks, int P) {
   extern __shared__ __align__(16) float tile[];
   const long long HW = (long long)H * W;
   const long long DHW = (long long)D * HW;
   const long long vox = (long long)N * DHW;                  // real voxels
-  const long long vox_p = (long long)N * (D + 2) * HW;       // padded voxels per group
+  const long long vox_p = (long long)N * (D + 2 * P) * HW;   // padded voxels per group
   const int Cs = G * 8 + 4;
-  if ((long long)blockIdx.x >= ntile_blocks) {               // zero planes: (g, n, first/last, hw) rows of 16 bytes
-    const long long total = (long long)G * N * 2 * HW;
+  if ((long long)blockIdx.x >= ntile_blocks) {               // zero planes: (g, n, 2 P planes, hw) rows of 16 bytes
+    const long long total = (long long)G * N * 2 * P * HW;
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     for (long long i = ((long long)blockIdx.x - ntile_blocks) * blockDim.x + threadIdx.x; i < total;
          i += (long long)(gridDim.x - ntile_blocks) * blockDim.x) {
       const long long hw = i % HW;
       long long r = i / HW;
-      const int which = (int)(r % 2); r /= 2;
+      const int which = (int)(r % (2 * P)); r /= 2 * P;
       const int n = (int)(r % N);
       const int g = (int)(r / N);
-      const long long pos = ((long long)n * (D + 2) + (which ? D + 1 : 0)) * HW + hw;
+      const long long pos = ((long long)n * (D + 2 * P) + (which < P ? which : D + which)) * HW + hw;
       reinterpret_cast<uint4*>(hi)[(long long)g * vox_p + pos] = z;
       if (lo) reinterpret_cast<uint4*>(lo)[(long long)g * vox_p + pos] = z;
     }
@@ -406,59 +427,67 @@ __global__ void __launch_bounds__(256) pack_act_gp_tiled_kernel(const float* __r
     for (int j = 0; j < 8; ++j) split_bf16(f[j], h[j], l[j]);
     const long long gv = v0 + v;
     const long long n = gv / DHW, rem = gv - n * DHW;
-    const long long pos = (n * (D + 2) + 1) * HW + rem;
+    const long long pos = (n * (D + 2 * P) + P) * HW + rem;
     reinterpret_cast<uint4*>(hi)[(long long)g * vox_p + pos] = *reinterpret_cast<const uint4*>(h);
     if (lo) reinterpret_cast<uint4*>(lo)[(long long)g * vox_p + pos] = *reinterpret_cast<const uint4*>(l);
   }
 }
 
 static int launch_pack_w_halo(const float* w, __nv_bfloat16* out, int Cout, int Cin, int Npad, int G, int nsteps, int parts, int mode,
-                              cudaStream_t st) {
+                              int T, cudaStream_t st) {
   const long long wt = (long long)nsteps * 2 * parts * Npad * 8;
-  pack_w_halo_kernel<<<(unsigned)std::min<long long>(cdiv(wt, 256), 4LL * num_sms()), 256, 0, st>>>(w, out, Cout, Cin, Npad, G, nsteps, parts, mode);
+  pack_w_halo_kernel<<<(unsigned)std::min<long long>(cdiv(wt, 256), 4LL * num_sms()), 256, 0, st>>>(w, out, Cout, Cin, Npad, G, nsteps, parts, mode, T);
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;
 }
 
 // host-side launcher (also used by conv_tc_hx.cu, conv_tc_wgrad_ds.cu, conv_fused.cu)
+int launch_pack_act_gp_pad(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int C, int G, int P, cudaStream_t st);
 int launch_pack_act_gp(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int C, int G, cudaStream_t st) {
+  return launch_pack_act_gp_pad(x, hi, lo, N, D, H, W, C, G, 1, st);
+}
+// P zero planes before and after every sample (P = 1 for 3^3 kernels, 2 for 5^3)
+int launch_pack_act_gp_pad(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int C, int G, int P, cudaStream_t st) {
   const char* e = getenv("CFUN_PACK_TILED");          // "0": the one-thread-per-row kernel (A/B measurements)
   const int Cs = G * 8 + 4;
   int TV = std::min(128, (12288 / Cs) / 32 * 32);
   if ((C & 3) == 0 && C >= 32 && TV >= 32 && !(e && e[0] == '0')) {     // below 32 channels the row-per-thread kernel is faster (20 ch: 0.154 vs 0.178 ms)
     const long long vox = (long long)N * D * H * W;
     const long long ntile = cdiv(vox, TV);
-    const long long zrows = (long long)G * N * 2 * H * W;
+    const long long zrows = (long long)G * N * 2 * P * H * W;
     const long long nz = std::max<long long>(1, std::min<long long>(cdiv(zrows, 256), 2LL * num_sms()));
-    pack_act_gp_tiled_kernel<<<(unsigned)(ntile + nz), 256, (size_t)TV * Cs * sizeof(float), st>>>(x, hi, lo, N, D, H, W, C, G, TV, ntile);
+    pack_act_gp_tiled_kernel<<<(unsigned)(ntile + nz), 256, (size_t)TV * Cs * sizeof(float), st>>>(x, hi, lo, N, D, H, W, C, G, TV, ntile, P);
     CFUN_LAUNCH_CHECK();
     return CFUN_OK;
   }
-  long long total = (long long)G * N * (D + 2) * H * W;
-  pack_act_gp_kernel<<<(unsigned)std::min<long long>(cdiv(total, 256), 32LL * num_sms()), 256, 0, st>>>(x, hi, lo, N, D, H, W, C, G);
+  long long total = (long long)G * N * (D + 2 * P) * H * W;
+  pack_act_gp_kernel<<<(unsigned)std::min<long long>(cdiv(total, 256), 32LL * num_sms()), 256, 0, st>>>(x, hi, lo, N, D, H, W, C, G, P);
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;
 }
 
 struct HlPlan {
-  int Cs, Ct, N, D, H, W, Kp, Gp, G, nsteps, Npad, tmem_cols, resident, sps, bstages;
+  int Cs, Ct, N, D, H, W, Kp, Gp, G, nsteps, Npad, tmem_cols, resident, sps, bstages, KS;
   size_t off_ah, off_al, off_w, total, act_bytes, w_bytes, smem;
 };
 
 static bool make_hl_plan(const cfun_conv3d_desc* d, int pass, HlPlan& pl) {
   if (!d || d->sD != 1 || d->sH != 1 || d->sW != 1) return false;
-  if (d->kD != 3 || d->kH != 3 || d->kW != 3 || d->pD != 1 || d->pH != 1 || d->pW != 1) return false;
+  if (d->kD != d->kH || d->kD != d->kW || (d->kD != 3 && d->kD != 5)) return false;
+  if (d->pD != d->kD / 2 || d->pH != d->kD / 2 || d->pW != d->kD / 2) return false;
+  pl.KS = d->kD;
   if (pass == CFUN_PASS_FWD) { pl.Cs = d->Cin; pl.Ct = d->Cout; }
   else if (pass == CFUN_PASS_BWD_DATA) { pl.Cs = d->Cout; pl.Ct = d->Cin; }
   else return false;
   pl.N = d->N; pl.D = d->Din; pl.H = d->Hin; pl.W = d->Win;
   if (pl.H < 8 || pl.W < 8) return false;
+  const int T = pl.KS * pl.KS * pl.KS, HL_PLANE = hl_plane(pl.KS);
   if ((long long)pl.W * 8 > 0x7fffffffLL) return false;
   pl.Kp = (int)align_up((size_t)pl.Cs, 16);
   pl.Gp = pl.Kp / 8;                                       // groups in the pack (16-channel granularity, shared with hx / wgrad)
   pl.G = (int)cdiv(pl.Cs, 8);                              // groups that hold real channels: the only ones loaded and multiplied
-  if (pl.G > HL_MAX_G) return false;
-  pl.nsteps = (27 * pl.G + 1) / 2;
+  if (pl.G > (pl.KS == 3 ? HL_MAX_G : 1)) return false;     // 5^3: one channel group (the 8 -> 8 out_upscale_conv)
+  pl.nsteps = (T * pl.G + 1) / 2;
   pl.Npad = (int)align_up((size_t)pl.Ct, 16);
   if (pl.Npad > 128) return false;                         // [hi | lo] accumulator pairs, double buffered: 4 * Npad <= 512
   int cols = 32;
@@ -479,7 +508,7 @@ static bool make_hl_plan(const cfun_conv3d_desc* d, int pass, HlPlan& pl) {
     if (pl.bstages < 2) return false;
     pl.smem = 2048 + a_bytes + (size_t)pl.bstages * pl.sps * step_bytes;
   }
-  pl.act_bytes = align_up((size_t)pl.Gp * pl.N * (pl.D + 2) * pl.H * pl.W * 16, 1024);
+  pl.act_bytes = align_up((size_t)pl.Gp * pl.N * (pl.D + 2 * (pl.KS / 2)) * pl.H * pl.W * 16, 1024);
   pl.off_ah = 0; pl.off_al = pl.act_bytes; pl.off_w = 2 * pl.act_bytes;
   pl.total = 2 * pl.act_bytes + pl.w_bytes + 2048;
   return true;
@@ -492,6 +521,7 @@ bool hl_supported(const cfun_conv3d_desc* d, int pass) {
   if (x && x[0] == 'o') return false;
   HlPlan pl;
   if (!make_hl_plan(d, pass, pl)) return false;
+  if (pl.KS == 5) return true;            // any channel counts up to 8 (8 -> 8 heart, 3 -> 3 LiTS): the pack has a scalar path
   return pl.Cs >= 16 && (pl.Cs & 3) == 0 && pl.Ct >= 8;
 }
 size_t hl_workspace(const cfun_conv3d_desc* d, int pass) {
@@ -525,18 +555,20 @@ int hl_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const floa
   __nv_bfloat16* wp = reinterpret_cast<__nv_bfloat16*>(base + pl.off_w);
   {
     if (!(ext_hi && ext_ready)) {
-      int prc = launch_pack_act_gp(src, ah, split ? al : nullptr, pl.N, pl.D, pl.H, pl.W, pl.Cs, pl.Gp, st);
+      int prc = launch_pack_act_gp_pad(src, ah, split ? al : nullptr, pl.N, pl.D, pl.H, pl.W, pl.Cs, pl.Gp, pl.KS / 2, st);
       if (prc != CFUN_OK) return prc;
     }
-    int prc = launch_pack_w_halo(w, wp, d->Cout, d->Cin, pl.Npad, pl.G, pl.nsteps, parts, pass == CFUN_PASS_BWD_DATA ? 1 : 0, st);
+    int prc = launch_pack_w_halo(w, wp, d->Cout, d->Cin, pl.Npad, pl.G, pl.nsteps, parts, pass == CFUN_PASS_BWD_DATA ? 1 : 0,
+                                 pl.KS * pl.KS * pl.KS, st);
     if (prc != CFUN_OK) return prc;
   }
   CUtensorMap mh, ml;
   for (int part = 0; part < 2; ++part) {
     void* b = part == 0 ? (void*)ah : (void*)(split ? al : ah);
-    cuuint64_t dims[4] = {(cuuint64_t)pl.W * 8, (cuuint64_t)pl.H, (cuuint64_t)pl.N * (pl.D + 2), (cuuint64_t)pl.Gp};
-    cuuint64_t strides[3] = {(cuuint64_t)pl.W * 16, (cuuint64_t)pl.H * pl.W * 16, (cuuint64_t)pl.N * (pl.D + 2) * pl.H * pl.W * 16};
-    cuuint32_t box[4] = {HL_WH * 8, HL_HH, 3, 1};
+    const cuuint64_t planes = (cuuint64_t)pl.N * (pl.D + 2 * (pl.KS / 2));
+    cuuint64_t dims[4] = {(cuuint64_t)pl.W * 8, (cuuint64_t)pl.H, planes, (cuuint64_t)pl.Gp};
+    cuuint64_t strides[3] = {(cuuint64_t)pl.W * 16, (cuuint64_t)pl.H * pl.W * 16, planes * pl.H * pl.W * 16};
+    cuuint32_t box[4] = {(cuuint32_t)hl_wh(pl.KS) * 8, (cuuint32_t)hl_hh(pl.KS), (cuuint32_t)pl.KS, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     CUresult r = get_tensor_map_encoder()(part == 0 ? &mh : &ml, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, b, dims, strides, box, es,
                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -554,23 +586,24 @@ int hl_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const floa
   p.resident = pl.resident; p.bstages = pl.bstages;
   p.wpack = reinterpret_cast<const uint8_t*>(wp);
   const unsigned grid = (unsigned)std::min<long long>(p.ntiles, num_sms());
-#define CFUN_HL_LAUNCH(GG)                                                                                                   \
-  case GG: {                                                                                                                 \
-    static bool attr_set = false;                                                                                            \
-    if (!attr_set) {                                                                                                         \
-      CFUN_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<GG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));     \
-      CFUN_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<GG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));    \
-      attr_set = true;                                                                                                       \
-    }                                                                                                                        \
-    timing_begin(st);                                                                                                        \
-    if (split) conv_tc_halo_kernel<GG, true><<<grid, HL_THREADS, pl.smem, st>>>(mh, ml, p);                                  \
-    else conv_tc_halo_kernel<GG, false><<<grid, HL_THREADS, pl.smem, st>>>(mh, ml, p);                                       \
-    timing_end(st);                                                                                                          \
-    break;                                                                                                                   \
+#define CFUN_HL_LAUNCH(GG, KK)                                                                                                  \
+  case GG + 16 * KK: {                                                                                                          \
+    static bool attr_set = false;                                                                                               \
+    if (!attr_set) {                                                                                                            \
+      CFUN_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<GG, true, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));  \
+      CFUN_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<GG, false, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      attr_set = true;                                                                                                          \
+    }                                                                                                                           \
+    timing_begin(st);                                                                                                           \
+    if (split) conv_tc_halo_kernel<GG, true, KK><<<grid, HL_THREADS, pl.smem, st>>>(mh, ml, p);                                 \
+    else conv_tc_halo_kernel<GG, false, KK><<<grid, HL_THREADS, pl.smem, st>>>(mh, ml, p);                                      \
+    timing_end(st);                                                                                                             \
+    break;                                                                                                                      \
   }
-  switch (pl.G) {
-    CFUN_HL_LAUNCH(2) CFUN_HL_LAUNCH(3) CFUN_HL_LAUNCH(4) CFUN_HL_LAUNCH(5) CFUN_HL_LAUNCH(6) CFUN_HL_LAUNCH(7) CFUN_HL_LAUNCH(8)
-    default: set_error("conv3d halo: unsupported channel group count %d", pl.G); return CFUN_ERR_INVALID;
+  switch (pl.G + 16 * pl.KS) {
+    CFUN_HL_LAUNCH(2, 3) CFUN_HL_LAUNCH(3, 3) CFUN_HL_LAUNCH(4, 3) CFUN_HL_LAUNCH(5, 3) CFUN_HL_LAUNCH(6, 3) CFUN_HL_LAUNCH(7, 3)
+    CFUN_HL_LAUNCH(8, 3) CFUN_HL_LAUNCH(1, 5)
+    default: set_error("conv3d halo: unsupported channel group count %d for kernel size %d", pl.G, pl.KS); return CFUN_ERR_INVALID;
   }
 #undef CFUN_HL_LAUNCH
   CFUN_LAUNCH_CHECK();

@@ -25,11 +25,13 @@ namespace cfun {
 constexpr int DS_THREADS = 192;
 constexpr int DS_WT = 8;                         // tile width (voxels) = one K atom
 constexpr int DS_LINE = DS_WT * 16;              // 128 B: one line of one channel group
-constexpr int DS_MAX_GT = 5;                     // dY channel groups per M tile: 5 x 3 kd = 15 of 16 row groups
+constexpr int DS_MAX_GT = 5;                     // dY channel groups per M tile: 5 x 3 kd = 15 of 16 row groups (3 x 5 kd for 5^3 kernels)
 constexpr int DS_MAX_STAGES = 6;
 
 int launch_pack_act_gp(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int C, int G,
                        cudaStream_t st);   // conv_tc_halo.cu
+int launch_pack_act_gp_pad(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int C, int G, int P,
+                           cudaStream_t st);
 int simt_bias_grad(const float* dy, long long M, int C, float* dbias, cudaStream_t st);
 
 __device__ __forceinline__ uint64_t make_desc_mn_ds(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -53,8 +55,9 @@ struct DsParams {
   int Gt;                     // dY channel groups per M tile (<= 5)
   int Gx;                     // X channel groups of this launch's Cin slice
   int slices;                 // Cin slices of Gx groups = gridDim.y (slice s: input channels from s * 8 Gx)
+  int KS;                     // kernel size (3 or 5): KS dY planes are stacked along M, taps = KS^3, zero padding KS / 2
   int nkw, nkh;               // stacked kw copies / kh views
-  int kw_list[3], kh_list[3];
+  int kw_list[5], kh_list[5];
   int kd_mask;                // bit kd set = this kd plane of dW is wanted
   int Ntot;                   // MMA N: 8 * Gx * nkw rounded up to 16 (the padding columns read whatever follows, never stored)
   int tilesH, tilesW;
@@ -109,14 +112,15 @@ conv_tc_wgrad_ds_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid
         const int n = (int)(t / p.D);
         mbar_arrive_expect_tx(&full_bar[slot], (uint32_t)(parts * (p.y_bytes + p.x_bytes)));
         uint8_t* sb = ring + (size_t)slot * p.stage_bytes;
-        const int plane0 = n * (p.D + 2) + pl;           // padded index of dY plane pl-1 (and of X plane pl, minus one)
+        const int pad = p.KS >> 1;
+        const int plane0 = n * (p.D + 2 * pad) + pl;     // padded index of dY plane pl - pad (and of X plane pl, minus pad)
         for (int part = 0; part < parts; ++part) {
           tma_load_4d_ds(part == 0 ? &map_yh : &map_yl, &full_bar[slot], sb + (size_t)part * p.y_bytes, wb * DS_WT * 8,
-                         hb * p.HT, plane0, g0);
+                         hb * p.HT, plane0, g0);        // box: 8 w x HT h x KS planes x Gt groups
           uint8_t* xb = sb + (size_t)parts * p.y_bytes + (size_t)part * p.x_bytes;
           for (int k = 0; k < p.nkw; ++k)
             tma_load_4d_ds(part == 0 ? &map_xh : &map_xl, &full_bar[slot], xb + (size_t)k * p.Gx * p.xp,
-                           (wb * DS_WT - 1 + p.kw_list[k]) * 8, hb * p.HT - 1, plane0 + 1, ci0 >> 3);
+                           (wb * DS_WT - pad + p.kw_list[k]) * 8, hb * p.HT - pad, plane0 + pad, ci0 >> 3);
         }
       }
     }
@@ -164,14 +168,15 @@ conv_tc_wgrad_ds_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid
     if (leader) umma_commit(tmem_full_bar);
     __syncwarp();
   } else {
-    // accumulator row = (channel group g, d-shift s, channel): row group rg = 3 g + s, s <-> dY plane p-1+s <-> kd = 2 - s
+    // accumulator row = (channel group g, d-shift s, channel): row group rg = KS g + s, s <-> dY plane p-pad+s <-> kd = KS-1-s
     // accumulator column (within the kh block) = (kw copy, channel group, channel)
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const int rg = row >> 3;
-    const int g = rg / 3, s = rg - g * 3;
+    const int g = rg / p.KS, s = rg - g * p.KS;
     const int co = (g0 + g) * 8 + (row & 7);
-    const int kd = 2 - s;
+    const int kd = p.KS - 1 - s;
+    const int T = p.KS * p.KS * p.KS;
     const bool row_ok = g < p.Gt && co < p.Cout && ((p.kd_mask >> kd) & 1);
     const int ncopy = p.Gx * 8;
     mbar_wait(tmem_full_bar, 0, 430);
@@ -189,8 +194,8 @@ conv_tc_wgrad_ds_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid
               const int k = col / ncopy;
               const int ci = ci0 + (col - k * ncopy);
               if (k < p.nkw && ci < p.Cin) {
-                const int tap = kd * 9 + p.kh_list[t] * 3 + p.kw_list[k];
-                atomicAdd(p.dw + ((long long)co * p.Cin + ci) * 27 + tap, __uint_as_float(r[i]));
+                const int tap = (kd * p.KS + p.kh_list[t]) * p.KS + p.kw_list[k];
+                atomicAdd(p.dw + ((long long)co * p.Cin + ci) * T + tap, __uint_as_float(r[i]));
               }
             }
           }
@@ -207,17 +212,21 @@ conv_tc_wgrad_ds_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid
 }
 
 struct DsPlan {
-  int Gy_total, Gt, Gx, mtiles, stages, tmem_cols, HT, Ntot, nkw, nkh;
+  int Gy_total, Gt, Gx, mtiles, stages, tmem_cols, HT, Ntot, nkw, nkh, KS;
   int Gx_total, slices;        // input channels are processed in `slices` launches of Gx groups
   int yp, xp, y_bytes, x_bytes, stage_bytes;
   size_t act_y, act_x, off_yh, off_yl, off_xh, off_xl, total, smem;
 };
 
-static bool make_ds_plan(const cfun_conv3d_desc* d, DsPlan& pl, int nkh = 3, int nkw = 3) {
+static bool make_ds_plan(const cfun_conv3d_desc* d, DsPlan& pl, int nkh = 0, int nkw = 0) {
   if (!d || d->sD != 1 || d->sH != 1 || d->sW != 1) return false;
-  if (d->kD != 3 || d->kH != 3 || d->kW != 3 || d->pD != 1 || d->pH != 1 || d->pW != 1) return false;
+  if (d->kD != d->kH || d->kD != d->kW || (d->kD != 3 && d->kD != 5)) return false;
+  if (d->pD != d->kD / 2 || d->pH != d->kD / 2 || d->pW != d->kD / 2) return false;
   if (d->Hin < 8 || d->Win < 8) return false;
-  if (nkh < 1 || nkh > 3 || nkw < 1 || nkw > 3) return false;
+  pl.KS = d->kD;
+  if (nkh == 0) nkh = pl.KS;
+  if (nkw == 0) nkw = pl.KS;
+  if (nkh < 1 || nkh > pl.KS || nkw < 1 || nkw > pl.KS) return false;
   pl.nkh = nkh; pl.nkw = nkw;
   pl.Gy_total = (int)cdiv(d->Cout, 8);
   pl.Gx_total = (int)align_up((size_t)d->Cin, 16) / 8;    // groups in the X pack (shared with the forward: 16-channel chunks)
@@ -236,14 +245,14 @@ static bool make_ds_plan(const cfun_conv3d_desc* d, DsPlan& pl, int nkh = 3, int
   int cols = 32;
   while (cols < nkh * pl.Ntot) cols <<= 1;
   pl.tmem_cols = cols;
-  pl.mtiles = (int)cdiv(pl.Gy_total, DS_MAX_GT);
+  pl.mtiles = (int)cdiv(pl.Gy_total, 16 / pl.KS);           // KS stacked planes per group: 5 groups (3^3) or 3 groups (5^3) per M tile
   pl.Gt = (int)cdiv(pl.Gy_total, pl.mtiles);              // balanced M tiles (10 groups -> 2 x 5, 6 -> 2 x 3)
   // tile height: 16 lines when at least 3 pipeline stages fit, else 8
   const size_t budget = 227 * 1024 - 2048;
   pl.HT = 0;
   for (int ht = (d->Hin >= 16 ? 16 : 8); ht >= 8; ht -= 8) {
-    const int yp = ht * DS_LINE, xp = (ht + 2) * DS_LINE;
-    const size_t yb = (size_t)pl.Gt * 3 * yp, xb = (size_t)nkw * pl.Gx * xp;
+    const int yp = ht * DS_LINE, xp = (ht + pl.KS - 1) * DS_LINE;
+    const size_t yb = (size_t)pl.Gt * pl.KS * yp, xb = (size_t)nkw * pl.Gx * xp;
     const size_t stage = align_up(2 * (yb + xb), 1024);
     // M = 128 always reads 16 dY planes and N = Ntot may read one X plane more than was loaded: keep that inside the allocation
     const size_t slack = (size_t)16 * yp + xp;
@@ -256,14 +265,18 @@ static bool make_ds_plan(const cfun_conv3d_desc* d, DsPlan& pl, int nkh = 3, int
     }
   }
   if (pl.HT == 0) return false;
-  pl.act_y = align_up((size_t)pl.Gy_total * d->N * (d->Dout + 2) * d->Hout * d->Wout * 16, 1024);
-  pl.act_x = align_up((size_t)pl.Gx_total * d->N * (d->Din + 2) * d->Hin * d->Win * 16, 1024);
+  const int pad = pl.KS / 2;
+  pl.act_y = align_up((size_t)pl.Gy_total * d->N * (d->Dout + 2 * pad) * d->Hout * d->Wout * 16, 1024);
+  pl.act_x = align_up((size_t)pl.Gx_total * d->N * (d->Din + 2 * pad) * d->Hin * d->Win * 16, 1024);
   pl.off_yh = 0; pl.off_yl = pl.act_y; pl.off_xh = 2 * pl.act_y; pl.off_xl = 2 * pl.act_y + pl.act_x;
   pl.total = 2 * pl.act_y + 2 * pl.act_x + 2048;
   return true;
 }
 
-static bool ds_shape_ok(const cfun_conv3d_desc* d) { return d->Cin >= 16 && (d->Cin & 3) == 0 && d->Cout >= 8 && (d->Cout & 3) == 0; }
+static bool ds_shape_ok(const cfun_conv3d_desc* d) {
+  if (d->kD == 5) return d->Cin <= 16 && d->Cout >= 8 && (d->Cout & 3) == 0;      // out_upscale_conv (8 -> 8): the pack has a scalar path
+  return d->Cin >= 16 && (d->Cin & 3) == 0 && d->Cout >= 8 && (d->Cout & 3) == 0;
+}
 
 bool ds_supported(const cfun_conv3d_desc* d) {
   const char* e = getenv("CFUN_TC_WGDS");        // "0" falls back to the channel-major kernel (A/B measurements)
@@ -290,14 +303,14 @@ static int encode_gp_map_ds(CUtensorMap* m, void* base, int W, int H, long long 
   return CFUN_OK;
 }
 
-// tap_mask (bits kh*3+kw) must be a product set {kh} x {kw}
-static bool split_tap_mask(int tap_mask, int* kh_list, int& nkh, int* kw_list, int& nkw) {
+// tap_mask (bits kh*KS+kw) must be a product set {kh} x {kw}
+static bool split_tap_mask(int tap_mask, int KS, int* kh_list, int& nkh, int* kw_list, int& nkw) {
   int khm = 0, kwm = 0;
-  for (int t = 0; t < 9; ++t) if ((tap_mask >> t) & 1) { khm |= 1 << (t / 3); kwm |= 1 << (t % 3); }
+  for (int t = 0; t < KS * KS; ++t) if ((tap_mask >> t) & 1) { khm |= 1 << (t / KS); kwm |= 1 << (t % KS); }
   nkh = nkw = 0;
-  for (int i = 0; i < 3; ++i) { kh_list[i] = kw_list[i] = 0; }
-  for (int i = 0; i < 3; ++i) { if ((khm >> i) & 1) kh_list[nkh++] = i; if ((kwm >> i) & 1) kw_list[nkw++] = i; }
-  for (int a = 0; a < nkh; ++a) for (int b = 0; b < nkw; ++b) if (!((tap_mask >> (kh_list[a] * 3 + kw_list[b])) & 1)) return false;
+  for (int i = 0; i < 5; ++i) { kh_list[i] = kw_list[i] = 0; }
+  for (int i = 0; i < KS; ++i) { if ((khm >> i) & 1) kh_list[nkh++] = i; if ((kwm >> i) & 1) kw_list[nkw++] = i; }
+  for (int a = 0; a < nkh; ++a) for (int b = 0; b < nkw; ++b) if (!((tap_mask >> (kh_list[a] * KS + kw_list[b])) & 1)) return false;
   return nkh > 0 && nkw > 0;
 }
 
@@ -305,19 +318,21 @@ static bool split_tap_mask(int tap_mask, int* kh_list, int& nkh, int* kw_list, i
 // gy_pack: channel groups the dY pack was written with (>= Gy_total; the fused backward shares the data gradient's pack,
 // whose group count is rounded up to a multiple of 2 -- the extra group is zeros)
 int ds_launch(const cfun_conv3d_desc* d, const DsPlan& pl, __nv_bfloat16* yh, __nv_bfloat16* yl, __nv_bfloat16* xh,
-              __nv_bfloat16* xl, float* dw, bool split, int gy_pack, cudaStream_t st, int tap_mask = 0x1FF, int kd_mask = 7) {
+              __nv_bfloat16* xl, float* dw, bool split, int gy_pack, cudaStream_t st, int tap_mask = -1, int kd_mask = -1) {
   CUtensorMap myh, myl, mxh, mxl;
   int rc;
-  const long long planes = (long long)d->N * (d->Din + 2);
-  if ((rc = encode_gp_map_ds(&myh, yh, d->Wout, d->Hout, planes, gy_pack, DS_WT * 8, pl.HT, 3, pl.Gt)) != CFUN_OK) return rc;
-  if ((rc = encode_gp_map_ds(&myl, split ? yl : yh, d->Wout, d->Hout, planes, gy_pack, DS_WT * 8, pl.HT, 3, pl.Gt)) != CFUN_OK) return rc;
-  if ((rc = encode_gp_map_ds(&mxh, xh, d->Win, d->Hin, planes, pl.Gx_total, DS_WT * 8, pl.HT + 2, 1, pl.Gx)) != CFUN_OK) return rc;
-  if ((rc = encode_gp_map_ds(&mxl, split ? xl : xh, d->Win, d->Hin, planes, pl.Gx_total, DS_WT * 8, pl.HT + 2, 1, pl.Gx)) != CFUN_OK) return rc;
+  if (tap_mask < 0) tap_mask = (1 << (pl.KS * pl.KS)) - 1;
+  if (kd_mask < 0) kd_mask = (1 << pl.KS) - 1;
+  const long long planes = (long long)d->N * (d->Din + 2 * (pl.KS / 2));
+  if ((rc = encode_gp_map_ds(&myh, yh, d->Wout, d->Hout, planes, gy_pack, DS_WT * 8, pl.HT, pl.KS, pl.Gt)) != CFUN_OK) return rc;
+  if ((rc = encode_gp_map_ds(&myl, split ? yl : yh, d->Wout, d->Hout, planes, gy_pack, DS_WT * 8, pl.HT, pl.KS, pl.Gt)) != CFUN_OK) return rc;
+  if ((rc = encode_gp_map_ds(&mxh, xh, d->Win, d->Hin, planes, pl.Gx_total, DS_WT * 8, pl.HT + pl.KS - 1, 1, pl.Gx)) != CFUN_OK) return rc;
+  if ((rc = encode_gp_map_ds(&mxl, split ? xl : xh, d->Win, d->Hin, planes, pl.Gx_total, DS_WT * 8, pl.HT + pl.KS - 1, 1, pl.Gx)) != CFUN_OK) return rc;
 
   DsParams p;
   p.N = d->N; p.D = d->Din; p.H = d->Hin; p.W = d->Win; p.Cout = d->Cout; p.Cin = d->Cin;
-  p.HT = pl.HT; p.Gt = pl.Gt; p.Gx = pl.Gx; p.Ntot = pl.Ntot;
-  CFUN_CHECK_ARG(split_tap_mask(tap_mask, p.kh_list, p.nkh, p.kw_list, p.nkw));
+  p.HT = pl.HT; p.Gt = pl.Gt; p.Gx = pl.Gx; p.Ntot = pl.Ntot; p.KS = pl.KS;
+  CFUN_CHECK_ARG(split_tap_mask(tap_mask, pl.KS, p.kh_list, p.nkh, p.kw_list, p.nkw));
   CFUN_CHECK_ARG(p.nkh == pl.nkh && p.nkw == pl.nkw);
   p.kd_mask = kd_mask;
   p.tilesH = (int)cdiv(d->Hin, pl.HT); p.tilesW = (int)cdiv(d->Win, DS_WT);
@@ -360,9 +375,9 @@ int ds_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* d
   __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(base + pl.off_xh);
   __nv_bfloat16* xl = reinterpret_cast<__nv_bfloat16*>(base + pl.off_xl);
   int prc;
-  if ((prc = launch_pack_act_gp(dy, yh, split ? yl : nullptr, d->N, d->Dout, d->Hout, d->Wout, d->Cout, pl.Gy_total, st)) != CFUN_OK) return prc;
-  if ((prc = launch_pack_act_gp(x, xh, split ? xl : nullptr, d->N, d->Din, d->Hin, d->Win, d->Cin, pl.Gx_total, st)) != CFUN_OK) return prc;
-  CFUN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * d->Cin * 27, st));
+  if ((prc = launch_pack_act_gp_pad(dy, yh, split ? yl : nullptr, d->N, d->Dout, d->Hout, d->Wout, d->Cout, pl.Gy_total, pl.KS / 2, st)) != CFUN_OK) return prc;
+  if ((prc = launch_pack_act_gp_pad(x, xh, split ? xl : nullptr, d->N, d->Din, d->Hin, d->Win, d->Cin, pl.Gx_total, pl.KS / 2, st)) != CFUN_OK) return prc;
+  CFUN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * d->Cin * pl.KS * pl.KS * pl.KS, st));
   int rc = ds_launch(d, pl, yh, yl, xh, xl, dw, split, pl.Gy_total, st);
   if (rc != CFUN_OK) return rc;
   if (dbias) return simt_bias_grad(dy, (long long)d->N * d->Dout * d->Hout * d->Wout, d->Cout, dbias, st);
@@ -384,8 +399,8 @@ int ds_bwd_weight_packed(const cfun_conv3d_desc* d, __nv_bfloat16* yh, __nv_bflo
 // and written (dw is zero elsewhere).  conv_s2d.cu uses it with {kh,kw in {0,1}} x {kd in {0,1}}: the 2x2x2 space-to-depth
 // kernel is the corresponding corner of a 3x3x3 / pad-1 kernel.
 static bool make_masked_plan(const cfun_conv3d_desc* d, int tap_mask, DsPlan& pl) {
-  int khl[3], kwl[3], nkh, nkw;
-  if (!split_tap_mask(tap_mask & 0x1FF, khl, nkh, kwl, nkw)) return false;
+  int khl[5], kwl[5], nkh, nkw;
+  if (!d || d->kD != 3 || !split_tap_mask(tap_mask & 0x1FF, 3, khl, nkh, kwl, nkw)) return false;
   return make_ds_plan(d, pl, nkh, nkw);
 }
 bool ds_masked_supported(const cfun_conv3d_desc* d, int tap_mask) {
