@@ -26,8 +26,8 @@ int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const floa
                int tapmask);
 int ds_bwd_weight_packed(const cfun_conv3d_desc* d, __nv_bfloat16* yh, __nv_bfloat16* yl, int gy_pack, __nv_bfloat16* xh,
                          __nv_bfloat16* xl, float* dw, cudaStream_t st);
-int launch_pack_act_gp(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int C, int G,
-                       cudaStream_t st);
+int launch_pack_act_gp_pad(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int C, int G, int P,
+                           cudaStream_t st);
 int simt_bias_grad(const float* dy, long long M, int C, float* dbias, cudaStream_t st);
 
 static bool fused_ok(const cfun_conv3d_desc* d) {
@@ -89,7 +89,8 @@ extern "C" int cfun_conv3d_bwd_fused(const cfun_conv3d_desc* d, const void* xpac
   const int gy = (int)align_up((size_t)d->Cout, 16) / 8;
   int rc;
   if (dx || dw) {
-    if ((rc = launch_pack_act_gp(dy, yh, yl, d->N, d->Dout, d->Hout, d->Wout, d->Cout, gy, st)) != CFUN_OK) return rc;
+    // zero planes before / after every sample = the kernel's padding (1 for 3^3, 2 for 5^3)
+    if ((rc = launch_pack_act_gp_pad(dy, yh, yl, d->N, d->Dout, d->Hout, d->Wout, d->Cout, gy, d->kD / 2, st)) != CFUN_OK) return rc;
   }
   if (dx) {
     if ((rc = run_conv(d, CFUN_PASS_BWD_DATA, nullptr, w, nullptr, dx, 0, iws, ws_bytes - (2 * act_y + (base - (size_t)ws)), yh, yl, true, st)) != CFUN_OK) return rc;

@@ -4,8 +4,8 @@
 // the generic implicit GEMM ran 3-6x off the bandwidth roofline (its tiles assume Cout >= 16).
 //   forward        y[v][co]  = sum_ci x[v][ci] w[co][ci] (+ bias, ReLU)   one thread per voxel pair, weights in shared memory
 //   data gradient  dx[v][ci] = sum_co dy[v][co] w[co][ci]                 same
-//   weight gradient dw[co][ci] = sum_v dy[v][co] x[v][ci]                 thread = (ci, co), persistent blocks, atomic flush
-//                                                                         (opt-in only: slower than the generic kernel)
+//   weight gradient dw[co][ci] = sum_v dy[v][co] x[v][ci]                 4 x 2 register tiles over shared-memory staged chunks,
+//                                                                         persistent blocks, one atomic flush
 // Arithmetic is plain fp32 FMA (the exact-mode CUDA-core path).
 #include "common.cuh"
 
@@ -89,22 +89,60 @@ __global__ void __launch_bounds__(PW_THREADS) pw_dgrad_kernel(const float* __res
   }
 }
 
-// thread = (ci, co) with ci fastest: x[v][ci] loads are coalesced over ci, dy[v][co] is a broadcast within each co group
-__global__ void __launch_bounds__(1024) pw_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
-                                                        long long M, int Cin, int Cout, long long rows_per_block) {
-  const int ci = threadIdx.x % Cin, co = threadIdx.x / Cin;
-  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  long long v = r0;
-  for (; v + 3 < r1; v += 4) {
-    const float x0 = __ldg(x + v * Cin + ci), x1 = __ldg(x + (v + 1) * Cin + ci), x2 = __ldg(x + (v + 2) * Cin + ci),
-                x3 = __ldg(x + (v + 3) * Cin + ci);
-    const float g0 = __ldg(dy + v * Cout + co), g1 = __ldg(dy + (v + 1) * Cout + co), g2 = __ldg(dy + (v + 2) * Cout + co),
-                g3 = __ldg(dy + (v + 3) * Cout + co);
-    a0 = fmaf(x0, g0, a0); a1 = fmaf(x1, g1, a1); a2 = fmaf(x2, g2, a2); a3 = fmaf(x3, g3, a3);
+// Round 2: register-tiled weight gradient.  A thread owns a 4 (ci) x 2 (co) tile of dW; a block stages PW2_V voxels of x and dy
+// in shared memory (coalesced float4 / float2 rows) and its thread groups -- one group = (Cin / 4) x (Cout_p / 2) threads --
+// walk disjoint voxel subsets of the chunk: one LDS.128 + one LDS.64 per 8 FMAs, so the kernel is bound by the HBM read of x
+// and dy (0.68 GB at 40 -> 8 @ 4 x 96^3) instead of by shared-memory instruction issue.  One atomic flush per block.
+constexpr int PW2_V = 128;
+__global__ void __launch_bounds__(PW_THREADS) pw_wgrad2_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                               float* __restrict__ dw, long long M, int Cin, int Cout, int Cop) {
+  extern __shared__ __align__(16) float sm[];            // xs[PW2_V][Cin] then gs[PW2_V][Cop]
+  float* xs = sm;
+  float* gs = sm + (size_t)PW2_V * Cin;
+  const int tci = Cin >> 2, tco = Cop >> 1;              // thread tiles along ci / co
+  const int gsize = tci * tco;
+  const int ngroups = PW_THREADS / gsize;
+  const int grp = threadIdx.x / gsize, tin = threadIdx.x - grp * gsize;
+  const bool active = grp < ngroups;
+  const int c4 = tin % tci, o2 = tin / tci;
+  float acc[2][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+  const long long nchunks = (M + PW2_V - 1) / PW2_V;
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const long long v0 = ch * PW2_V;
+    const int nv = (int)min((long long)PW2_V, M - v0);
+    __syncthreads();
+    const int x4 = nv * tci;
+    for (int i = threadIdx.x; i < x4; i += PW_THREADS)
+      reinterpret_cast<float4*>(xs)[i] = __ldg(reinterpret_cast<const float4*>(x + v0 * Cin) + i);
+    for (int i = threadIdx.x; i < nv * Cop; i += PW_THREADS) {
+      const int v = i / Cop, c = i - v * Cop;
+      gs[i] = c < Cout ? __ldg(dy + (v0 + v) * Cout + c) : 0.f;
+    }
+    __syncthreads();
+    if (active) {
+      for (int v = grp; v < nv; v += ngroups) {
+        const float4 xv = *reinterpret_cast<const float4*>(xs + (size_t)v * Cin + 4 * c4);
+        const float2 gv = *reinterpret_cast<const float2*>(gs + (size_t)v * Cop + 2 * o2);
+        acc[0][0] = fmaf(gv.x, xv.x, acc[0][0]); acc[0][1] = fmaf(gv.x, xv.y, acc[0][1]);
+        acc[0][2] = fmaf(gv.x, xv.z, acc[0][2]); acc[0][3] = fmaf(gv.x, xv.w, acc[0][3]);
+        acc[1][0] = fmaf(gv.y, xv.x, acc[1][0]); acc[1][1] = fmaf(gv.y, xv.y, acc[1][1]);
+        acc[1][2] = fmaf(gv.y, xv.z, acc[1][2]); acc[1][3] = fmaf(gv.y, xv.w, acc[1][3]);
+      }
+    }
   }
-  for (; v < r1; ++v) a0 = fmaf(__ldg(x + v * Cin + ci), __ldg(dy + v * Cout + co), a0);
-  atomicAdd(dw + (long long)co * Cin + ci, (a0 + a1) + (a2 + a3));
+  if (active) {
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int co = 2 * o2 + a;
+      if (co < Cout)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) atomicAdd(dw + (long long)co * Cin + 4 * c4 + b, acc[a][b]);
+    }
+  }
 }
 
 int simt_bias_grad(const float* dy, long long M, int C, float* dbias, cudaStream_t st);
@@ -116,9 +154,13 @@ bool pw_supported(const cfun_conv3d_desc* d, int pass) {
   if (d->Cout > 8 || d->Cout < 1 || (d->Cin & 3) || d->Cin > PW_MAX_CIN || d->Cin < 4) return false;
   // measured on B200 (tools/conv_cases.py pw): the forward wins everywhere (40->8 @ 4x96^3: 0.34 -> 0.18 ms), the data
   // gradient only for narrow inputs (0.46 -> 0.27 ms at 40 channels, slower from 80 up), the weight gradient nowhere
-  // (0.69 -> 1.0 ms) -- it stays on the generic kernel unless CFUN_CONV_PW=w asks for it
+  // (0.69 -> 1.0 ms with the round-1 kernel; the register-tiled pw_wgrad2_kernel of round 2 takes it)
   if (pass == CFUN_PASS_BWD_DATA && d->Cin > 48) return false;
-  if (pass == CFUN_PASS_BWD_WEIGHT && (!(e && e[0] == 'w') || d->Cin * d->Cout > 1024)) return false;
+  if (pass == CFUN_PASS_BWD_WEIGHT) {
+    const int cop = (d->Cout + 1) & ~1;
+    if ((d->Cin >> 2) * (cop >> 1) > PW_THREADS) return false;
+    if ((size_t)PW2_V * (d->Cin + cop) * sizeof(float) > 200 * 1024) return false;
+  }
   return true;
 }
 
@@ -147,9 +189,15 @@ int pw_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float* d
   CFUN_CHECK_ARG(pw_supported(d, CFUN_PASS_BWD_WEIGHT) && x && dy && dw);
   const long long M = pw_rows(d);
   CFUN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * d->Cin, st));
-  const long long blocks = std::max<long long>(1, std::min<long long>(cdiv(M, 256), 4LL * num_sms()));
-  const long long rpb = cdiv(M, blocks);
-  pw_wgrad_kernel<<<(unsigned)cdiv(M, rpb), d->Cin * d->Cout, 0, st>>>(x, dy, dw, M, d->Cin, d->Cout, rpb);
+  const int cop = (d->Cout + 1) & ~1;
+  const size_t smem = (size_t)PW2_V * (d->Cin + cop) * sizeof(float);
+  static size_t attr_smem = 0;
+  if (smem > 48 * 1024 && smem > attr_smem) {
+    CFUN_CUDA(cudaFuncSetAttribute(pw_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_smem = 200 * 1024;
+  }
+  const long long blocks = std::max<long long>(1, std::min<long long>(cdiv(M, PW2_V), (smem > 64 * 1024 ? 1LL : 3LL) * num_sms()));
+  pw_wgrad2_kernel<<<(unsigned)blocks, PW_THREADS, smem, st>>>(x, dy, dw, M, d->Cin, d->Cout, cop);
   CFUN_LAUNCH_CHECK();
   if (dbias) return simt_bias_grad(dy, M, d->Cout, dbias, st);
   return CFUN_OK;

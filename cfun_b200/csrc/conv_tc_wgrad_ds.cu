@@ -391,7 +391,7 @@ int ds_bwd_weight_packed(const cfun_conv3d_desc* d, __nv_bfloat16* yh, __nv_bflo
   DsPlan pl;
   CFUN_CHECK_ARG(make_ds_plan(d, pl));
   CFUN_CHECK_ARG(yh && yl && xh && xl && dw && gy_pack >= pl.Gy_total);
-  CFUN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * d->Cin * 27, st));
+  CFUN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->Cout * d->Cin * pl.KS * pl.KS * pl.KS, st));
   return ds_launch(d, pl, yh, yl, xh, xl, dw, true, gy_pack, st);
 }
 

@@ -33,6 +33,10 @@ CONV_CASES = [
     (1, 8, 10, 10, 10, 8, 5, 1, 2, False),                      # out_upscale_conv 5^3
     (1, 32, 6, 6, 6, 2, 1, 1, 0, True),                         # RPN class head
     (1, 32, 6, 6, 6, 6, 1, 1, 0, True),                         # RPN bbox head
+    (3, 40, 9, 10, 11, 8, 1, 1, 0, False),                      # U-Net segmentation head conv3d_l4 (40 -> 8): pw_wgrad2_kernel, ragged chunk
+    (2, 160, 5, 6, 7, 8, 1, 1, 0, False),                       # ds2_1x1_conv3d (160 -> 8): 160 thread tiles, one voxel group
+    (1, 256, 8, 8, 8, 2, 1, 1, 0, True),                        # RPN class head at full width (256 -> 2)
+    (1, 12, 5, 5, 5, 5, 1, 1, 0, False),                        # odd Cout (padded to 6 in the co tile)
     (1, 1, 12, 12, 12, 20, 3, 1, 1, False),                     # U-Net first conv (Cin = 1)
     (1, 48, 8, 8, 8, 80, 3, 1, 1, True),                        # >64 output channels
     (3, 24, 5, 7, 6, 36, 3, 1, 1, True),                        # odd everything
@@ -483,25 +487,26 @@ def test_conv3d_tcgen05_strided_tiny_and_stacked_wgrad(ops, case):
 
 
 @pytest.mark.parametrize("case", [(2, 24, 12, 16, 16, 40, True), (1, 40, 12, 24, 16, 20, False), (1, 160, 5, 16, 16, 80, True),
-                                  (1, 128, 8, 16, 16, 256, True)])
+                                  (1, 128, 8, 16, 16, 256, True), (2, 8, 6, 16, 24, 8, True, 5)])
 def test_conv3d_fused_backward_keeps_forward_pack(ops, case):
     """AUTO picks the fused path (cfun_conv3d_fwd_keep_pack + cfun_conv3d_bwd_fused) for these shapes: same results as
     the three separate calls and as fp32, including the no-input-gradient case (first layer of a network)."""
     import ctypes as C
     from cfun_b200._lib import lib
-    N, Cin, D, H, W, Cout, need_dx = case
+    N, Cin, D, H, W, Cout, need_dx = case[:7]
+    k = case[7] if len(case) > 7 else 3            # 5: out_upscale_conv (two zero planes per sample in the shared packs)
     g = torch.Generator().manual_seed(sum(case[:6]))
     x = torch.randn(N, Cin, D, H, W, generator=g)
-    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) * (1.0 / (Cin * 27) ** 0.5)
+    w = torch.randn(Cout, Cin, k, k, k, generator=g) * (1.0 / (Cin * k ** 3) ** 0.5)
     b = torch.randn(Cout, generator=g)
     xr, wr, br = x.clone().requires_grad_(need_dx), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
-    yr = F.conv3d(xr, wr, br, padding=1)
+    yr = F.conv3d(xr, wr, br, padding=k // 2)
     dy = torch.randn(yr.shape, generator=g)
     yr.backward(dy)
-    d = ops._conv_desc(x.shape, w.shape, 1, 1)
+    d = ops._conv_desc(x.shape, w.shape, 1, k // 2)
     assert lib.cfun_conv3d_pack_bytes(C.byref(d)) > 0, "the fused path must take this shape"
     xc, wc, bc = x.cuda().requires_grad_(need_dx), w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
-    yc = ops.conv3d(xc, wc, bc, 1, 1)
+    yc = ops.conv3d(xc, wc, bc, 1, k // 2)
     assert yc.grad_fn is not None and yc.grad_fn.fused
     yc.backward(dy.cuda())
     torch.cuda.synchronize()
