@@ -80,6 +80,8 @@ SIGNATURES = {
     "cfun_sobel_edge_workspace_size": (_sz, [_i, _i, _i, _i, _i, _i]),
     "cfun_sobel_edge_loss_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "cfun_sobel_edge_loss_bwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _sz, _p]),
+    "cfun_mask_ce_fwd": (_i, [_p, _p, _ll, _i, _p, _p, _p, _p]),
+    "cfun_mask_ce_bwd": (_i, [_p, _p, _ll, _i, _p, _p, _p, _p, _p]),
     "cfun_sumsq": (_i, [_p, _ll, _p, _p]),
     "cfun_sgd_clip_step": (_i, [_p, _p, _p, _p, _ll, _p, _f, _f, _f, _f, _i, _p]),
     "cfun_mold_volume_i16": (_i, [_p, _i, _i, _i, _p, _p, _p]),

@@ -369,7 +369,7 @@ def compute_mrcnn_mask_loss(target_masks, target_class_ids, pred_masks, class_we
         return _zero_loss(target_class_ids)
     pos = torch.nonzero(target_class_ids > 0)[:, 0]
     y_true = _mask_index(target_masks, pos)
-    return F.cross_entropy(pred_masks[pos], y_true, weight=class_weight)
+    return ops.mask_cross_entropy(pred_masks[pos], y_true, class_weight)
 
 
 def compute_mrcnn_mask_edge_loss(target_masks, target_class_ids, pred_masks, mode="magnitude"):
@@ -511,8 +511,12 @@ class HeadsTail(nn.Module):
         try:
             if run_cls:
                 c_logits, _, c_bbox = self.classifier([p2, p3], rois)
+            need_probs = self.stage == 'finetune' or (self.staged and self.stage != 'beginning')     # only the edge loss reads them
             if run_mask:
-                m_logits, m_probs = self.mask([image, image], p_rois)
+                if need_probs:
+                    m_logits, m_probs = self.mask([image, image], p_rois)
+                else:       # Mask.forward without its softmax (model.py:796-801): 2 passes over the 113 MB logits nobody reads
+                    m_logits = unet(pyramid_roi_align([p_rois, image, image], self.mask.pool_size, self.mask.test_flag))
         finally:
             unet.injected_drop = saved
         l_cls = l_box = l_mask = l_edge = zero
@@ -521,7 +525,7 @@ class HeadsTail(nn.Module):
             l_cls = F.cross_entropy(c_logits, binary)
             l_box = F.smooth_l1_loss(c_bbox[:P, 1, :], deltas[:P])
         if run_mask:
-            l_mask = F.cross_entropy(m_logits, mask_index, weight=self.class_weight_t)
+            l_mask = ops.mask_cross_entropy(m_logits, mask_index, self.class_weight_t)
             if self.stage == 'finetune' or (self.staged and self.stage != 'beginning'):
                 l_edge = ops.sobel_edge_loss(m_probs, mask_index, self.edge_mode).reshape(())
         return torch.stack([l_cls, l_box, l_mask, l_edge])

@@ -620,6 +620,39 @@ def sobel_edge_loss(pred_probs, tgt_index, mode=SOBEL_MAGNITUDE):
     return SobelEdgeLossFn.apply(pred_probs, tgt_index, mode)
 
 
+class MaskCEFn(Function):
+    """nn.CrossEntropyLoss(weight) between mask logits [P,ncls,d,h,w] and class-index targets [P,d,h,w] (reference
+    model.py:909-935, LiTS_2017/model.py:926): one fused pass forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, logits, target, weight):
+        _require_cuda(logits, target, weight)
+        logits = to_cl(logits)
+        P, ncls = logits.shape[0], logits.shape[1]
+        target = target.contiguous()
+        assert target.dtype == torch.int64 and target.numel() * ncls == logits.numel()
+        if weight is not None:
+            weight = weight.contiguous().float()
+        acc = torch.empty(2, dtype=torch.float64, device=logits.device)
+        loss = torch.empty((), device=logits.device)
+        _run("cfun_mask_ce_fwd", _ptr(logits), _ptr(target), target.numel(), ncls, _ptr(weight), _ptr(acc), _ptr(loss), _stream())
+        ctx.save_for_backward(logits, target, weight, acc)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        logits, target, weight, acc = ctx.saved_tensors
+        g = dloss.reshape(1).contiguous().float()
+        P, ncls, D, H, W = logits.shape
+        dl = empty_cl(P, ncls, D, H, W, logits.device)
+        _run("cfun_mask_ce_bwd", _ptr(logits), _ptr(target), target.numel(), ncls, _ptr(weight), _ptr(acc), _ptr(g), _ptr(dl), _stream())
+        return dl, None, None
+
+
+def mask_cross_entropy(logits, target_index, weight=None):
+    return MaskCEFn.apply(logits, target_index, weight)
+
+
 # --------------------------------------------------------------------------------------------------------
 # optimizer tail / input molding
 # --------------------------------------------------------------------------------------------------------

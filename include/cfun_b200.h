@@ -206,6 +206,18 @@ int cfun_sobel_edge_loss_bwd(const float* pred, const long long* tgt_index, int 
                              const float* grad_scale, float* dpred, void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Mask cross-entropy -- replaces nn.CrossEntropyLoss over the mask logits (model.py:909-935; with class weights
+ * LiTS_2017/model.py:926).  logits channels-last [V][C] fp32 (V = P*d*h*w), target int64 [V] class ids, weight NULL or [C].
+ * loss = sum_v w[y_v] * (logsumexp(x_v) - x_v[y_v]) / sum_v w[y_v]   (torch's 'mean' reduction).
+ * acc: 2 doubles owned by the caller (zeroed by the forward, read by the backward).
+ * backward: dlogits[v][c] = grad_scale[0] * w[y_v] * (softmax(x_v)[c] - [c == y_v]) / sum_v w[y_v].
+ * ------------------------------------------------------------------------------------------ */
+int cfun_mask_ce_fwd(const float* logits, const long long* target, long long V, int C, const float* weight, double* acc,
+                     float* loss, void* stream);
+int cfun_mask_ce_bwd(const float* logits, const long long* target, long long V, int C, const float* weight, const double* acc,
+                     const float* grad_scale, float* dlogits, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * optimizer tail -- replaces clip_grad_norm_(5.0) + SGD(momentum, weight decay) (model.py:1538-1545,1641-1644)
  * over one flat fp32 parameter / gradient / momentum buffer.  wd_mask[i] in {0,1} marks decayed elements.
  * ------------------------------------------------------------------------------------------ */

@@ -586,3 +586,21 @@ def test_conv3d_benchmarked_shapes_fwd_dgrad_wgrad(ops, case):
         # forward / data gradient contract 27 * Cin <= 3456 products; the weight gradient 3.5 M voxels, accumulated in the fp32
         # TMEM accumulator over 24 k-voxel split-K chunks per CTA and combined with fp32 atomics: measured 8e-5
         assert rms < (2e-4 if name == "wgrad" else 2e-5) and rms32 < rms, (name, rms, rms32)
+
+
+@pytest.mark.parametrize("case", [(2, 8, 6, 7, 9, False), (3, 3, 5, 8, 6, True), (1, 5, 4, 4, 4, True)])
+def test_mask_cross_entropy_fused(ops, case):
+    """cfun_mask_ce_fwd / bwd against F.cross_entropy (mean reduction, optional class weights as in LiTS_2017/model.py:926)"""
+    P, C, D, H, W, weighted = case
+    g = torch.Generator().manual_seed(P * 100 + C)
+    x = torch.randn(P, C, D, H, W, generator=g) * 3
+    y = torch.randint(0, C, (P, D, H, W), generator=g)
+    w = (torch.rand(C, generator=g) * 5 + 0.1) if weighted else None
+    xr = x.clone().requires_grad_(True)
+    lr = F.cross_entropy(xr, y, weight=w)
+    (lr * 1.7).backward()
+    xc = cuda(x).requires_grad_(True)
+    lc = ops.mask_cross_entropy(xc, cuda(y), cuda(w) if weighted else None)
+    (lc * 1.7).backward()
+    assert abs(float(lc) - float(lr)) < 1e-5 * abs(float(lr))
+    assert rel_err(xc.grad.cpu().numpy(), xr.grad.numpy()) < 1e-5
