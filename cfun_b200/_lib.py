@@ -64,6 +64,7 @@ SIGNATURES = {
     "cfun_maxpool2_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "cfun_tc_debug_status": (_i, [C.POINTER(C.c_int)]),
     "cfun_pack_split_bf16": (_i, [_p, _p, _p, _ll, _i, _i, _p]),
+    "cfun_pack_act_gp": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "cfun_roi_crop_resize_fwd": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p]),
     "cfun_roi_crop_resize_bwd": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p]),
     "cfun_roi_level": (_i, [_p, _i, _p, _p]),

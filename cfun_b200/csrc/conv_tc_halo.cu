@@ -376,24 +376,25 @@ __global__ void __launch_bounds__(256) pack_w_halo_kernel(const float* __restric
   }
 }
 
-// Same pack through a shared-memory transpose: a block reads TV consecutive voxels x C channels with coalesced float4 loads
-// (the voxel-major reads of pack_act_gp_kernel touch 32-byte pieces 4 C bytes apart) and writes, per channel group, TV
+// Same pack through a shared-memory transpose.  Persistent blocks walk tiles of TV consecutive voxels: the tile (TV * C
+// contiguous floats of x) is fetched with 16-byte cp.async into one of two shared-memory buffers while the previous tile
+// is converted, so every block always has a tile of loads in flight; the conversion writes, per channel group, TV
 // consecutive 16-byte rows.  Row pitch G*8 + 4 floats keeps the 16-byte shared-memory reads of a quarter warp on distinct
-// banks.  Blocks [ntile_blocks, gridDim.x) zero the d = -1 / D padding planes.
+// banks; channels >= C of the last group read as zero.  Blocks [nwork, gridDim.x) zero the 2 P padding planes per sample.
 __global__ void __launch_bounds__(256) pack_act_gp_tiled_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                                                                 __nv_bfloat16* __restrict__ lo, int N, int D, int H, int W, int C, int G,
-                                                                int TV, long long ntile_blocks, int P) {
+                                                                int TV, long long ntiles, int nwork, int P) {
   extern __shared__ __align__(16) float tile[];
   const long long HW = (long long)H * W;
   const long long DHW = (long long)D * HW;
   const long long vox = (long long)N * DHW;                  // real voxels
   const long long vox_p = (long long)N * (D + 2 * P) * HW;   // padded voxels per group
   const int Cs = G * 8 + 4;
-  if ((long long)blockIdx.x >= ntile_blocks) {               // zero planes: (g, n, 2 P planes, hw) rows of 16 bytes
+  if ((int)blockIdx.x >= nwork) {                            // zero planes: (g, n, 2 P planes, hw) rows of 16 bytes
     const long long total = (long long)G * N * 2 * P * HW;
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    for (long long i = ((long long)blockIdx.x - ntile_blocks) * blockDim.x + threadIdx.x; i < total;
-         i += (long long)(gridDim.x - ntile_blocks) * blockDim.x) {
+    for (long long i = ((long long)blockIdx.x - nwork) * blockDim.x + threadIdx.x; i < total;
+         i += (long long)(gridDim.x - nwork) * blockDim.x) {
       const long long hw = i % HW;
       long long r = i / HW;
       const int which = (int)(r % (2 * P)); r /= 2 * P;
@@ -405,31 +406,51 @@ __global__ void __launch_bounds__(256) pack_act_gp_tiled_kernel(const float* __r
     }
     return;
   }
-  const long long v0 = (long long)blockIdx.x * TV;
-  const int nv = (int)min((long long)TV, vox - v0);
   const int c4n = C >> 2;
-  for (int i = threadIdx.x; i < nv * c4n; i += blockDim.x) {
-    const int v = i / c4n, c4 = i - v * c4n;
-    const float4 f = __ldg(reinterpret_cast<const float4*>(x + (v0 + v) * (long long)C) + c4);
-    *reinterpret_cast<float4*>(tile + v * Cs + 4 * c4) = f;
-  }
-  const int padc = G * 8 - C;                                // zero the channels beyond C (multiple of 4)
-  for (int i = threadIdx.x; i < nv * padc; i += blockDim.x) tile[(i / padc) * Cs + C + (i % padc)] = 0.f;
-  __syncthreads();
-  for (int i = threadIdx.x; i < nv * G; i += blockDim.x) {
-    const int g = i / nv, v = i - g * nv;
-    const float4 a = *reinterpret_cast<const float4*>(tile + v * Cs + 8 * g);
-    const float4 b = *reinterpret_cast<const float4*>(tile + v * Cs + 8 * g + 4);
-    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    __align__(16) __nv_bfloat16 h[8];
-    __align__(16) __nv_bfloat16 l[8];
+  const int buf_floats = TV * Cs;
+  auto fetch = [&](long long t, int b) {
+    const long long v0 = t * TV;
+    const int nv = (int)min((long long)TV, vox - v0);
+    const float* src = x + v0 * (long long)C;
+    float* dst = tile + b * buf_floats;
+    for (int i = threadIdx.x; i < nv * c4n; i += blockDim.x) {
+      const int v = i / c4n, c4 = i - v * c4n;
+      const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst + v * Cs + 4 * c4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + 4 * (long long)i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  long long t = blockIdx.x;
+  int b = 0;
+  if (t < ntiles) fetch(t, 0);
+  for (; t < ntiles; t += nwork, b ^= 1) {
+    if (t + nwork < ntiles) {
+      fetch(t + nwork, b ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const long long v0 = t * TV;
+    const int nv = (int)min((long long)TV, vox - v0);
+    const float* cur = tile + b * buf_floats;
+    for (int i = threadIdx.x; i < nv * G; i += blockDim.x) {
+      const int g = i / nv, v = i - g * nv;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bq = a;
+      if (8 * g < C) a = *reinterpret_cast<const float4*>(cur + v * Cs + 8 * g);
+      if (8 * g + 4 < C) bq = *reinterpret_cast<const float4*>(cur + v * Cs + 8 * g + 4);
+      const float f[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
+      __align__(16) __nv_bfloat16 h[8];
+      __align__(16) __nv_bfloat16 l[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) split_bf16(f[j], h[j], l[j]);
-    const long long gv = v0 + v;
-    const long long n = gv / DHW, rem = gv - n * DHW;
-    const long long pos = (n * (D + 2 * P) + P) * HW + rem;
-    reinterpret_cast<uint4*>(hi)[(long long)g * vox_p + pos] = *reinterpret_cast<const uint4*>(h);
-    if (lo) reinterpret_cast<uint4*>(lo)[(long long)g * vox_p + pos] = *reinterpret_cast<const uint4*>(l);
+      for (int j = 0; j < 8; ++j) split_bf16(f[j], h[j], l[j]);
+      const long long gv = v0 + v;
+      const long long n = gv / DHW, rem = gv - n * DHW;
+      const long long pos = (n * (D + 2 * P) + P) * HW + rem;
+      reinterpret_cast<uint4*>(hi)[(long long)g * vox_p + pos] = *reinterpret_cast<const uint4*>(h);
+      if (lo) reinterpret_cast<uint4*>(lo)[(long long)g * vox_p + pos] = *reinterpret_cast<const uint4*>(l);
+    }
+    __syncthreads();                                         // buffer b is refilled by the fetch of the next iteration
   }
 }
 
@@ -450,13 +471,14 @@ int launch_pack_act_gp(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int
 int launch_pack_act_gp_pad(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int C, int G, int P, cudaStream_t st) {
   const char* e = getenv("CFUN_PACK_TILED");          // "0": the one-thread-per-row kernel (A/B measurements)
   const int Cs = G * 8 + 4;
-  int TV = std::min(128, (12288 / Cs) / 32 * 32);
-  if ((C & 3) == 0 && C >= 32 && TV >= 32 && !(e && e[0] == '0')) {     // below 32 channels the row-per-thread kernel is faster (20 ch: 0.154 vs 0.178 ms)
+  const int TV = std::min(128, (6144 / Cs) / 32 * 32);  // two buffers of <= 24 KB: 4 blocks per SM
+  if ((C & 3) == 0 && C > 16 && TV >= 32 && !(e && e[0] == '0')) {   // <= 16 channels: the row-per-thread kernel is faster (8 ch: 0.040 vs 0.064 ms)
     const long long vox = (long long)N * D * H * W;
     const long long ntile = cdiv(vox, TV);
     const long long zrows = (long long)G * N * 2 * P * H * W;
-    const long long nz = std::max<long long>(1, std::min<long long>(cdiv(zrows, 256), 2LL * num_sms()));
-    pack_act_gp_tiled_kernel<<<(unsigned)(ntile + nz), 256, (size_t)TV * Cs * sizeof(float), st>>>(x, hi, lo, N, D, H, W, C, G, TV, ntile, P);
+    const int nz = (int)std::max<long long>(1, std::min<long long>(cdiv(zrows, 1024), (long long)num_sms()));
+    const int nwork = (int)std::min<long long>(ntile, 4LL * num_sms());
+    pack_act_gp_tiled_kernel<<<(unsigned)(nwork + nz), 256, (size_t)2 * TV * Cs * sizeof(float), st>>>(x, hi, lo, N, D, H, W, C, G, TV, ntile, nwork, P);
     CFUN_LAUNCH_CHECK();
     return CFUN_OK;
   }
@@ -465,6 +487,19 @@ int launch_pack_act_gp_pad(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo,
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;
 }
+
+}  // namespace cfun
+
+// The operand pack on its own, for layout tests and bandwidth measurements (tools/ew_bench.py); the convolutions call
+// launch_pack_act_gp_pad directly.  hi / lo: [G][N*(D+2P)][H][W][8] bf16 each, G >= ceil(C/8); lo may be NULL.
+extern "C" int cfun_pack_act_gp(const float* x, void* hi, void* lo, int N, int D, int H, int W, int C, int G, int P, void* stream) {
+  using namespace cfun;
+  CFUN_CHECK_ARG(x && hi && N > 0 && D > 0 && H > 0 && W > 0 && C > 0 && G * 8 >= C && P >= 1 && P <= 2);
+  return launch_pack_act_gp_pad(x, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), N, D, H, W, C, G, P,
+                                as_stream(stream));
+}
+
+namespace cfun {
 
 struct HlPlan {
   int Cs, Ct, N, D, H, W, Kp, Gp, G, nsteps, Npad, tmem_cols, resident, sps, bstages, KS;

@@ -42,39 +42,86 @@ struct Vec<1> {
 // ---------------------------------------------------------------------------------------------------------
 // instance-norm statistics
 // ---------------------------------------------------------------------------------------------------------
+// Block-level tail of the per-(n,c) reductions: thread (q, rr) parks its V partial sums of each of the NS statistics in
+// shared memory [NS][R][C]; the K = NS*C columns are then summed over the R rows in double by blockDim/K threads each
+// (two stages), and one atomic per column leaves the block.  Shared memory: NS*R*C floats + 256 doubles.
+template <int V, int NS>
+__device__ __forceinline__ void block_reduce_stats(float* sm, const float (*part)[V], int q, int rr, int R, int C,
+                                                   bool active, double* __restrict__ acc_n) {
+  if (active) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int j = 0; j < V; ++j) sm[(s * R + rr) * C + q * V + j] = part[s][j];
+  }
+  __syncthreads();
+  const int K = NS * C;
+  int groups = (int)blockDim.x / K;
+  if (groups > R) groups = R;
+  if (groups > 1) {
+    double* sm2 = reinterpret_cast<double*>(sm + NS * R * C);   // NS*R*C is even for NS = 2
+    const int t = threadIdx.x;
+    if (t < groups * K) {
+      const int col = t % K, grp = t / K;
+      const int s = col / C, c = col - s * C;
+      double a = 0.0;
+      for (int k = grp; k < R; k += groups) a += (double)sm[(s * R + k) * C + c];
+      sm2[grp * K + col] = a;
+    }
+    __syncthreads();
+    if (t < K) {
+      const int s = t / C, c = t - s * C;
+      double a = 0.0;
+      for (int g = 0; g < groups; ++g) a += sm2[g * K + t];
+      atomicAdd(&acc_n[c * 2 + s], a);
+    }
+  } else {
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+      const int s = i / C, c = i - s * C;
+      double a = 0.0;
+      for (int k = 0; k < R; ++k) a += (double)sm[(s * R + k) * C + c];
+      atomicAdd(&acc_n[c * 2 + s], a);
+    }
+  }
+}
+
 template <int V>
 __global__ void __launch_bounds__(256) in_stats_kernel(const float* __restrict__ x, long long S, int C, int CV, int R,
                                                        long long rows_per_block, double* __restrict__ acc) {
-  extern __shared__ double sm[];  // [2*C]
+  extern __shared__ float smf[];  // [2][R][C]
+  constexpr int U = 8;
   const int n = blockIdx.y;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < 2 * C; i += blockDim.x) sm[i] = 0.0;
-  __syncthreads();
+  const int q = threadIdx.x % CV, rr = threadIdx.x / CV;
+  const bool active = rr < R;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > S) r1 = S;
-  for (int q = tid % CV, rr = tid / CV; q < CV && rr < R; q += CV * R) {  // executes once for active threads
-    float s[V], ss[V];
+  float part[2][V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) s[j] = ss[j] = 0.f;
-    const float* base = x + ((long long)n * S) * C + q * V;
-    for (long long r = r0 + rr; r < r1; r += R) {
+  for (int j = 0; j < V; ++j) part[0][j] = part[1][j] = 0.f;
+  if (active) {
+    long long row = r0 + rr;
+    const float* xp = x + ((long long)n * S + row) * C + q * V;
+    const long long sx = (long long)R * C;
+    for (; row + (long long)(U - 1) * R < r1; row += (long long)U * R) {
+      float v[U][V];
+#pragma unroll
+      for (int u = 0; u < U; ++u) Vec<V>::load(xp + u * sx, v[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < V; ++j) { part[0][j] += v[u][j]; part[1][j] = fmaf(v[u][j], v[u][j], part[1][j]); }
+      xp += U * sx;
+    }
+    for (; row < r1; row += R) {
       float v[V];
-      Vec<V>::load(base + r * C, v);
+      Vec<V>::load(xp, v);
 #pragma unroll
-      for (int j = 0; j < V; ++j) { s[j] += v[j]; ss[j] = fmaf(v[j], v[j], ss[j]); }
-    }
-#pragma unroll
-    for (int j = 0; j < V; ++j) {
-      atomicAdd(&sm[q * V + j], (double)s[j]);
-      atomicAdd(&sm[C + q * V + j], (double)ss[j]);
+      for (int j = 0; j < V; ++j) { part[0][j] += v[j]; part[1][j] = fmaf(v[j], v[j], part[1][j]); }
+      xp += sx;
     }
   }
-  __syncthreads();
-  for (int i = tid; i < C; i += blockDim.x) {
-    atomicAdd(&acc[((long long)n * C + i) * 2 + 0], sm[i]);
-    atomicAdd(&acc[((long long)n * C + i) * 2 + 1], sm[C + i]);
-  }
+  block_reduce_stats<V, 2>(smf, part, q, rr, R, C, active, acc + (long long)n * C * 2);
 }
 
 __global__ void in_finalize_kernel(const double* __restrict__ acc, long long NC, double invS, float eps,
@@ -142,28 +189,170 @@ __global__ void __launch_bounds__(256) affine_act_fwd_kernel(const float* __rest
   }
 }
 
-// backward: per-sample blocks so that instance-norm reductions can be fused
-template <int V>
-__global__ void __launch_bounds__(256) affine_act_bwd_kernel(const float* __restrict__ x, const float* __restrict__ a,
-                                                             const float* __restrict__ b, int a_nstride,
-                                                             const float* __restrict__ r, const float* __restrict__ dy,
-                                                             float* __restrict__ dx, float* __restrict__ dr,
-                                                             double* __restrict__ stat_acc, int D, int H, int W, int C,
-                                                             int Ctot, int c_off, int up, float slope, int CV, int R,
-                                                             long long rows_per_block) {
-  extern __shared__ double sm[];  // [2*C] when stat_acc
+// up == 1 fast path: the RowMap layout of the reduction kernels (no per-element division, the per-(n,c) constants in
+// registers, U independent 16-byte loads per operand in flight per thread)
+template <int V, int U>
+__global__ void __launch_bounds__(256) affine_act_rows_kernel(const float* __restrict__ x, const float* __restrict__ a,
+                                                              const float* __restrict__ b, int a_nstride,
+                                                              const float* __restrict__ r, float* __restrict__ y,
+                                                              long long S, int C, int Ctot, int c_off, float slope,
+                                                              int CV, int R, long long rows_per_block) {
   const int n = blockIdx.y;
-  const int tid = threadIdx.x;
-  const long long S = (long long)D * H * W;
-  if (stat_acc) {
-    for (int i = tid; i < 2 * C; i += blockDim.x) sm[i] = 0.0;
-    __syncthreads();
+  const int q = threadIdx.x % CV, rr = threadIdx.x / CV;
+  if (rr >= R) return;
+  const int c = q * V;
+  float av[V], bv[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) { av[j] = 1.f; bv[j] = 0.f; }
+  if (a) {
+    Vec<V>::load(a + (long long)n * a_nstride + c, av);
+    Vec<V>::load(b + (long long)n * a_nstride + c, bv);
   }
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > S) r1 = S;
-  const int q = tid % CV, rr = tid / CV;
-  if (rr < R) {
+  long long row = r0 + rr;
+  const long long vox0 = (long long)n * S + row;
+  const float* xp = x + vox0 * C + c;
+  const float* rp = r ? r + vox0 * C + c : nullptr;
+  float* yp = y + vox0 * Ctot + c_off + c;
+  const long long sx = (long long)R * C, sy = (long long)R * Ctot;
+  for (; row + (long long)(U - 1) * R < r1; row += (long long)U * R) {
+    float v[U][V];
+#pragma unroll
+    for (int u = 0; u < U; ++u) Vec<V>::load(xp + u * sx, v[u]);
+    if (rp) {
+      float rv[U][V];
+#pragma unroll
+      for (int u = 0; u < U; ++u) Vec<V>::load(rp + u * sx, rv[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[u][j] = fmaf(v[u][j], av[j], bv[j]) + rv[u][j];
+      rp += U * sx;
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[u][j] = fmaf(v[u][j], av[j], bv[j]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[u][j] = v[u][j] > 0.f ? v[u][j] : v[u][j] * slope;
+      Vec<V>::store(yp + u * sy, v[u]);
+    }
+    xp += U * sx;
+    yp += U * sy;
+  }
+  for (; row < r1; row += R) {
+    float v[V];
+    Vec<V>::load(xp, v);
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = fmaf(v[j], av[j], bv[j]);
+    if (rp) {
+      float rv[V];
+      Vec<V>::load(rp, rv);
+#pragma unroll
+      for (int j = 0; j < V; ++j) v[j] += rv[j];
+      rp += sx;
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * slope;
+    Vec<V>::store(yp, v);
+    xp += sx;
+    yp += sy;
+  }
+}
+
+// backward: per-sample blocks so that instance-norm reductions can be fused
+struct ActBwdArgs {
+  const float* x; const float* r; const float* dy;
+  float* dx; float* dr;
+  int D, H, W, C, Ctot, c_off;
+  float slope;
+  bool stats;
+};
+
+// UU consecutive rows (stride R) of one thread: all loads first, then the arithmetic and the stores
+template <int V, int UU, bool UP2>
+__device__ __forceinline__ void act_bwd_rows(const ActBwdArgs& p, int n, long long S, long long row, int R, int c,
+                                             const float* av, const float* bv, float (*part)[V]) {
+  float xv[UU][V], rv[UU][V], g[UU][V];
+#pragma unroll
+  for (int u = 0; u < UU; ++u) Vec<V>::load(p.x + ((long long)n * S + row + (long long)u * R) * p.C + c, xv[u]);
+  if (p.r) {
+#pragma unroll
+    for (int u = 0; u < UU; ++u) Vec<V>::load(p.r + ((long long)n * S + row + (long long)u * R) * p.C + c, rv[u]);
+  }
+#pragma unroll
+  for (int u = 0; u < UU; ++u) {
+    const long long rw = row + (long long)u * R;
+    if (!UP2) {
+      Vec<V>::load(p.dy + ((long long)n * S + rw) * p.Ctot + p.c_off + c, g[u]);
+    } else {
+      long long t = rw;
+      const int w = (int)(t % p.W); t /= p.W;
+      const int h = (int)(t % p.H); t /= p.H;
+      const int d = (int)t;
+      const int H2 = p.H * 2, W2 = p.W * 2;
+      float t8[8][V];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const long long o = (((long long)n * (p.D * 2) + (2 * d + (k >> 2))) * H2 + (2 * h + ((k >> 1) & 1))) * W2 +
+                            (2 * w + (k & 1));
+        Vec<V>::load(p.dy + o * p.Ctot + p.c_off + c, t8[k]);
+      }
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc += t8[k][j];  // same summation order as the z, y, x loop nest
+        g[u][j] = acc;
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < UU; ++u) {
+    const long long vox = (long long)n * S + row + (long long)u * R;
+    float xh[V], o[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      xh[j] = fmaf(xv[u][j], av[j], bv[j]);
+      const float pre = p.r ? xh[j] + rv[u][j] : xh[j];
+      g[u][j] = pre > 0.f ? g[u][j] : g[u][j] * p.slope;
+    }
+    if (p.dr) Vec<V>::store(p.dr + vox * p.C + c, g[u]);
+    if (p.stats) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) { part[0][j] += g[u][j]; part[1][j] = fmaf(g[u][j], xh[j], part[1][j]); }
+      Vec<V>::store(p.dx + vox * p.C + c, g[u]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] = g[u][j] * av[j];
+      Vec<V>::store(p.dx + vox * p.C + c, o);
+    }
+  }
+}
+
+template <int V, bool UP2>
+__global__ void __launch_bounds__(256) affine_act_bwd_kernel(const ActBwdArgs p, const float* __restrict__ a,
+                                                             const float* __restrict__ b, int a_nstride,
+                                                             double* __restrict__ stat_acc, int CV, int R,
+                                                             long long rows_per_block) {
+  extern __shared__ float smf[];  // [2][R][C] when stat_acc
+  constexpr int U = UP2 ? 1 : 4;
+  const int n = blockIdx.y;
+  const long long S = (long long)p.D * p.H * p.W;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > S) r1 = S;
+  const int q = threadIdx.x % CV, rr = threadIdx.x / CV;
+  const bool active = rr < R;
+  float part[2][V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) part[0][j] = part[1][j] = 0.f;
+  if (active) {
     const int c = q * V;
     float av[V], bv[V];
 #pragma unroll
@@ -172,76 +361,12 @@ __global__ void __launch_bounds__(256) affine_act_bwd_kernel(const float* __rest
       Vec<V>::load(a + (long long)n * a_nstride + c, av);
       Vec<V>::load(b + (long long)n * a_nstride + c, bv);
     }
-    float s1[V], s2[V];
-#pragma unroll
-    for (int j = 0; j < V; ++j) s1[j] = s2[j] = 0.f;
-    for (long long row = r0 + rr; row < r1; row += R) {
-      const long long vox = (long long)n * S + row;
-      float xv[V], pre[V], g[V];
-      Vec<V>::load(x + vox * C + c, xv);
-#pragma unroll
-      for (int j = 0; j < V; ++j) pre[j] = fmaf(xv[j], av[j], bv[j]);
-      float xh[V];
-#pragma unroll
-      for (int j = 0; j < V; ++j) xh[j] = pre[j];
-      if (r) {
-        float rv[V];
-        Vec<V>::load(r + vox * C + c, rv);
-#pragma unroll
-        for (int j = 0; j < V; ++j) pre[j] += rv[j];
-      }
-      if (up == 1) {
-        Vec<V>::load(dy + vox * Ctot + c_off + c, g);
-      } else {
-        long long t = row;
-        int w = (int)(t % W); t /= W;
-        int h = (int)(t % H); t /= H;
-        int d = (int)t;
-        const int H2 = H * 2, W2 = W * 2;
-#pragma unroll
-        for (int j = 0; j < V; ++j) g[j] = 0.f;
-#pragma unroll
-        for (int dz = 0; dz < 2; ++dz)
-#pragma unroll
-          for (int dy_ = 0; dy_ < 2; ++dy_)
-#pragma unroll
-            for (int dx_ = 0; dx_ < 2; ++dx_) {
-              long long o = (((long long)n * (D * 2) + (2 * d + dz)) * H2 + (2 * h + dy_)) * W2 + (2 * w + dx_);
-              float t4[V];
-              Vec<V>::load(dy + o * Ctot + c_off + c, t4);
-#pragma unroll
-              for (int j = 0; j < V; ++j) g[j] += t4[j];
-            }
-      }
-#pragma unroll
-      for (int j = 0; j < V; ++j) g[j] = pre[j] > 0.f ? g[j] : g[j] * slope;
-      if (dr) Vec<V>::store(dr + vox * C + c, g);
-      if (stat_acc) {
-#pragma unroll
-        for (int j = 0; j < V; ++j) { s1[j] += g[j]; s2[j] = fmaf(g[j], xh[j], s2[j]); }
-        Vec<V>::store(dx + vox * C + c, g);
-      } else {
-        float o[V];
-#pragma unroll
-        for (int j = 0; j < V; ++j) o[j] = g[j] * av[j];
-        Vec<V>::store(dx + vox * C + c, o);
-      }
-    }
-    if (stat_acc) {
-#pragma unroll
-      for (int j = 0; j < V; ++j) {
-        atomicAdd(&sm[c + j], (double)s1[j]);
-        atomicAdd(&sm[C + c + j], (double)s2[j]);
-      }
-    }
+    long long row = r0 + rr;
+    for (; row + (long long)(U - 1) * R < r1; row += (long long)U * R) act_bwd_rows<V, U, UP2>(p, n, S, row, R, c, av, bv, part);
+    if (U > 1)
+      for (; row < r1; row += R) act_bwd_rows<V, 1, UP2>(p, n, S, row, R, c, av, bv, part);
   }
-  if (stat_acc) {
-    __syncthreads();
-    for (int i = tid; i < C; i += blockDim.x) {
-      atomicAdd(&stat_acc[((long long)n * C + i) * 2 + 0], sm[i]);
-      atomicAdd(&stat_acc[((long long)n * C + i) * 2 + 1], sm[C + i]);
-    }
-  }
+  if (stat_acc) block_reduce_stats<V, 2>(smf, part, q, rr, R, p.C, active, stat_acc + (long long)n * p.C * 2);
 }
 
 // dx = a * (g - s1/S - xhat * s2/S),  xhat = x*a + b, g stored in dx
@@ -249,28 +374,69 @@ template <int V>
 __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ a,
                                                            const float* __restrict__ b,
                                                            const double* __restrict__ stat_acc, float* __restrict__ dx,
-                                                           int N, long long S, int C) {
-  const int CV = C / V;
-  const long long total = (long long)N * S * CV;
+                                                           long long S, int C, int CV, int R, long long rows_per_block) {
+  constexpr int U = 4;
+  const int n = blockIdx.y;
+  const int q = threadIdx.x % CV, rr = threadIdx.x / CV;
+  if (rr >= R) return;
+  const int c = q * V;
   const double invS = 1.0 / (double)S;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int q = (int)(i % CV);
-    long long vox = i / CV;
-    int n = (int)(vox / S);
-    int c = q * V;
-    float xv[V], g[V], av[V], bv[V], o[V];
-    Vec<V>::load(x + vox * C + c, xv);
-    Vec<V>::load(dx + vox * C + c, g);
-    Vec<V>::load(a + (long long)n * C + c, av);
-    Vec<V>::load(b + (long long)n * C + c, bv);
+  float av[V], bv[V], m1[V], m2[V];
+  Vec<V>::load(a + (long long)n * C + c, av);
+  Vec<V>::load(b + (long long)n * C + c, bv);
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    m1[j] = (float)(stat_acc[((long long)n * C + c + j) * 2 + 0] * invS);
+    m2[j] = (float)(stat_acc[((long long)n * C + c + j) * 2 + 1] * invS);
+  }
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > S) r1 = S;
+  long long row = r0 + rr;
+  const long long off0 = ((long long)n * S + row) * C + c;
+  const float* xp = x + off0;
+  float* gp = dx + off0;
+  const long long sx = (long long)R * C;
+  for (; row + (long long)(U - 1) * R < r1; row += (long long)U * R) {
+    float xv[U][V], g[U][V];
+#pragma unroll
+    for (int u = 0; u < U; ++u) Vec<V>::load(xp + u * sx, xv[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float4 t;
+      if (V == 4) {
+        t = *reinterpret_cast<const float4*>(gp + u * sx);
+        g[u][0] = t.x; g[u][1 % V] = t.y; g[u][2 % V] = t.z; g[u][3 % V] = t.w;
+      } else {
+        g[u][0] = gp[u * sx];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float o[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float xh = fmaf(xv[u][j], av[j], bv[j]);
+        o[j] = av[j] * (g[u][j] - m1[j] - xh * m2[j]);
+      }
+      Vec<V>::store(gp + u * sx, o);
+    }
+    xp += U * sx;
+    gp += U * sx;
+  }
+  for (; row < r1; row += R) {
+    float xv[V], g[V], o[V];
+    Vec<V>::load(xp, xv);
+#pragma unroll
+    for (int j = 0; j < V; ++j) g[j] = gp[j];
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      float m1 = (float)(stat_acc[((long long)n * C + c + j) * 2 + 0] * invS);
-      float m2 = (float)(stat_acc[((long long)n * C + c + j) * 2 + 1] * invS);
-      float xh = fmaf(xv[j], av[j], bv[j]);
-      o[j] = av[j] * (g[j] - m1 - xh * m2);
+      const float xh = fmaf(xv[j], av[j], bv[j]);
+      o[j] = av[j] * (g[j] - m1[j] - xh * m2[j]);
     }
-    Vec<V>::store(dx + vox * C + c, o);
+    Vec<V>::store(gp, o);
+    xp += sx;
+    gp += sx;
   }
 }
 
@@ -381,6 +547,14 @@ __global__ void mold_transpose_kernel(const short* __restrict__ v, int H, int W,
   }
 }
 
+// rows of one sample per block for the RowMap kernels: about `per_sm` blocks per SM over the whole launch (16 for the
+// streaming kernels; 6 for the reductions, whose blocks each end in 2C double atomics on the same N*C addresses), at
+// least 8 iterations of R rows each
+static long long rows_per_block(long long S, int N, int R, int per_sm = 16) {
+  const long long blocks_per_sample = std::max<long long>(1, (long long)per_sm * num_sms() / N);
+  return std::max<long long>((long long)R * 8, cdiv(S, blocks_per_sample));
+}
+
 static int pick_blocks(long long total) {
   long long b = cdiv(total, 256);
   long long cap = 32LL * num_sms();
@@ -399,9 +573,9 @@ extern "C" int cfun_instnorm_stats(const float* x, int N, long long S, int C, fl
   const int V = (C % 4 == 0) ? 4 : 1;
   CFUN_CHECK_ARG(C / V <= 256);
   RowMap rm = make_rowmap(C, V);
-  long long rpb = std::max<long long>((long long)rm.R * 8, cdiv(S, std::max<long long>(1, 8LL * num_sms() / N)));
+  long long rpb = rows_per_block(S, N, rm.R, 6);
   dim3 grid((unsigned)cdiv(S, rpb), N);
-  size_t smem = sizeof(double) * 2 * C;
+  size_t smem = sizeof(float) * 2 * rm.R * C + sizeof(double) * 256;
   if (V == 4) in_stats_kernel<4><<<grid, 256, smem, st>>>(x, S, C, rm.CV, rm.R, rpb, acc);
   else in_stats_kernel<1><<<grid, 256, smem, st>>>(x, S, C, rm.CV, rm.R, rpb, acc);
   CFUN_LAUNCH_CHECK();
@@ -420,8 +594,18 @@ extern "C" int cfun_affine_act_fwd(const float* x, const float* a, const float* 
   cudaStream_t st = as_stream(stream);
   const bool v4 = (C % 4 == 0) && (Ctot % 4 == 0) && (c_off % 4 == 0) && (a_nstride % 4 == 0);
   long long total = (long long)N * D * H * W * (v4 ? C / 4 : C);
-  if (v4) affine_act_fwd_kernel<4><<<pick_blocks(total), 256, 0, st>>>(x, a, b, a_nstride, r, y, N, D, H, W, C, Ctot, c_off, up, slope);
-  else affine_act_fwd_kernel<1><<<pick_blocks(total), 256, 0, st>>>(x, a, b, a_nstride, r, y, N, D, H, W, C, Ctot, c_off, up, slope);
+  if (up == 1 && C / (v4 ? 4 : 1) <= 256) {
+    RowMap rm = make_rowmap(C, v4 ? 4 : 1);
+    const long long S = (long long)D * H * W;
+    long long rpb = rows_per_block(S, N, rm.R);
+    dim3 grid((unsigned)cdiv(S, rpb), N);
+    if (v4) affine_act_rows_kernel<4, 4><<<grid, 256, 0, st>>>(x, a, b, a_nstride, r, y, S, C, Ctot, c_off, slope, rm.CV, rm.R, rpb);
+    else affine_act_rows_kernel<1, 4><<<grid, 256, 0, st>>>(x, a, b, a_nstride, r, y, S, C, Ctot, c_off, slope, rm.CV, rm.R, rpb);
+  } else if (v4) {
+    affine_act_fwd_kernel<4><<<pick_blocks(total), 256, 0, st>>>(x, a, b, a_nstride, r, y, N, D, H, W, C, Ctot, c_off, up, slope);
+  } else {
+    affine_act_fwd_kernel<1><<<pick_blocks(total), 256, 0, st>>>(x, a, b, a_nstride, r, y, N, D, H, W, C, Ctot, c_off, up, slope);
+  }
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;
 }
@@ -440,11 +624,14 @@ extern "C" int cfun_affine_act_bwd(const float* x, const float* a, const float* 
   CFUN_CHECK_ARG(C / V <= 256);
   RowMap rm = make_rowmap(C, V);
   const long long S = (long long)D * H * W;
-  long long rpb = std::max<long long>((long long)rm.R * 4, cdiv(S, std::max<long long>(1, 8LL * num_sms() / N)));
+  long long rpb = rows_per_block(S, N, rm.R, stat_acc ? 6 : 16);
   dim3 grid((unsigned)cdiv(S, rpb), N);
-  size_t smem = stat_acc ? sizeof(double) * 2 * C : 0;
-  if (v4) affine_act_bwd_kernel<4><<<grid, 256, smem, st>>>(x, a, b, a_nstride, r, dy, dx, dr, stat_acc, D, H, W, C, Ctot, c_off, up, slope, rm.CV, rm.R, rpb);
-  else affine_act_bwd_kernel<1><<<grid, 256, smem, st>>>(x, a, b, a_nstride, r, dy, dx, dr, stat_acc, D, H, W, C, Ctot, c_off, up, slope, rm.CV, rm.R, rpb);
+  size_t smem = stat_acc ? sizeof(float) * 2 * rm.R * C + sizeof(double) * 256 : 0;
+  ActBwdArgs p{x, r, dy, dx, dr, D, H, W, C, Ctot, c_off, slope, stat_acc != nullptr};
+  if (v4 && up == 1) affine_act_bwd_kernel<4, false><<<grid, 256, smem, st>>>(p, a, b, a_nstride, stat_acc, rm.CV, rm.R, rpb);
+  else if (v4) affine_act_bwd_kernel<4, true><<<grid, 256, smem, st>>>(p, a, b, a_nstride, stat_acc, rm.CV, rm.R, rpb);
+  else if (up == 1) affine_act_bwd_kernel<1, false><<<grid, 256, smem, st>>>(p, a, b, a_nstride, stat_acc, rm.CV, rm.R, rpb);
+  else affine_act_bwd_kernel<1, true><<<grid, 256, smem, st>>>(p, a, b, a_nstride, stat_acc, rm.CV, rm.R, rpb);
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;
 }
@@ -454,9 +641,12 @@ extern "C" int cfun_instnorm_bwd_apply(const float* x, const float* a, const flo
   CFUN_CHECK_ARG(x && a && b && stat_acc && dx && N > 0 && S > 0 && C > 0);
   cudaStream_t st = as_stream(stream);
   const bool v4 = (C % 4 == 0);
-  long long total = (long long)N * S * (v4 ? C / 4 : C);
-  if (v4) in_bwd_apply_kernel<4><<<pick_blocks(total), 256, 0, st>>>(x, a, b, stat_acc, dx, N, S, C);
-  else in_bwd_apply_kernel<1><<<pick_blocks(total), 256, 0, st>>>(x, a, b, stat_acc, dx, N, S, C);
+  CFUN_CHECK_ARG(C / (v4 ? 4 : 1) <= 256);
+  RowMap rm = make_rowmap(C, v4 ? 4 : 1);
+  long long rpb = rows_per_block(S, N, rm.R);
+  dim3 grid((unsigned)cdiv(S, rpb), N);
+  if (v4) in_bwd_apply_kernel<4><<<grid, 256, 0, st>>>(x, a, b, stat_acc, dx, S, C, rm.CV, rm.R, rpb);
+  else in_bwd_apply_kernel<1><<<grid, 256, 0, st>>>(x, a, b, stat_acc, dx, S, C, rm.CV, rm.R, rpb);
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;
 }

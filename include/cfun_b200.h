@@ -141,6 +141,10 @@ int cfun_maxpool2_bwd(const float* x, const float* y, const float* dy, float* dx
 int cfun_tc_debug_status(int* out8_host);
 /* split fp32 -> (hi, lo) bf16 pairs, channel-padded NDHWC, the operand format of the tcgen05 convs */
 int cfun_pack_split_bf16(const float* x, void* hi, void* lo, long long rows, int C, int Cpad, void* stream);
+/* group-planar split pack of an NDHWC activation, the operand format of the halo / hx / weight-gradient kernels:
+ * hi, lo: [G][N*(D+2P)][H][W][8] bf16, P zero planes before and after every sample, G >= ceil(C/8), lo may be NULL.
+ * Exposed for layout tests and bandwidth measurements; the convolutions pack internally. */
+int cfun_pack_act_gp(const float* x, void* hi, void* lo, int N, int D, int H, int W, int C, int G, int P, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * RoI crop + trilinear(align_corners=True) resize -- replaces model.RoI_Align (model.py:265-289) and the

@@ -108,10 +108,15 @@ def test_fc_conv(ops, M, Nout, C, pool):
     assert rel_err(bc.grad.cpu().numpy(), br.grad.numpy()) < TOL
 
 
-@pytest.mark.parametrize("C,up,use_drop", [(20, 1, False), (40, 2, False), (8, 1, True), (160, 1, True), (320, 2, False)])
-def test_instnorm_lrelu(ops, C, up, use_drop):
+@pytest.mark.parametrize("C,up,use_drop,dims", [(20, 1, False, (5, 6, 7)), (40, 2, False, (5, 6, 7)), (8, 1, True, (5, 6, 7)),
+                                                (160, 1, True, (5, 6, 7)), (320, 2, False, (5, 6, 7)),
+                                                # enough rows for several blocks and the unrolled main loops
+                                                (20, 1, True, (40, 36, 44)), (40, 1, False, (33, 31, 29)),
+                                                (8, 1, False, (48, 40, 40)), (6, 1, False, (17, 19, 23)),
+                                                (16, 2, False, (20, 24, 28))])
+def test_instnorm_lrelu(ops, C, up, use_drop, dims):
     g = torch.Generator().manual_seed(C + up)
-    N, D, H, W = 2, 5, 6, 7
+    N, (D, H, W) = 2, dims
     x = torch.randn(N, C, D, H, W, generator=g) * 2 + 0.5
     drop = ((torch.rand(N, C, generator=g) > 0.6).float() / 0.4) if use_drop else None
     xr = x.clone().requires_grad_(True)
@@ -126,6 +131,28 @@ def test_instnorm_lrelu(ops, C, up, use_drop):
     yc.backward(cuda(dy))
     assert rel_err(yc.detach().cpu().numpy(), yr.detach().numpy()) < TOL
     assert rel_err(xc.grad.cpu().numpy(), xr.grad.numpy()) < 2 * TOL
+
+
+@pytest.mark.parametrize("C,G,P,dims", [(20, 3, 1, (6, 10, 12)), (40, 5, 1, (9, 16, 24)), (40, 5, 2, (5, 8, 8)), (16, 2, 1, (7, 9, 11)),
+                                        (20, 4, 1, (3, 5, 7)), (80, 10, 1, (4, 12, 12)), (320, 40, 1, (3, 6, 6)), (6, 1, 2, (4, 5, 6))])
+def test_pack_act_gp_layout(ops, C, G, P, dims):
+    """the operand pack of the tcgen05 convolutions: group-planar [G][N*(D+2P)][H][W][8] split bf16 with P zero planes on
+    both sides of every sample; hi = bf16(x), lo = bf16(x - hi), channels >= C zero -- bit-exact"""
+    from cfun_b200.ops import _run, _ptr, _stream
+    g = torch.Generator().manual_seed(C * 7 + P)
+    N, (D, H, W) = 2, dims
+    x = torch.randn(N, D, H, W, C, generator=g) * 3
+    xc = x.cuda()
+    hi = torch.full((G, N * (D + 2 * P), H, W, 8), 7.0, dtype=torch.bfloat16, device="cuda")
+    lo = torch.full_like(hi, 7.0)
+    _run("cfun_pack_act_gp", _ptr(xc), _ptr(hi), _ptr(lo), N, D, H, W, C, G, P, _stream())
+    xp = torch.zeros(N, D + 2 * P, H, W, G * 8)
+    xp[:, P:P + D, :, :, :C] = x
+    eh = xp.to(torch.bfloat16)
+    el = (xp - eh.float()).to(torch.bfloat16)
+    to_gp = lambda t: t.reshape(N * (D + 2 * P), H, W, G, 8).permute(3, 0, 1, 2, 4).contiguous()
+    assert torch.equal(hi.cpu().view(torch.int16), to_gp(eh).view(torch.int16))
+    assert torch.equal(lo.cpu().view(torch.int16), to_gp(el).view(torch.int16))
 
 
 def test_cat_channels_fwd_bwd(ops):
