@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-library-baseline", action="store_true")
     ap.add_argument("--profile-calls", default=None, help="write a per-library-call timing table of one eager step here")
     ap.add_argument("--kernel-table", default=None, help="write a per-kernel CUPTI table of one eager step here")
+    ap.add_argument("--gap-table", default=None, help="write the device idle gaps of one step (graphs as benchmarked) here")
     ap.add_argument("--conv-algo", default="auto", choices=["auto", "simt", "tc", "tc1"])
     ap.add_argument("--no-graphs", action="store_true", help="run the heads eagerly instead of as CUDA graphs")
     return ap.parse_args()
@@ -607,6 +608,41 @@ def run_ours(args):
             f.write("# total kernel time %.2f ms over %d launches\n" % (tot, sum(v[0] for v in agg.values())))
             for name, (n, tt) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                 f.write("%9.3f ms %5.1f%% %5d  %s\n" % (tt, 100 * tt / tot, n, name[:140]))
+
+    if args.gap_table and rank == 0:       # off the clock: where the device idles inside one step as benchmarked
+        from torch.profiler import profile, ProfilerActivity
+        net.enable_graphs(True)
+        for _ in range(2):
+            run_step(net.train_step_device, *dev_inputs[0])
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(4):      # back to back as in the timed loop: the host runs ahead of the device across steps
+                run_step(net.train_step_device, *dev_inputs[0])
+            torch.cuda.synchronize()
+        evs = sorted((ev.time_range.start, ev.time_range.end, ev.name) for ev in prof.events()
+                     if ev.device_type is not None and str(ev.device_type).endswith("CUDA"))
+        marks = [e[0] for e in evs if "mold_transpose_kernel" in e[2]]      # one per step
+        if len(marks) >= 4:
+            evs = [e for e in evs if marks[2] <= e[0] < marks[3]]          # the third step, steady state
+        busy_end, gaps, busy = evs[0][0], [], 0.0
+        prev_name = "-"
+        for st_, en_, name in evs:
+            if st_ > busy_end:
+                gaps.append((st_ - busy_end, busy_end - evs[0][0], prev_name, name))
+            if en_ > busy_end:
+                busy += en_ - max(st_, busy_end)
+                busy_end, prev_name = en_, name
+        span = busy_end - evs[0][0]
+        with open(args.gap_table, "w") as f:
+            f.write("# one %d^3 train step as benchmarked (CUDA graphs on, third of four back-to-back steps), CUPTI timeline: first kernel start -> last kernel end\n" % dim)
+            f.write("# span %.3f ms, device busy %.3f ms, idle %.3f ms in %d gaps (%d launches)\n"
+                    % (span / 1e3, busy / 1e3, (span - busy) / 1e3, len(gaps), len(evs)))
+            f.write("# idle by size: " + ", ".join("%s %.3f ms" % (lbl, sum(g[0] for g in gaps if lo_ <= g[0] < hi_) / 1e3)
+                                                  for lbl, lo_, hi_ in (("<5us", 0, 5), ("5-20us", 5, 20), ("20-100us", 20, 100),
+                                                                        (">=100us", 100, 1e12))) + "\n")
+            f.write("# gap_us  at_ms  after kernel -> before kernel\n")
+            for g, at, a, b in sorted(gaps, reverse=True)[:60]:
+                f.write("%8.1f %7.3f  %s -> %s\n" % (g, at / 1e3, a[:70], b[:70]))
 
     if rank != 0:
         if world > 1:

@@ -77,6 +77,8 @@ SIGNATURES = {
     "cfun_iou3d_eps": (_i, [_p, _p, _i, _p, _p]),
     "cfun_bbox_overlaps3d": (_i, [_p, _i, _p, _i, _p, _p]),
     "cfun_box_refinement": (_i, [_p, _p, _i, C.POINTER(C.c_float), _p, _p]),
+    "cfun_roi_candidates": (_i, [_p, _p, _p, _i, C.POINTER(C.c_float), _p, _i, C.c_float, _p, _p, _p, _p, _p, _p, _p]),
+    "cfun_roi_targets": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _p, C.POINTER(C.c_float), _p, _p, _p, _p]),
     "cfun_mask_target_crop": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _p, _p]),
     "cfun_sobel_edge_workspace_size": (_sz, [_i, _i, _i, _i, _i, _i]),
     "cfun_sobel_edge_loss_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),

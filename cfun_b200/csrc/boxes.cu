@@ -219,6 +219,15 @@ __global__ void gather_boxes_kernel(const float* __restrict__ rows, const int* _
 // ---------------------------------------------------------------------------------------------------------
 // overlaps / refinement / levels / mask targets
 // ---------------------------------------------------------------------------------------------------------
+// IoU of model.bbox_overlaps (model.py:374-410): no epsilon, 0/0 = NaN for two empty boxes
+__device__ __forceinline__ float overlap_rn(const float* a, const float* b) {
+  float z1 = fmaxf(a[0], b[0]), y1 = fmaxf(a[1], b[1]), x1 = fmaxf(a[2], b[2]);
+  float z2 = fminf(a[3], b[3]), y2 = fminf(a[4], b[4]), x2 = fminf(a[5], b[5]);
+  float inter = __fmul_rn(__fmul_rn(fmaxf(__fsub_rn(x2, x1), 0.f), fmaxf(__fsub_rn(y2, y1), 0.f)), fmaxf(__fsub_rn(z2, z1), 0.f));
+  float uni = __fsub_rn(__fadd_rn(vol_rn(a), vol_rn(b)), inter);
+  return __fdiv_rn(inter, uni);
+}
+
 __global__ void overlaps_kernel(const float* __restrict__ b1, int n1, const float* __restrict__ b2, int n2, float* __restrict__ iou) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n1 * n2) return;
@@ -226,11 +235,7 @@ __global__ void overlaps_kernel(const float* __restrict__ b1, int n1, const floa
   float a[6], b[6];
 #pragma unroll
   for (int c = 0; c < 6; ++c) { a[c] = b1[(long long)i * 6 + c]; b[c] = b2[(long long)j * 6 + c]; }
-  float z1 = fmaxf(a[0], b[0]), y1 = fmaxf(a[1], b[1]), x1 = fmaxf(a[2], b[2]);
-  float z2 = fminf(a[3], b[3]), y2 = fminf(a[4], b[4]), x2 = fminf(a[5], b[5]);
-  float inter = __fmul_rn(__fmul_rn(fmaxf(__fsub_rn(x2, x1), 0.f), fmaxf(__fsub_rn(y2, y1), 0.f)), fmaxf(__fsub_rn(z2, z1), 0.f));
-  float uni = __fsub_rn(__fadd_rn(vol_rn(a), vol_rn(b)), inter);
-  iou[t] = __fdiv_rn(inter, uni);
+  iou[t] = overlap_rn(a, b);
 }
 
 // utils.compute_iou (utils.py:50-70): one box against many, with the +1e-6 of the NMS IoU
@@ -243,18 +248,129 @@ __global__ void iou_eps_kernel(const float* __restrict__ box, const float* __res
   out[i] = iou_rn(a, vol_rn(a), b, vol_rn(b));
 }
 
+// utils.box_refinement (utils.py:101-128) of one box against its ground-truth box
+__device__ __forceinline__ void refinement_rn(const float* box, const float* gt, const F6& sd, float* out) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    float s = __fsub_rn(box[3 + j], box[j]);
+    float c = __fadd_rn(box[j], __fmul_rn(0.5f, s));
+    float gs = __fsub_rn(gt[3 + j], gt[j]);
+    float gc = __fadd_rn(gt[j], __fmul_rn(0.5f, gs));
+    out[j] = __fdiv_rn(__fdiv_rn(__fsub_rn(gc, c), s), sd.v[j]);
+    out[3 + j] = __fdiv_rn(logf(__fdiv_rn(gs, s)), sd.v[3 + j]);
+  }
+}
+
 __global__ void refinement_kernel(const float* __restrict__ box, const float* __restrict__ gt, int n, F6 sd, float* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  refinement_rn(box + i * 6, gt + i * 6, sd, out + i * 6);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// detection targets without host round trips (model.detection_target_layer, model.py:414-563, split at its one
+// data-dependent point: the two torch.randperm draws on the host generator need the candidate counts)
+// ---------------------------------------------------------------------------------------------------------
+// Part A, one block: normalised proposals (= gather_boxes), per-proposal max IoU / argmax over the ground-truth boxes
+// (= bbox_overlaps + max), and the ascending index lists of the positive (IoU >= thr) and negative (IoU < thr) proposals
+// (= the two torch.nonzero calls), with their lengths.  A NaN IoU is in neither list, as with the reference's comparisons.
+__global__ void __launch_bounds__(1024) roi_candidates_kernel(const float* __restrict__ boxes, const int* __restrict__ keep,
+                                                              const int* __restrict__ count, int max_rows, F6 div,
+                                                              const float* __restrict__ gt, int G, float thr, float* __restrict__ rois,
+                                                              float* __restrict__ iou_max, int* __restrict__ assign,
+                                                              int* __restrict__ pos_list, int* __restrict__ neg_list,
+                                                              int* __restrict__ counts) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base[2];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = min(max(*count, 0), max_rows);
+  if (tid == 0) { s_base[0] = 0; s_base[1] = 0; }
+  __syncthreads();
+  for (int base = 0; base < max_rows; base += 1024) {
+    const int i = base + tid;
+    int flag = 0;
+    if (i < max_rows) {
+      float r[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      float mx = 0.f;
+      int arg = 0;
+      if (i < n) {
+        const int src = keep[i];
 #pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    float s = __fsub_rn(box[i * 6 + 3 + j], box[i * 6 + j]);
-    float c = __fadd_rn(box[i * 6 + j], __fmul_rn(0.5f, s));
-    float gs = __fsub_rn(gt[i * 6 + 3 + j], gt[i * 6 + j]);
-    float gc = __fadd_rn(gt[i * 6 + j], __fmul_rn(0.5f, gs));
-    out[i * 6 + j] = __fdiv_rn(__fdiv_rn(__fsub_rn(gc, c), s), sd.v[j]);
-    out[i * 6 + 3 + j] = __fdiv_rn(logf(__fdiv_rn(gs, s)), sd.v[3 + j]);
+        for (int j = 0; j < 6; ++j) r[j] = __fdiv_rn(boxes[(long long)src * 6 + j], div.v[j]);
+        bool nan = false;
+        mx = -INFINITY;
+        for (int g = 0; g < G; ++g) {
+          float b[6];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) b[j] = gt[g * 6 + j];
+          const float v = overlap_rn(r, b);
+          if (v != v) nan = true;
+          if (v > mx) { mx = v; arg = g; }      // first occurrence of the maximum
+        }
+        if (nan) mx = __int_as_float(0x7fc00000);
+        flag = (mx >= thr) ? 1 : ((mx < thr) ? 2 : 0);
+      }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) rois[(long long)i * 6 + j] = r[j];
+      iou_max[i] = mx;
+      assign[i] = arg;
+    }
+    // block-wide exclusive scan of (positive flag | negative flag << 16)
+    const int v = (flag == 1 ? 1 : 0) | (flag == 2 ? (1 << 16) : 0);
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      s_warp[lane] = w;                     // inclusive over warps
+    }
+    __syncthreads();
+    const int excl = incl - v + (warp ? s_warp[warp - 1] : 0);
+    if (flag == 1) pos_list[s_base[0] + (excl & 0xffff)] = i;
+    if (flag == 2) neg_list[s_base[1] + (excl >> 16)] = i;
+    const int total = s_warp[31];
+    __syncthreads();
+    if (tid == 0) { s_base[0] += total & 0xffff; s_base[1] += total >> 16; }
+    __syncthreads();
   }
+  if (tid == 0) { counts[0] = n; counts[1] = s_base[0]; counts[2] = s_base[1]; }
+}
+
+// Part B: rows 0..P-1 = positives pos_list[perm[i]], rows P..R-1 = negatives neg_list[perm[i]]; class id and box deltas of the
+// matched ground-truth box for the positives, zeros for the negatives (model.py:457-470, 545-560)
+__global__ void roi_targets_kernel(const float* __restrict__ rois, const int* __restrict__ assign, const int* __restrict__ pos_list,
+                                   const int* __restrict__ neg_list, const long long* __restrict__ perm, int P, int R,
+                                   const float* __restrict__ gt, const int* __restrict__ gt_cls, F6 sd, float* __restrict__ out_rois,
+                                   long long* __restrict__ cls, float* __restrict__ deltas) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R) return;
+  const int src = i < P ? pos_list[perm[i]] : neg_list[perm[i]];
+  float r[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) { r[j] = rois[(long long)src * 6 + j]; out_rois[i * 6 + j] = r[j]; }
+  float d[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  long long c = 0;
+  if (i < P) {
+    const int g = assign[src];
+    float b[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) b[j] = gt[g * 6 + j];
+    refinement_rn(r, b, sd, d);
+    c = gt_cls[g];
+  }
+  cls[i] = c;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) deltas[i * 6 + j] = d[j];
 }
 
 __global__ void roi_level_kernel(const float* __restrict__ boxes, int n, int* __restrict__ level) {
@@ -409,6 +525,30 @@ extern "C" int cfun_bbox_overlaps3d(const float* boxes1, int n1, const float* bo
   if (n1 == 0 || n2 == 0) return CFUN_OK;
   CFUN_CHECK_ARG(boxes1 && boxes2 && iou);
   overlaps_kernel<<<(unsigned)cdiv((long long)n1 * n2, 256), 256, 0, as_stream(stream)>>>(boxes1, n1, boxes2, n2, iou);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
+extern "C" int cfun_roi_candidates(const float* boxes_sorted, const int* keep, const int* count, int max_rows, const float* div6_host,
+                                   const float* gt_boxes, int n_gt, float iou_threshold, float* rois, float* iou_max, int* assign,
+                                   int* pos_list, int* neg_list, int* counts3, void* stream) {
+  CFUN_CHECK_ARG(boxes_sorted && keep && count && gt_boxes && rois && iou_max && assign && pos_list && neg_list && counts3);
+  CFUN_CHECK_ARG(max_rows > 0 && max_rows <= (1 << 20) && n_gt > 0);
+  roi_candidates_kernel<<<1, 1024, 0, as_stream(stream)>>>(boxes_sorted, keep, count, max_rows, to_f6(div6_host, 1.f), gt_boxes, n_gt,
+                                                          iou_threshold, rois, iou_max, assign, pos_list, neg_list, counts3);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
+extern "C" int cfun_roi_targets(const float* rois, const int* assign, const int* pos_list, const int* neg_list, const long long* perm,
+                                int P, int R, const float* gt_boxes, const int* gt_class_ids, const float* std6_host, float* out_rois,
+                                long long* class_ids, float* deltas, void* stream) {
+  CFUN_CHECK_ARG(P >= 0 && R >= P);
+  if (R == 0) return CFUN_OK;
+  CFUN_CHECK_ARG(rois && assign && pos_list && neg_list && perm && gt_boxes && gt_class_ids && out_rois && class_ids && deltas);
+  roi_targets_kernel<<<(unsigned)cdiv(R, 128), 128, 0, as_stream(stream)>>>(rois, assign, pos_list, neg_list, perm, P, R, gt_boxes,
+                                                                          gt_class_ids, to_f6(std6_host, 1.f), out_rois, class_ids,
+                                                                          deltas);
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;
 }

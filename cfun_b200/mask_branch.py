@@ -64,7 +64,7 @@ class Modified3DUNet(nn.Module):
         if not (self.training and self.use_dropout):
             return [None] * 5
         if self.injected_drop is not None:
-            return [m[:n].reshape(n, -1).to(device=device, dtype=torch.float32) for m in self.injected_drop]
+            return [m[:n].reshape(min(n, m.shape[0]), -1).to(device=device, dtype=torch.float32) for m in self.injected_drop]
         b, keep = self.base_n_filter, 1.0 - self.dropout_p
         return [torch.bernoulli(torch.full((n, b * m), keep, device=device)) / keep for m in (1, 2, 4, 8, 16)]
 

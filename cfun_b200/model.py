@@ -102,6 +102,23 @@ def proposal_layer(inputs, proposal_count, nms_threshold, anchors, config=None):
     return rois.unsqueeze(0)
 
 
+def proposal_layer_device(inputs, proposal_count, nms_threshold, anchors, config):
+    """proposal_layer up to (not including) its read-back of the kept count: -> (boxes [k,6] in pixels and descending
+    score order, keep int32 [proposal_count], count int32 [1]), all on the device.  The training step feeds these to
+    detection_targets_begin, which normalises the kept boxes exactly as proposal_layer does."""
+    probs = inputs[0].squeeze(0)
+    deltas = inputs[1].squeeze(0)
+    A = anchors.shape[0]
+    scores = probs[:, 1].detach().contiguous()
+    order = ops.sort_desc(scores)
+    k = min(config.PRE_NMS_LIMIT, A)
+    height, width, depth = [int(v) for v in config.IMAGE_SHAPE[:3]]
+    boxes, _ = ops.decode_clip(anchors, deltas, None, order, k, config.RPN_BBOX_STD_DEV,
+                               (0, 0, 0, depth, height, width))
+    keep, count = ops.nms3d(boxes, nms_threshold, proposal_count)
+    return boxes, keep, count
+
+
 # ---------------------------------------------------------------------------------------------------------
 #  RoI crop-resize ("RoIAlign")
 # ---------------------------------------------------------------------------------------------------------
@@ -199,6 +216,72 @@ def detection_target_layer(proposals, gt_class_ids, gt_boxes, gt_masks, config):
     if positive_count > 0:
         return positive_rois, positive_rois, roi_gt_class_ids.long(), deltas, masks
     return empty, empty, torch.zeros(0, dtype=torch.long, device=dev), empty, torch.zeros(0, device=dev)
+
+
+def detection_targets_begin(boxes, keep, count, gt_boxes, config, extra_counts=None):
+    """First half of detection_target_layer for the training step, with no host round trip: one kernel normalises the
+    kept proposals, takes max / argmax IoU against the ground-truth boxes and compacts the positive / negative index
+    lists (ops.roi_candidates); the three counts (+ extra_counts, any int32 device vector the caller wants read back at
+    the same time) start their copy to pinned host memory.  Returns the state detection_targets_finish consumes."""
+    height, width, depth = [int(v) for v in config.IMAGE_SHAPE[:3]]
+    gt_boxes = gt_boxes.squeeze(0) if gt_boxes.dim() == 3 else gt_boxes
+    rois, assign, pos_list, neg_list, counts = ops.roi_candidates(boxes, keep, count, (depth, height, width, depth, height, width),
+                                                                  gt_boxes, config.DETECTION_TARGET_IOU_THRESHOLD)
+    if extra_counts is not None:
+        counts = torch.cat([counts, extra_counts.to(torch.int32)])
+    host = torch.empty(counts.shape[0], dtype=torch.int32, pin_memory=True)
+    host.copy_(counts, non_blocking=True)
+    ready = torch.cuda.Event()
+    ready.record()
+    return dict(rois=rois, assign=assign, pos_list=pos_list, neg_list=neg_list, host=host, ready=ready, gt_boxes=gt_boxes)
+
+
+def detection_targets_finish(state, gt_class_ids, gt_masks, config):
+    """Second half: the step's ONE wait on the device (the counts), the two torch.randperm draws on the host generator in the
+    reference's order (model.py:441-444, 523-526), then one kernel for the sampled RoIs, class ids and box deltas
+    (ops.roi_targets) and one for the mask targets.  Same return values as detection_target_layer (the reference-shaped
+    function above, which the parity tests compare this against); also returns the extra counts read back."""
+    state["ready"].synchronize()
+    host = state["host"].tolist()
+    n, n_pos, n_neg = host[:3]
+    extra = host[3:]
+    rois_all = state["rois"]
+    dev = rois_all.device
+    gt_class_ids = gt_class_ids.squeeze(0) if gt_class_ids.dim() == 2 else gt_class_ids
+    if gt_masks.dim() in (5, 4) and gt_masks.shape[0] == 1:
+        gt_masks = gt_masks.squeeze(0)
+    empty = torch.zeros((0, 6), device=dev)
+    none = (empty, empty, torch.zeros(0, dtype=torch.long, device=dev), empty, torch.zeros(0, device=dev))
+    if n == 0 or n_pos == 0:
+        return none, extra
+    rnd = bool(getattr(config, "ROI_COUNT_ROUND", False))
+    want = config.TRAIN_ROIS_PER_IMAGE * config.ROI_POSITIVE_RATIO
+    want = int(round(want)) if rnd else int(want)
+    perm_p = torch.randperm(n_pos)[:want]
+    P = int(perm_p.numel())
+    if P == 0:
+        return none, extra
+    perm_n = None
+    if n_neg > 0:
+        want = (1.0 / config.ROI_POSITIVE_RATIO) * P - P
+        want = int(round(want)) if rnd else int(want)
+        perm_n = torch.randperm(n_neg)[:want]
+    Rn = int(perm_n.numel()) if perm_n is not None else 0
+    R = P + Rn
+    perm_host = torch.empty(R, dtype=torch.int64, pin_memory=True)
+    perm_host[:P] = perm_p
+    if Rn:
+        perm_host[P:] = perm_n
+    perm = perm_host.to(dev, non_blocking=True)
+    rois, class_ids, deltas = ops.roi_targets(rois_all, state["assign"], state["pos_list"], state["neg_list"], perm, P, R,
+                                              state["gt_boxes"], gt_class_ids, config.BBOX_STD_DEV)
+    positive_rois = rois[:P]
+    label = _label_volume(gt_masks)
+    dense = bool(getattr(config, "DENSE_MASK_TARGETS", False))
+    onehot, index = ops.mask_target_crop(label, positive_rois, getattr(config, "NUM_CLASSES", 8) if gt_masks.dim() == 3 else gt_masks.shape[0],
+                                         config.MASK_SHAPE, onehot=dense, index=not dense)
+    masks = onehot if dense else index
+    return (positive_rois, rois, class_ids, deltas, masks), extra
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -336,6 +419,42 @@ def compute_rpn_bbox_loss(target_bbox, rpn_match, rpn_bbox):
     ind = torch.nonzero(rpn_match == 1)
     rpn_bbox = rpn_bbox[ind[:, 0], ind[:, 1]]
     return F.smooth_l1_loss(rpn_bbox, target_bbox[0, :rpn_bbox.shape[0], :])
+
+
+def _nonzero_static(mask, size):
+    """ascending indices of the True entries of a 1-D mask, padded with -1 to `size`, without a host round trip"""
+    try:
+        return torch.nonzero_static(mask, size=size, fill_value=-1)[:, 0]
+    except (AttributeError, NotImplementedError, RuntimeError):
+        n = mask.shape[0]
+        pos = torch.cumsum(mask, 0) - 1
+        out = torch.full((size + 1,), -1, dtype=torch.long, device=mask.device)
+        slot = torch.where(mask, pos.clamp(max=size), torch.full_like(pos, size))
+        out.scatter_(0, slot, torch.arange(n, device=mask.device))
+        out[size] = -1
+        return out[:size]
+
+
+def compute_rpn_losses_static(rpn_match, target_bbox, rpn_class_logits, rpn_pred_bbox, max_anchors):
+    """compute_rpn_class_loss + compute_rpn_bbox_loss (reference model.py:836-873) for batch 1 without their torch.nonzero
+    read-backs: the <= max_anchors non-neutral anchors (RPN_TRAIN_ANCHORS_PER_IMAGE, the cap build_rpn_targets enforces)
+    are gathered into fixed-size index lists, padded rows carry weight 0.  Also returns the int32 device vector
+    [non-neutral, positive] so that the caller can verify the cap when it next reads from the device."""
+    m = rpn_match.reshape(-1)
+    valid, pos = m != 0, m == 1
+    counts = torch.stack([valid.sum(), pos.sum()]).to(torch.int32)
+    ind = _nonzero_static(valid, max_anchors)
+    w = (ind >= 0).to(rpn_class_logits.dtype)
+    idx = ind.clamp(min=0)
+    ce = F.cross_entropy(rpn_class_logits[0].index_select(0, idx), (m.index_select(0, idx) == 1).long(), reduction='none')
+    class_loss = (ce * w).sum() / w.sum()
+    T = min(max_anchors, target_bbox.shape[1])
+    pind = _nonzero_static(pos, T)
+    pw = (pind >= 0).to(rpn_pred_bbox.dtype)
+    pred = rpn_pred_bbox[0].index_select(0, pind.clamp(min=0))
+    l1 = F.smooth_l1_loss(pred, target_bbox[0, :T, :], reduction='none') * pw[:, None]
+    bbox_loss = l1.sum() / (pw.sum() * pred.shape[1])
+    return class_loss, bbox_loss, counts
 
 
 def _zero_loss(like):
@@ -550,6 +669,8 @@ class MaskRCNN(nn.Module):
         self.build(config=config, test_flag=test_flag)
         self.initialize_weights()
         self._graphed_tails = None
+        self._roi_scale = None         # [d,h,w,d,h,w] on the device (proposal / ground-truth box normalisation)
+        self._unit_drops = None        # all-ones Dropout3d masks for eval-mode / LiTS heads tails
         self._graph_ws_gen = 0
         self.graph_kernel_counts = {}
         self.graph_replays = {}
@@ -658,15 +779,17 @@ class MaskRCNN(nn.Module):
         return [rpn_class_logits, rpn_bbox, target_class_ids, mrcnn_class_logits, target_deltas, mrcnn_bbox, target_mask,
                 mrcnn_mask, mrcnn_mask_logits]
 
-    def rpn_proposals(self, molded_images, mode):
-        """backbone + FPN + RPN on both levels + proposal layer (reference model.py:1409-1437)"""
+    def rpn_proposals(self, molded_images, mode, device_only=False):
+        """backbone + FPN + RPN on both levels + proposal layer (reference model.py:1409-1437).  device_only: the last
+        element is proposal_layer_device's (boxes, keep, count) instead of the [1,n,6] proposals (no read-back)."""
         cfg = self.config
         p2_out, p3_out = self.fpn(molded_images)
         layer_outputs = [self.rpn(p) for p in (p2_out, p3_out)]
         rpn_class_logits, rpn_class, rpn_bbox = [torch.cat(list(o), dim=1) for o in zip(*layer_outputs)]
         proposal_count = cfg.POST_NMS_ROIS_TRAINING if mode == "training" else cfg.POST_NMS_ROIS_INFERENCE
-        rpn_rois = proposal_layer([rpn_class, rpn_bbox], proposal_count=proposal_count,
-                                  nms_threshold=cfg.RPN_NMS_THRESHOLD, anchors=self.anchors, config=cfg)
+        layer = proposal_layer_device if device_only else proposal_layer
+        rpn_rois = layer([rpn_class, rpn_bbox], proposal_count=proposal_count,
+                         nms_threshold=cfg.RPN_NMS_THRESHOLD, anchors=self.anchors, config=cfg)
         return p2_out, p3_out, rpn_class_logits, rpn_class, rpn_bbox, rpn_rois
 
     def weighted_loss(self, losses):
@@ -685,27 +808,42 @@ class MaskRCNN(nn.Module):
         cfg = self.config
         dev = images.device
         frozen = bool(getattr(cfg, "STAGED_LOSSES", False)) and cfg.STAGE != 'beginning'    # LiTS: detector frozen, mask losses only
+        # Everything up to the heads is enqueued without a host round trip; the single wait of the step is the read-back of
+        # the proposal / positive / negative counts that size the two host-generator permutations (detection_targets_finish).
         with torch.set_grad_enabled(not frozen):
-            p2, p3, rpn_class_logits, rpn_class, rpn_pred_bbox, rpn_rois = self.rpn_proposals(images, 'training')
+            p2, p3, rpn_class_logits, rpn_class, rpn_pred_bbox, prop = self.rpn_proposals(images, 'training', device_only=True)
         h, w, d = cfg.IMAGE_SHAPE[:3]
-        scale = _f32([d, h, w, d, h, w], dev)
-        p_rois, rois, target_class_ids, target_deltas, target_mask = \
-            detection_target_layer(rpn_rois, gt_class_ids, gt_boxes / scale, gt_masks, cfg)
-        P, R = int(p_rois.shape[0]), int(rois.shape[0])
-        self.last_roi_counts = (P, R)
+        if self._roi_scale is None or self._roi_scale.device != dev:
+            self._roi_scale = _f32([d, h, w, d, h, w], dev)
         zero = _zero_loss(rpn_class_logits)
+        rpn_counts = None
+        cap = int(cfg.RPN_TRAIN_ANCHORS_PER_IMAGE)
         if frozen:
             rpn_class_loss = rpn_bbox_loss = zero
         else:
+            rpn_class_loss, rpn_bbox_loss, rpn_counts = compute_rpn_losses_static(rpn_match, rpn_bbox, rpn_class_logits,
+                                                                                  rpn_pred_bbox, cap)
+        unet = self.mask.modified_u_net
+        max_p = max(1, int(round(cfg.TRAIN_ROIS_PER_IMAGE * cfg.ROI_POSITIVE_RATIO)))
+        drops_all = unet._drop_masks(max_p, dev)          # drawn for the largest possible positive count, sliced below
+        state = detection_targets_begin(*prop, gt_boxes / self._roi_scale, cfg, extra_counts=rpn_counts)
+        (p_rois, rois, target_class_ids, target_deltas, target_mask), extra = \
+            detection_targets_finish(state, gt_class_ids, gt_masks, cfg)
+        if rpn_counts is not None and (extra[0] > cap or extra[1] > min(cap, rpn_bbox.shape[1])):
+            # more non-neutral anchors than build_rpn_targets ever emits: the fixed-size gather dropped some -- redo exactly
             rpn_class_loss = compute_rpn_class_loss(rpn_match, rpn_class_logits)
             rpn_bbox_loss = compute_rpn_bbox_loss(rpn_bbox, rpn_match, rpn_pred_bbox)
+        P, R = int(p_rois.shape[0]), int(rois.shape[0])
+        self.last_roi_counts = (P, R)
         if P > 0:
             if target_mask.dim() == 5:
                 target_mask = torch.argmax(target_mask.long(), dim=1)
-            unet = self.mask.modified_u_net
-            drops = unet._drop_masks(P, dev)
-            if drops[0] is None:
-                drops = [torch.ones((P, unet.base_n_filter * m), device=dev) for m in (1, 2, 4, 8, 16)]
+            if drops_all[0] is None:
+                if self._unit_drops is None or self._unit_drops[0].device != dev or self._unit_drops[0].shape[0] < P:
+                    self._unit_drops = [torch.ones((max(P, max_p), unet.base_n_filter * m), device=dev) for m in (1, 2, 4, 8, 16)]
+                drops = [t[:P] for t in self._unit_drops]
+            else:
+                drops = [t[:P] for t in drops_all]
             if self._graphed_tails and ops.workspace_generation() != self._graph_ws_gen:
                 # the shared conv workspace was reallocated after these graphs were captured (a larger RoI split or image):
                 # they hold the freed buffer's address in kernel arguments and tensor maps -- drop them, re-capture lazily

@@ -563,6 +563,36 @@ def box_refinement(box, gt_box, std6=(1, 1, 1, 1, 1, 1)):
     return out
 
 
+def roi_candidates(boxes_sorted, keep, count, div6, gt_boxes_norm, iou_threshold):
+    """Device half A of detection_target_layer: -> (rois [max,6] normalised, assign int32 [max], pos_list, neg_list int32 [max],
+    counts int32 [3] = {proposals, positives, negatives}); nothing is read back."""
+    _require_cuda(boxes_sorted, keep, count, gt_boxes_norm)
+    dev = boxes_sorted.device
+    max_rows = keep.shape[0]
+    gt = gt_boxes_norm.detach().contiguous().float()
+    rois = torch.empty((max_rows, 6), device=dev)
+    iou_max = torch.empty(max_rows, device=dev)
+    ints = torch.empty((3, max_rows), dtype=torch.int32, device=dev)
+    counts = torch.empty(3, dtype=torch.int32, device=dev)
+    _run("cfun_roi_candidates", _ptr(boxes_sorted.contiguous()), _ptr(keep), _ptr(count), max_rows, f6(div6), _ptr(gt), gt.shape[0],
+         float(iou_threshold), _ptr(rois), _ptr(iou_max), _ptr(ints[0]), _ptr(ints[1]), _ptr(ints[2]), _ptr(counts), _stream())
+    return rois, ints[0], ints[1], ints[2], counts
+
+
+def roi_targets(rois, assign, pos_list, neg_list, perm, P, R, gt_boxes_norm, gt_class_ids, std6):
+    """Device half B: perm int64 [R] on the device (positions in pos_list for rows < P, in neg_list after).
+    -> (rois [R,6], class ids int64 [R], deltas [R,6])."""
+    dev = rois.device
+    gt = gt_boxes_norm.detach().contiguous().float()
+    cls_in = gt_class_ids.to(torch.int32).contiguous()
+    out = torch.empty((R, 6), device=dev)
+    cls = torch.empty(R, dtype=torch.int64, device=dev)
+    deltas = torch.empty((R, 6), device=dev)
+    _run("cfun_roi_targets", _ptr(rois), _ptr(assign), _ptr(pos_list), _ptr(neg_list), _ptr(perm), int(P), int(R), _ptr(gt),
+         _ptr(cls_in), f6(std6), _ptr(out), _ptr(cls), _ptr(deltas), _stream())
+    return out, cls, deltas
+
+
 def mask_target_crop(label_dhw, rois, ncls, mask_shape, onehot=True, index=True):
     """label_dhw int32 [D,H,W]; rois [P,6] normalised.  Returns (onehot float64 [P,ncls,*mask_shape] | None,
     class index int64 [P,*mask_shape] | None)."""

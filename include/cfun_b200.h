@@ -188,6 +188,20 @@ int cfun_gather_boxes(const float* rows, const int* idx, const int* count, int m
 int cfun_iou3d_eps(const float* box, const float* boxes, int n, float* out, void* stream);
 int cfun_bbox_overlaps3d(const float* boxes1, int n1, const float* boxes2, int n2, float* iou, void* stream);
 int cfun_box_refinement(const float* box, const float* gt_box, int n, const float* std6_host, float* deltas, void* stream);
+/* model.detection_target_layer (model.py:414-563) without host round trips, split at its one data-dependent point (the
+ * two torch.randperm draws on the host generator need the candidate counts):
+ *   cfun_roi_candidates  rois[max_rows,6] = boxes_sorted[keep[i]] / div6 (rows >= *count zero) = the proposal normalisation;
+ *                        iou_max / assign = max and argmax IoU over the n_gt ground-truth boxes (bbox_overlaps + max);
+ *                        pos_list / neg_list = ascending indices with IoU >= / < threshold (the two torch.nonzero calls);
+ *                        counts3 = {*count, positives, negatives}.  One launch, one block.
+ *   cfun_roi_targets     rows 0..P-1 = rois[pos_list[perm[i]]], rows P..R-1 = rois[neg_list[perm[i]]]; class id and
+ *                        box_refinement deltas of the matched ground-truth box for the positives, zeros for the negatives. */
+int cfun_roi_candidates(const float* boxes_sorted, const int* keep, const int* count, int max_rows, const float* div6_host,
+                        const float* gt_boxes, int n_gt, float iou_threshold, float* rois, float* iou_max, int* assign,
+                        int* pos_list, int* neg_list, int* counts3, void* stream);
+int cfun_roi_targets(const float* rois, const int* assign, const int* pos_list, const int* neg_list, const long long* perm,
+                     int P, int R, const float* gt_boxes, const int* gt_class_ids, const float* std6_host, float* out_rois,
+                     long long* class_ids, float* deltas, void* stream);
 /* label: int32 [D,H,W] class-id volume; rois [P,6] normalised; out: one-hot float64 [P,ncls,md,mh,mw]
  * (the reference's target layout, model.py:481-493) and/or class index int64 [P,md,mh,mw] (either may be NULL). */
 int cfun_mask_target_crop(const int* label, int D, int H, int W, const float* rois, int P, int ncls, int md, int mh,

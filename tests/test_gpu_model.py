@@ -398,3 +398,88 @@ def test_lits_variant_matches_lits_reference_golden():
     frozen = [k for k, p in M.MaskRCNN(cfg, "/tmp/_cfun_test").named_parameters() if not p.requires_grad]
     assert any(k.startswith("fpn.") for k in frozen) and any(k.startswith("rpn.") for k in frozen)
     assert not any(k.startswith("mask.") for k in frozen)
+
+
+@pytest.mark.parametrize("case", [dict(n=300, count=180, G=1, max_rows=256, seed=1), dict(n=1500, count=1500, G=7, max_rows=2000, seed=2),
+                                  dict(n=2500, count=2300, G=3, max_rows=2300, seed=3), dict(n=40, count=0, G=1, max_rows=64, seed=4),
+                                  dict(n=600, count=500, G=2, max_rows=512, seed=5, far=True)])
+def test_fused_detection_targets_match_reference_shaped_layer(case):
+    """The training step's no-read-back target path (detection_targets_begin / _finish: ops.roi_candidates +
+    ops.roi_targets) returns exactly what proposal normalisation + detection_target_layer (the reference-shaped function,
+    model.py:414-563) return for the same host-generator state."""
+    from cfun_b200 import model as M, ops, config as Cf
+    cfg = Cf.heart_config(64, "beginning", mask_pool=16, anchor_scales=(8, 16), **SMALL)
+    cfg.TRAIN_ROIS_PER_IMAGE, cfg.ROI_POSITIVE_RATIO = 40, 0.33
+    g = torch.Generator().manual_seed(case["seed"])
+    n, G = case["n"], case["G"]
+    dim = 64.0
+    gt_c = torch.rand(G, 3, generator=g) * 30 + 17
+    gt_s = torch.rand(G, 3, generator=g) * 10 + 8
+    gt = torch.cat([gt_c - gt_s / 2, gt_c + gt_s / 2], 1)
+    # proposals: jittered copies of the ground-truth boxes (a spread of IoUs around the 0.5 threshold) and random boxes
+    which = torch.randint(0, G, (n,), generator=g)
+    jit = torch.randn(n, 6, generator=g) * (6.0 if case.get("far") else 2.5)
+    boxes = (gt[which] + jit).clamp(0, dim)
+    rnd = torch.rand(n, 6, generator=g) * dim
+    rnd = torch.cat([torch.minimum(rnd[:, :3], rnd[:, 3:]), torch.maximum(rnd[:, :3], rnd[:, 3:])], 1)
+    boxes = torch.where((torch.arange(n) % 3 == 0)[:, None], rnd, boxes)
+    boxes[::17, 3:] = boxes[::17, :3]                         # a few empty boxes
+    keep = torch.randperm(n, generator=g)[:case["max_rows"]].sort().values.to(torch.int32)
+    keep = torch.cat([keep, torch.zeros(max(0, case["max_rows"] - keep.numel()), dtype=torch.int32)])
+    count = torch.tensor([case["count"]], dtype=torch.int32)
+    label = torch.randint(0, 8, (64, 64, 64), generator=g, dtype=torch.int32)
+    cls = torch.arange(1, G + 1, dtype=torch.int32)
+    scale = torch.tensor([dim] * 6)
+    boxes_c, keep_c, count_c, gt_c_, label_c, cls_c = [t.cuda() for t in (boxes, keep, count, gt / scale, label, cls)]
+    # reference-shaped path: normalise + slice (proposal_layer's tail), then detection_target_layer
+    nk = int(count.item())
+    rois_ref = ops.gather_boxes(boxes_c, keep_c, count_c, max(nk, 1), (dim,) * 6)[:nk]
+    torch.manual_seed(1234 + case["seed"])
+    ref = M.detection_target_layer(rois_ref.unsqueeze(0), cls_c.unsqueeze(0), gt_c_.unsqueeze(0), label_c, cfg)
+    torch.manual_seed(1234 + case["seed"])
+    extra_in = torch.tensor([5, 3], dtype=torch.int32).cuda()
+    state = M.detection_targets_begin(boxes_c, keep_c, count_c, gt_c_.unsqueeze(0), cfg, extra_counts=extra_in)
+    new, extra = M.detection_targets_finish(state, cls_c.unsqueeze(0), label_c, cfg)
+    assert extra == [5, 3]
+    assert [tuple(t.shape) for t in new] == [tuple(t.shape) for t in ref]
+    for a, b in zip(new, ref):
+        assert a.dtype == b.dtype and torch.equal(a, b)
+    if nk:
+        assert ref[0].shape[0] > 0 or case["count"] == 0      # the synthetic cases do produce positives
+
+
+def test_rpn_losses_static_match_reference_shaped_losses():
+    """compute_rpn_losses_static (fixed-size gathers, no read-back) == compute_rpn_class_loss / compute_rpn_bbox_loss
+    (model.py:836-873), values and gradients"""
+    from cfun_b200 import model as M
+    g = torch.Generator().manual_seed(9)
+    A, K = 5000, 256
+    for npos, nneg in ((37, 120), (128, 128), (1, 0), (0, 9)):
+        m = torch.zeros(A, dtype=torch.int32)
+        perm = torch.randperm(A, generator=g)
+        m[perm[:npos]] = 1
+        m[perm[npos:npos + nneg]] = -1
+        tgt = torch.zeros(1, K, 6)
+        tgt[0, :npos] = torch.randn(npos, 6, generator=g)
+        logits = torch.randn(1, A, 2, generator=g)
+        pred = torch.randn(1, A, 6, generator=g) * 2
+        out = []
+        for fn in ("ref", "static"):
+            lg, pb = logits.clone().cuda().requires_grad_(True), pred.clone().cuda().requires_grad_(True)
+            mm, tt = m.cuda().view(1, -1, 1), tgt.cuda()
+            if fn == "ref":
+                lc, lb = M.compute_rpn_class_loss(mm, lg), M.compute_rpn_bbox_loss(tt, mm, pb)
+            else:
+                lc, lb, counts = M.compute_rpn_losses_static(mm, tt, lg, pb, K)
+                assert counts.tolist() == [npos + nneg, npos]
+            if npos:
+                (lc * 1.5 + lb * 0.7).backward()
+            else:
+                lc.backward()
+            out.append((lc.item(), lb.item(), lg.grad.cpu(), pb.grad.cpu() if pb.grad is not None else None))
+        (c0, b0, gl0, gp0), (c1, b1, gl1, gp1) = out
+        assert abs(c0 - c1) <= 2e-6 * abs(c0)
+        assert (np.isnan(b0) and np.isnan(b1)) if npos == 0 else abs(b0 - b1) <= 2e-6 * abs(b0)
+        assert torch.allclose(gl0, gl1, rtol=1e-5, atol=1e-9)
+        if npos:
+            assert torch.allclose(gp0, gp1, rtol=1e-5, atol=1e-9)
