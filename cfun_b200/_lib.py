@@ -50,11 +50,13 @@ SIGNATURES = {
     "cfun_conv3d_pack_bytes": (_sz, [_D]),
     "cfun_conv3d_bwd_fused_workspace_size": (_sz, [_D]),
     "cfun_conv3d_fwd_keep_pack": (_i, [_D, _p, _p, _p, _p, _i, _p, _sz, _p, _sz, _p]),
+    "cfun_conv3d_fwd_stats": (_i, [_D, _p, _p, _p, _p, _i, _p, _sz, _p, _p, _sz, _p]),
     "cfun_conv3d_bwd_fused": (_i, [_D, _p, _sz, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "cfun_fc_fwd": (_i, [_i, _i, _ll, _p, _p, _p, _p, _p]),
     "cfun_fc_bwd_data": (_i, [_i, _i, _ll, _p, _p, _p, _p]),
     "cfun_fc_bwd_weight": (_i, [_i, _i, _ll, _p, _p, _p, _p, _p]),
     "cfun_instnorm_stats": (_i, [_p, _i, _ll, _i, _f, _p, _p, _p, _p]),
+    "cfun_instnorm_finalize": (_i, [_p, _i, _ll, _i, _f, _p, _p, _p]),
     "cfun_affine_act_fwd": (_i, [_p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p]),
     "cfun_affine_act_bwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p]),
     "cfun_instnorm_bwd_apply": (_i, [_p, _p, _p, _p, _p, _i, _ll, _i, _p]),

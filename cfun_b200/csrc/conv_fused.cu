@@ -20,10 +20,11 @@ size_t hl_pack_bytes(const cfun_conv3d_desc* d, int pass);
 size_t hx_pack_bytes(const cfun_conv3d_desc* d, int pass);
 size_t tc_workspace(const cfun_conv3d_desc* d, int pass);
 int hl_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
-               int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st);
+               int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st,
+               double* stat_acc);
 int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
                int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st,
-               int tapmask);
+               int tapmask, double* stat_acc);
 int ds_bwd_weight_packed(const cfun_conv3d_desc* d, __nv_bfloat16* yh, __nv_bfloat16* yl, int gy_pack, __nv_bfloat16* xh,
                          __nv_bfloat16* xl, float* dw, cudaStream_t st);
 int launch_pack_act_gp_pad(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int C, int G, int P,
@@ -44,9 +45,10 @@ static size_t act_bytes(const cfun_conv3d_desc* d, int pass) {
   return hl_supported(d, pass) ? hl_pack_bytes(d, pass) : hx_pack_bytes(d, pass);
 }
 static int run_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
-                    void* ws, size_t ws_bytes, __nv_bfloat16* hi, __nv_bfloat16* lo, bool ready, cudaStream_t st) {
-  if (hl_supported(d, pass)) return hl_conv_ex(d, pass, src, w, bias, dst, epi, 3, ws, ws_bytes, hi, lo, ready, st);
-  return hx_conv_ex(d, pass, src, w, bias, dst, epi, 3, ws, ws_bytes, hi, lo, ready, st, 0x7FFFFFF);
+                    void* ws, size_t ws_bytes, __nv_bfloat16* hi, __nv_bfloat16* lo, bool ready, cudaStream_t st,
+                    double* stat_acc = nullptr) {
+  if (hl_supported(d, pass)) return hl_conv_ex(d, pass, src, w, bias, dst, epi, 3, ws, ws_bytes, hi, lo, ready, st, stat_acc);
+  return hx_conv_ex(d, pass, src, w, bias, dst, epi, 3, ws, ws_bytes, hi, lo, ready, st, 0x7FFFFFF, stat_acc);
 }
 }  // namespace cfun
 
@@ -72,6 +74,24 @@ extern "C" int cfun_conv3d_fwd_keep_pack(const cfun_conv3d_desc* d, const float*
   __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(xpack);
   __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(xpack) + act);
   return run_conv(d, CFUN_PASS_FWD, x, w, bias, y, epi_flags, ws, ws_bytes, hi, lo, false, as_stream(stream));
+}
+
+// cfun_conv3d_fwd_keep_pack whose epilogue also accumulates the InstanceNorm statistics of y: stat_acc [N][Cout][2] doubles
+// (sum, sum of squares over the sample's voxels), zeroed here -- what cfun_instnorm_stats would compute in a separate pass
+// over y; cfun_instnorm_finalize turns them into mean / rstd.
+extern "C" int cfun_conv3d_fwd_stats(const cfun_conv3d_desc* d, const float* x, const float* w, const float* bias, float* y,
+                                     int epi_flags, void* xpack, size_t xpack_bytes, double* stat_acc, void* ws, size_t ws_bytes,
+                                     void* stream) {
+  CFUN_CHECK_ARG(fused_ok(d));
+  CFUN_CHECK_ARG(x && w && y && xpack && ws && stat_acc);
+  CFUN_CHECK_ARG(!(epi_flags & CFUN_EPI_BIAS) || bias);
+  const size_t act = act_bytes(d, CFUN_PASS_FWD);
+  CFUN_CHECK_ARG(xpack_bytes >= 2 * act && ((size_t)xpack & 127) == 0);
+  cudaStream_t st = as_stream(stream);
+  CFUN_CUDA(cudaMemsetAsync(stat_acc, 0, sizeof(double) * 2 * (size_t)d->N * d->Cout, st));
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(xpack);
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(xpack) + act);
+  return run_conv(d, CFUN_PASS_FWD, x, w, bias, y, epi_flags, ws, ws_bytes, hi, lo, false, st, stat_acc);
 }
 
 extern "C" int cfun_conv3d_bwd_fused(const cfun_conv3d_desc* d, const void* xpack, size_t xpack_bytes, const float* dy,

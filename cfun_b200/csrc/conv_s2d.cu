@@ -34,7 +34,7 @@ bool hx_supported(const cfun_conv3d_desc* d, int pass);                      // 
 size_t hx_workspace(const cfun_conv3d_desc* d, int pass);
 int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
                int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st,
-               int tapmask);
+               int tapmask, double* stat_acc = nullptr);
 constexpr int S2D_MASK27 = 0x361B;    // taps (kd,kh,kw) in {0,1}^3 of the embedding 3x3x3 kernel: bits {0,1,3,4,9,10,12,13}
 constexpr int S2D_TAPMASK = 0x1B;     // (kh,kw) in {0,1}^2 -> kh*3+kw in {0,1,3,4}
 constexpr int S2D_KDMASK = 0x3;       // kd in {0,1}

@@ -247,25 +247,24 @@ __global__ void __launch_bounds__(256) igemm_kernel(ConvGeo g, const float* __re
   }
 }
 
-// packed weight matrices.  w is (Cout, Cin, taps).
-__global__ void pack_w_fwd_kernel(const float* __restrict__ w, float* __restrict__ Bm, int Cout, int Cin, int taps, int ldb) {
-  long long total = (long long)Cout * Cin * taps;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int tap = (int)(i % taps);
-    long long r = i / taps;
-    int ci = (int)(r % Cin);
-    int co = (int)(r / Cin);
-    Bm[((long long)tap * Cin + ci) * ldb + co] = w[i];
+// packed weight matrices.  w is (Cout, Cin, taps).  The kernels write the whole zero-padded matrix [rows_pad][ldb] (the
+// GEMM kernels read the padding), so no memset precedes them.
+__global__ void pack_w_fwd_kernel(const float* __restrict__ w, float* __restrict__ Bm, int Cout, int Cin, int taps, int ldb,
+                                  int rows_pad) {
+  const int total = rows_pad * ldb;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / ldb, co = i - r * ldb;
+    const int tap = r / Cin, ci = r - tap * Cin;
+    Bm[i] = (tap < taps && co < Cout) ? __ldg(w + ((long long)co * Cin + ci) * taps + tap) : 0.f;
   }
 }
-__global__ void pack_w_dgrad_kernel(const float* __restrict__ w, float* __restrict__ Bm, int Cout, int Cin, int taps, int ldb) {
-  long long total = (long long)Cout * Cin * taps;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int tap = (int)(i % taps);
-    long long r = i / taps;
-    int ci = (int)(r % Cin);
-    int co = (int)(r / Cin);
-    Bm[((long long)tap * Cout + co) * ldb + ci] = w[i];
+__global__ void pack_w_dgrad_kernel(const float* __restrict__ w, float* __restrict__ Bm, int Cout, int Cin, int taps, int ldb,
+                                    int rows_pad) {
+  const int total = rows_pad * ldb;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / ldb, ci = i - r * ldb;
+    const int tap = r / Cout, co = r - tap * Cout;
+    Bm[i] = (tap < taps && ci < Cin) ? __ldg(w + ((long long)co * Cin + ci) * taps + tap) : 0.f;
   }
 }
 __global__ void unpack_dw_kernel(const float* __restrict__ dWm, float* __restrict__ dw, int Cout, int Cin, int taps, int ldb) {
@@ -480,9 +479,19 @@ static int launch_igemm(const ConvGeo& g, const float* src, const float* Bm, con
     if (vec) igemm_kernel<MODE, 256, 16, 4, 4, true><<<grid, 256, 0, st>>>(g, src, Bm, bias, dst, epi);
     else igemm_kernel<MODE, 256, 16, 4, 4, false><<<grid, 256, 0, st>>>(g, src, Bm, bias, dst, epi);
   } else if (g.Ct <= 32) {
-    dim3 grid((unsigned)cdiv(g.M, 256), (unsigned)cdiv(g.Ct, 32));
-    if (vec) igemm_kernel<MODE, 256, 32, 8, 4, true><<<grid, 256, 0, st>>>(g, src, Bm, bias, dst, epi);
-    else igemm_kernel<MODE, 256, 32, 8, 4, false><<<grid, 256, 0, st>>>(g, src, Bm, bias, dst, epi);
+    if (cdiv(g.M, 256) < num_sms()) {      // less than one wave of 256-row tiles (16^3 .. 32^3 backbone stages): half-height tiles
+      dim3 grid((unsigned)cdiv(g.M, 128), (unsigned)cdiv(g.Ct, 32));
+      if (vec) igemm_kernel<MODE, 128, 32, 4, 4, true><<<grid, 256, 0, st>>>(g, src, Bm, bias, dst, epi);
+      else igemm_kernel<MODE, 128, 32, 4, 4, false><<<grid, 256, 0, st>>>(g, src, Bm, bias, dst, epi);
+    } else {
+      dim3 grid((unsigned)cdiv(g.M, 256), (unsigned)cdiv(g.Ct, 32));
+      if (vec) igemm_kernel<MODE, 256, 32, 8, 4, true><<<grid, 256, 0, st>>>(g, src, Bm, bias, dst, epi);
+      else igemm_kernel<MODE, 256, 32, 8, 4, false><<<grid, 256, 0, st>>>(g, src, Bm, bias, dst, epi);
+    }
+  } else if (cdiv(g.M, 128) * cdiv(g.Ct, 64) < num_sms()) {
+    dim3 grid((unsigned)cdiv(g.M, 64), (unsigned)cdiv(g.Ct, 64));
+    if (vec) igemm_kernel<MODE, 64, 64, 4, 4, true><<<grid, 256, 0, st>>>(g, src, Bm, bias, dst, epi);
+    else igemm_kernel<MODE, 64, 64, 4, 4, false><<<grid, 256, 0, st>>>(g, src, Bm, bias, dst, epi);
   } else {
     dim3 grid((unsigned)cdiv(g.M, 128), (unsigned)cdiv(g.Ct, 64));
     if (vec) igemm_kernel<MODE, 128, 64, 8, 4, true><<<grid, 256, 0, st>>>(g, src, Bm, bias, dst, epi);
@@ -501,10 +510,10 @@ int simt_conv_fwd(const cfun_conv3d_desc* d, const float* x, const float* w, con
   size_t need = simt_workspace(d, CFUN_PASS_FWD);
   if (ws_bytes < need) { set_error("conv3d_fwd: workspace %zu < %zu", ws_bytes, need); return CFUN_ERR_WORKSPACE; }
   float* Bm = reinterpret_cast<float*>(align_up((size_t)ws, 256));
-  CFUN_CUDA(cudaMemsetAsync(Bm, 0, align_up((size_t)g.Ktot, 64) * (size_t)g.ldb * sizeof(float), st));
   int taps = g.kD * g.kH * g.kW;
-  long long tot = (long long)d->Cout * d->Cin * taps;
-  pack_w_fwd_kernel<<<(unsigned)std::min<long long>(cdiv(tot, 256), 4096), 256, 0, st>>>(w, Bm, d->Cout, d->Cin, taps, g.ldb);
+  const int rows_pad = (int)align_up((size_t)g.Ktot, 64);
+  CFUN_CHECK_ARG((long long)rows_pad * g.ldb < (1LL << 31));
+  pack_w_fwd_kernel<<<(unsigned)std::min<long long>(cdiv((long long)rows_pad * g.ldb, 256), 4096), 256, 0, st>>>(w, Bm, d->Cout, d->Cin, taps, g.ldb, rows_pad);
   CFUN_LAUNCH_CHECK();
   return launch_igemm<0>(g, x, Bm, bias, y, epi, st);
 }
@@ -517,10 +526,10 @@ int simt_conv_bwd_data(const cfun_conv3d_desc* d, const float* dy, const float* 
   size_t need = simt_workspace(d, CFUN_PASS_BWD_DATA);
   if (ws_bytes < need) { set_error("conv3d_bwd_data: workspace %zu < %zu", ws_bytes, need); return CFUN_ERR_WORKSPACE; }
   float* Bm = reinterpret_cast<float*>(align_up((size_t)ws, 256));
-  CFUN_CUDA(cudaMemsetAsync(Bm, 0, align_up((size_t)g.Ktot, 64) * (size_t)g.ldb * sizeof(float), st));
   int taps = g.kD * g.kH * g.kW;
-  long long tot = (long long)d->Cout * d->Cin * taps;
-  pack_w_dgrad_kernel<<<(unsigned)std::min<long long>(cdiv(tot, 256), 4096), 256, 0, st>>>(w, Bm, d->Cout, d->Cin, taps, g.ldb);
+  const int rows_pad = (int)align_up((size_t)g.Ktot, 64);
+  CFUN_CHECK_ARG((long long)rows_pad * g.ldb < (1LL << 31));
+  pack_w_dgrad_kernel<<<(unsigned)std::min<long long>(cdiv((long long)rows_pad * g.ldb, 256), 4096), 256, 0, st>>>(w, Bm, d->Cout, d->Cin, taps, g.ldb, rows_pad);
   CFUN_LAUNCH_CHECK();
   return launch_igemm<1>(g, dy, Bm, nullptr, dx, 0, st);
 }
@@ -546,9 +555,9 @@ int simt_conv_bwd_weight(const cfun_conv3d_desc* d, const float* x, const float*
   const int Cout = g.Ct;
   const int bnc = Cout <= 16 ? 16 : (Cout <= 32 ? 32 : 64);
   const unsigned gx = (unsigned)cdiv(g.Ktot, 64), gy = (unsigned)cdiv(Cout, bnc);
-  // enough splits for ~6 waves, each at least 512 rows
+  // enough splits for ~6 waves, each at least 128 rows (8 tiles of 16: the 16^3 backbone stages would otherwise run on 40 blocks)
   long long want = cdiv(6LL * num_sms(), (long long)gx * gy);
-  long long splits = std::max<long long>(1, std::min<long long>(want, cdiv(g.M, 512)));
+  long long splits = std::max<long long>(1, std::min<long long>(want, cdiv(g.M, 128)));
   splits = std::min<long long>(splits, 65535);
   long long rps = align_up((size_t)cdiv(g.M, splits), 16);
   splits = cdiv(g.M, rps);

@@ -94,6 +94,7 @@ struct HlParams {
   const float* bias;
   float* y;
   const uint8_t* wpack;       // [step][khalf2][part][Npad][8] bf16 (hi rows, then lo rows)
+  double* stat_acc;           // optional [N][Cout][2]: per-(sample, channel) sum and sum of squares of y (InstanceNorm statistics)
 };
 
 template <int G, bool SPLIT, int KS>
@@ -107,6 +108,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
   uint64_t* t_full = b_empty + HL_MAX_BSTAGES;                    // [2]
   uint64_t* t_empty = t_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  __shared__ float s_stat[4][128];                                // per epilogue warp [2][64] statistics partials (p.stat_acc)
   uint8_t* base = smem_raw + 1024 + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
 
   constexpr int T = KS * KS * KS, PAD = KS / 2;
@@ -128,6 +130,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
     fence_barrier_init();
   }
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) (&s_stat[0][0])[i] = 0.f;
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -279,16 +282,16 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
         tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * nrows + j), r);
         if (parts == 2) tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * nrows + p.Npad + j), r2);
         tmem_ld_wait();
-        if (ok) {
-          float v[16];
+        float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float f = __uint_as_float(r[i]);
-            if (parts == 2) f += __uint_as_float(r2[i]);
-            if ((p.epi & CFUN_EPI_BIAS) && j + i < p.Cout) f += __ldg(p.bias + j + i);
-            if (p.epi & CFUN_EPI_RELU) f = fmaxf(f, 0.f);
-            v[i] = f;
-          }
+        for (int i = 0; i < 16; ++i) {
+          float f = __uint_as_float(r[i]);
+          if (parts == 2) f += __uint_as_float(r2[i]);
+          if ((p.epi & CFUN_EPI_BIAS) && j + i < p.Cout) f += __ldg(p.bias + j + i);
+          if (p.epi & CFUN_EPI_RELU) f = fmaxf(f, 0.f);
+          v[i] = ok ? f : 0.f;
+        }
+        if (ok) {
           if (vec && j + 16 <= p.Cout) {
 #pragma unroll
             for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(yrow + j + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -298,10 +301,30 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
               if (j + i < p.Cout) yrow[j + i] = v[i];
           }
         }
+        if (p.stat_acc && j < p.Cout) {
+          if (p.Cout <= 64) warp_stats16_shared(v, s_stat[quad], j, p.Cout, lane);
+          else warp_stats16(v, p.stat_acc + (long long)n * p.Cout * 2, j, p.Cout, lane);
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[buf]);     // 4 epilogue warps -> barrier count 4
+      if (p.stat_acc && p.Cout <= 64) {
+        // flush the CTA's partial sums every 16 tiles, at a sample boundary and after the last tile (uniform over the 4 warps)
+        const long long next = tile + gridDim.x;
+        const bool flush = (local & 15) == 15 || next >= p.ntiles || next / ((long long)p.D * p.tilesH * p.tilesW) != n;
+        if (flush) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const int e = (int)threadIdx.x - 64;       // 0..127 over the epilogue warps
+          const int st_ = e >> 6, c = e & 63;
+          if (c < p.Cout) {
+            const double t = ((double)s_stat[0][e] + (double)s_stat[1][e]) + ((double)s_stat[2][e] + (double)s_stat[3][e]);
+            s_stat[0][e] = s_stat[1][e] = s_stat[2][e] = s_stat[3][e] = 0.f;
+            if (t != 0.0) atomicAdd(p.stat_acc + ((long long)n * p.Cout + c) * 2 + st_, t);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+      }
     }
   }
   tc_fence_before();
@@ -530,7 +553,7 @@ static bool make_hl_plan(const cfun_conv3d_desc* d, int pass, HlPlan& pl) {
   pl.tmem_cols = cols;
   const size_t a_bytes = (size_t)pl.G * 2 * HL_PLANE;
   const size_t step_bytes = (size_t)2 * 2 * pl.Npad * 16;
-  const size_t budget = 227 * 1024 - 2048 - a_bytes;
+  const size_t budget = 227 * 1024 - 2048 - 2048 - a_bytes;     // 2 KB header + alignment slack, 2 KB static (s_stat)
   pl.w_bytes = align_up((size_t)pl.nsteps * step_bytes, 1024);
   const char* e = getenv("CFUN_HL_RESIDENT");              // "0": always stream the weights (A/B measurements)
   if (pl.w_bytes <= budget && !(e && e[0] == '0')) {
@@ -567,7 +590,8 @@ size_t hl_workspace(const cfun_conv3d_desc* d, int pass) {
 // ext_hi / ext_lo (optional): caller-owned buffers for the split-bf16 activation pack (pl.act_bytes each, see
 // hl_pack_bytes); ext_ready = the pack is already in them (fused backward, forward pack kept for the weight gradient).
 int hl_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
-               int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st);
+               int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st,
+               double* stat_acc = nullptr);
 int hl_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
             int nsplit, void* ws, size_t ws_bytes, cudaStream_t st) {
   return hl_conv_ex(d, pass, src, w, bias, dst, epi, nsplit, ws, ws_bytes, nullptr, nullptr, false, st);
@@ -577,7 +601,8 @@ size_t hl_pack_bytes(const cfun_conv3d_desc* d, int pass) {
   return make_hl_plan(d, pass, pl) ? pl.act_bytes : 0;
 }
 int hl_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
-               int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st) {
+               int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st,
+               double* stat_acc) {
   HlPlan pl;
   CFUN_CHECK_ARG(make_hl_plan(d, pass, pl));
   CFUN_CHECK_ARG((src || ext_ready) && w && dst && ws && get_tensor_map_encoder());
@@ -620,13 +645,14 @@ int hl_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const floa
   p.epi = epi; p.bias = bias; p.y = dst;
   p.resident = pl.resident; p.bstages = pl.bstages;
   p.wpack = reinterpret_cast<const uint8_t*>(wp);
+  p.stat_acc = stat_acc;
   const unsigned grid = (unsigned)std::min<long long>(p.ntiles, num_sms());
 #define CFUN_HL_LAUNCH(GG, KK)                                                                                                  \
   case GG + 16 * KK: {                                                                                                          \
     static bool attr_set = false;                                                                                               \
     if (!attr_set) {                                                                                                            \
-      CFUN_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<GG, true, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));  \
-      CFUN_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<GG, false, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+      CFUN_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<GG, true, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));  \
+      CFUN_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<GG, false, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024)); \
       attr_set = true;                                                                                                          \
     }                                                                                                                           \
     timing_begin(st);                                                                                                           \

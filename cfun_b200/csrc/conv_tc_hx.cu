@@ -89,6 +89,7 @@ struct HxParams {
   const float* bias;
   float* y;
   const uint8_t* wpack;       // [ntile][chunk][kd][tap9][kgroup2][part][Npad][8] bf16 (hi rows, then lo rows)
+  double* stat_acc;           // optional [N][Cout][2]: per-(sample, channel) sum and sum of squares of y (InstanceNorm statistics)
 };
 
 // TPS: taps per weight stage, 9 (one kd plane) or 3 (one (kd, kh) row) -- compile-time so the issue loop is straight-line.
@@ -307,16 +308,16 @@ conv_tc_hx_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
           tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * nrows + j), r);
           if (parts == 2) tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * nrows + p.Npad + j), r2);
           tmem_ld_wait();
-          if (ok) {
-            float v[16];
+          float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float f = __uint_as_float(r[i]);
-              if (parts == 2) f += __uint_as_float(r2[i]);
-              if ((p.epi & CFUN_EPI_BIAS) && ch0 + j + i < p.Cout) f += __ldg(p.bias + ch0 + j + i);
-              if (p.epi & CFUN_EPI_RELU) f = fmaxf(f, 0.f);
-              v[i] = f;
-            }
+          for (int i = 0; i < 16; ++i) {
+            float f = __uint_as_float(r[i]);
+            if (parts == 2) f += __uint_as_float(r2[i]);
+            if ((p.epi & CFUN_EPI_BIAS) && ch0 + j + i < p.Cout) f += __ldg(p.bias + ch0 + j + i);
+            if (p.epi & CFUN_EPI_RELU) f = fmaxf(f, 0.f);
+            v[i] = ok ? f : 0.f;
+          }
+          if (ok) {
             if (vec && ch0 + j + 16 <= p.Cout) {
 #pragma unroll
               for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(yrow + j + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
@@ -326,6 +327,7 @@ conv_tc_hx_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
                 if (ch0 + j + i < p.Cout) yrow[j + i] = v[i];
             }
           }
+          if (p.stat_acc) warp_stats16(v, p.stat_acc + (long long)n * p.Cout * 2, ch0 + j, p.Cout, lane);
         }
         if ((p.debug & 8) && quad == 0 && live) {     // bring-up: raw operand words of this CTA's rings into channels 0..7 of voxel 0
           uint32_t r0[16];
@@ -360,31 +362,44 @@ conv_tc_hx_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_consta
 }
 
 // w (Cout, Cin, 27) fp32 -> [ntile][chunk][kd][tap9][kgroup2][part][Npad][8] bf16.  mode 1 = data gradient (rows = ci,
-// k = co, taps mirrored).
+// k = co, taps mirrored).  One warp per (output row, group of 8 k): it reads the 8 x 27 source floats (one contiguous run
+// of 216 in forward mode, 8 runs of 27 in data-gradient mode) coalesced into shared memory, then lanes 0..26 each split one
+// tap's 8 values and store the 16-byte hi / lo rows.
 __global__ void __launch_bounds__(256) pack_w_hx_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout,
                                                         int Cin, int Npad, int ntn, int CPC, int parts, int mode) {
-  const long long total = (long long)ntn * CPC * 3 * parts * 9 * 2 * Npad * 8;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    long long r = i;
-    const int e = (int)(r % 8); r /= 8;
-    const int row = (int)(r % Npad); r /= Npad;
-    const int part = (int)(r % parts); r /= parts;
-    const int kg = (int)(r % 2); r /= 2;
-    const int t9 = (int)(r % 9); r /= 9;
-    const int kd = (int)(r % 3); r /= 3;
-    const int c = (int)(r % CPC);
-    const int nt = (int)(r / CPC);
-    const int k = c * 16 + kg * 8 + e;
-    const int nrow = nt * Npad + row;
-    int tap = kd * 9 + t9;
-    int co, ci;
-    if (mode == 0) { co = nrow; ci = k; }
-    else { co = k; ci = nrow; tap = 26 - tap; }
-    float v = 0.f;
-    if (co < Cout && ci < Cin) v = w[((long long)co * Cin + ci) * 27 + tap];
-    __nv_bfloat16 h, l;
-    split_bf16(v, h, l);
-    out[i] = part == 0 ? h : l;
+  __shared__ float sm[8][8 * 27 + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kgroups = CPC * 2;
+  const int units = ntn * Npad * kgroups;
+  const int rows_src = mode == 0 ? Cout : Cin, k_src = mode == 0 ? Cin : Cout;
+  float* buf = sm[warp];
+  for (int u = blockIdx.x * 8 + warp; u < units; u += gridDim.x * 8) {
+    const int nrow = u / kgroups, kgi = u - nrow * kgroups;
+    const int k0 = kgi * 8;
+    for (int t = lane; t < 216; t += 32) {
+      const int j = t / 27, tap = t - j * 27;
+      float v = 0.f;
+      if (nrow < rows_src && k0 + j < k_src) {
+        const long long idx = mode == 0 ? ((long long)nrow * Cin + (k0 + j)) * 27 + tap : ((long long)(k0 + j) * Cin + nrow) * 27 + tap;
+        v = __ldg(w + idx);
+      }
+      buf[t] = v;
+    }
+    __syncwarp();
+    if (lane < 27) {
+      const int tap_o = mode == 0 ? lane : 26 - lane;
+      const int kd = tap_o / 9, t9 = tap_o - kd * 9;
+      const int nt = nrow / Npad, row = nrow - nt * Npad;
+      const int c = kgi >> 1, kg = kgi & 1;
+      __align__(16) __nv_bfloat16 h[8];
+      __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split_bf16(buf[j * 27 + lane], h[j], l[j]);
+      const long long o = ((((((long long)nt * CPC + c) * 3 + kd) * 9 + t9) * 2 + kg) * parts) * Npad + row;     // 16-byte rows
+      reinterpret_cast<uint4*>(out)[o] = *reinterpret_cast<const uint4*>(h);
+      if (parts == 2) reinterpret_cast<uint4*>(out)[o + Npad] = *reinterpret_cast<const uint4*>(l);
+    }
+    __syncwarp();
   }
 }
 
@@ -476,7 +491,7 @@ static void pick_cluster(size_t smem, long long ntiles, size_t w_pass_bytes, int
 
 int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
                int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st,
-               int tapmask = 0x7FFFFFF);
+               int tapmask = 0x7FFFFFF, double* stat_acc = nullptr);
 int hx_conv(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
             int nsplit, void* ws, size_t ws_bytes, cudaStream_t st) {
   return hx_conv_ex(d, pass, src, w, bias, dst, epi, nsplit, ws, ws_bytes, nullptr, nullptr, false, st);
@@ -489,7 +504,7 @@ size_t hx_pack_bytes(const cfun_conv3d_desc* d, int pass) {
 // tapmask: live taps of w (bit kd*9+kh*3+kw); masked taps are assumed to hold zero weights and are skipped
 int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const float* w, const float* bias, float* dst, int epi,
                int nsplit, void* ws, size_t ws_bytes, __nv_bfloat16* ext_hi, __nv_bfloat16* ext_lo, bool ext_ready, cudaStream_t st,
-               int tapmask) {
+               int tapmask, double* stat_acc) {
   HxPlan pl;
   CFUN_CHECK_ARG(make_hx_plan(d, pass, pl));
   CFUN_CHECK_ARG((src || ext_ready) && w && dst && ws && get_tensor_map_encoder());
@@ -504,8 +519,8 @@ int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const floa
   if (!(ext_hi && ext_ready))
     if ((rc = launch_pack_act_gp(src, ah, split ? al : nullptr, pl.N, pl.D, pl.H, pl.W, pl.Cs, pl.G, st)) != CFUN_OK) return rc;
   {
-    long long wt = (long long)pl.ntn * pl.CPC * 3 * parts * 9 * 2 * pl.Npad * 8;
-    pack_w_hx_kernel<<<(unsigned)std::min<long long>(cdiv(wt, 256), 4LL * num_sms()), 256, 0, st>>>(w, wp, d->Cout, d->Cin, pl.Npad, pl.ntn, pl.CPC, parts, pass == CFUN_PASS_BWD_DATA ? 1 : 0);
+    const long long units = (long long)pl.ntn * pl.Npad * pl.CPC * 2;     // one warp each
+    pack_w_hx_kernel<<<(unsigned)std::min<long long>(cdiv(units, 8), 16LL * num_sms()), 256, 0, st>>>(w, wp, d->Cout, d->Cin, pl.Npad, pl.ntn, pl.CPC, parts, pass == CFUN_PASS_BWD_DATA ? 1 : 0);
     CFUN_LAUNCH_CHECK();
   }
   static bool attr_set = false;
@@ -539,6 +554,7 @@ int hx_conv_ex(const cfun_conv3d_desc* d, int pass, const float* src, const floa
   p.tmem_cols = pl.tmem_cols;
   p.epi = epi; p.bias = bias; p.y = dst;
   p.wpack = reinterpret_cast<const uint8_t*>(wp);
+  p.stat_acc = stat_acc;
   p.TPS = pl.TPS; p.bstages = pl.bstages;
   p.b_stage_bytes = split ? pl.b_stage_bytes : pl.b_stage_bytes / 2;
   int cluster, grid;

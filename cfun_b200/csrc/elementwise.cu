@@ -585,6 +585,16 @@ extern "C" int cfun_instnorm_stats(const float* x, int N, long long S, int C, fl
   return CFUN_OK;
 }
 
+// mean / rstd from statistics accumulated elsewhere (the conv epilogue of cfun_conv3d_fwd_stats)
+extern "C" int cfun_instnorm_finalize(const double* acc, int N, long long S, int C, float eps, float* mean, float* rstd,
+                                      void* stream) {
+  CFUN_CHECK_ARG(acc && mean && rstd && N > 0 && S > 0 && C > 0);
+  const long long NC = (long long)N * C;
+  in_finalize_kernel<<<(unsigned)cdiv(NC, 256), 256, 0, as_stream(stream)>>>(acc, NC, 1.0 / (double)S, eps, mean, rstd);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
 extern "C" int cfun_affine_act_fwd(const float* x, const float* a, const float* b, int a_nstride, const float* r,
                                    float* y, int N, int D, int H, int W, int C, int Ctot, int c_off, int up, float slope,
                                    void* stream) {

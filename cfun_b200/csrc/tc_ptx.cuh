@@ -152,6 +152,40 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_tensor_map_encoder();   // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no libcuda link)
 
+// InstanceNorm statistics from a conv epilogue: v[16] = 16 channels of this lane's output voxel (zeros where the lane holds
+// no voxel).  A butterfly transpose-reduce (31 shuffles for the 32 values v, v^2) leaves lane L with the warp total of
+// channel L & 15 (L < 16: sum, L >= 16: sum of squares).
+__device__ __forceinline__ float warp_stats16_reduce(const float* v, int lane) {
+  float a[32];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { a[i] = v[i]; a[16 + i] = v[i] * v[i]; }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int k = 0; k < off; ++k) {
+      const float send = upper ? a[k] : a[k + off];
+      const float keep = upper ? a[k + off] : a[k];
+      a[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return a[0];
+}
+// ... straight into acc_n[(ch0 + c) * 2 + stat], the layout cfun_instnorm_stats accumulates into (one double atomic per lane)
+__device__ __forceinline__ void warp_stats16(const float* v, double* __restrict__ acc_n, int ch0, int Cout, int lane) {
+  const float t = warp_stats16_reduce(v, lane);
+  const int c = ch0 + (lane & 15);
+  if (c < Cout) atomicAdd(acc_n + (long long)c * 2 + (lane >> 4), (double)t);
+}
+// ... or into this warp's private shared-memory accumulator s_warp[2][64] (plain read-modify-write: lane L is the only
+// writer of its slot, so the sums are run-to-run deterministic), which conv_tc_halo.cu flushes every few tiles -- every CTA
+// works on the same sample at the same time, so per-tile global atomics would all land on the same 2 Cout doubles
+__device__ __forceinline__ void warp_stats16_shared(const float* v, float* s_warp, int ch0, int Cout, int lane) {
+  const float t = warp_stats16_reduce(v, lane);
+  const int c = ch0 + (lane & 15);
+  if (c < Cout) s_warp[(lane >> 4) * 64 + c] += t;
+}
+
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(v);
   lo = __float2bfloat16_rn(v - __bfloat162float(hi));

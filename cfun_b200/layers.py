@@ -9,10 +9,11 @@ from . import ops
 class Conv3d(nn.Conv3d):
     """nn.Conv3d parameter layout (Cout, Cin, kD, kH, kW); forward = hand-written sm_100a conv (ops.conv3d)."""
 
-    def forward(self, x, relu=False):
+    def forward(self, x, relu=False, in_stats=False):
+        """in_stats: the caller feeds the result straight to ops.instnorm_lrelu (see ops.conv3d)"""
         if self.dilation != (1, 1, 1) or self.groups != 1 or self.padding_mode != "zeros":
             raise RuntimeError("cfun_b200.Conv3d supports dilation=1, groups=1, zero padding (all the reference uses)")
-        return ops.conv3d(x, self.weight, self.bias, self.stride, self.padding, relu)
+        return ops.conv3d(x, self.weight, self.bias, self.stride, self.padding, relu, in_stats)
 
 
 class FrozenBatchNorm3d(nn.BatchNorm3d):

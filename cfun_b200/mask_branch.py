@@ -3,7 +3,7 @@
 Same class name, constructor signature, attribute names and state_dict keys as reference mask_branch.py:11-122; the
 forward (mask_branch.py:124-220) is re-expressed over fused passes: every InstanceNorm3d -> LeakyReLU (-> nearest x2)
 chain, including a preceding Dropout3d channel mask, is one statistics kernel + one apply kernel (ops.instnorm_lrelu),
-and every Conv3d is ops.conv3d."""
+and every Conv3d is ops.conv3d; where a conv feeds a norm directly, the statistics come out of the conv's epilogue."""
 import torch
 import torch.nn as nn
 
@@ -86,10 +86,10 @@ class Modified3DUNet(nn.Module):
         # levels 2..5 context (mask_branch.py:138-183)
         ctx = {}
         for lvl in (2, 3, 4, 5):
-            out = getattr(self, "conv3d_c%d" % lvl)(out)
+            out = getattr(self, "conv3d_c%d" % lvl)(out, in_stats=True)
             residual = out
             conv = getattr(self, "norm_lrelu_conv_c%d" % lvl)[2]
-            out = conv(IN(out))
+            out = conv(IN(out), in_stats=True)           # in_stats: the conv epilogue accumulates the next norm's sums
             out = conv(IN(out, drop=drops[lvl - 1]))     # dropout -> norm -> lrelu -> conv
             out = out + residual
             if lvl < 5:
@@ -97,26 +97,26 @@ class Modified3DUNet(nn.Module):
                 ctx[lvl] = out
 
         def up_block(seq, t):   # norm -> lrelu -> upsample x2 -> conv -> norm -> lrelu
-            return IN(seq[3](IN(t, up=2)))
+            return IN(seq[3](IN(t, up=2), in_stats=True))
 
         out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l0, out)
-        out = IN(self.conv3d_l0(out))
+        out = IN(self.conv3d_l0(out, in_stats=True))
         out = ops.cat_channels(out, ctx[4])
-        out = IN(self.conv_norm_lrelu_l1[0](out))
+        out = IN(self.conv_norm_lrelu_l1[0](out, in_stats=True))
         out = self.conv3d_l1(out)
         out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l1, out)
         out = ops.cat_channels(out, ctx[3])
-        out = IN(self.conv_norm_lrelu_l2[0](out))
+        out = IN(self.conv_norm_lrelu_l2[0](out, in_stats=True))
         ds2 = out
         out = self.conv3d_l2(out)
         out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l2, out)
         out = ops.cat_channels(out, ctx[2])
-        out = IN(self.conv_norm_lrelu_l3[0](out))
+        out = IN(self.conv_norm_lrelu_l3[0](out, in_stats=True))
         ds3 = out
         out = self.conv3d_l3(out)
         out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l3, out)
         out = ops.cat_channels(out, context_1)
-        out = IN(self.conv_norm_lrelu_l4[0](out))
+        out = IN(self.conv_norm_lrelu_l4[0](out, in_stats=True))
         out_pred = self.conv3d_l4(out)
         # deep supervision (mask_branch.py:209-215)
         s = ops.upsample2x(self.ds2_1x1_conv3d(ds2)) + self.ds3_1x1_conv3d(ds3)

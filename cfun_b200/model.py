@@ -597,6 +597,20 @@ class Dataset(torch.utils.data.Dataset):
 # ---------------------------------------------------------------------------------------------------------
 #  Heads + head losses as one static-shape callable (CUDA-graph capturable: no host syncs, no dynamic shapes)
 # ---------------------------------------------------------------------------------------------------------
+class PendingLosses:
+    """The 7 loss scalars of one step on their way to pinned host memory (train_step_from_host(wait=False))."""
+
+    def __init__(self, dev_tensor):
+        self.host = torch.empty(dev_tensor.shape, dtype=dev_tensor.dtype, pin_memory=True)
+        self.host.copy_(dev_tensor, non_blocking=True)
+        self.ready = torch.cuda.Event()
+        self.ready.record()
+
+    def result(self):
+        self.ready.synchronize()
+        return self.host
+
+
 class HeadsTail(nn.Module):
     """classifier head + mask head + their four losses for a fixed (P positives, R RoIs) split, positives first
     (the layout detection_target_layer produces).  Numerically the same ops as Classifier / Mask / compute_*_loss; the
@@ -923,12 +937,16 @@ class MaskRCNN(nn.Module):
         gt_class_ids = torch.arange(1, cfg.NUM_CLASSES, dtype=torch.int32, device=vol_i16.device)
         return self.train_step_device(optimizer, vol_i16, label_hwd, rpn_match, rpn_bbox, gt_boxes, gt_class_ids)
 
-    def train_step_from_host(self, optimizer, step_inputs):
-        """The end-to-end call: pinned host buffers of one volume -> H2D -> train_step_device -> D2H of the 7 losses."""
+    def train_step_from_host(self, optimizer, step_inputs, wait=True):
+        """The end-to-end call: pinned host buffers of one volume -> H2D -> train_step_device -> D2H of the 7 losses.
+        wait=False returns a PendingLosses instead of blocking: the copy into pinned host memory is queued behind the step
+        and .result() waits for it -- a training loop reads step i's losses while step i+1 is already running, so the host
+        never leaves the device without queued work between steps."""
         dev = self.anchors.device
         args = [t.to(dev, non_blocking=True) for t in step_inputs.tensors()]
         out = self.train_step_device(optimizer, *args)
-        return out.cpu()
+        pending = PendingLosses(out)
+        return pending.result() if wait else pending
 
     # -- inference ------------------------------------------------------------------------------------------
     def detect(self, images):

@@ -173,7 +173,7 @@ def set_conv_algo(algo):
 
 class Conv3dFn(Function):
     @staticmethod
-    def forward(ctx, x, w, b, stride, padding, relu):
+    def forward(ctx, x, w, b, stride, padding, relu, stats_out=None):
         _require_cuda(x, w, b)
         x = to_cl(x)
         w = w.contiguous()
@@ -187,7 +187,15 @@ class Conv3dFn(Function):
         # split-bf16 pack of x for the weight gradient, and the backward packs dy once for both gradients.
         pack_bytes = lib.cfun_conv3d_pack_bytes(C.byref(d)) if (algo == ALGO_AUTO and ctx.needs_input_grad[1]) else 0
         xpack = None
-        if pack_bytes:
+        if pack_bytes and stats_out is not None:
+            # the consumer is an InstanceNorm: its per-(sample, channel) sums come out of the conv epilogue (stats_out is a
+            # one-element list the caller reads the accumulator from; it stays empty on the other dispatch paths)
+            xpack = torch.empty(pack_bytes, dtype=torch.uint8, device=x.device)
+            acc = torch.empty(2 * d.N * d.Cout, dtype=torch.float64, device=x.device)
+            _run("cfun_conv3d_fwd_stats", C.byref(d), _ptr(x), _ptr(w), _ptr(b), _ptr(y), epi, _ptr(xpack), xpack.numel(),
+                 _ptr(acc), _ptr(ws), ws.numel(), _stream(), tag=_conv_tag(d, PASS_FWD, algo) if _prof["on"] else "")
+            stats_out.append(acc)
+        elif pack_bytes:
             xpack = torch.empty(pack_bytes, dtype=torch.uint8, device=x.device)
             _run("cfun_conv3d_fwd_keep_pack", C.byref(d), _ptr(x), _ptr(w), _ptr(b), _ptr(y), epi, _ptr(xpack), xpack.numel(),
                  _ptr(ws), ws.numel(), _stream(), tag=_conv_tag(d, PASS_FWD, algo) if _prof["on"] else "")
@@ -223,7 +231,7 @@ class Conv3dFn(Function):
             ws = workspace(ws_bytes, dy.device)
             _run("cfun_conv3d_bwd_fused", C.byref(d), _ptr(xpack), xpack.numel(), _ptr(dy), _ptr(w), _ptr(dx), _ptr(dw), _ptr(db),
                  _ptr(ws), ws.numel(), _stream(), tag=_conv_tag(d, PASS_BWD_WEIGHT, ctx.algo) if _prof["on"] else "")
-            return dx, dw, db, None, None, None
+            return dx, dw, db, None, None, None, None
         if ctx.needs_input_grad[0]:
             dx = empty_cl(d.N, d.Cin, d.Din, d.Hin, d.Win, dy.device)
             ws_bytes = lib.cfun_conv3d_workspace_size(C.byref(d), PASS_BWD_DATA, ctx.algo)
@@ -237,11 +245,20 @@ class Conv3dFn(Function):
             ws = workspace(ws_bytes, dy.device)
             _run("cfun_conv3d_bwd_weight", C.byref(d), _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), ctx.algo, _ptr(ws),
                  ws.numel(), _stream(), tag=_conv_tag(d, PASS_BWD_WEIGHT, ctx.algo) if _prof["on"] else "")
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
-def conv3d(x, w, b=None, stride=1, padding=0, relu=False):
-    return Conv3dFn.apply(x, w, b, stride, padding, relu)
+def conv3d(x, w, b=None, stride=1, padding=0, relu=False, in_stats=False):
+    """in_stats=True: the output feeds an InstanceNorm (ops.instnorm_lrelu); where the conv runs on the halo-family tcgen05
+    kernels its epilogue accumulates the norm's statistics, which ride along on the returned tensor (y._cfun_in_stats)
+    and save the norm its own pass over y."""
+    if not in_stats:
+        return Conv3dFn.apply(x, w, b, stride, padding, relu)
+    holder = []
+    y = Conv3dFn.apply(x, w, b, stride, padding, relu, holder)
+    if holder:
+        y._cfun_in_stats = holder[0]
+    return y
 
 
 class FcConvFn(Function):
@@ -366,15 +383,19 @@ class InstNormActFn(Function):
     as one statistics pass + one apply pass.  drop: None or per-(n,c) Dropout3d scale [N,C] (0 or 1/(1-p))."""
 
     @staticmethod
-    def forward(ctx, x, drop, eps, slope, up):
+    def forward(ctx, x, drop, eps, slope, up, acc=None):
         _require_cuda(x, drop)
         x = to_cl(x)
         N, Cc, D, H, W = x.shape
         S = D * H * W
-        acc = torch.empty(2 * N * Cc, dtype=torch.float64, device=x.device)
         mean = torch.empty((N, Cc), device=x.device)
         rstd = torch.empty((N, Cc), device=x.device)
-        _run("cfun_instnorm_stats", _ptr(x), N, S, Cc, float(eps), _ptr(acc), _ptr(mean), _ptr(rstd), _stream())
+        if acc is not None:      # sums accumulated by the producing conv's epilogue (ops.conv3d(in_stats=True))
+            assert acc.dtype == torch.float64 and acc.numel() == 2 * N * Cc
+            _run("cfun_instnorm_finalize", _ptr(acc), N, S, Cc, float(eps), _ptr(mean), _ptr(rstd), _stream())
+        else:
+            acc = torch.empty(2 * N * Cc, dtype=torch.float64, device=x.device)
+            _run("cfun_instnorm_stats", _ptr(x), N, S, Cc, float(eps), _ptr(acc), _ptr(mean), _ptr(rstd), _stream())
         if drop is None:
             a = rstd
             b = -mean * rstd
@@ -404,11 +425,11 @@ class InstNormActFn(Function):
         _run("cfun_affine_act_bwd", _ptr(x), _ptr(a), _ptr(b), Cc, None, _ptr(dy), _ptr(dx), None, _ptr(acc), N, D, H, W,
              Cc, Cc, 0, up, slope, _stream())
         _run("cfun_instnorm_bwd_apply", _ptr(x), _ptr(a), _ptr(b), _ptr(acc), _ptr(dx), N, D * H * W, Cc, _stream())
-        return dx, None, None, None, None
+        return dx, None, None, None, None, None
 
 
 def instnorm_lrelu(x, drop=None, eps=1e-5, slope=0.01, up=1):
-    return InstNormActFn.apply(x, drop, eps, slope, up)
+    return InstNormActFn.apply(x, drop, eps, slope, up, getattr(x, "_cfun_in_stats", None))
 
 
 class MaxPool2Fn(Function):

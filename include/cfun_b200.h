@@ -91,6 +91,13 @@ size_t cfun_conv3d_pack_bytes(const cfun_conv3d_desc* d);
 size_t cfun_conv3d_bwd_fused_workspace_size(const cfun_conv3d_desc* d);
 int cfun_conv3d_fwd_keep_pack(const cfun_conv3d_desc* d, const float* x, const float* w, const float* bias, float* y,
                               int epi_flags, void* xpack, size_t xpack_bytes, void* ws, size_t ws_bytes, void* stream);
+/* cfun_conv3d_fwd_keep_pack whose epilogue also accumulates the InstanceNorm statistics of y (mask_branch.py:18: every
+ * U-Net conv is followed by InstanceNorm3d): stat_acc [N][Cout][2] doubles = per-(sample, channel) sum and sum of squares,
+ * zeroed by the call; cfun_instnorm_finalize turns them into mean / rstd.  Saves the separate read of y that
+ * cfun_instnorm_stats makes. */
+int cfun_conv3d_fwd_stats(const cfun_conv3d_desc* d, const float* x, const float* w, const float* bias, float* y,
+                          int epi_flags, void* xpack, size_t xpack_bytes, double* stat_acc, void* ws, size_t ws_bytes,
+                          void* stream);
 int cfun_conv3d_bwd_fused(const cfun_conv3d_desc* d, const void* xpack, size_t xpack_bytes, const float* dy, const float* w,
                           float* dx, float* dw, float* dbias, void* ws, size_t ws_bytes, void* stream);
 
@@ -128,6 +135,7 @@ int cfun_affine_act_bwd(const float* x, const float* a, const float* b, int a_ns
 /* dx = a * (g - mean_s(g) - xhat * mean_s(g*xhat)) in place on dx (which holds g), xhat = x*a + b with the same
  * per-(n,c) coefficients a[N*C], b[N*C] the forward used (a = rstd, b = -mean*rstd; a dropout channel scale m folds in
  * as a = m*rstd', b = -m*mean*rstd'). */
+int cfun_instnorm_finalize(const double* acc, int N, long long S, int C, float eps, float* mean, float* rstd, void* stream);
 int cfun_instnorm_bwd_apply(const float* x, const float* a, const float* b, const double* stat_acc, float* dx, int N,
                             long long S, int C, void* stream);
 /* torch.cat([a, b], dim=1) of two NDHWC tensors with M = N*D*H*W rows (mask_branch.py:189,197,204,211) and its backward */

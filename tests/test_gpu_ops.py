@@ -631,3 +631,30 @@ def test_mask_cross_entropy_fused(ops, case):
     (lc * 1.7).backward()
     assert abs(float(lc) - float(lr)) < 1e-5 * abs(float(lr))
     assert rel_err(xc.grad.cpu().numpy(), xr.grad.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("case", [dict(N=2, Cin=20, Cout=20, dims=(6, 19, 27)), dict(N=3, Cin=40, Cout=24, dims=(5, 16, 16)),
+                                  dict(N=4, Cin=40, Cout=40, dims=(20, 40, 48)), dict(N=2, Cin=24, Cout=72, dims=(5, 16, 16)),
+                                  dict(N=2, Cin=80, Cout=80, dims=(4, 12, 20)), dict(N=1, Cin=128, Cout=256, dims=(4, 16, 16))])
+def test_conv3d_epilogue_instnorm_statistics(ops, case):
+    """ops.conv3d(in_stats=True): the per-(sample, channel) sums the conv epilogue accumulates equal the separate
+    statistics pass over its output (cfun_instnorm_stats), so instnorm_lrelu gives the same result either way."""
+    g = torch.Generator().manual_seed(case["Cin"])
+    N, Cin, Cout, (D, H, W) = case["N"], case["Cin"], case["Cout"], case["dims"]
+    x = cuda(torch.randn(N, Cin, D, H, W, generator=g)).requires_grad_(True)
+    w = (torch.randn(Cout, Cin, 3, 3, 3, generator=g) * 0.1).cuda().requires_grad_(True)
+    b = torch.randn(Cout, generator=g).cuda().requires_grad_(True)
+    y = ops.conv3d(x, w, b, 1, 1, False, in_stats=True)
+    acc = getattr(y, "_cfun_in_stats", None)
+    assert acc is not None, "shape did not route to the halo-family kernels"
+    yd = y.detach()
+    ref = torch.stack([yd.double().sum(dim=(2, 3, 4)), yd.double().square().sum(dim=(2, 3, 4))], dim=2).reshape(-1)
+    scale = torch.stack([yd.double().abs().sum(dim=(2, 3, 4)), yd.double().square().sum(dim=(2, 3, 4))], dim=2).reshape(-1)
+    assert float(((acc - ref).abs() / scale).max()) < 2e-6          # fp32 partial sums, double totals
+    out_fused = ops.instnorm_lrelu(y)
+    y2 = yd.clone()
+    out_sep = ops.instnorm_lrelu(y2)
+    assert rel_err(out_fused.detach().cpu().numpy(), out_sep.cpu().numpy()) < 2e-6
+    dy = cuda(torch.randn(out_fused.shape, generator=g))
+    out_fused.backward(dy)          # gradients flow through norm and conv as before
+    assert x.grad is not None and w.grad is not None and torch.isfinite(w.grad).all()
