@@ -51,8 +51,10 @@ struct TcParams {
   int stages;
   int tmem_cols;
   int epi;
+  int ksplit;        // > 1: blockIdx.z covers a slice of the K chunks and writes raw partial sums to part[z]
   const float* bias;
   float* y;
+  float* part;       // [ksplit][N*Do*Ho*Wo][Cout]
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -73,8 +75,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
   const int chunk_bytes = parts * (TC_A_BYTES + b_bytes);
   const int stage_bytes = TC_KCH * chunk_bytes;
   const int taps = p.kD * p.kH * p.kW;
-  const int total_chunks = taps * p.CPC;
-  const int nstage_iters = (total_chunks + TC_KCH - 1) / TC_KCH;
+  const int all_chunks = taps * p.CPC;
+  const int q_begin = (int)(((long long)all_chunks * blockIdx.z) / p.ksplit);
+  const int total_chunks = (int)(((long long)all_chunks * (blockIdx.z + 1)) / p.ksplit);     // end of this CTA's chunk range
+  const int nstage_iters = (total_chunks - q_begin + TC_KCH - 1) / TC_KCH;
 
   // tile coordinates
   int t = blockIdx.x;
@@ -102,7 +106,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int q = 0;
+      int q = q_begin;
       for (int it = 0; it < nstage_iters; ++it) {
         const int slot = it % p.stages;
         const uint32_t ph = (uint32_t)((it / p.stages) & 1);
@@ -136,7 +140,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t hiword = (uint32_t)(make_desc_sw32(0) >> 32);
       const uint32_t lbo1 = 1u << 16;
-      int q = 0;
+      int q = q_begin;
       uint32_t acc = 0;
       for (int it = 0; it < nstage_iters; ++it) {
         const int slot = it % p.stages;
@@ -180,7 +184,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
     const int on = n + row / (p.Wt * p.Ht * p.Dt);
     const int od = d0 + ld, oh = h0 + lh, ow = w0 + lw;
     const bool vox_ok = on < p.N && od < p.Do && oh < p.Ho && ow < p.Wo;
-    float* yrow = p.y + ((((long long)on * p.Do + od) * p.Ho + oh) * p.Wo + ow) * (long long)p.Cout;
+    const bool raw = p.ksplit > 1;             // partial sums: bias / ReLU are applied by reduce_split_kernel
+    float* yrow = (raw ? p.part + (long long)blockIdx.z * ((long long)p.N * p.Do * p.Ho * p.Wo * p.Cout) : p.y) +
+                  ((((long long)on * p.Do + od) * p.Ho + oh) * p.Wo + ow) * (long long)p.Cout;
     mbar_wait(tmem_full_bar, 0, 30);
     tc_fence_after();
     const bool vec = (p.Cout & 3) == 0;
@@ -194,8 +200,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float f = __uint_as_float(r[i]);
-          if ((p.epi & CFUN_EPI_BIAS) && c0 + i < p.Cout) f += __ldg(p.bias + c0 + i);
-          if (p.epi & CFUN_EPI_RELU) f = fmaxf(f, 0.f);
+          if (!raw && (p.epi & CFUN_EPI_BIAS) && c0 + i < p.Cout) f += __ldg(p.bias + c0 + i);
+          if (!raw && (p.epi & CFUN_EPI_RELU)) f = fmaxf(f, 0.f);
           v[i] = f;
         }
         if (vec && c0 + 16 <= p.Cout) {
@@ -214,6 +220,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// y = sum over the K splits of conv_tc_kernel's partial tiles, in split order (deterministic), + bias, ReLU
+__global__ void __launch_bounds__(256) reduce_split_kernel(const float* __restrict__ part, int ksplit, long long total4, int C4,
+                                                           const float* __restrict__ bias, int epi, float* __restrict__ y) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(part) + i);
+    for (int z = 1; z < ksplit; ++z) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(part) + (long long)z * total4 + i);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (epi & CFUN_EPI_BIAS) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + (int)(i % C4));
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    if (epi & CFUN_EPI_RELU) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+    reinterpret_cast<float4*>(y)[i] = a;
   }
 }
 
@@ -298,7 +322,8 @@ struct TcPlan {
   int Kp, Np, BN, ntiles_n;
   int bn, bd, bh, bw;        // output box (bn samples x bd x bh x bw voxels = 128 rows)
   int tilesN, tilesD, tilesH, tilesW;
-  size_t off_ah, off_al, off_bh, off_bl, total;
+  size_t off_ah, off_al, off_bh, off_bl, off_part, total;
+  int ksplit;                // CTAs sharing one output tile along K (taps x channel chunks); > 1: partial sums + reduce_split_kernel
 };
 
 // 128-row output box = bn samples x bd x bh x bw voxels, every extent a power of two not larger than the tensor's (the
@@ -347,6 +372,16 @@ static bool make_plan(const cfun_conv3d_desc* d, int pass, TcPlan& pl) {
   const size_t act = align_up(rows * pl.Kp * 2, 1024);
   const size_t wgt = align_up((size_t)pl.kD * pl.kH * pl.kW * (size_t)(pl.BN * pl.ntiles_n) * pl.Kp * 2, 1024);
   pl.off_ah = 0; pl.off_al = act; pl.off_bh = 2 * act; pl.off_bl = 2 * act + wgt; pl.total = 2 * act + 2 * wgt + 2048;
+  // Few output tiles and a long contraction (the 6^3 x 320-channel bottom of the U-Net: ~20 CTAs each streaming 27 taps x 20
+  // chunks): split K over blockIdx.z so the launch fills the SMs; the partial tiles are summed in a fixed order afterwards.
+  const long long base_ctas = (long long)pl.tilesN * pl.tilesD * pl.tilesH * pl.tilesW * pl.ntiles_n;
+  const int chunks = pl.kD * pl.kH * pl.kW * (pl.Kp / 16);
+  pl.ksplit = 1;
+  const char* e = getenv("CFUN_TC_KSPLIT");                // "0": never split (A/B measurements)
+  if (2 * base_ctas <= num_sms() && !(e && e[0] == '0'))
+    pl.ksplit = (int)std::max<long long>(1, std::min<long long>(std::min<long long>(num_sms() / base_ctas, chunks / 16), 16));
+  pl.off_part = pl.total;
+  if (pl.ksplit > 1) pl.total += align_up((size_t)pl.ksplit * pl.N * pl.Dt_ * pl.Ht_ * pl.Wt_ * pl.Ct * sizeof(float), 1024);
   return true;
 }
 
@@ -499,9 +534,19 @@ static int run_tc(const cfun_conv3d_desc* d, int pass, const float* src, const f
     CFUN_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  dim3 grid((unsigned)((long long)pl.tilesN * pl.tilesD * pl.tilesH * pl.tilesW), (unsigned)pl.ntiles_n);
+  int ksplit = pl.ksplit;
+  if ((pl.Ct & 3) || (bias && ((size_t)bias & 15))) ksplit = 1;      // reduce_split_kernel works on float4
+  p.ksplit = ksplit;
+  p.part = reinterpret_cast<float*>(base + pl.off_part);
+  dim3 grid((unsigned)((long long)pl.tilesN * pl.tilesD * pl.tilesH * pl.tilesW), (unsigned)pl.ntiles_n, (unsigned)ksplit);
   conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(mah, mal, mbh, mbl, p);
   CFUN_LAUNCH_CHECK();
+  if (ksplit > 1) {
+    const long long total4 = (long long)pl.N * pl.Dt_ * pl.Ht_ * pl.Wt_ * pl.Ct / 4;
+    reduce_split_kernel<<<(unsigned)std::min<long long>(cdiv(total4, 256), 4LL * num_sms()), 256, 0, st>>>(p.part, ksplit, total4, pl.Ct / 4,
+                                                                                                       bias, epi, dst);
+    CFUN_LAUNCH_CHECK();
+  }
   return CFUN_OK;
 }
 

@@ -411,6 +411,8 @@ TC_CASES = [
     (1, 16, 12, 12, 12, 320, 3, 1, True, False),       # two N tiles of 160
     (1, 32, 10, 10, 16, 16, 5, 2, False, False),       # 5^3 kernel (out_upscale_conv family)
     (1, 48, 8, 8, 20, 24, 3, 0, True, False),          # no padding
+    (2, 64, 4, 4, 4, 96, 3, 1, True, True),            # one output tile, K split over 6 CTAs + ordered reduce (bias + ReLU there)
+    (4, 320, 6, 6, 6, 320, 3, 1, False, False),        # bottom of the U-Net: few tiles x 540 K chunks, split K
 ]
 
 
