@@ -57,6 +57,9 @@ SIGNATURES = {
     "cfun_fc_bwd_weight": (_i, [_i, _i, _ll, _p, _p, _p, _p, _p]),
     "cfun_instnorm_stats": (_i, [_p, _i, _ll, _i, _f, _p, _p, _p, _p]),
     "cfun_instnorm_finalize": (_i, [_p, _i, _ll, _i, _f, _p, _p, _p]),
+    "cfun_instnorm_bwd_apply_pack": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p]),
+    "cfun_conv3d_dy_pack_geometry": (_sz, [_D, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "cfun_conv3d_bwd_fused_packed": (_i, [_D, _p, _sz, _p, _sz, _p, _p, _p, _p, _sz, _p]),
     "cfun_affine_act_fwd": (_i, [_p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p]),
     "cfun_affine_act_bwd": (_i, [_p, _p, _p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p]),
     "cfun_instnorm_bwd_apply": (_i, [_p, _p, _p, _p, _p, _i, _ll, _i, _p]),
@@ -65,6 +68,7 @@ SIGNATURES = {
     "cfun_maxpool2_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "cfun_maxpool2_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "cfun_tc_debug_status": (_i, [C.POINTER(C.c_int)]),
+    "cfun_stream_capture_status": (_i, [_p]),
     "cfun_pack_split_bf16": (_i, [_p, _p, _p, _ll, _i, _i, _p]),
     "cfun_pack_act_gp": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "cfun_roi_crop_resize_fwd": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _i, _p, _i, _p]),

@@ -61,3 +61,11 @@ extern "C" int cfun_device_is_sm100(void) {
   if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
   return major == 10 ? 1 : 0;
 }
+
+// bring-up aid (CFUN_DEBUG_CAPTURE=1 in ops.py): 0 = stream not capturing, 1 = capturing, 2 = capture invalidated
+extern "C" int cfun_stream_capture_status(void* stream) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaError_t e = cudaStreamIsCapturing(reinterpret_cast<cudaStream_t>(stream), &st);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return 2; }
+  return st == cudaStreamCaptureStatusNone ? 0 : (st == cudaStreamCaptureStatusActive ? 1 : 2);
+}

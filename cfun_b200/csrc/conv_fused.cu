@@ -94,6 +94,41 @@ extern "C" int cfun_conv3d_fwd_stats(const cfun_conv3d_desc* d, const float* x, 
   return run_conv(d, CFUN_PASS_FWD, x, w, bias, y, epi_flags, ws, ws_bytes, hi, lo, false, st, stat_acc);
 }
 
+// geometry of the dY pack cfun_conv3d_bwd_fused builds internally, for callers that produce it themselves
+// (cfun_instnorm_bwd_apply_pack): groups of 8 channels, zero planes per side, bytes of hi + lo (0 = shape not eligible)
+extern "C" size_t cfun_conv3d_dy_pack_geometry(const cfun_conv3d_desc* d, int* groups, int* pad_planes) {
+  if (!fused_ok(d)) return 0;
+  if (groups) *groups = (int)align_up((size_t)d->Cout, 16) / 8;
+  if (pad_planes) *pad_planes = d->kD / 2;
+  return 2 * act_bytes(d, CFUN_PASS_BWD_DATA);
+}
+
+// cfun_conv3d_bwd_fused with the dY pack already made (ypack: hi then lo, each half of cfun_conv3d_dy_pack_geometry's bytes)
+extern "C" int cfun_conv3d_bwd_fused_packed(const cfun_conv3d_desc* d, const void* xpack, size_t xpack_bytes, void* ypack,
+                                            size_t ypack_bytes, const float* w, float* dx, float* dw, void* ws, size_t ws_bytes,
+                                            void* stream) {
+  CFUN_CHECK_ARG(fused_ok(d));
+  CFUN_CHECK_ARG(ypack && w && ws && (dx || dw));
+  cudaStream_t st = as_stream(stream);
+  const size_t act_y = act_bytes(d, CFUN_PASS_BWD_DATA);
+  CFUN_CHECK_ARG(ypack_bytes >= 2 * act_y && ((size_t)ypack & 127) == 0);
+  __nv_bfloat16* yh = reinterpret_cast<__nv_bfloat16*>(ypack);
+  __nv_bfloat16* yl = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(ypack) + act_y);
+  const int gy = (int)align_up((size_t)d->Cout, 16) / 8;
+  int rc;
+  if (dx) {
+    if ((rc = run_conv(d, CFUN_PASS_BWD_DATA, nullptr, w, nullptr, dx, 0, ws, ws_bytes, yh, yl, true, st)) != CFUN_OK) return rc;
+  }
+  if (dw) {
+    const size_t act_x = act_bytes(d, CFUN_PASS_FWD);
+    CFUN_CHECK_ARG(xpack && xpack_bytes >= 2 * act_x);
+    __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(const_cast<void*>(xpack));
+    __nv_bfloat16* xl = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(const_cast<void*>(xpack)) + act_x);
+    if ((rc = ds_bwd_weight_packed(d, yh, yl, gy, xh, xl, dw, st)) != CFUN_OK) return rc;
+  }
+  return CFUN_OK;
+}
+
 extern "C" int cfun_conv3d_bwd_fused(const cfun_conv3d_desc* d, const void* xpack, size_t xpack_bytes, const float* dy,
                                      const float* w, float* dx, float* dw, float* dbias, void* ws, size_t ws_bytes, void* stream) {
   CFUN_CHECK_ARG(fused_ok(d));

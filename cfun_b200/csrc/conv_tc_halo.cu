@@ -477,6 +477,32 @@ __global__ void __launch_bounds__(256) pack_act_gp_tiled_kernel(const float* __r
   }
 }
 
+// the 2 P zero planes per sample of a group-planar pack on their own (for packs whose data planes another kernel writes:
+// cfun_instnorm_bwd_apply_pack)
+__global__ void __launch_bounds__(256) pack_zero_planes_kernel(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int N,
+                                                               int D, int H, int W, int G, int P) {
+  const long long HW = (long long)H * W;
+  const long long vox_p = (long long)N * (D + 2 * P) * HW;
+  const long long total = (long long)G * N * 2 * P * HW;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long hw = i % HW;
+    long long r = i / HW;
+    const int which = (int)(r % (2 * P)); r /= 2 * P;
+    const int n = (int)(r % N);
+    const int g = (int)(r / N);
+    const long long pos = ((long long)n * (D + 2 * P) + (which < P ? which : D + which)) * HW + hw;
+    reinterpret_cast<uint4*>(hi)[(long long)g * vox_p + pos] = z;
+    if (lo) reinterpret_cast<uint4*>(lo)[(long long)g * vox_p + pos] = z;
+  }
+}
+int launch_pack_zero_planes(__nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int G, int P, cudaStream_t st) {
+  const long long total = (long long)G * N * 2 * P * H * W;
+  pack_zero_planes_kernel<<<(unsigned)std::max<long long>(1, std::min<long long>(cdiv(total, 256), 2LL * num_sms())), 256, 0, st>>>(hi, lo, N, D, H, W, G, P);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
 static int launch_pack_w_halo(const float* w, __nv_bfloat16* out, int Cout, int Cin, int Npad, int G, int nsteps, int parts, int mode,
                               int T, cudaStream_t st) {
   const long long wt = (long long)nsteps * 2 * parts * Npad * 8;

@@ -5,7 +5,17 @@
 // BatchNorm3d + ReLU + residual add (backbone.py:26-114), MaxPool3d (backbone.py:127), mold_image (model.py:1902).
 #include "common.cuh"
 
+#include <cuda_bf16.h>
+
 namespace cfun {
+
+int launch_pack_zero_planes(__nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int G, int P, cudaStream_t st);   // conv_tc_halo.cu
+
+// hi = bf16(v), lo = bf16(v - hi): the operand split of the tcgen05 convs (tc_ptx.cuh split_bf16)
+__device__ __forceinline__ void split_bf16_ew(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
 
 // Thread layout shared by the per-(n,c) reduction kernels: a block owns `rows_per_block` consecutive voxels of one
 // sample; thread t handles vector-channel q = t % CV (V channels each) of rows r = t / CV, r + R, ...
@@ -440,6 +450,85 @@ __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const float* __restri
   }
 }
 
+// in_bwd_apply whose result goes straight into the split-bf16 group-planar operand pack of the producing conv's backward
+// (conv_fused.cu) instead of an fp32 tensor: hi/lo [G][N*(D+2P)][H][W][8]; thread = one 16-byte pack row (8 channels of one
+// voxel, the second quad or the whole row may lie in the pack's zero padding beyond C).  g: the un-normalised gradient that
+// affine_act_bwd left in its dx buffer (read only).
+__global__ void __launch_bounds__(256) in_bwd_apply_pack_kernel(const float* __restrict__ x, const float* __restrict__ a,
+                                                                const float* __restrict__ b, const double* __restrict__ stat_acc,
+                                                                const float* __restrict__ g, long long S, int C, int G, int R,
+                                                                long long rows_per_block, __nv_bfloat16* __restrict__ hi,
+                                                                __nv_bfloat16* __restrict__ lo, long long plane_rows, long long vox_p,
+                                                                long long pad_rows) {
+  constexpr int U = 2;
+  const int n = blockIdx.y;
+  const int q = threadIdx.x % G, rr = threadIdx.x / G;
+  if (rr >= R) return;
+  const int c = q * 8;
+  const int nq = c >= C ? 0 : (c + 4 >= C ? 1 : 2);          // real channel quads of this row (C is a multiple of 4)
+  const double invS = 1.0 / (double)S;
+  float av[8], bv[8], m1[8], m2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) av[j] = bv[j] = m1[j] = m2[j] = 0.f;
+  for (int h = 0; h < nq; ++h) {
+    Vec<4>::load(a + (long long)n * C + c + 4 * h, av + 4 * h);
+    Vec<4>::load(b + (long long)n * C + c + 4 * h, bv + 4 * h);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      m1[4 * h + j] = (float)(stat_acc[((long long)n * C + c + 4 * h + j) * 2 + 0] * invS);
+      m2[4 * h + j] = (float)(stat_acc[((long long)n * C + c + 4 * h + j) * 2 + 1] * invS);
+    }
+  }
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > S) r1 = S;
+  // pack row of (sample n, voxel row): group q, position n * plane_rows + pad_rows + row
+  uint4* ohi = reinterpret_cast<uint4*>(hi) + (long long)q * vox_p + (long long)n * plane_rows + pad_rows;
+  uint4* olo = reinterpret_cast<uint4*>(lo) + (long long)q * vox_p + (long long)n * plane_rows + pad_rows;
+  auto emit = [&](long long row, const float* xv, const float* gv) {
+    __align__(16) __nv_bfloat16 h[8];
+    __align__(16) __nv_bfloat16 l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = fmaf(xv[j], av[j], bv[j]);
+      split_bf16_ew(av[j] * (gv[j] - m1[j] - xh * m2[j]), h[j], l[j]);      // padding channels: av = 0 -> +0
+    }
+    ohi[row] = *reinterpret_cast<const uint4*>(h);
+    olo[row] = *reinterpret_cast<const uint4*>(l);
+  };
+  long long row = r0 + rr;
+  const long long off0 = ((long long)n * S + row) * C + c;
+  const float* xp = x + off0;
+  const float* gp = g + off0;
+  const long long sx = (long long)R * C;
+  for (; row + (long long)(U - 1) * R < r1; row += (long long)U * R) {
+    float xv[U][8], gv[U][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xv[u][j] = gv[u][j] = 0.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (nq > 0) { Vec<4>::load(xp + u * sx, xv[u]); Vec<4>::load(gp + u * sx, gv[u]); }
+      if (nq > 1) { Vec<4>::load(xp + u * sx + 4, xv[u] + 4); Vec<4>::load(gp + u * sx + 4, gv[u] + 4); }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) emit(row + (long long)u * R, xv[u], gv[u]);
+    xp += U * sx;
+    gp += U * sx;
+  }
+  for (; row < r1; row += R) {
+    float xv[8], gv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) xv[j] = gv[j] = 0.f;
+    if (nq > 0) { Vec<4>::load(xp, xv); Vec<4>::load(gp, gv); }
+    if (nq > 1) { Vec<4>::load(xp + 4, xv + 4); Vec<4>::load(gp + 4, gv + 4); }
+    emit(row, xv, gv);
+    xp += sx;
+    gp += sx;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // 2x2x2 max pool, stride 2 (even extents)
 // ---------------------------------------------------------------------------------------------------------
@@ -678,6 +767,25 @@ __global__ void __launch_bounds__(256) cat2_kernel(float* __restrict__ a, float*
     if (SPLIT) *src = *cat;
     else *cat = *src;
   }
+}
+
+extern "C" int cfun_instnorm_bwd_apply_pack(const float* x, const float* a, const float* b, const double* stat_acc, const float* g,
+                                            int N, int D, int H, int W, int C, void* hi, void* lo, int G, int P, void* stream) {
+  CFUN_CHECK_ARG(x && a && b && stat_acc && g && hi && lo && N > 0 && D > 0 && H > 0 && W > 0 && C > 0);
+  CFUN_CHECK_ARG((C & 3) == 0 && G * 8 >= C && G <= 256 && P >= 1 && P <= 2);
+  cudaStream_t st = as_stream(stream);
+  __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(hi);
+  __nv_bfloat16* l = reinterpret_cast<__nv_bfloat16*>(lo);
+  int rc = launch_pack_zero_planes(h, l, N, D, H, W, G, P, st);
+  if (rc != CFUN_OK) return rc;
+  const long long S = (long long)D * H * W, HW = (long long)H * W;
+  const int R = 256 / G;                        // thread = (row, channel group): G threads per voxel row
+  long long rpb = rows_per_block(S, N, R);
+  dim3 grid((unsigned)cdiv(S, rpb), N);
+  in_bwd_apply_pack_kernel<<<grid, 256, 0, st>>>(x, a, b, stat_acc, g, S, C, G, R, rpb, h, l, (long long)(D + 2 * P) * HW,
+                                                 (long long)N * (D + 2 * P) * HW, (long long)P * HW);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
 }
 
 extern "C" int cfun_cat2_channels(const float* a, int C1, const float* b, int C2, float* out, long long M, void* stream) {

@@ -70,6 +70,9 @@ class Modified3DUNet(nn.Module):
 
     def forward(self, x):
         IN = ops.instnorm_lrelu
+
+        def CIN(conv, t, drop=None):     # IN(conv(t), drop): one autograd node where the conv has the fused tcgen05 backward
+            return ops.conv_in_lrelu(t, conv.weight, conv.bias, conv.stride, conv.padding, drop)
         drops = self._drop_masks(x.shape[0], x.device)
         # level 1 context (mask_branch.py:125-136)
         out = self.conv3d_c1_1(x)
@@ -89,34 +92,34 @@ class Modified3DUNet(nn.Module):
             out = getattr(self, "conv3d_c%d" % lvl)(out, in_stats=True)
             residual = out
             conv = getattr(self, "norm_lrelu_conv_c%d" % lvl)[2]
-            out = conv(IN(out), in_stats=True)           # in_stats: the conv epilogue accumulates the next norm's sums
-            out = conv(IN(out, drop=drops[lvl - 1]))     # dropout -> norm -> lrelu -> conv
+            out = CIN(conv, IN(out), drop=drops[lvl - 1])     # conv -> dropout -> norm -> lrelu as one fused node
+            out = conv(out)
             out = out + residual
             if lvl < 5:
                 out = IN(out)
                 ctx[lvl] = out
 
         def up_block(seq, t):   # norm -> lrelu -> upsample x2 -> conv -> norm -> lrelu
-            return IN(seq[3](IN(t, up=2), in_stats=True))
+            return CIN(seq[3], IN(t, up=2))
 
         out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l0, out)
         out = IN(self.conv3d_l0(out, in_stats=True))
         out = ops.cat_channels(out, ctx[4])
-        out = IN(self.conv_norm_lrelu_l1[0](out, in_stats=True))
+        out = CIN(self.conv_norm_lrelu_l1[0], out)
         out = self.conv3d_l1(out)
         out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l1, out)
         out = ops.cat_channels(out, ctx[3])
-        out = IN(self.conv_norm_lrelu_l2[0](out, in_stats=True))
+        out = CIN(self.conv_norm_lrelu_l2[0], out)
         ds2 = out
         out = self.conv3d_l2(out)
         out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l2, out)
         out = ops.cat_channels(out, ctx[2])
-        out = IN(self.conv_norm_lrelu_l3[0](out, in_stats=True))
+        out = CIN(self.conv_norm_lrelu_l3[0], out)
         ds3 = out
         out = self.conv3d_l3(out)
         out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l3, out)
         out = ops.cat_channels(out, context_1)
-        out = IN(self.conv_norm_lrelu_l4[0](out, in_stats=True))
+        out = CIN(self.conv_norm_lrelu_l4[0], out)
         out_pred = self.conv3d_l4(out)
         # deep supervision (mask_branch.py:209-215)
         s = ops.upsample2x(self.ds2_1x1_conv3d(ds2)) + self.ds3_1x1_conv3d(ds3)

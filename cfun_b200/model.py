@@ -904,7 +904,19 @@ class MaskRCNN(nn.Module):
         # references the shared classifier / mask modules) so that self._tail stays the eager path
         fresh = HeadsTail(self.classifier, self.mask, self.config.STAGE, self.config).ensure_device(p2.device)
         fresh.train(self.training)
-        graphed = torch.cuda.make_graphed_callables(fresh, args, num_warmup_iters=1, allow_unused_input=True)
+        # Nothing may be destroyed while the capture is open: stale graphs dropped just before (workspace reallocation) sit in
+        # reference cycles, and a cyclic collection that happened to run mid-capture would destroy them there (cudaGraphExec /
+        # pool release are not capturable) -- collect now, keep the collector off until both graphs are captured.
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            graphed = torch.cuda.make_graphed_callables(fresh, args, num_warmup_iters=1, allow_unused_input=True)
+        finally:
+            if gc_was_on:
+                gc.enable()
         # kernels per replay (forward + backward): launches during capture = (1 warm-up + 1 capture) iterations
         self.graph_kernel_counts[(P, R)] = (launch_count() - n0) // 2
         if self._graphed_tails and ops.workspace_generation() != self._graph_ws_gen:

@@ -7,6 +7,8 @@ live on a CUDA device, and a missing / failing library raises.
 Activation layout: logical [N,C,D,H,W] tensors whose memory is N,D,H,W,C (torch.channels_last_3d).
 """
 import ctypes as C
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -125,8 +127,24 @@ def _conv_tag(d, pass_id, algo):
                                                           d.sD, d.sH, d.sW, picked)
 
 
+_CAPTURE_DEBUG = bool(int(os.environ.get("CFUN_DEBUG_CAPTURE", "0")))
+
+
+def _capture_state():
+    """0 = not capturing, 1 = capturing, 2 = capture invalidated (bring-up aid, CFUN_DEBUG_CAPTURE=1)"""
+    return int(lib.cfun_stream_capture_status(_stream()))
+
+
 def _run(name, *args, tag=""):
     _calls["n"] += 1
+    if _CAPTURE_DEBUG:
+        before = _capture_state()
+        rc = getattr(lib, name)(*args)
+        after = _capture_state()
+        if before == 2 or after == 2:
+            raise RuntimeError("stream capture invalidated %s %s (rc=%d, %s)" % ("before" if before == 2 else "inside", name, rc, tag))
+        check(rc, name)
+        return
     if _prof["on"]:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
@@ -396,17 +414,7 @@ class InstNormActFn(Function):
         else:
             acc = torch.empty(2 * N * Cc, dtype=torch.float64, device=x.device)
             _run("cfun_instnorm_stats", _ptr(x), N, S, Cc, float(eps), _ptr(acc), _ptr(mean), _ptr(rstd), _stream())
-        if drop is None:
-            a = rstd
-            b = -mean * rstd
-        else:
-            m = drop.reshape(N, Cc).float()
-            var = 1.0 / (rstd * rstd) - eps
-            rstd2 = torch.rsqrt(m * m * var + eps)
-            a = m * rstd2
-            b = -(m * mean) * rstd2
-        a = a.contiguous()
-        b = b.contiguous()
+        a, b = _in_coeffs(mean, rstd, drop, N, Cc, eps)
         y = empty_cl(N, Cc, D * up, H * up, W * up, x.device)
         _run("cfun_affine_act_fwd", _ptr(x), _ptr(a), _ptr(b), Cc, None, _ptr(y), N, D, H, W, Cc, Cc, 0, up, float(slope),
              _stream())
@@ -426,6 +434,84 @@ class InstNormActFn(Function):
              Cc, Cc, 0, up, slope, _stream())
         _run("cfun_instnorm_bwd_apply", _ptr(x), _ptr(a), _ptr(b), _ptr(acc), _ptr(dx), N, D * H * W, Cc, _stream())
         return dx, None, None, None, None, None
+
+
+def _in_coeffs(mean, rstd, drop, N, Cc, eps):
+    """per-(sample, channel) scale / shift of InstanceNorm applied to x * drop (drop: None or the Dropout3d channel scale)"""
+    if drop is None:
+        return rstd.contiguous(), (-mean * rstd).contiguous()
+    m = drop.reshape(N, Cc).float()
+    var = 1.0 / (rstd * rstd) - eps
+    rstd2 = torch.rsqrt(m * m * var + eps)
+    return (m * rstd2).contiguous(), (-(m * mean) * rstd2).contiguous()
+
+
+class ConvInstNormActFn(Function):
+    """Conv3d (3^3, stride 1, no bias, on the halo-family tcgen05 kernels) -> [Dropout3d channel scale] -> InstanceNorm3d ->
+    LeakyReLU (-> nearest x2) as ONE autograd node, so that the conv output's gradient never exists in fp32:
+    forward  = cfun_conv3d_fwd_stats (norm statistics from the conv epilogue) + finalize + one apply pass;
+    backward = activation/norm backward statistics pass, then cfun_instnorm_bwd_apply_pack writes the norm's input gradient
+    straight into the split-bf16 operand pack that cfun_conv3d_bwd_fused_packed feeds to the data- and weight-gradient
+    kernels (the unfused path writes it in fp32 and re-reads it to pack it)."""
+
+    @staticmethod
+    def forward(ctx, x, w, drop, stride, padding, eps, slope, up):
+        _require_cuda(x, w, drop)
+        x = to_cl(x)
+        w = w.contiguous()
+        d = _conv_desc(x.shape, w.shape, stride, padding)
+        N, Cc, D, H, W = d.N, d.Cout, d.Dout, d.Hout, d.Wout
+        y = empty_cl(N, Cc, D, H, W, x.device)
+        ws = workspace(lib.cfun_conv3d_workspace_size(C.byref(d), PASS_FWD, ALGO_AUTO), x.device)
+        xpack = torch.empty(lib.cfun_conv3d_pack_bytes(C.byref(d)), dtype=torch.uint8, device=x.device)
+        acc = torch.empty(2 * N * Cc, dtype=torch.float64, device=x.device)
+        _run("cfun_conv3d_fwd_stats", C.byref(d), _ptr(x), _ptr(w), None, _ptr(y), 0, _ptr(xpack), xpack.numel(), _ptr(acc),
+             _ptr(ws), ws.numel(), _stream(), tag=_conv_tag(d, PASS_FWD, ALGO_AUTO) if _prof["on"] else "")
+        mean = torch.empty((N, Cc), device=x.device)
+        rstd = torch.empty((N, Cc), device=x.device)
+        _run("cfun_instnorm_finalize", _ptr(acc), N, D * H * W, Cc, float(eps), _ptr(mean), _ptr(rstd), _stream())
+        a, b = _in_coeffs(mean, rstd, drop, N, Cc, eps)
+        z = empty_cl(N, Cc, D * up, H * up, W * up, x.device)
+        _run("cfun_affine_act_fwd", _ptr(y), _ptr(a), _ptr(b), Cc, None, _ptr(z), N, D, H, W, Cc, Cc, 0, up, float(slope), _stream())
+        ctx.save_for_backward(xpack, w, y, a, b)
+        ctx.d, ctx.cfg = d, (float(slope), up)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        xpack, w, y, a, b = ctx.saved_tensors
+        d = ctx.d
+        slope, up = ctx.cfg
+        N, Cc, D, H, W = d.N, d.Cout, d.Dout, d.Hout, d.Wout
+        dz = to_cl(dz)
+        dev = dz.device
+        g = empty_cl(N, Cc, D, H, W, dev)
+        acc = torch.empty(2 * N * Cc, dtype=torch.float64, device=dev)
+        _run("cfun_affine_act_bwd", _ptr(y), _ptr(a), _ptr(b), Cc, None, _ptr(dz), _ptr(g), None, _ptr(acc), N, D, H, W, Cc, Cc, 0, up,
+             slope, _stream())
+        G, P = C.c_int(0), C.c_int(0)
+        ybytes = lib.cfun_conv3d_dy_pack_geometry(C.byref(d), C.byref(G), C.byref(P))
+        ypack = torch.empty(ybytes, dtype=torch.uint8, device=dev)
+        _run("cfun_instnorm_bwd_apply_pack", _ptr(y), _ptr(a), _ptr(b), _ptr(acc), _ptr(g), N, D, H, W, Cc, _ptr(ypack),
+             C.c_void_p(ypack.data_ptr() + ybytes // 2), G.value, P.value, _stream())
+        del g
+        dx = empty_cl(d.N, d.Cin, d.Din, d.Hin, d.Win, dev) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        if dx is not None or dw is not None:
+            ws = workspace(lib.cfun_conv3d_bwd_fused_workspace_size(C.byref(d)), dev)
+            _run("cfun_conv3d_bwd_fused_packed", C.byref(d), _ptr(xpack), xpack.numel(), _ptr(ypack), ypack.numel(), _ptr(w), _ptr(dx),
+                 _ptr(dw), _ptr(ws), ws.numel(), _stream(), tag=_conv_tag(d, PASS_BWD_WEIGHT, ALGO_AUTO) if _prof["on"] else "")
+        return dx, dw, None, None, None, None, None, None
+
+
+def conv_in_lrelu(x, w, b=None, stride=1, padding=0, drop=None, eps=1e-5, slope=0.01, up=1):
+    """instnorm_lrelu(conv3d(x, w, b), drop) -- as one fused node (ConvInstNormActFn) where the conv runs with the fused tcgen05
+    backward and has no bias, else as the two separate ops (with the epilogue statistics where available)."""
+    if b is None and _default_algo["algo"] == ALGO_AUTO and x.is_cuda and w.requires_grad and torch.is_grad_enabled():
+        d = _conv_desc(tuple(x.shape), tuple(w.shape), stride, padding)
+        if d.Cout % 4 == 0 and lib.cfun_conv3d_pack_bytes(C.byref(d)) and lib.cfun_conv3d_dy_pack_geometry(C.byref(d), None, None):
+            return ConvInstNormActFn.apply(x, w, drop, stride, padding, eps, slope, up)
+    return instnorm_lrelu(conv3d(x, w, b, stride, padding, False, in_stats=True), drop, eps, slope, up)
 
 
 def instnorm_lrelu(x, drop=None, eps=1e-5, slope=0.01, up=1):

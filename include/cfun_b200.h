@@ -100,6 +100,13 @@ int cfun_conv3d_fwd_stats(const cfun_conv3d_desc* d, const float* x, const float
                           void* stream);
 int cfun_conv3d_bwd_fused(const cfun_conv3d_desc* d, const void* xpack, size_t xpack_bytes, const float* dy, const float* w,
                           float* dx, float* dw, float* dbias, void* ws, size_t ws_bytes, void* stream);
+/* The same backward with the dY pack made by the caller (cfun_instnorm_bwd_apply_pack writes the InstanceNorm backward's
+ * result straight into it, so the conv's output gradient never exists in fp32):
+ *   cfun_conv3d_dy_pack_geometry  -> bytes of hi + lo (0 = not eligible), channel groups, zero planes per side */
+size_t cfun_conv3d_dy_pack_geometry(const cfun_conv3d_desc* d, int* groups, int* pad_planes);
+int cfun_conv3d_bwd_fused_packed(const cfun_conv3d_desc* d, const void* xpack, size_t xpack_bytes, void* ypack,
+                                 size_t ypack_bytes, const float* w, float* dx, float* dw, void* ws, size_t ws_bytes,
+                                 void* stream);
 
 /* Classifier.conv1 (model.py:758): a kernel-size == input-size conv, i.e. a [M,K]x[Nout,K]^T product with
  * K = Cin*kD*kH*kW (221184) and M = #RoIs (12).  x is NCDHW-contiguous [M,K]; w is [Nout,K]. */
@@ -138,6 +145,10 @@ int cfun_affine_act_bwd(const float* x, const float* a, const float* b, int a_ns
 int cfun_instnorm_finalize(const double* acc, int N, long long S, int C, float eps, float* mean, float* rstd, void* stream);
 int cfun_instnorm_bwd_apply(const float* x, const float* a, const float* b, const double* stat_acc, float* dx, int N,
                             long long S, int C, void* stream);
+/* cfun_instnorm_bwd_apply writing split-bf16 group-planar pack rows (hi, lo: [G][N*(D+2P)][H][W][8], zero planes
+ * included) instead of fp32; g = the buffer cfun_affine_act_bwd left the un-normalised gradient in */
+int cfun_instnorm_bwd_apply_pack(const float* x, const float* a, const float* b, const double* stat_acc, const float* g,
+                                 int N, int D, int H, int W, int C, void* hi, void* lo, int G, int P, void* stream);
 /* torch.cat([a, b], dim=1) of two NDHWC tensors with M = N*D*H*W rows (mask_branch.py:189,197,204,211) and its backward */
 int cfun_cat2_channels(const float* a, int C1, const float* b, int C2, float* out, long long M, void* stream);
 int cfun_split2_channels(const float* cat, int C1, int C2, float* a, float* b, long long M, void* stream);
@@ -147,6 +158,8 @@ int cfun_maxpool2_bwd(const float* x, const float* y, const float* dy, float* dx
 /* debugging aid for the tcgen05 pipelines: out[0] != 0 means an mbarrier wait timed out (out[0]-1 = wait site,
  * out[1..5] = blockIdx.x, blockIdx.y, threadIdx.x, parity, spins).  Synchronises the device; reading resets the record. */
 int cfun_tc_debug_status(int* out8_host);
+/* bring-up aid: 0 = stream not capturing, 1 = capturing into a CUDA graph, 2 = its capture has been invalidated */
+int cfun_stream_capture_status(void* stream);
 /* split fp32 -> (hi, lo) bf16 pairs, channel-padded NDHWC, the operand format of the tcgen05 convs */
 int cfun_pack_split_bf16(const float* x, void* hi, void* lo, long long rows, int C, int Cpad, void* stream);
 /* group-planar split pack of an NDHWC activation, the operand format of the halo / hx / weight-gradient kernels:

@@ -660,3 +660,43 @@ def test_conv3d_epilogue_instnorm_statistics(ops, case):
     dy = cuda(torch.randn(out_fused.shape, generator=g))
     out_fused.backward(dy)          # gradients flow through norm and conv as before
     assert x.grad is not None and w.grad is not None and torch.isfinite(w.grad).all()
+
+
+@pytest.mark.parametrize("case", [dict(N=2, Cin=20, Cout=20, dims=(6, 19, 27), drop=False, up=1), dict(N=3, Cin=40, Cout=20, dims=(5, 16, 16), drop=True, up=1),
+                                  dict(N=2, Cin=80, Cout=80, dims=(4, 12, 20), drop=True, up=1), dict(N=2, Cin=40, Cout=40, dims=(7, 16, 24), drop=False, up=1),
+                                  dict(N=1, Cin=160, Cout=80, dims=(24, 24, 24), drop=False, up=1)])
+def test_conv_in_lrelu_fused_node_matches_separate_ops(ops, case):
+    """ops.conv_in_lrelu (one autograd node: the norm backward writes the conv's output gradient straight into the split-bf16
+    operand pack) == instnorm_lrelu(conv3d(x)): same forward, same input gradient bit for bit (the pack holds exactly
+    split(dx)), weight gradient equal up to the atomics' summation order."""
+    g = torch.Generator().manual_seed(case["Cin"] + case["Cout"])
+    N, Cin, Cout, (D, H, W) = case["N"], case["Cin"], case["Cout"], case["dims"]
+    x = torch.randn(N, Cin, D, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) * 0.1
+    drop = ((torch.rand(N, Cout, generator=g) > 0.6).float() / 0.4).cuda() if case["drop"] else None
+    # fp32 PyTorch reference first: the incoming gradient is zeroed wherever the normalised value is within 1e-3 of the
+    # LeakyReLU kink, where paths that differ by ~1e-5 may pick different slopes
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    t = F.conv3d(xr, wr, None, padding=1)
+    if case["drop"]:
+        t = t * drop.cpu().view(N, Cout, 1, 1, 1)
+    tn = F.instance_norm(t, eps=1e-5)
+    zr = F.leaky_relu(tn, 0.01)
+    dz = cuda(torch.randn(zr.shape, generator=g) * (tn.detach().abs() > 1e-3).float())
+    zr.backward(dz.cpu())
+    res = []
+    for fused in (True, False):
+        xc, wc = cuda(x).requires_grad_(True), w.cuda().requires_grad_(True)
+        if fused:
+            z = ops.conv_in_lrelu(xc, wc, None, 1, 1, drop)
+            assert type(z.grad_fn).__name__.startswith("ConvInstNormActFn"), "shape did not take the fused node"
+        else:
+            z = ops.instnorm_lrelu(ops.conv3d(xc, wc, None, 1, 1), drop)
+        z.backward(dz)
+        res.append((z.detach(), xc.grad, wc.grad))
+    (z1, dx1, dw1), (z0, dx0, dw0) = res
+    assert rel_err(z1.cpu().numpy(), z0.cpu().numpy()) < 2e-6          # statistics: epilogue partial sums vs separate pass
+    assert rel_err(dx1.cpu().numpy(), dx0.cpu().numpy()) < 1e-5
+    assert rel_err(dw1.cpu().numpy(), dw0.cpu().numpy()) < 1e-5
+    assert rel_err(z1.cpu().numpy(), zr.detach().numpy()) < TOL
+    assert rel_err(dx1.cpu().numpy(), xr.grad.numpy()) < 5 * TOL
