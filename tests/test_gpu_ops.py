@@ -37,6 +37,9 @@ CONV_CASES = [
     (2, 160, 5, 6, 7, 8, 1, 1, 0, False),                       # ds2_1x1_conv3d (160 -> 8): 160 thread tiles, one voxel group
     (1, 256, 8, 8, 8, 2, 1, 1, 0, True),                        # RPN class head at full width (256 -> 2)
     (1, 12, 5, 5, 5, 5, 1, 1, 0, False),                        # odd Cout (padded to 6 in the co tile)
+    (2, 40, 21, 30, 33, 8, 1, 1, 0, True),                      # streaming pointwise kernels (pw_fwd2 / pw_dgrad2): several tiles per block, ragged last tile
+    (1, 80, 17, 20, 24, 8, 1, 1, 0, False),                     # ds3_1x1_conv3d (80 -> 8): 128-voxel tiles
+    (1, 32, 16, 18, 20, 6, 1, 1, 0, True),                      # RPN bbox head, Cout not a multiple of 4 (plain dY staging in the weight gradient)
     (1, 1, 12, 12, 12, 20, 3, 1, 1, False),                     # U-Net first conv (Cin = 1)
     (1, 48, 8, 8, 8, 80, 3, 1, 1, True),                        # >64 output channels
     (3, 24, 5, 7, 6, 36, 3, 1, 1, True),                        # odd everything
