@@ -57,6 +57,8 @@ SIGNATURES = {
     "cfun_fc_bwd_weight": (_i, [_i, _i, _ll, _p, _p, _p, _p, _p]),
     "cfun_instnorm_stats": (_i, [_p, _i, _ll, _i, _f, _p, _p, _p, _p]),
     "cfun_instnorm_finalize": (_i, [_p, _i, _ll, _i, _f, _p, _p, _p]),
+    "cfun_add_act_stats": (_i, [_p, _p, _p, _p, _i, _ll, _i, _f, _f, _p, _p, _p, _p]),
+    "cfun_instnorm_bwd_apply_extra": (_i, [_p, _p, _p, _p, _p, _i, _ll, _i, _p, _f, _p]),
     "cfun_instnorm_bwd_apply_pack": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p]),
     "cfun_conv3d_dy_pack_geometry": (_sz, [_D, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cfun_conv3d_bwd_fused_packed": (_i, [_D, _p, _sz, _p, _sz, _p, _p, _p, _p, _sz, _p]),

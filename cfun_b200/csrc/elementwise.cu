@@ -380,11 +380,14 @@ __global__ void __launch_bounds__(256) affine_act_bwd_kernel(const ActBwdArgs p,
 }
 
 // dx = a * (g - s1/S - xhat * s2/S),  xhat = x*a + b, g stored in dx
-template <int V>
+// EXTRA: + leaky_relu'(x) * de -- the gradient of a second consumer lrelu(x) of the norm's input (the U-Net's level-1
+// context branch, cfun_add_act_stats), so that the two gradients are never summed in a pass of their own
+template <int V, bool EXTRA>
 __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ a,
                                                            const float* __restrict__ b,
                                                            const double* __restrict__ stat_acc, float* __restrict__ dx,
-                                                           long long S, int C, int CV, int R, long long rows_per_block) {
+                                                           long long S, int C, int CV, int R, long long rows_per_block,
+                                                           const float* __restrict__ de, float slope) {
   constexpr int U = 4;
   const int n = blockIdx.y;
   const int q = threadIdx.x % CV, rr = threadIdx.x / CV;
@@ -406,11 +409,16 @@ __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const float* __restri
   const long long off0 = ((long long)n * S + row) * C + c;
   const float* xp = x + off0;
   float* gp = dx + off0;
+  const float* ep = EXTRA ? de + off0 : nullptr;
   const long long sx = (long long)R * C;
   for (; row + (long long)(U - 1) * R < r1; row += (long long)U * R) {
-    float xv[U][V], g[U][V];
+    float xv[U][V], g[U][V], ev[U][V];
 #pragma unroll
     for (int u = 0; u < U; ++u) Vec<V>::load(xp + u * sx, xv[u]);
+    if (EXTRA) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) Vec<V>::load(ep + u * sx, ev[u]);
+    }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       float4 t;
@@ -428,26 +436,89 @@ __global__ void __launch_bounds__(256) in_bwd_apply_kernel(const float* __restri
       for (int j = 0; j < V; ++j) {
         const float xh = fmaf(xv[u][j], av[j], bv[j]);
         o[j] = av[j] * (g[u][j] - m1[j] - xh * m2[j]);
+        if (EXTRA) o[j] += xv[u][j] > 0.f ? ev[u][j] : ev[u][j] * slope;
       }
       Vec<V>::store(gp + u * sx, o);
     }
     xp += U * sx;
     gp += U * sx;
+    if (EXTRA) ep += U * sx;
   }
   for (; row < r1; row += R) {
-    float xv[V], g[V], o[V];
+    float xv[V], g[V], o[V], ev[V];
     Vec<V>::load(xp, xv);
+    if (EXTRA) Vec<V>::load(ep, ev);
 #pragma unroll
     for (int j = 0; j < V; ++j) g[j] = gp[j];
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       const float xh = fmaf(xv[j], av[j], bv[j]);
       o[j] = av[j] * (g[j] - m1[j] - xh * m2[j]);
+      if (EXTRA) o[j] += xv[j] > 0.f ? ev[j] : ev[j] * slope;
     }
     Vec<V>::store(gp, o);
     xp += sx;
     gp += sx;
+    if (EXTRA) ep += sx;
   }
+}
+
+// s = a + b, ctx = leaky_relu(s), and the InstanceNorm statistics of s, in one pass (the U-Net's level-1 residual sum feeds
+// both the skip connection and the norm: mask_branch.py:132-136)
+template <int V>
+__global__ void __launch_bounds__(256) add_act_stats_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                            float* __restrict__ s, float* __restrict__ ctx, float slope, long long S,
+                                                            int C, int CV, int R, long long rows_per_block, double* __restrict__ acc) {
+  extern __shared__ float smf[];  // [2][R][C] + 256 doubles
+  constexpr int U = 4;
+  const int n = blockIdx.y;
+  const int q = threadIdx.x % CV, rr = threadIdx.x / CV;
+  const bool active = rr < R;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > S) r1 = S;
+  float part[2][V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) part[0][j] = part[1][j] = 0.f;
+  if (active) {
+    long long row = r0 + rr;
+    const long long off0 = ((long long)n * S + row) * C + q * V;
+    const float* ap = a + off0;
+    const float* bp = b + off0;
+    float* sp = s + off0;
+    float* cp = ctx + off0;
+    const long long sx = (long long)R * C;
+    auto one = [&](const float* av, const float* bv, long long o) {
+      float sv[V], cv[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        sv[j] = av[j] + bv[j];
+        cv[j] = sv[j] > 0.f ? sv[j] : sv[j] * slope;
+        part[0][j] += sv[j];
+        part[1][j] = fmaf(sv[j], sv[j], part[1][j]);
+      }
+      Vec<V>::store(sp + o, sv);
+      Vec<V>::store(cp + o, cv);
+    };
+    for (; row + (long long)(U - 1) * R < r1; row += (long long)U * R) {
+      float av[U][V], bv[U][V];
+#pragma unroll
+      for (int u = 0; u < U; ++u) Vec<V>::load(ap + u * sx, av[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) Vec<V>::load(bp + u * sx, bv[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) one(av[u], bv[u], u * sx);
+      ap += U * sx; bp += U * sx; sp += U * sx; cp += U * sx;
+    }
+    for (; row < r1; row += R) {
+      float av[V], bv[V];
+      Vec<V>::load(ap, av);
+      Vec<V>::load(bp, bv);
+      one(av, bv, 0);
+      ap += sx; bp += sx; sp += sx; cp += sx;
+    }
+  }
+  block_reduce_stats<V, 2>(smf, part, q, rr, R, C, active, acc + (long long)n * C * 2);
 }
 
 // in_bwd_apply whose result goes straight into the split-bf16 group-planar operand pack of the producing conv's backward
@@ -744,8 +815,46 @@ extern "C" int cfun_instnorm_bwd_apply(const float* x, const float* a, const flo
   RowMap rm = make_rowmap(C, v4 ? 4 : 1);
   long long rpb = rows_per_block(S, N, rm.R);
   dim3 grid((unsigned)cdiv(S, rpb), N);
-  if (v4) in_bwd_apply_kernel<4><<<grid, 256, 0, st>>>(x, a, b, stat_acc, dx, S, C, rm.CV, rm.R, rpb);
-  else in_bwd_apply_kernel<1><<<grid, 256, 0, st>>>(x, a, b, stat_acc, dx, S, C, rm.CV, rm.R, rpb);
+  if (v4) in_bwd_apply_kernel<4, false><<<grid, 256, 0, st>>>(x, a, b, stat_acc, dx, S, C, rm.CV, rm.R, rpb, nullptr, 0.f);
+  else in_bwd_apply_kernel<1, false><<<grid, 256, 0, st>>>(x, a, b, stat_acc, dx, S, C, rm.CV, rm.R, rpb, nullptr, 0.f);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
+// cfun_instnorm_bwd_apply + leaky_relu'(x, slope) * dextra: the norm's input x also fed a LeakyReLU whose output gradient is
+// dextra (cfun_add_act_stats) -- both gradients of x in one pass
+extern "C" int cfun_instnorm_bwd_apply_extra(const float* x, const float* a, const float* b, const double* stat_acc, float* dx,
+                                             int N, long long S, int C, const float* dextra, float slope, void* stream) {
+  CFUN_CHECK_ARG(x && a && b && stat_acc && dx && dextra && N > 0 && S > 0 && C > 0);
+  cudaStream_t st = as_stream(stream);
+  const bool v4 = (C % 4 == 0);
+  CFUN_CHECK_ARG(C / (v4 ? 4 : 1) <= 256);
+  RowMap rm = make_rowmap(C, v4 ? 4 : 1);
+  long long rpb = rows_per_block(S, N, rm.R);
+  dim3 grid((unsigned)cdiv(S, rpb), N);
+  if (v4) in_bwd_apply_kernel<4, true><<<grid, 256, 0, st>>>(x, a, b, stat_acc, dx, S, C, rm.CV, rm.R, rpb, dextra, slope);
+  else in_bwd_apply_kernel<1, true><<<grid, 256, 0, st>>>(x, a, b, stat_acc, dx, S, C, rm.CV, rm.R, rpb, dextra, slope);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
+// s = a + b, ctx = leaky_relu(s, slope), InstanceNorm statistics of s (acc, mean, rstd as cfun_instnorm_stats) in one pass
+extern "C" int cfun_add_act_stats(const float* a, const float* b, float* s, float* ctx, int N, long long S, int C, float slope,
+                                  float eps, double* acc, float* mean, float* rstd, void* stream) {
+  CFUN_CHECK_ARG(a && b && s && ctx && acc && mean && rstd && N > 0 && S > 0 && C > 0 && C <= 1024);
+  cudaStream_t st = as_stream(stream);
+  CFUN_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * (size_t)N * C, st));
+  const int V = (C % 4 == 0) ? 4 : 1;
+  CFUN_CHECK_ARG(C / V <= 256);
+  RowMap rm = make_rowmap(C, V);
+  long long rpb = rows_per_block(S, N, rm.R, 6);
+  dim3 grid((unsigned)cdiv(S, rpb), N);
+  size_t smem = sizeof(float) * 2 * rm.R * C + sizeof(double) * 256;
+  if (V == 4) add_act_stats_kernel<4><<<grid, 256, smem, st>>>(a, b, s, ctx, slope, S, C, rm.CV, rm.R, rpb, acc);
+  else add_act_stats_kernel<1><<<grid, 256, smem, st>>>(a, b, s, ctx, slope, S, C, rm.CV, rm.R, rpb, acc);
+  CFUN_LAUNCH_CHECK();
+  long long NC = (long long)N * C;
+  in_finalize_kernel<<<(unsigned)cdiv(NC, 256), 256, 0, st>>>(acc, NC, 1.0 / (double)S, eps, mean, rstd);
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;
 }

@@ -83,9 +83,7 @@ class Modified3DUNet(nn.Module):
         else:   # lrelu(dropout(out)): the channel scale folds into the activation pass
             out = ops.affine_act(out, drops[0], torch.zeros_like(drops[0]), None, 0.01, 1)
         out = self.lrelu_conv_c1[1](out)
-        out = out + residual_1
-        context_1 = ops.leaky_relu(out)
-        out = IN(out)
+        context_1, out = ops.add_lrelu_instnorm(out, residual_1)     # s = out + residual_1 -> (lrelu(s), IN(s)) as one node
         # levels 2..5 context (mask_branch.py:138-183)
         ctx = {}
         for lvl in (2, 3, 4, 5):

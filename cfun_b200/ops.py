@@ -514,6 +514,50 @@ def conv_in_lrelu(x, w, b=None, stride=1, padding=0, drop=None, eps=1e-5, slope=
     return instnorm_lrelu(conv3d(x, w, b, stride, padding, False, in_stats=True), drop, eps, slope, up)
 
 
+class AddActInstNormFn(Function):
+    """(leaky_relu(a + b), leaky_relu(InstanceNorm3d(a + b))) as one node: the U-Net's level-1 residual sum feeds both the skip
+    connection and the norm (reference mask_branch.py:132-136).  Forward: one pass writes the sum, the skip activation and
+    the norm statistics, one pass applies the norm; backward: the statistics pass, then ONE pass adds the norm's and the skip's
+    gradients of the sum (unfused: add, lrelu, stats, apply forward; norm backward, lrelu backward, accumulate backward)."""
+
+    @staticmethod
+    def forward(ctx, a, b, eps, slope):
+        _require_cuda(a, b)
+        a, b = to_cl(a), to_cl(b)
+        N, Cc, D, H, W = a.shape
+        S = D * H * W
+        dev = a.device
+        s, c, y = (empty_cl(N, Cc, D, H, W, dev) for _ in range(3))
+        acc = torch.empty(2 * N * Cc, dtype=torch.float64, device=dev)
+        mean = torch.empty((N, Cc), device=dev)
+        rstd = torch.empty((N, Cc), device=dev)
+        _run("cfun_add_act_stats", _ptr(a), _ptr(b), _ptr(s), _ptr(c), N, S, Cc, float(slope), float(eps), _ptr(acc), _ptr(mean),
+             _ptr(rstd), _stream())
+        ca, cb = _in_coeffs(mean, rstd, None, N, Cc, eps)
+        _run("cfun_affine_act_fwd", _ptr(s), _ptr(ca), _ptr(cb), Cc, None, _ptr(y), N, D, H, W, Cc, Cc, 0, 1, float(slope), _stream())
+        ctx.save_for_backward(s, ca, cb)
+        ctx.slope = float(slope)
+        return c, y
+
+    @staticmethod
+    def backward(ctx, dc, dy):
+        s, ca, cb = ctx.saved_tensors
+        N, Cc, D, H, W = s.shape
+        dc, dy = to_cl(dc), to_cl(dy)
+        ds = empty_cl(N, Cc, D, H, W, s.device)
+        acc = torch.empty(2 * N * Cc, dtype=torch.float64, device=s.device)
+        _run("cfun_affine_act_bwd", _ptr(s), _ptr(ca), _ptr(cb), Cc, None, _ptr(dy), _ptr(ds), None, _ptr(acc), N, D, H, W, Cc, Cc, 0, 1,
+             ctx.slope, _stream())
+        _run("cfun_instnorm_bwd_apply_extra", _ptr(s), _ptr(ca), _ptr(cb), _ptr(acc), _ptr(ds), N, D * H * W, Cc, _ptr(dc), ctx.slope,
+             _stream())
+        return ds, ds, None, None
+
+
+def add_lrelu_instnorm(a, b, eps=1e-5, slope=0.01):
+    """s = a + b -> (leaky_relu(s), instnorm_lrelu(s))"""
+    return AddActInstNormFn.apply(a, b, eps, slope)
+
+
 def instnorm_lrelu(x, drop=None, eps=1e-5, slope=0.01, up=1):
     return InstNormActFn.apply(x, drop, eps, slope, up, getattr(x, "_cfun_in_stats", None))
 

@@ -145,6 +145,14 @@ int cfun_affine_act_bwd(const float* x, const float* a, const float* b, int a_ns
 int cfun_instnorm_finalize(const double* acc, int N, long long S, int C, float eps, float* mean, float* rstd, void* stream);
 int cfun_instnorm_bwd_apply(const float* x, const float* a, const float* b, const double* stat_acc, float* dx, int N,
                             long long S, int C, void* stream);
+/* The U-Net's level-1 residual sum feeds both the skip connection and the norm (mask_branch.py:132-136:
+ * out += residual_1; context_1 = lrelu(out); out = inorm3d_c1(out)):
+ *   cfun_add_act_stats             s = a + b, ctx = leaky_relu(s), statistics of s (as cfun_instnorm_stats) in one pass
+ *   cfun_instnorm_bwd_apply_extra  cfun_instnorm_bwd_apply + leaky_relu'(x) * dextra: both gradients of s in one pass */
+int cfun_add_act_stats(const float* a, const float* b, float* s, float* ctx, int N, long long S, int C, float slope, float eps,
+                       double* acc, float* mean, float* rstd, void* stream);
+int cfun_instnorm_bwd_apply_extra(const float* x, const float* a, const float* b, const double* stat_acc, float* dx, int N,
+                                  long long S, int C, const float* dextra, float slope, void* stream);
 /* cfun_instnorm_bwd_apply writing split-bf16 group-planar pack rows (hi, lo: [G][N*(D+2P)][H][W][8], zero planes
  * included) instead of fp32; g = the buffer cfun_affine_act_bwd left the un-normalised gradient in */
 int cfun_instnorm_bwd_apply_pack(const float* x, const float* a, const float* b, const double* stat_acc, const float* g,

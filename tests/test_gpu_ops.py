@@ -703,3 +703,23 @@ def test_conv_in_lrelu_fused_node_matches_separate_ops(ops, case):
     assert rel_err(dw1.cpu().numpy(), dw0.cpu().numpy()) < 1e-5
     assert rel_err(z1.cpu().numpy(), zr.detach().numpy()) < TOL
     assert rel_err(dx1.cpu().numpy(), xr.grad.numpy()) < 5 * TOL
+
+
+@pytest.mark.parametrize("C,dims", [(20, (9, 10, 11)), (20, (40, 36, 44)), (8, (12, 20, 28)), (6, (7, 9, 5))])
+def test_add_lrelu_instnorm_fused_node(ops, C, dims):
+    """ops.add_lrelu_instnorm(a, b) == (leaky_relu(a + b), leaky_relu(instance_norm(a + b))), values and both input gradients"""
+    g = torch.Generator().manual_seed(C + dims[0])
+    N, (D, H, W) = 2, dims
+    a, b = torch.randn(N, C, D, H, W, generator=g) * 2, torch.randn(N, C, D, H, W, generator=g) + 0.3
+    ar, br = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    sr = ar + br
+    cr, yr = F.leaky_relu(sr, 0.01), F.leaky_relu(F.instance_norm(sr, eps=1e-5), 0.01)
+    dc, dy = torch.randn(cr.shape, generator=g), torch.randn(yr.shape, generator=g)
+    (cr * dc + yr * dy).sum().backward()
+    ac, bc = cuda(a).requires_grad_(True), cuda(b).requires_grad_(True)
+    c, y = ops.add_lrelu_instnorm(ac, bc)
+    (c * cuda(dc) + y * cuda(dy)).sum().backward()
+    assert rel_err(c.detach().cpu().numpy(), cr.detach().numpy()) < 1e-6
+    assert rel_err(y.detach().cpu().numpy(), yr.detach().numpy()) < TOL
+    assert rel_err(ac.grad.cpu().numpy(), ar.grad.numpy()) < 2 * TOL
+    assert torch.equal(ac.grad, bc.grad)
