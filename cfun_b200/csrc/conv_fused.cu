@@ -30,6 +30,9 @@ int ds_bwd_weight_packed(const cfun_conv3d_desc* d, __nv_bfloat16* yh, __nv_bflo
 int launch_pack_act_gp_pad(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int C, int G, int P,
                            cudaStream_t st);
 int simt_bias_grad(const float* dy, long long M, int C, float* dbias, cudaStream_t st);
+bool pack_cat_supported(int C1, int C2, int G);
+int launch_pack_cat_gp_pad(const float* a, int C1, const float* b, int C2, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H,
+                           int W, int G, int P, cudaStream_t st);
 
 static bool fused_ok(const cfun_conv3d_desc* d) {
   const char* e = getenv("CFUN_CONV_FUSED");      // "0": separate fwd / dgrad / wgrad calls (A/B measurements)
@@ -92,6 +95,29 @@ extern "C" int cfun_conv3d_fwd_stats(const cfun_conv3d_desc* d, const float* x, 
   __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(xpack);
   __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(xpack) + act);
   return run_conv(d, CFUN_PASS_FWD, x, w, bias, y, epi_flags, ws, ws_bytes, hi, lo, false, st, stat_acc);
+}
+
+// cfun_conv3d_fwd_stats whose input is the channel concatenation [a (C1 channels) | b (C2 channels)], C1 + C2 == d->Cin (the
+// U-Net decoder's torch.cat((up, skip), dim=1) -> conv, mask_branch.py:185-205): the operand pack is built straight from the two
+// tensors, the concatenated fp32 tensor never exists.  cfun_conv3d_cat_supported: 1 if this call handles the shape.
+extern "C" int cfun_conv3d_cat_supported(const cfun_conv3d_desc* d, int C1, int C2) {
+  if (!fused_ok(d) || C1 + C2 != d->Cin) return 0;
+  return pack_cat_supported(C1, C2, (int)align_up((size_t)d->Cin, 16) / 8) ? 1 : 0;
+}
+extern "C" int cfun_conv3d_fwd_stats_cat(const cfun_conv3d_desc* d, const float* a, int C1, const float* b, int C2, const float* w,
+                                         float* y, void* xpack, size_t xpack_bytes, double* stat_acc, void* ws, size_t ws_bytes,
+                                         void* stream) {
+  CFUN_CHECK_ARG(cfun_conv3d_cat_supported(d, C1, C2));
+  CFUN_CHECK_ARG(a && b && w && y && xpack && ws);
+  const size_t act = act_bytes(d, CFUN_PASS_FWD);
+  CFUN_CHECK_ARG(xpack_bytes >= 2 * act && ((size_t)xpack & 127) == 0);
+  cudaStream_t st = as_stream(stream);
+  if (stat_acc) CFUN_CUDA(cudaMemsetAsync(stat_acc, 0, sizeof(double) * 2 * (size_t)d->N * d->Cout, st));
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(xpack);
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(xpack) + act);
+  int rc = launch_pack_cat_gp_pad(a, C1, b, C2, hi, lo, d->N, d->Din, d->Hin, d->Win, (int)align_up((size_t)d->Cin, 16) / 8, d->kD / 2, st);
+  if (rc != CFUN_OK) return rc;
+  return run_conv(d, CFUN_PASS_FWD, nullptr, w, nullptr, y, 0, ws, ws_bytes, hi, lo, true, st, stat_acc);
 }
 
 // geometry of the dY pack cfun_conv3d_bwd_fused builds internally, for callers that produce it themselves

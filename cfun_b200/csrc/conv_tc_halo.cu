@@ -404,9 +404,12 @@ __global__ void __launch_bounds__(256) pack_w_halo_kernel(const float* __restric
 // is converted, so every block always has a tile of loads in flight; the conversion writes, per channel group, TV
 // consecutive 16-byte rows.  Row pitch G*8 + 4 floats keeps the 16-byte shared-memory reads of a quarter warp on distinct
 // banks; channels >= C of the last group read as zero.  Blocks [nwork, gridDim.x) zero the 2 P padding planes per sample.
+// x2 != NULL: the source is the channel concatenation [x (C - C2 channels) | x2 (C2 channels)] of two tensors (the U-Net's
+// torch.cat((up, skip), dim=1) feeding a conv: the concatenated fp32 tensor is never written).
 __global__ void __launch_bounds__(256) pack_act_gp_tiled_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                                                                 __nv_bfloat16* __restrict__ lo, int N, int D, int H, int W, int C, int G,
-                                                                int TV, long long ntiles, int nwork, int P) {
+                                                                int TV, long long ntiles, int nwork, int P,
+                                                                const float* __restrict__ x2, int C2) {
   extern __shared__ __align__(16) float tile[];
   const long long HW = (long long)H * W;
   const long long DHW = (long long)D * HW;
@@ -434,12 +437,13 @@ __global__ void __launch_bounds__(256) pack_act_gp_tiled_kernel(const float* __r
   auto fetch = [&](long long t, int b) {
     const long long v0 = t * TV;
     const int nv = (int)min((long long)TV, vox - v0);
-    const float* src = x + v0 * (long long)C;
     float* dst = tile + b * buf_floats;
+    const int C1 = C - C2, c4a = C1 >> 2;
     for (int i = threadIdx.x; i < nv * c4n; i += blockDim.x) {
       const int v = i / c4n, c4 = i - v * c4n;
+      const float* src = c4 < c4a ? x + (v0 + v) * (long long)C1 + 4 * c4 : x2 + (v0 + v) * (long long)C2 + 4 * (c4 - c4a);
       const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst + v * Cs + 4 * c4);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + 4 * (long long)i) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -527,12 +531,33 @@ int launch_pack_act_gp_pad(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo,
     const long long zrows = (long long)G * N * 2 * P * H * W;
     const int nz = (int)std::max<long long>(1, std::min<long long>(cdiv(zrows, 1024), (long long)num_sms()));
     const int nwork = (int)std::min<long long>(ntile, 4LL * num_sms());
-    pack_act_gp_tiled_kernel<<<(unsigned)(nwork + nz), 256, (size_t)2 * TV * Cs * sizeof(float), st>>>(x, hi, lo, N, D, H, W, C, G, TV, ntile, nwork, P);
+    pack_act_gp_tiled_kernel<<<(unsigned)(nwork + nz), 256, (size_t)2 * TV * Cs * sizeof(float), st>>>(x, hi, lo, N, D, H, W, C, G, TV, ntile, nwork, P, nullptr, 0);
     CFUN_LAUNCH_CHECK();
     return CFUN_OK;
   }
   long long total = (long long)G * N * (D + 2 * P) * H * W;
   pack_act_gp_kernel<<<(unsigned)std::min<long long>(cdiv(total, 256), 32LL * num_sms()), 256, 0, st>>>(x, hi, lo, N, D, H, W, C, G, P);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
+// pack of the channel concatenation [a (C1) | b (C2)]; false = shape not handled by the tiled kernel (caller concatenates first)
+bool pack_cat_supported(int C1, int C2, int G) {
+  const int Cs = G * 8 + 4;
+  const int TV = std::min(128, (6144 / Cs) / 32 * 32);
+  return C1 > 0 && C2 > 0 && (C1 & 3) == 0 && (C2 & 3) == 0 && C1 + C2 > 16 && G * 8 >= C1 + C2 && TV >= 32;
+}
+int launch_pack_cat_gp_pad(const float* a, int C1, const float* b, int C2, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H,
+                           int W, int G, int P, cudaStream_t st) {
+  CFUN_CHECK_ARG(pack_cat_supported(C1, C2, G));
+  const int Cs = G * 8 + 4;
+  const int TV = std::min(128, (6144 / Cs) / 32 * 32);
+  const long long vox = (long long)N * D * H * W;
+  const long long ntile = cdiv(vox, TV);
+  const long long zrows = (long long)G * N * 2 * P * H * W;
+  const int nz = (int)std::max<long long>(1, std::min<long long>(cdiv(zrows, 1024), (long long)num_sms()));
+  const int nwork = (int)std::min<long long>(ntile, 4LL * num_sms());
+  pack_act_gp_tiled_kernel<<<(unsigned)(nwork + nz), 256, (size_t)2 * TV * Cs * sizeof(float), st>>>(a, hi, lo, N, D, H, W, C1 + C2, G, TV, ntile, nwork, P, b, C2);
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;
 }

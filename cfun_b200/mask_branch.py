@@ -71,8 +71,8 @@ class Modified3DUNet(nn.Module):
     def forward(self, x):
         IN = ops.instnorm_lrelu
 
-        def CIN(conv, t, drop=None):     # IN(conv(t), drop): one autograd node where the conv has the fused tcgen05 backward
-            return ops.conv_in_lrelu(t, conv.weight, conv.bias, conv.stride, conv.padding, drop)
+        def CIN(conv, t, drop=None, t2=None):     # IN(conv(cat(t, t2)), drop): one autograd node where the conv has the fused backward
+            return ops.conv_in_lrelu(t, conv.weight, conv.bias, conv.stride, conv.padding, drop, x2=t2)
         drops = self._drop_masks(x.shape[0], x.device)
         # level 1 context (mask_branch.py:125-136)
         out = self.conv3d_c1_1(x)
@@ -102,22 +102,18 @@ class Modified3DUNet(nn.Module):
 
         out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l0, out)
         out = IN(self.conv3d_l0(out, in_stats=True))
-        out = ops.cat_channels(out, ctx[4])
-        out = CIN(self.conv_norm_lrelu_l1[0], out)
+        out = CIN(self.conv_norm_lrelu_l1[0], out, t2=ctx[4])        # conv(cat(out, skip)): the pack is built from the two tensors
         out = self.conv3d_l1(out)
         out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l1, out)
-        out = ops.cat_channels(out, ctx[3])
-        out = CIN(self.conv_norm_lrelu_l2[0], out)
+        out = CIN(self.conv_norm_lrelu_l2[0], out, t2=ctx[3])        # conv(cat(out, skip)): the pack is built from the two tensors
         ds2 = out
         out = self.conv3d_l2(out)
         out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l2, out)
-        out = ops.cat_channels(out, ctx[2])
-        out = CIN(self.conv_norm_lrelu_l3[0], out)
+        out = CIN(self.conv_norm_lrelu_l3[0], out, t2=ctx[2])        # conv(cat(out, skip)): the pack is built from the two tensors
         ds3 = out
         out = self.conv3d_l3(out)
         out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l3, out)
-        out = ops.cat_channels(out, context_1)
-        out = CIN(self.conv_norm_lrelu_l4[0], out)
+        out = CIN(self.conv_norm_lrelu_l4[0], out, t2=context_1)        # conv(cat(out, skip)): the pack is built from the two tensors
         out_pred = self.conv3d_l4(out)
         # deep supervision (mask_branch.py:209-215)
         s = ops.upsample2x(self.ds2_1x1_conv3d(ds2)) + self.ds3_1x1_conv3d(ds3)

@@ -455,18 +455,27 @@ class ConvInstNormActFn(Function):
     kernels (the unfused path writes it in fp32 and re-reads it to pack it)."""
 
     @staticmethod
-    def forward(ctx, x, w, drop, stride, padding, eps, slope, up):
-        _require_cuda(x, w, drop)
+    def forward(ctx, x, w, drop, stride, padding, eps, slope, up, x2=None):
+        """x2: the conv input is torch.cat((x, x2), dim=1) -- packed straight from the two tensors, never materialised"""
+        _require_cuda(x, w, drop, x2)
         x = to_cl(x)
         w = w.contiguous()
-        d = _conv_desc(x.shape, w.shape, stride, padding)
+        c1 = x.shape[1]
+        c2 = 0 if x2 is None else x2.shape[1]
+        d = _conv_desc((x.shape[0], c1 + c2) + tuple(x.shape[2:]), w.shape, stride, padding)
         N, Cc, D, H, W = d.N, d.Cout, d.Dout, d.Hout, d.Wout
         y = empty_cl(N, Cc, D, H, W, x.device)
         ws = workspace(lib.cfun_conv3d_workspace_size(C.byref(d), PASS_FWD, ALGO_AUTO), x.device)
         xpack = torch.empty(lib.cfun_conv3d_pack_bytes(C.byref(d)), dtype=torch.uint8, device=x.device)
         acc = torch.empty(2 * N * Cc, dtype=torch.float64, device=x.device)
-        _run("cfun_conv3d_fwd_stats", C.byref(d), _ptr(x), _ptr(w), None, _ptr(y), 0, _ptr(xpack), xpack.numel(), _ptr(acc),
-             _ptr(ws), ws.numel(), _stream(), tag=_conv_tag(d, PASS_FWD, ALGO_AUTO) if _prof["on"] else "")
+        if x2 is None:
+            _run("cfun_conv3d_fwd_stats", C.byref(d), _ptr(x), _ptr(w), None, _ptr(y), 0, _ptr(xpack), xpack.numel(), _ptr(acc),
+                 _ptr(ws), ws.numel(), _stream(), tag=_conv_tag(d, PASS_FWD, ALGO_AUTO) if _prof["on"] else "")
+        else:
+            x2 = to_cl(x2)
+            _run("cfun_conv3d_fwd_stats_cat", C.byref(d), _ptr(x), c1, _ptr(x2), c2, _ptr(w), _ptr(y), _ptr(xpack), xpack.numel(),
+                 _ptr(acc), _ptr(ws), ws.numel(), _stream(), tag=_conv_tag(d, PASS_FWD, ALGO_AUTO) if _prof["on"] else "")
+        ctx.split = (c1, c2)
         mean = torch.empty((N, Cc), device=x.device)
         rstd = torch.empty((N, Cc), device=x.device)
         _run("cfun_instnorm_finalize", _ptr(acc), N, D * H * W, Cc, float(eps), _ptr(mean), _ptr(rstd), _stream())
@@ -495,22 +504,38 @@ class ConvInstNormActFn(Function):
         _run("cfun_instnorm_bwd_apply_pack", _ptr(y), _ptr(a), _ptr(b), _ptr(acc), _ptr(g), N, D, H, W, Cc, _ptr(ypack),
              C.c_void_p(ypack.data_ptr() + ybytes // 2), G.value, P.value, _stream())
         del g
-        dx = empty_cl(d.N, d.Cin, d.Din, d.Hin, d.Win, dev) if ctx.needs_input_grad[0] else None
+        c1, c2 = ctx.split
+        want_dx = ctx.needs_input_grad[0] or (c2 > 0 and ctx.needs_input_grad[8])
+        dx = empty_cl(d.N, d.Cin, d.Din, d.Hin, d.Win, dev) if want_dx else None
         dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
         if dx is not None or dw is not None:
             ws = workspace(lib.cfun_conv3d_bwd_fused_workspace_size(C.byref(d)), dev)
             _run("cfun_conv3d_bwd_fused_packed", C.byref(d), _ptr(xpack), xpack.numel(), _ptr(ypack), ypack.numel(), _ptr(w), _ptr(dx),
                  _ptr(dw), _ptr(ws), ws.numel(), _stream(), tag=_conv_tag(d, PASS_BWD_WEIGHT, ALGO_AUTO) if _prof["on"] else "")
-        return dx, dw, None, None, None, None, None, None
+        dx2 = None
+        if c2 > 0 and dx is not None:      # gradient of the concatenation -> its two sources
+            da = empty_cl(d.N, c1, d.Din, d.Hin, d.Win, dev)
+            dx2 = empty_cl(d.N, c2, d.Din, d.Hin, d.Win, dev)
+            _run("cfun_split2_channels", _ptr(dx), c1, c2, _ptr(da), _ptr(dx2), d.N * d.Din * d.Hin * d.Win, _stream())
+            dx = da
+        return dx, dw, None, None, None, None, None, None, dx2
 
 
-def conv_in_lrelu(x, w, b=None, stride=1, padding=0, drop=None, eps=1e-5, slope=0.01, up=1):
+def conv_in_lrelu(x, w, b=None, stride=1, padding=0, drop=None, eps=1e-5, slope=0.01, up=1, x2=None):
     """instnorm_lrelu(conv3d(x, w, b), drop) -- as one fused node (ConvInstNormActFn) where the conv runs with the fused tcgen05
-    backward and has no bias, else as the two separate ops (with the epilogue statistics where available)."""
+    backward and has no bias, else as the two separate ops (with the epilogue statistics where available).
+    x2: the conv input is torch.cat((x, x2), dim=1); in the fused node the concatenation is never materialised."""
     if b is None and _default_algo["algo"] == ALGO_AUTO and x.is_cuda and w.requires_grad and torch.is_grad_enabled():
-        d = _conv_desc(tuple(x.shape), tuple(w.shape), stride, padding)
+        cin = x.shape[1] + (0 if x2 is None else x2.shape[1])
+        d = _conv_desc((x.shape[0], cin) + tuple(x.shape[2:]), tuple(w.shape), stride, padding)
         if d.Cout % 4 == 0 and lib.cfun_conv3d_pack_bytes(C.byref(d)) and lib.cfun_conv3d_dy_pack_geometry(C.byref(d), None, None):
-            return ConvInstNormActFn.apply(x, w, drop, stride, padding, eps, slope, up)
+            if x2 is None:
+                return ConvInstNormActFn.apply(x, w, drop, stride, padding, eps, slope, up, None)
+            if x2.shape[0] == x.shape[0] and x2.shape[2:] == x.shape[2:] and \
+                    lib.cfun_conv3d_cat_supported(C.byref(d), int(x.shape[1]), int(x2.shape[1])):
+                return ConvInstNormActFn.apply(x, w, drop, stride, padding, eps, slope, up, x2)
+    if x2 is not None:
+        x = cat_channels(x, x2)
     return instnorm_lrelu(conv3d(x, w, b, stride, padding, False, in_stats=True), drop, eps, slope, up)
 
 

@@ -100,6 +100,12 @@ int cfun_conv3d_fwd_stats(const cfun_conv3d_desc* d, const float* x, const float
                           void* stream);
 int cfun_conv3d_bwd_fused(const cfun_conv3d_desc* d, const void* xpack, size_t xpack_bytes, const float* dy, const float* w,
                           float* dx, float* dw, float* dbias, void* ws, size_t ws_bytes, void* stream);
+/* cfun_conv3d_fwd_stats on the channel concatenation [a (C1) | b (C2)] (the U-Net decoder's torch.cat((up, skip), 1) -> conv,
+ * mask_branch.py:185-205): the operand pack is built from the two tensors, the concatenated tensor never exists.
+ * stat_acc may be NULL. */
+int cfun_conv3d_cat_supported(const cfun_conv3d_desc* d, int C1, int C2);
+int cfun_conv3d_fwd_stats_cat(const cfun_conv3d_desc* d, const float* a, int C1, const float* b, int C2, const float* w, float* y,
+                              void* xpack, size_t xpack_bytes, double* stat_acc, void* ws, size_t ws_bytes, void* stream);
 /* The same backward with the dY pack made by the caller (cfun_instnorm_bwd_apply_pack writes the InstanceNorm backward's
  * result straight into it, so the conv's output gradient never exists in fp32):
  *   cfun_conv3d_dy_pack_geometry  -> bytes of hi + lo (0 = not eligible), channel groups, zero planes per side */

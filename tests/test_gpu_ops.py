@@ -723,3 +723,31 @@ def test_add_lrelu_instnorm_fused_node(ops, C, dims):
     assert rel_err(y.detach().cpu().numpy(), yr.detach().numpy()) < TOL
     assert rel_err(ac.grad.cpu().numpy(), ar.grad.numpy()) < 2 * TOL
     assert torch.equal(ac.grad, bc.grad)
+
+
+@pytest.mark.parametrize("case", [dict(N=2, C1=20, C2=20, Cout=40, dims=(6, 19, 27)), dict(N=3, C1=40, C2=40, Cout=80, dims=(5, 16, 16)),
+                                  dict(N=1, C1=80, C2=80, Cout=160, dims=(6, 12, 12)), dict(N=2, C1=12, C2=28, Cout=24, dims=(4, 9, 17), fused=False)])     # last: a shape outside the fused backward -> cat + separate ops
+def test_conv_in_lrelu_on_concatenated_inputs(ops, case):
+    """ops.conv_in_lrelu(a, w, x2=b): the operand pack is built straight from the two tensors (cfun_conv3d_fwd_stats_cat) ==
+    conv_in_lrelu(torch.cat((a, b), 1), w): same output, and the gradient of the concatenation split back to a and b"""
+    g = torch.Generator().manual_seed(case["C1"] + case["Cout"])
+    N, C1, C2, Cout, (D, H, W) = case["N"], case["C1"], case["C2"], case["Cout"], case["dims"]
+    a, b = torch.randn(N, C1, D, H, W, generator=g), torch.randn(N, C2, D, H, W, generator=g)
+    w = torch.randn(Cout, C1 + C2, 3, 3, 3, generator=g) * 0.1
+    res = []
+    dz = None
+    for fused in (True, False):
+        ac, bc, wc = cuda(a).requires_grad_(True), cuda(b).requires_grad_(True), w.cuda().requires_grad_(True)
+        if fused:
+            z = ops.conv_in_lrelu(ac, wc, None, 1, 1, None, x2=bc)
+            assert type(z.grad_fn).__name__.startswith("ConvInstNormActFn") == case.get("fused", True)
+        else:
+            z = ops.conv_in_lrelu(torch.cat((ac, bc), 1), wc, None, 1, 1, None)
+        if dz is None:
+            dz = cuda(torch.randn(z.shape, generator=g))
+        z.backward(dz)
+        res.append((z.detach(), ac.grad, bc.grad, wc.grad))
+    (z1, da1, db1, dw1), (z0, da0, db0, dw0) = res
+    assert torch.equal(z1, z0) or rel_err(z1.cpu().numpy(), z0.cpu().numpy()) < 2e-6
+    assert rel_err(da1.cpu().numpy(), da0.cpu().numpy()) < 1e-5 and rel_err(db1.cpu().numpy(), db0.cpu().numpy()) < 1e-5
+    assert rel_err(dw1.cpu().numpy(), dw0.cpu().numpy()) < 1e-5
