@@ -212,7 +212,7 @@ conv_tc_wgrad_ds_kernel(const __grid_constant__ CUtensorMap map_yh, const __grid
 }
 
 struct DsPlan {
-  int Gy_total, Gt, Gx, mtiles, stages, tmem_cols, HT, Ntot, nkw, nkh, KS;
+  int Gy_total, Gt, Gx, mtiles, stages, tmem_cols, HT, Ntot, nkw, nkh, KS, ctas_per_sm;
   int Gx_total, slices;        // input channels are processed in `slices` launches of Gx groups
   int yp, xp, y_bytes, x_bytes, stage_bytes;
   size_t act_y, act_x, off_yh, off_yl, off_xh, off_xl, total, smem;
@@ -265,6 +265,29 @@ static bool make_ds_plan(const cfun_conv3d_desc* d, DsPlan& pl, int nkh = 0, int
     }
   }
   if (pl.HT == 0) return false;
+  // Two co-resident CTAs per SM where two pipeline stages of an 8- or 16-line tile fit in half the shared memory and the
+  // accumulators in half the TMEM (thin layers): the CTAs' barrier hand-shakes overlap each other's MMAs (see conv_tc_halo.cu).
+  // CFUN_DS_CTAS=1 keeps one CTA per SM (A/B measurements).
+  pl.ctas_per_sm = 1;
+  {
+    const char* c1 = getenv("CFUN_DS_CTAS");
+    const size_t cap2 = 111 * 1024 - 2048;
+    if (!(c1 && c1[0] == '1') && pl.tmem_cols <= 256) {
+      for (int ht = (d->Hin >= 16 ? 16 : 8); ht >= 8; ht -= 8) {
+        const int yp = ht * DS_LINE, xp = (ht + pl.KS - 1) * DS_LINE;
+        const size_t yb = (size_t)pl.Gt * pl.KS * yp, xb = (size_t)nkw * pl.Gx * xp;
+        const size_t stage = align_up(2 * (yb + xb), 1024);
+        const size_t slack = (size_t)16 * yp + xp;
+        if (slack + 2 * stage > cap2) continue;
+        const int st = (int)std::min<size_t>(DS_MAX_STAGES, (cap2 - slack) / stage);
+        pl.HT = ht; pl.yp = yp; pl.xp = xp; pl.y_bytes = (int)yb; pl.x_bytes = (int)xb; pl.stage_bytes = (int)stage;
+        pl.stages = st;
+        pl.smem = 2048 + (size_t)st * stage + slack;
+        pl.ctas_per_sm = 2;
+        break;
+      }
+    }
+  }
   const int pad = pl.KS / 2;
   pl.act_y = align_up((size_t)pl.Gy_total * d->N * (d->Dout + 2 * pad) * d->Hout * d->Wout * 16, 1024);
   pl.act_x = align_up((size_t)pl.Gx_total * d->N * (d->Din + 2 * pad) * d->Hin * d->Win * 16, 1024);
@@ -344,7 +367,7 @@ int ds_launch(const cfun_conv3d_desc* d, const DsPlan& pl, __nv_bfloat16* yh, __
   p.slices = pl.slices;
   // split-K over CTAs: every (M tile, Cin slice) pair owns its own dW block, so the more of those there are the fewer
   // voxel splits (and atomic flushes of the same block) are needed to fill the SMs
-  long long ctas = std::max<long long>(1, num_sms() / (pl.mtiles * pl.slices));
+  long long ctas = std::max<long long>(1, (long long)pl.ctas_per_sm * num_sms() / (pl.mtiles * pl.slices));
   ctas = std::min<long long>(ctas, cdiv(p.units_total, 4));
   p.units_per_cta = cdiv(p.units_total, ctas);
   ctas = cdiv(p.units_total, p.units_per_cta);
