@@ -230,7 +230,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
           }
           constexpr int STAGES_PER_TILE = []() { int n = 0; for (int gg = 0; gg < G; ++gg) { const int sb = hl_seg_begin(T, gg); const int se = hl_seg_begin(T, gg + 1) < NSTEPS ? hl_seg_begin(T, gg + 1) : NSTEPS; n += (se - sb + HL_HALF - 1) / HL_HALF; } return n; }();
           const uint32_t cnt = (uint32_t)it * STAGES_PER_TILE + (uint32_t)(before + h);
-          const uint32_t lap = __umulhi(cnt, ring_inv);
+          const uint32_t lap = ring_n == 1u ? cnt : __umulhi(cnt, ring_inv);       // (the reciprocal overflows for a one-stage ring)
           const uint32_t st = cnt - lap * ring_n;
           uint32_t bw;
           if (p.resident) bw = b_base + (uint32_t)s0 * stepw;
@@ -615,7 +615,8 @@ static bool make_hl_plan(const cfun_conv3d_desc* d, int pass, HlPlan& pl) {
   {
     const char* c1 = getenv("CFUN_HL_CTAS");
     const size_t cap2 = 111 * 1024;
-    if (!(c1 && c1[0] == '1') && pl.tmem_cols <= 256 && 2048 + a_bytes + 2 * HL_HALF * step_bytes <= cap2) {
+    const size_t min_stages = (c1 && c1[0] == '2') ? 1 : 2;       // "2": also with a single weight stage (experiment)
+    if (!(c1 && c1[0] == '1') && pl.tmem_cols <= 256 && 2048 + a_bytes + min_stages * HL_HALF * step_bytes <= cap2) {
       const size_t budget2 = cap2 - 2048 - a_bytes;
       pl.ctas_per_sm = 2;
       if (pl.w_bytes <= budget2 && !(e && e[0] == '0')) {
