@@ -62,6 +62,8 @@ SIGNATURES = {
     "cfun_instnorm_bwd_apply_pack": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p]),
     "cfun_conv3d_dy_pack_geometry": (_sz, [_D, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cfun_conv3d_cat_supported": (_i, [_D, _i, _i]),
+    "cfun_conv3d_preact_supported": (_i, [_D]),
+    "cfun_conv3d_fwd_keep_pack_preact": (_i, [_D, _p, _p, _f, _p, _p, _p, _i, _p, _sz, _p, _sz, _p]),
     "cfun_conv3d_fwd_stats_cat": (_i, [_D, _p, _i, _p, _i, _p, _p, _p, _sz, _p, _p, _sz, _p]),
     "cfun_conv3d_bwd_fused_packed": (_i, [_D, _p, _sz, _p, _sz, _p, _p, _p, _p, _sz, _p]),
     "cfun_affine_act_fwd": (_i, [_p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p]),

@@ -30,6 +30,9 @@ int ds_bwd_weight_packed(const cfun_conv3d_desc* d, __nv_bfloat16* yh, __nv_bflo
 int launch_pack_act_gp_pad(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H, int W, int C, int G, int P,
                            cudaStream_t st);
 int simt_bias_grad(const float* dy, long long M, int C, float* dbias, cudaStream_t st);
+bool pack_preact_supported(int C, int G);
+int launch_pack_preact_gp_pad(const float* x, const float* scale, float slope, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H,
+                              int W, int C, int G, int P, cudaStream_t st);
 bool pack_cat_supported(int C1, int C2, int G);
 int launch_pack_cat_gp_pad(const float* a, int C1, const float* b, int C2, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H,
                            int W, int G, int P, cudaStream_t st);
@@ -118,6 +121,31 @@ extern "C" int cfun_conv3d_fwd_stats_cat(const cfun_conv3d_desc* d, const float*
   int rc = launch_pack_cat_gp_pad(a, C1, b, C2, hi, lo, d->N, d->Din, d->Hin, d->Win, (int)align_up((size_t)d->Cin, 16) / 8, d->kD / 2, st);
   if (rc != CFUN_OK) return rc;
   return run_conv(d, CFUN_PASS_FWD, nullptr, w, nullptr, y, 0, ws, ws_bytes, hi, lo, true, st, stat_acc);
+}
+
+// cfun_conv3d_fwd_keep_pack on leaky_relu(x * scale[n][c], slope) (scale NULL = 1): the activation / Dropout3d channel scale that
+// precede the conv (mask_branch.py:127-131: conv3d_c1_2(lrelu(out)), lrelu_conv_c1(lrelu(dropout(out)))) are applied on the
+// way into the operand pack; the activated tensor is never written.  The kept pack holds the activated values, so
+// cfun_conv3d_bwd_fused returns the gradient w.r.t. the ACTIVATED input; cfun_affine_act_bwd(x, scale, 0, ...) finishes it.
+extern "C" int cfun_conv3d_preact_supported(const cfun_conv3d_desc* d) {
+  if (!fused_ok(d)) return 0;
+  return pack_preact_supported(d->Cin, (int)align_up((size_t)d->Cin, 16) / 8) ? 1 : 0;
+}
+extern "C" int cfun_conv3d_fwd_keep_pack_preact(const cfun_conv3d_desc* d, const float* x, const float* scale, float slope,
+                                                const float* w, const float* bias, float* y, int epi_flags, void* xpack,
+                                                size_t xpack_bytes, void* ws, size_t ws_bytes, void* stream) {
+  CFUN_CHECK_ARG(cfun_conv3d_preact_supported(d));
+  CFUN_CHECK_ARG(x && w && y && xpack && ws);
+  CFUN_CHECK_ARG(!(epi_flags & CFUN_EPI_BIAS) || bias);
+  const size_t act = act_bytes(d, CFUN_PASS_FWD);
+  CFUN_CHECK_ARG(xpack_bytes >= 2 * act && ((size_t)xpack & 127) == 0);
+  cudaStream_t st = as_stream(stream);
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(xpack);
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(xpack) + act);
+  int rc = launch_pack_preact_gp_pad(x, scale, slope, hi, lo, d->N, d->Din, d->Hin, d->Win, d->Cin, (int)align_up((size_t)d->Cin, 16) / 8,
+                                     d->kD / 2, st);
+  if (rc != CFUN_OK) return rc;
+  return run_conv(d, CFUN_PASS_FWD, nullptr, w, bias, y, epi_flags, ws, ws_bytes, hi, lo, true, st);
 }
 
 // geometry of the dY pack cfun_conv3d_bwd_fused builds internally, for callers that produce it themselves

@@ -406,10 +406,13 @@ __global__ void __launch_bounds__(256) pack_w_halo_kernel(const float* __restric
 // banks; channels >= C of the last group read as zero.  Blocks [nwork, gridDim.x) zero the 2 P padding planes per sample.
 // x2 != NULL: the source is the channel concatenation [x (C - C2 channels) | x2 (C2 channels)] of two tensors (the U-Net's
 // torch.cat((up, skip), dim=1) feeding a conv: the concatenated fp32 tensor is never written).
+// act != 0: the pack holds leaky_relu(x * act_scale[n][c], act_slope) (act_scale NULL = 1): the LeakyReLU / Dropout3d that
+// precede a conv (mask_branch.py:127-131) applied on the way into its operand pack, bit-identical to affine_act_fwd.
 __global__ void __launch_bounds__(256) pack_act_gp_tiled_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                                                                 __nv_bfloat16* __restrict__ lo, int N, int D, int H, int W, int C, int G,
                                                                 int TV, long long ntiles, int nwork, int P,
-                                                                const float* __restrict__ x2, int C2) {
+                                                                const float* __restrict__ x2, int C2, int act,
+                                                                const float* __restrict__ act_scale, float act_slope) {
   extern __shared__ __align__(16) float tile[];
   const long long HW = (long long)H * W;
   const long long DHW = (long long)D * HW;
@@ -466,13 +469,22 @@ __global__ void __launch_bounds__(256) pack_act_gp_tiled_kernel(const float* __r
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bq = a;
       if (8 * g < C) a = *reinterpret_cast<const float4*>(cur + v * Cs + 8 * g);
       if (8 * g + 4 < C) bq = *reinterpret_cast<const float4*>(cur + v * Cs + 8 * g + 4);
-      const float f[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
+      float f[8] = {a.x, a.y, a.z, a.w, bq.x, bq.y, bq.z, bq.w};
+      const long long gv = v0 + v;
+      const long long n = gv / DHW, rem = gv - n * DHW;
+      if (act) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = 8 * g + j;
+          const float m = (act_scale && c < C) ? __ldg(act_scale + n * C + c) : 1.f;
+          const float t = fmaf(f[j], m, 0.f);
+          f[j] = t > 0.f ? t : t * act_slope;
+        }
+      }
       __align__(16) __nv_bfloat16 h[8];
       __align__(16) __nv_bfloat16 l[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) split_bf16(f[j], h[j], l[j]);
-      const long long gv = v0 + v;
-      const long long n = gv / DHW, rem = gv - n * DHW;
       const long long pos = (n * (D + 2 * P) + P) * HW + rem;
       reinterpret_cast<uint4*>(hi)[(long long)g * vox_p + pos] = *reinterpret_cast<const uint4*>(h);
       if (lo) reinterpret_cast<uint4*>(lo)[(long long)g * vox_p + pos] = *reinterpret_cast<const uint4*>(l);
@@ -531,7 +543,7 @@ int launch_pack_act_gp_pad(const float* x, __nv_bfloat16* hi, __nv_bfloat16* lo,
     const long long zrows = (long long)G * N * 2 * P * H * W;
     const int nz = (int)std::max<long long>(1, std::min<long long>(cdiv(zrows, 1024), (long long)num_sms()));
     const int nwork = (int)std::min<long long>(ntile, 4LL * num_sms());
-    pack_act_gp_tiled_kernel<<<(unsigned)(nwork + nz), 256, (size_t)2 * TV * Cs * sizeof(float), st>>>(x, hi, lo, N, D, H, W, C, G, TV, ntile, nwork, P, nullptr, 0);
+    pack_act_gp_tiled_kernel<<<(unsigned)(nwork + nz), 256, (size_t)2 * TV * Cs * sizeof(float), st>>>(x, hi, lo, N, D, H, W, C, G, TV, ntile, nwork, P, nullptr, 0, 0, nullptr, 0.f);
     CFUN_LAUNCH_CHECK();
     return CFUN_OK;
   }
@@ -557,7 +569,28 @@ int launch_pack_cat_gp_pad(const float* a, int C1, const float* b, int C2, __nv_
   const long long zrows = (long long)G * N * 2 * P * H * W;
   const int nz = (int)std::max<long long>(1, std::min<long long>(cdiv(zrows, 1024), (long long)num_sms()));
   const int nwork = (int)std::min<long long>(ntile, 4LL * num_sms());
-  pack_act_gp_tiled_kernel<<<(unsigned)(nwork + nz), 256, (size_t)2 * TV * Cs * sizeof(float), st>>>(a, hi, lo, N, D, H, W, C1 + C2, G, TV, ntile, nwork, P, b, C2);
+  pack_act_gp_tiled_kernel<<<(unsigned)(nwork + nz), 256, (size_t)2 * TV * Cs * sizeof(float), st>>>(a, hi, lo, N, D, H, W, C1 + C2, G, TV, ntile, nwork, P, b, C2, 0, nullptr, 0.f);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
+// pack of leaky_relu(x * scale[n][c], slope); false from pack_preact_supported = shape not handled by the tiled kernel
+bool pack_preact_supported(int C, int G) {
+  const int Cs = G * 8 + 4;
+  const int TV = std::min(128, (6144 / Cs) / 32 * 32);
+  return (C & 3) == 0 && C > 16 && G * 8 >= C && TV >= 32;
+}
+int launch_pack_preact_gp_pad(const float* x, const float* scale, float slope, __nv_bfloat16* hi, __nv_bfloat16* lo, int N, int D, int H,
+                              int W, int C, int G, int P, cudaStream_t st) {
+  CFUN_CHECK_ARG(pack_preact_supported(C, G));
+  const int Cs = G * 8 + 4;
+  const int TV = std::min(128, (6144 / Cs) / 32 * 32);
+  const long long vox = (long long)N * D * H * W;
+  const long long ntile = cdiv(vox, TV);
+  const long long zrows = (long long)G * N * 2 * P * H * W;
+  const int nz = (int)std::max<long long>(1, std::min<long long>(cdiv(zrows, 1024), (long long)num_sms()));
+  const int nwork = (int)std::min<long long>(ntile, 4LL * num_sms());
+  pack_act_gp_tiled_kernel<<<(unsigned)(nwork + nz), 256, (size_t)2 * TV * Cs * sizeof(float), st>>>(x, hi, lo, N, D, H, W, C, G, TV, ntile, nwork, P, nullptr, 0, 1, scale, slope);
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;
 }

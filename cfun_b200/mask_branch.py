@@ -77,12 +77,11 @@ class Modified3DUNet(nn.Module):
         # level 1 context (mask_branch.py:125-136)
         out = self.conv3d_c1_1(x)
         residual_1 = out
-        out = self.conv3d_c1_2(ops.leaky_relu(out))
-        if drops[0] is None:
-            out = ops.leaky_relu(out)
-        else:   # lrelu(dropout(out)): the channel scale folds into the activation pass
-            out = ops.affine_act(out, drops[0], torch.zeros_like(drops[0]), None, 0.01, 1)
-        out = self.lrelu_conv_c1[1](out)
+        # lrelu -> conv and dropout -> lrelu -> conv: the activation (and the Dropout3d channel scale) are applied on the way
+        # into the conv's operand pack (ops.lrelu_conv3d)
+        c12, c13 = self.conv3d_c1_2, self.lrelu_conv_c1[1]
+        out = ops.lrelu_conv3d(out, c12.weight, c12.bias, c12.stride, c12.padding)
+        out = ops.lrelu_conv3d(out, c13.weight, c13.bias, c13.stride, c13.padding, scale=drops[0])
         context_1, out = ops.add_lrelu_instnorm(out, residual_1)     # s = out + residual_1 -> (lrelu(s), IN(s)) as one node
         # levels 2..5 context (mask_branch.py:138-183)
         ctx = {}

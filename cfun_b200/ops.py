@@ -279,6 +279,59 @@ def conv3d(x, w, b=None, stride=1, padding=0, relu=False, in_stats=False):
     return y
 
 
+class PreActConv3dFn(Function):
+    """conv3d(leaky_relu(x * scale[n,c], slope), w) with the activation applied on the way into the conv's operand pack (the
+    activated tensor is never written): the U-Net's conv3d_c1_2(lrelu(out)) and lrelu_conv_c1(lrelu(dropout3d(out)))
+    (reference mask_branch.py:127-131).  Backward = the fused conv backward on the kept pack, then the activation backward."""
+
+    @staticmethod
+    def forward(ctx, x, w, scale, slope, stride, padding):
+        _require_cuda(x, w, scale)
+        x = to_cl(x)
+        w = w.contiguous()
+        d = _conv_desc(x.shape, w.shape, stride, padding)
+        if scale is not None:
+            scale = scale.reshape(d.N, d.Cin).float().contiguous()
+        y = empty_cl(d.N, d.Cout, d.Dout, d.Hout, d.Wout, x.device)
+        ws = workspace(lib.cfun_conv3d_workspace_size(C.byref(d), PASS_FWD, ALGO_AUTO), x.device)
+        xpack = torch.empty(lib.cfun_conv3d_pack_bytes(C.byref(d)), dtype=torch.uint8, device=x.device)
+        _run("cfun_conv3d_fwd_keep_pack_preact", C.byref(d), _ptr(x), _ptr(scale), float(slope), _ptr(w), None, _ptr(y), 0, _ptr(xpack),
+             xpack.numel(), _ptr(ws), ws.numel(), _stream(), tag=_conv_tag(d, PASS_FWD, ALGO_AUTO) if _prof["on"] else "")
+        ctx.save_for_backward(xpack, w, x, scale)
+        ctx.d, ctx.slope = d, float(slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xpack, w, x, scale = ctx.saved_tensors
+        d = ctx.d
+        dy = to_cl(dy)
+        dev = dy.device
+        da = empty_cl(d.N, d.Cin, d.Din, d.Hin, d.Win, dev) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        ws = workspace(lib.cfun_conv3d_bwd_fused_workspace_size(C.byref(d)), dev)
+        _run("cfun_conv3d_bwd_fused", C.byref(d), _ptr(xpack), xpack.numel(), _ptr(dy), _ptr(w), _ptr(da), _ptr(dw), None,
+             _ptr(ws), ws.numel(), _stream(), tag=_conv_tag(d, PASS_BWD_WEIGHT, ALGO_AUTO) if _prof["on"] else "")
+        dx = None
+        if da is not None:      # gradient of the activated input -> gradient of x
+            dx = empty_cl(d.N, d.Cin, d.Din, d.Hin, d.Win, dev)
+            zero = torch.zeros_like(scale) if scale is not None else None
+            _run("cfun_affine_act_bwd", _ptr(x), _ptr(scale), _ptr(zero), d.Cin if scale is not None else 0, None, _ptr(da), _ptr(dx),
+                 None, None, d.N, d.Din, d.Hin, d.Win, d.Cin, d.Cin, 0, 1, ctx.slope, _stream())
+        return dx, dw, None, None, None, None
+
+
+def lrelu_conv3d(x, w, b=None, stride=1, padding=0, scale=None, slope=0.01):
+    """conv3d(leaky_relu(x * scale, slope), w, b): fused into the conv's operand pack where the conv has the fused tcgen05
+    backward and no bias (PreActConv3dFn), else the two separate ops.  scale: None or a per-(sample, channel) factor [N,C]."""
+    if b is None and _default_algo["algo"] == ALGO_AUTO and x.is_cuda and w.requires_grad and torch.is_grad_enabled():
+        d = _conv_desc(tuple(x.shape), tuple(w.shape), stride, padding)
+        if lib.cfun_conv3d_pack_bytes(C.byref(d)) and lib.cfun_conv3d_preact_supported(C.byref(d)):
+            return PreActConv3dFn.apply(x, w, scale, slope, stride, padding)
+    a = leaky_relu(x, slope) if scale is None else affine_act(x, scale, torch.zeros_like(scale), None, slope, 1)
+    return conv3d(a, w, b, stride, padding)
+
+
 class FcConvFn(Function):
     """Conv3d whose kernel covers the whole (un-padded) input: Classifier.conv1 (model.py:758).  x is consumed in
     NCDHW-contiguous order so K = (ci, kd, kh, kw) matches the checkpoint weight layout with no repack."""

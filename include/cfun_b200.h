@@ -100,6 +100,14 @@ int cfun_conv3d_fwd_stats(const cfun_conv3d_desc* d, const float* x, const float
                           void* stream);
 int cfun_conv3d_bwd_fused(const cfun_conv3d_desc* d, const void* xpack, size_t xpack_bytes, const float* dy, const float* w,
                           float* dx, float* dw, float* dbias, void* ws, size_t ws_bytes, void* stream);
+/* cfun_conv3d_fwd_keep_pack on leaky_relu(x * scale[n][c], slope) (scale NULL = 1) -- the LeakyReLU / Dropout3d that precede a
+ * conv (mask_branch.py:127-131) applied on the way into its operand pack; the activated tensor is never written.  The
+ * backward (cfun_conv3d_bwd_fused on the kept pack) yields the gradient w.r.t. the activated input; cfun_affine_act_bwd(x,
+ * scale, 0, ...) turns it into the gradient of x. */
+int cfun_conv3d_preact_supported(const cfun_conv3d_desc* d);
+int cfun_conv3d_fwd_keep_pack_preact(const cfun_conv3d_desc* d, const float* x, const float* scale, float slope, const float* w,
+                                     const float* bias, float* y, int epi_flags, void* xpack, size_t xpack_bytes, void* ws,
+                                     size_t ws_bytes, void* stream);
 /* cfun_conv3d_fwd_stats on the channel concatenation [a (C1) | b (C2)] (the U-Net decoder's torch.cat((up, skip), 1) -> conv,
  * mask_branch.py:185-205): the operand pack is built from the two tensors, the concatenated tensor never exists.
  * stat_acc may be NULL. */

@@ -751,3 +751,38 @@ def test_conv_in_lrelu_on_concatenated_inputs(ops, case):
     assert torch.equal(z1, z0) or rel_err(z1.cpu().numpy(), z0.cpu().numpy()) < 2e-6
     assert rel_err(da1.cpu().numpy(), da0.cpu().numpy()) < 1e-5 and rel_err(db1.cpu().numpy(), db0.cpu().numpy()) < 1e-5
     assert rel_err(dw1.cpu().numpy(), dw0.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("case", [dict(N=2, Cin=20, Cout=20, dims=(6, 19, 27), drop=False), dict(N=3, Cin=20, Cout=20, dims=(5, 16, 16), drop=True),
+                                  dict(N=2, Cin=40, Cout=24, dims=(7, 16, 24), drop=True)])
+def test_lrelu_conv3d_activation_fused_into_the_operand_pack(ops, case):
+    """ops.lrelu_conv3d: LeakyReLU (and the Dropout3d channel scale) applied on the way into the conv's operand pack ==
+    conv3d(affine_act(x)): forward and input gradient bit for bit, weight gradient up to the atomics' summation order"""
+    g = torch.Generator().manual_seed(case["Cin"] + case["dims"][0])
+    N, Cin, Cout, (D, H, W) = case["N"], case["Cin"], case["Cout"], case["dims"]
+    x = torch.randn(N, Cin, D, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, 3, generator=g) * 0.1
+    scale = ((torch.rand(N, Cin, generator=g) > 0.6).float() / 0.4).cuda() if case["drop"] else None
+    dy = None
+    res = []
+    for fused in (True, False):
+        xc, wc = cuda(x).requires_grad_(True), w.cuda().requires_grad_(True)
+        if fused:
+            y = ops.lrelu_conv3d(xc, wc, None, 1, 1, scale)
+            assert type(y.grad_fn).__name__.startswith("PreActConv3dFn"), "shape did not take the fused node"
+        else:
+            a = ops.leaky_relu(xc) if scale is None else ops.affine_act(xc, scale, torch.zeros_like(scale), None, 0.01, 1)
+            y = ops.conv3d(a, wc, None, 1, 1)
+        if dy is None:
+            dy = cuda(torch.randn(y.shape, generator=g))
+        y.backward(dy)
+        res.append((y.detach(), xc.grad, wc.grad))
+    (y1, dx1, dw1), (y0, dx0, dw0) = res
+    assert torch.equal(y1, y0)
+    assert torch.equal(dx1, dx0)
+    assert rel_err(dw1.cpu().numpy(), dw0.cpu().numpy()) < 1e-5
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    t = xr if scale is None else xr * scale.cpu().view(N, Cin, 1, 1, 1)
+    yr = F.conv3d(F.leaky_relu(t, 0.01), wr, None, padding=1)
+    yr.backward(dy.cpu())
+    assert rel_err(y1.cpu().numpy(), yr.detach().numpy()) < TOL and rel_err(dx1.cpu().numpy(), xr.grad.numpy()) < TOL
