@@ -305,3 +305,48 @@ def test_reference_arm_does_not_load_the_native_library():
             "assert 'cfun_b200.model' not in sys.modules and 'cfun_b200.ops' not in sys.modules; print('clean')") % ROOT
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "clean" in out.stdout, out.stderr[-2000:]
+
+
+def test_static_rpn_losses_equal_the_reference_shaped_losses_on_cpu():
+    """model.compute_rpn_losses_static (fixed-size gathers, no read-back; pure torch index algebra, so it runs here) against
+    compute_rpn_class_loss / compute_rpn_bbox_loss (reference model.py:836-873) and against the oracle, values and gradients;
+    also the scatter fallback of the padded nonzero"""
+    from cfun_b200 import model as M
+    g = torch.Generator().manual_seed(3)
+    A, K = 3000, 64
+    for npos, nneg in ((17, 40), (32, 32), (1, 0), (0, 5)):
+        m = torch.zeros(A, dtype=torch.int32)
+        perm = torch.randperm(A, generator=g)
+        m[perm[:npos]] = 1
+        m[perm[npos:npos + nneg]] = -1
+        tgt = torch.zeros(1, K, 6)
+        tgt[0, :npos] = torch.randn(npos, 6, generator=g)
+        logits = torch.randn(1, A, 2, generator=g)
+        pred = torch.randn(1, A, 6, generator=g) * 2
+        mm = m.view(1, -1, 1)
+        l0, p0 = logits.clone().requires_grad_(True), pred.clone().requires_grad_(True)
+        c0, b0 = M.compute_rpn_class_loss(mm, l0), M.compute_rpn_bbox_loss(tgt, mm, p0)
+        l1, p1 = logits.clone().requires_grad_(True), pred.clone().requires_grad_(True)
+        c1, b1, counts = M.compute_rpn_losses_static(mm, tgt, l1, p1, K)
+        assert counts.tolist() == [npos + nneg, npos]
+        assert torch.allclose(c0, c1, rtol=1e-6, atol=0)
+        assert (torch.isnan(b0).all() and torch.isnan(b1).all()) if npos == 0 else torch.allclose(b0, b1, rtol=1e-6, atol=0)
+        (c0 + (b0 if npos else 0)).sum().backward()
+        (c1 + (b1 if npos else 0)).sum().backward()
+        assert torch.allclose(l0.grad, l1.grad, rtol=1e-5, atol=1e-9)
+        if npos:
+            assert torch.allclose(p0.grad, p1.grad, rtol=1e-5, atol=1e-9)
+        if npos:
+            assert abs(float(O.rpn_class_loss(m, logits[0])) - float(c1)) < 1e-6 and abs(float(O.rpn_bbox_loss(tgt[0], m, pred[0])) - float(b1)) < 1e-6
+    mask = torch.rand(500, generator=g) > 0.9
+    want = torch.nonzero(mask)[:, 0]
+    for size in (int(mask.sum()) + 7, int(mask.sum())):
+        got = M._nonzero_static(mask, size)
+        real = torch.nonzero_static
+        try:
+            del torch.nonzero_static          # force the cumsum / scatter fallback
+            fb = M._nonzero_static(mask, size)
+        finally:
+            torch.nonzero_static = real
+        for idx in (got, fb):
+            assert idx.shape[0] == size and torch.equal(idx[:want.numel()], want) and bool((idx[want.numel():] == -1).all())
