@@ -61,6 +61,8 @@ SIGNATURES = {
     "cfun_instnorm_bwd_apply_extra": (_i, [_p, _p, _p, _p, _p, _i, _ll, _i, _p, _f, _p]),
     "cfun_instnorm_bwd_apply_pack": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _p]),
     "cfun_conv3d_dy_pack_geometry": (_sz, [_D, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "cfun_instnorm_up2_pack": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p, _i, _i, _p]),
+    "cfun_conv3d_fwd_stats_packed": (_i, [_D, _p, _sz, _p, _p, _p, _p, _sz, _p]),
     "cfun_conv3d_cat_supported": (_i, [_D, _i, _i]),
     "cfun_conv3d_preact_supported": (_i, [_D]),
     "cfun_conv3d_fwd_keep_pack_preact": (_i, [_D, _p, _p, _f, _p, _p, _p, _i, _p, _sz, _p, _sz, _p]),

@@ -148,6 +148,21 @@ extern "C" int cfun_conv3d_fwd_keep_pack_preact(const cfun_conv3d_desc* d, const
   return run_conv(d, CFUN_PASS_FWD, nullptr, w, bias, y, epi_flags, ws, ws_bytes, hi, lo, true, st);
 }
 
+// cfun_conv3d_fwd_stats on an X pack the caller has already filled (cfun_instnorm_up2_pack: the decoder's norm -> lrelu ->
+// upsample -> conv, where the upsampled fp32 tensor never exists); stat_acc may be NULL
+extern "C" int cfun_conv3d_fwd_stats_packed(const cfun_conv3d_desc* d, void* xpack, size_t xpack_bytes, const float* w, float* y,
+                                            double* stat_acc, void* ws, size_t ws_bytes, void* stream) {
+  CFUN_CHECK_ARG(fused_ok(d));
+  CFUN_CHECK_ARG(w && y && xpack && ws);
+  const size_t act = act_bytes(d, CFUN_PASS_FWD);
+  CFUN_CHECK_ARG(xpack_bytes >= 2 * act && ((size_t)xpack & 127) == 0);
+  cudaStream_t st = as_stream(stream);
+  if (stat_acc) CFUN_CUDA(cudaMemsetAsync(stat_acc, 0, sizeof(double) * 2 * (size_t)d->N * d->Cout, st));
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(xpack);
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(xpack) + act);
+  return run_conv(d, CFUN_PASS_FWD, nullptr, w, nullptr, y, 0, ws, ws_bytes, hi, lo, true, st, stat_acc);
+}
+
 // geometry of the dY pack cfun_conv3d_bwd_fused builds internally, for callers that produce it themselves
 // (cfun_instnorm_bwd_apply_pack): groups of 8 channels, zero planes per side, bytes of hi + lo (0 = shape not eligible)
 extern "C" size_t cfun_conv3d_dy_pack_geometry(const cfun_conv3d_desc* d, int* groups, int* pad_planes) {

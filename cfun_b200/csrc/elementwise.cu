@@ -600,6 +600,59 @@ __global__ void __launch_bounds__(256) in_bwd_apply_pack_kernel(const float* __r
   }
 }
 
+// InstanceNorm apply + LeakyReLU + nearest x2 upsampling written straight into the split-bf16 group-planar operand pack of the
+// conv that follows (the U-Net decoder's norm -> lrelu -> upsample -> conv, mask_branch.py:91-103): thread = (low-res voxel,
+// 8-channel group); the activated values are split once and the same 16-byte hi / lo rows go to the 2x2x2 output voxels.
+// The 8x larger upsampled fp32 tensor is never written.  hi/lo: [G][N*(2D+2P)][2H][2W][8].
+__global__ void __launch_bounds__(256) affine_act_up2_pack_kernel(const float* __restrict__ x, const float* __restrict__ a,
+                                                                  const float* __restrict__ b, int N, int D, int H, int W, int C,
+                                                                  float slope, __nv_bfloat16* __restrict__ hi,
+                                                                  __nv_bfloat16* __restrict__ lo, int G, int P) {
+  const long long vox = (long long)N * D * H * W;
+  const long long total = vox * G;
+  const int H2 = 2 * H, W2 = 2 * W;
+  const long long plane2 = (long long)H2 * W2;
+  const long long vox_p = (long long)N * (2 * D + 2 * P) * plane2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i / vox);
+    long long v = i - (long long)g * vox;
+    const int w = (int)(v % W); long long t = v / W;
+    const int h = (int)(t % H); t /= H;
+    const int d = (int)(t % D);
+    const int n = (int)(t / D);
+    const int c = 8 * g;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (c + 4 * q < C) {
+        float xv[4], av[4], bv[4];
+        Vec<4>::load(x + v * C + c + 4 * q, xv);
+        Vec<4>::load(a + (long long)n * C + c + 4 * q, av);
+        Vec<4>::load(b + (long long)n * C + c + 4 * q, bv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float y = fmaf(xv[j], av[j], bv[j]);
+          f[4 * q + j] = y > 0.f ? y : y * slope;
+        }
+      }
+    }
+    __align__(16) __nv_bfloat16 hh[8];
+    __align__(16) __nv_bfloat16 ll[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) split_bf16_ew(f[j], hh[j], ll[j]);
+    const uint4 hv = *reinterpret_cast<const uint4*>(hh), lv = *reinterpret_cast<const uint4*>(ll);
+    uint4* oh = reinterpret_cast<uint4*>(hi) + (long long)g * vox_p;
+    uint4* ol = reinterpret_cast<uint4*>(lo) + (long long)g * vox_p;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const long long pos = ((long long)n * (2 * D + 2 * P) + P + 2 * d + (k >> 2)) * plane2 + (long long)(2 * h + ((k >> 1) & 1)) * W2 +
+                            (2 * w + (k & 1));
+      oh[pos] = hv;
+      ol[pos] = lv;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // 2x2x2 max pool, stride 2 (even extents)
 // ---------------------------------------------------------------------------------------------------------
@@ -893,6 +946,21 @@ extern "C" int cfun_instnorm_bwd_apply_pack(const float* x, const float* a, cons
   dim3 grid((unsigned)cdiv(S, rpb), N);
   in_bwd_apply_pack_kernel<<<grid, 256, 0, st>>>(x, a, b, stat_acc, g, S, C, G, R, rpb, h, l, (long long)(D + 2 * P) * HW,
                                                  (long long)N * (D + 2 * P) * HW, (long long)P * HW);
+  CFUN_LAUNCH_CHECK();
+  return CFUN_OK;
+}
+
+extern "C" int cfun_instnorm_up2_pack(const float* x, const float* a, const float* b, int N, int D, int H, int W, int C, float slope,
+                                      void* hi, void* lo, int G, int P, void* stream) {
+  CFUN_CHECK_ARG(x && a && b && hi && lo && N > 0 && D > 0 && H > 0 && W > 0 && C > 0);
+  CFUN_CHECK_ARG((C & 3) == 0 && G * 8 >= C && P >= 1 && P <= 2);
+  cudaStream_t st = as_stream(stream);
+  __nv_bfloat16* h = reinterpret_cast<__nv_bfloat16*>(hi);
+  __nv_bfloat16* l = reinterpret_cast<__nv_bfloat16*>(lo);
+  int rc = launch_pack_zero_planes(h, l, N, 2 * D, 2 * H, 2 * W, G, P, st);
+  if (rc != CFUN_OK) return rc;
+  const long long total = (long long)N * D * H * W * G;
+  affine_act_up2_pack_kernel<<<pick_blocks(total), 256, 0, st>>>(x, a, b, N, D, H, W, C, slope, h, l, G, P);
   CFUN_LAUNCH_CHECK();
   return CFUN_OK;
 }

@@ -97,7 +97,10 @@ class Modified3DUNet(nn.Module):
                 ctx[lvl] = out
 
         def up_block(seq, t):   # norm -> lrelu -> upsample x2 -> conv -> norm -> lrelu
-            return CIN(seq[3], IN(t, up=2))
+            conv = seq[3]
+            if conv.stride == (1, 1, 1) and conv.padding == (1, 1, 1):
+                return ops.upnorm_conv_in_lrelu(t, conv.weight, conv.bias)     # the upsampled tensor is never materialised
+            return CIN(conv, IN(t, up=2))
 
         out = up_block(self.norm_lrelu_upscale_conv_norm_lrelu_l0, out)
         out = IN(self.conv3d_l0(out, in_stats=True))

@@ -574,6 +574,100 @@ class ConvInstNormActFn(Function):
         return dx, dw, None, None, None, None, None, None, dx2
 
 
+class UpNormConvInstNormActFn(Function):
+    """The U-Net decoder's up block -- InstanceNorm3d -> LeakyReLU -> Upsample(x2, nearest) -> Conv3d(3^3) -> InstanceNorm3d ->
+    LeakyReLU (reference mask_branch.py:91-103) -- as ONE autograd node: the first norm's apply pass writes the upsampled
+    activation straight into the conv's operand pack (cfun_instnorm_up2_pack; the 8x larger fp32 tensor is never written or
+    read), the conv epilogue accumulates the second norm's statistics, and the backward is ConvInstNormActFn's (the second
+    norm writes the conv's dY pack) followed by the first norm's upsample-aware backward."""
+
+    @staticmethod
+    def forward(ctx, t, w, eps, slope):
+        _require_cuda(t, w)
+        t = to_cl(t)
+        w = w.contiguous()
+        N, C1, D, H, W = t.shape
+        dev = t.device
+        acc1 = getattr(t, "_cfun_in_stats", None)
+        mean = torch.empty((N, C1), device=dev)
+        rstd = torch.empty((N, C1), device=dev)
+        if acc1 is not None:
+            _run("cfun_instnorm_finalize", _ptr(acc1), N, D * H * W, C1, float(eps), _ptr(mean), _ptr(rstd), _stream())
+        else:
+            acc1 = torch.empty(2 * N * C1, dtype=torch.float64, device=dev)
+            _run("cfun_instnorm_stats", _ptr(t), N, D * H * W, C1, float(eps), _ptr(acc1), _ptr(mean), _ptr(rstd), _stream())
+        a1, b1 = _in_coeffs(mean, rstd, None, N, C1, eps)
+        d = _conv_desc((N, C1, 2 * D, 2 * H, 2 * W), w.shape, 1, 1)
+        nb = lib.cfun_conv3d_pack_bytes(C.byref(d))
+        xpack = torch.empty(nb, dtype=torch.uint8, device=dev)
+        G = ((C1 + 15) // 16) * 2
+        _run("cfun_instnorm_up2_pack", _ptr(t), _ptr(a1), _ptr(b1), N, D, H, W, C1, float(slope), _ptr(xpack),
+             C.c_void_p(xpack.data_ptr() + nb // 2), G, 1, _stream())
+        Cc = d.Cout
+        y = empty_cl(N, Cc, d.Dout, d.Hout, d.Wout, dev)
+        ws = workspace(lib.cfun_conv3d_workspace_size(C.byref(d), PASS_FWD, ALGO_AUTO), dev)
+        acc2 = torch.empty(2 * N * Cc, dtype=torch.float64, device=dev)
+        _run("cfun_conv3d_fwd_stats_packed", C.byref(d), _ptr(xpack), nb, _ptr(w), _ptr(y), _ptr(acc2), _ptr(ws), ws.numel(), _stream(),
+             tag=_conv_tag(d, PASS_FWD, ALGO_AUTO) if _prof["on"] else "")
+        mean2 = torch.empty((N, Cc), device=dev)
+        rstd2 = torch.empty((N, Cc), device=dev)
+        _run("cfun_instnorm_finalize", _ptr(acc2), N, d.Dout * d.Hout * d.Wout, Cc, float(eps), _ptr(mean2), _ptr(rstd2), _stream())
+        a2, b2 = _in_coeffs(mean2, rstd2, None, N, Cc, eps)
+        z = empty_cl(N, Cc, d.Dout, d.Hout, d.Wout, dev)
+        _run("cfun_affine_act_fwd", _ptr(y), _ptr(a2), _ptr(b2), Cc, None, _ptr(z), N, d.Dout, d.Hout, d.Wout, Cc, Cc, 0, 1, float(slope),
+             _stream())
+        ctx.save_for_backward(t, a1, b1, xpack, w, y, a2, b2)
+        ctx.d, ctx.slope = d, float(slope)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        t, a1, b1, xpack, w, y, a2, b2 = ctx.saved_tensors
+        d, slope = ctx.d, ctx.slope
+        N, Cc, D2, H2, W2 = d.N, d.Cout, d.Dout, d.Hout, d.Wout
+        C1, D, H, W = d.Cin, D2 // 2, H2 // 2, W2 // 2
+        dz = to_cl(dz)
+        dev = dz.device
+        # second norm + conv: as ConvInstNormActFn.backward
+        g = empty_cl(N, Cc, D2, H2, W2, dev)
+        acc2 = torch.empty(2 * N * Cc, dtype=torch.float64, device=dev)
+        _run("cfun_affine_act_bwd", _ptr(y), _ptr(a2), _ptr(b2), Cc, None, _ptr(dz), _ptr(g), None, _ptr(acc2), N, D2, H2, W2, Cc, Cc, 0, 1,
+             slope, _stream())
+        Gy, Py = C.c_int(0), C.c_int(0)
+        ybytes = lib.cfun_conv3d_dy_pack_geometry(C.byref(d), C.byref(Gy), C.byref(Py))
+        ypack = torch.empty(ybytes, dtype=torch.uint8, device=dev)
+        _run("cfun_instnorm_bwd_apply_pack", _ptr(y), _ptr(a2), _ptr(b2), _ptr(acc2), _ptr(g), N, D2, H2, W2, Cc, _ptr(ypack),
+             C.c_void_p(ypack.data_ptr() + ybytes // 2), Gy.value, Py.value, _stream())
+        del g
+        need_t = ctx.needs_input_grad[0]
+        du = empty_cl(N, C1, D2, H2, W2, dev) if need_t else None           # gradient of the (never materialised) upsampled activation
+        dw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        if du is not None or dw is not None:
+            ws = workspace(lib.cfun_conv3d_bwd_fused_workspace_size(C.byref(d)), dev)
+            _run("cfun_conv3d_bwd_fused_packed", C.byref(d), _ptr(xpack), xpack.numel(), _ptr(ypack), ypack.numel(), _ptr(w), _ptr(du),
+                 _ptr(dw), _ptr(ws), ws.numel(), _stream(), tag=_conv_tag(d, PASS_BWD_WEIGHT, ALGO_AUTO) if _prof["on"] else "")
+        dt = None
+        if need_t:      # first norm: sums the 2x2x2 gradients, then the usual two passes
+            dt = empty_cl(N, C1, D, H, W, dev)
+            acc1 = torch.empty(2 * N * C1, dtype=torch.float64, device=dev)
+            _run("cfun_affine_act_bwd", _ptr(t), _ptr(a1), _ptr(b1), C1, None, _ptr(du), _ptr(dt), None, _ptr(acc1), N, D, H, W, C1, C1, 0, 2,
+                 slope, _stream())
+            _run("cfun_instnorm_bwd_apply", _ptr(t), _ptr(a1), _ptr(b1), _ptr(acc1), _ptr(dt), N, D * H * W, C1, _stream())
+        return dt, dw, None, None
+
+
+def upnorm_conv_in_lrelu(t, w, b=None, eps=1e-5, slope=0.01):
+    """instnorm_lrelu(conv3d(instnorm_lrelu(t, up=2), w, b, 1, 1)) -- the decoder's up block; one fused node where the conv has
+    the fused tcgen05 backward and no bias, else the separate ops."""
+    if b is None and _default_algo["algo"] == ALGO_AUTO and t.is_cuda and w.requires_grad and torch.is_grad_enabled() and \
+            t.shape[1] % 4 == 0 and tuple(w.shape[2:]) == (3, 3, 3):
+        N, C1, D, H, W = t.shape
+        d = _conv_desc((N, C1, 2 * D, 2 * H, 2 * W), tuple(w.shape), 1, 1)
+        if d.Cout % 4 == 0 and lib.cfun_conv3d_pack_bytes(C.byref(d)) and lib.cfun_conv3d_dy_pack_geometry(C.byref(d), None, None):
+            return UpNormConvInstNormActFn.apply(t, w, eps, slope)
+    return conv_in_lrelu(instnorm_lrelu(t, None, eps, slope, 2), w, b, 1, 1, None, eps, slope)
+
+
 def conv_in_lrelu(x, w, b=None, stride=1, padding=0, drop=None, eps=1e-5, slope=0.01, up=1, x2=None):
     """instnorm_lrelu(conv3d(x, w, b), drop) -- as one fused node (ConvInstNormActFn) where the conv runs with the fused tcgen05
     backward and has no bias, else as the two separate ops (with the epilogue statistics where available).

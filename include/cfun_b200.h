@@ -108,6 +108,14 @@ int cfun_conv3d_preact_supported(const cfun_conv3d_desc* d);
 int cfun_conv3d_fwd_keep_pack_preact(const cfun_conv3d_desc* d, const float* x, const float* scale, float slope, const float* w,
                                      const float* bias, float* y, int epi_flags, void* xpack, size_t xpack_bytes, void* ws,
                                      size_t ws_bytes, void* stream);
+/* The decoder's InstanceNorm -> LeakyReLU -> Upsample(x2, nearest) -> conv (mask_branch.py:91-103) without the upsampled
+ * tensor: cfun_instnorm_up2_pack applies the norm coefficients a, b [N][C] and the activation to the low-resolution x and
+ * writes the 2x2x2-replicated result straight into the conv's operand pack (hi, lo: [G][N*(2D+2P)][2H][2W][8], G =
+ * align16(C)/8, halves of cfun_conv3d_pack_bytes); cfun_conv3d_fwd_stats_packed runs the conv on that pack. */
+int cfun_instnorm_up2_pack(const float* x, const float* a, const float* b, int N, int D, int H, int W, int C, float slope,
+                           void* hi, void* lo, int G, int P, void* stream);
+int cfun_conv3d_fwd_stats_packed(const cfun_conv3d_desc* d, void* xpack, size_t xpack_bytes, const float* w, float* y,
+                                 double* stat_acc, void* ws, size_t ws_bytes, void* stream);
 /* cfun_conv3d_fwd_stats on the channel concatenation [a (C1) | b (C2)] (the U-Net decoder's torch.cat((up, skip), 1) -> conv,
  * mask_branch.py:185-205): the operand pack is built from the two tensors, the concatenated tensor never exists.
  * stat_acc may be NULL. */

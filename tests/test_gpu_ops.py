@@ -786,3 +786,38 @@ def test_lrelu_conv3d_activation_fused_into_the_operand_pack(ops, case):
     yr = F.conv3d(F.leaky_relu(t, 0.01), wr, None, padding=1)
     yr.backward(dy.cpu())
     assert rel_err(y1.cpu().numpy(), yr.detach().numpy()) < TOL and rel_err(dx1.cpu().numpy(), xr.grad.numpy()) < TOL
+
+
+@pytest.mark.parametrize("case", [dict(N=2, C1=40, Cout=20, dims=(5, 8, 12)), dict(N=3, C1=80, Cout=40, dims=(4, 8, 8)),
+                                  dict(N=1, C1=320, Cout=160, dims=(3, 6, 6)), dict(N=2, C1=20, Cout=20, dims=(3, 9, 7))])
+def test_upnorm_conv_in_lrelu_fused_up_block(ops, case):
+    """ops.upnorm_conv_in_lrelu (norm -> lrelu -> upsample x2 written straight into the conv's operand pack -> conv -> norm ->
+    lrelu as one node) == the separate ops: forward and input gradient bit for bit, weight gradient up to the atomics'
+    summation order; and against fp32 PyTorch"""
+    g = torch.Generator().manual_seed(case["C1"] + case["dims"][1])
+    N, C1, Cout, (D, H, W) = case["N"], case["C1"], case["Cout"], case["dims"]
+    t = torch.randn(N, C1, D, H, W, generator=g) * 2 + 0.3
+    w = torch.randn(Cout, C1, 3, 3, 3, generator=g) * 0.1
+    # fp32 PyTorch reference; the incoming gradient is zeroed within 1e-3 of the second LeakyReLU's kink
+    tr, wr = t.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    u = F.interpolate(F.leaky_relu(F.instance_norm(tr, eps=1e-5), 0.01), scale_factor=2, mode="nearest")
+    yn = F.instance_norm(F.conv3d(u, wr, None, padding=1), eps=1e-5)
+    zr = F.leaky_relu(yn, 0.01)
+    dz = cuda(torch.randn(zr.shape, generator=g) * (yn.detach().abs() > 1e-3).float())
+    zr.backward(dz.cpu())
+    res = []
+    for fused in (True, False):
+        tc, wc = cuda(t).requires_grad_(True), w.cuda().requires_grad_(True)
+        if fused:
+            z = ops.upnorm_conv_in_lrelu(tc, wc)
+            assert type(z.grad_fn).__name__.startswith("UpNormConvInstNormActFn"), "shape did not take the fused node"
+        else:
+            z = ops.conv_in_lrelu(ops.instnorm_lrelu(tc, None, 1e-5, 0.01, 2), wc, None, 1, 1)
+        z.backward(dz)
+        res.append((z.detach(), tc.grad, wc.grad))
+    (z1, dt1, dw1), (z0, dt0, dw0) = res
+    assert torch.equal(z1, z0)
+    assert torch.equal(dt1, dt0)
+    assert rel_err(dw1.cpu().numpy(), dw0.cpu().numpy()) < 1e-5
+    assert rel_err(z1.cpu().numpy(), zr.detach().numpy()) < TOL
+    assert rel_err(dt1.cpu().numpy(), tr.grad.numpy()) < 1e-3        # two InstanceNorm backward passes amplify the conv's 1e-5
